@@ -1,0 +1,228 @@
+/*
+ * vgposp.h -- C-ABI of libvgposp.so, the B200 (sm_100a) implementation of VGPosp's GP placement hot path.
+ *
+ * The reference (DL-WG/VGPosp) has no FFI layer: its boundary for this path is a set of Python module
+ * functions.  This header is the boundary a maintainer binds instead (ctypes
+ * stub: vgposp_b200/_ffi.py; reference-side patch: INTEGRATION.md).  Each entry point cites the
+ * reference interface it stands in for, as file:line under the reference tree.
+ *
+ * Conventions
+ *   - every function returns an int status (VGP_OK == 0); vgp_last_error() gives the thread-local text;
+ *   - all matrices are float64, row-major, with an explicit leading dimension in ELEMENTS;
+ *   - pointers named *_dev are device pointers on `device`; pointers named *_host are host pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ *     asynchronous on that stream unless stated otherwise;
+ *   - no hidden global state: handles are per device and not thread-safe;
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute call fails with
+ *     VGP_ERR_CUDA.
+ */
+#ifndef VGPOSP_H
+#define VGPOSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define VGP_OK 0
+#define VGP_ERR_INVALID 1      /* bad argument (shape, alignment, NULL)                         */
+#define VGP_ERR_CUDA 2         /* CUDA runtime/driver error, including "no device"              */
+#define VGP_ERR_NOT_PD 3       /* matrix not positive definite (the reference would pinv it)    */
+#define VGP_ERR_NOMEM 4
+#define VGP_ERR_STATE 5        /* call order / handle state                                     */
+
+#define VGP_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- runtime ---------------------------------- */
+int vgp_abi_version(void);
+const char *vgp_last_error(void);
+int vgp_device_count(int *count);
+/* name[<=len], SM count, total/free bytes of HBM */
+int vgp_device_info(int device, char *name, int len, int *sm_count, size_t *total_bytes, size_t *free_bytes);
+
+int vgp_malloc(int device, size_t bytes, void **ptr_dev);
+int vgp_free(int device, void *ptr_dev);
+int vgp_host_alloc(size_t bytes, void **ptr_host);          /* pinned */
+int vgp_host_free(void *ptr_host);
+int vgp_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int vgp_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int vgp_memcpy_d2d(int device, void *dst_dev, const void *src_dev, size_t bytes, void *stream);
+/* strided 2-D copies, widths in bytes (cudaMemcpy2DAsync) -- panels of a host matrix to the device */
+int vgp_memcpy2d_h2d(int device, void *dst_dev, size_t dpitch, const void *src_host, size_t spitch,
+                     size_t width_bytes, size_t rows, void *stream);
+int vgp_memcpy2d_d2h(int device, void *dst_host, size_t dpitch, const void *src_dev, size_t spitch,
+                     size_t width_bytes, size_t rows, void *stream);
+int vgp_memset(int device, void *dst_dev, int value, size_t bytes, void *stream);
+int vgp_stream_create(int device, void **stream);
+int vgp_stream_destroy(int device, void *stream);
+int vgp_stream_sync(int device, void *stream);
+/* CUDA-event timing on `stream`: start/stop return opaque events, elapsed gives milliseconds */
+int vgp_event_record(int device, void *stream, void **event);
+int vgp_event_elapsed_ms(int device, void *start_event, void *stop_event, float *ms); /* syncs on stop; frees both */
+
+/* ---------------------------------------------------------------- DLPack ----------------------------------- */
+/* Zero-copy view of a DLPack tensor (DLManagedTensor*, the payload of a "dltensor" capsule such as
+ * tf.experimental.dlpack.to_dlpack(t) or torch.utils.dlpack.to_dlpack(t)).  The library never takes
+ * ownership and never calls the deleter. */
+typedef struct vgp_tensor_view {
+    void *data;            /* data pointer + byte_offset already applied */
+    int32_t device_type;   /* DLDeviceType: 1 CPU, 2 CUDA, 3 CUDA-pinned host */
+    int32_t device_id;
+    int32_t ndim;
+    int32_t dtype_code;    /* DLDataTypeCode: 0 int, 1 uint, 2 float */
+    int32_t dtype_bits;
+    int32_t contiguous;    /* 1 if row-major contiguous (or strides == NULL) */
+    int64_t shape[8];
+    int64_t strides[8];    /* in elements */
+} vgp_tensor_view;
+int vgp_dlpack_view(const void *dl_managed_tensor, vgp_tensor_view *out);
+
+/* ---------------------------------------------------------------- (1) ExpQuad kernel matrix ---------------- */
+/* out[i][j] = amplitude^2 * exp(-|x1_i - x2_j|^2 / (2 length_scale^2)) + (i == diag_col0 + j ? diag_add : 0)
+ * Replaces tfkern.ExponentiatedQuadratic(amplitude, length_scale).matrix(x1, x2)
+ *   (call sites variational_Gaussian_process_example.py:55-57, 3D_sin_wave.py:158-159, main_tests.py:617-619;
+ *    factory hook gp_functions.py:160-163).
+ * x1_dev [n1, d], x2_dev [n2, d] row-major, d in [1, 8]; out_dev [n1, ld_out].  When x1_dev == x2_dev,
+ * n1 == n2 and diag_col0 == 0 the symmetric path computes each off-diagonal tile once. */
+int vgp_expquad_matrix(int device, const double *x1_dev, int64_t n1, const double *x2_dev, int64_t n2, int d,
+                       double amplitude, double length_scale, double diag_add, int64_t diag_col0,
+                       double *out_dev, int64_t ld_out, void *stream);
+
+/* ---------------------------------------------------------------- (2) dense float64 factorisations ---------- */
+/* C[m,n] = alpha * op(A) * op(B) + beta * C.  trans_a/trans_b: 0 = as stored, 1 = transposed.  Hand-written
+ * DMMA (mma.sync f64) kernel; stands for the tf.matmul / LinearOperator matmuls TFP issues inside the VGP loss
+ * (variational_Gaussian_process_example.py:68-74,96-99). */
+int vgp_dgemm(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+              const double *a_dev, int64_t lda, const double *b_dev, int64_t ldb, double beta, double *c_dev,
+              int64_t ldc, void *stream);
+/* In-place lower Cholesky A = L L^T (strict upper triangle is left untouched).  Replaces tf.linalg.cholesky
+ * inside tfd.GaussianProcess.log_prob / VariationalGaussianProcess (gp_functions.py:166-172,
+ * 3D_sin_wave.py:172).  Synchronous w.r.t. the host only for the final status read:
+ * *info_host = 0, or 1 + index of the first non-positive pivot (then returns VGP_ERR_NOT_PD). */
+int vgp_potrf(int device, double *a_dev, int64_t n, int64_t lda, int *info_host, void *stream);
+/* Full symmetric inverse of an SPD matrix, in place (potrf + trtri + lauum + mirror).  Replaces the
+ * pseudo-inverses of placement_algorithm2.py:399-405 on the well-conditioned inputs where pinv == inv. */
+int vgp_spd_inverse(int device, double *a_dev, int64_t n, int64_t lda, int *info_host, void *stream);
+/* Triangular solves with the lower factor: side 0: op(L) X = B (B is [n, nrhs]), side 1: X op(L) = B
+ * (B is [nrhs, n]); trans 0: op(L) = L, 1: op(L) = L^T.  In place on B.  Replaces
+ * LinearOperatorLowerTriangular.solve in the VGP loss / GPRM (gp_functions.py:290-296). */
+int vgp_trsm(int device, int side, int trans, int64_t n, int64_t nrhs, const double *l_dev, int64_t ldl,
+             double *b_dev, int64_t ldb, void *stream);
+
+/* ---------------------------------------------------------------- exact GP (a2, a3) ------------------------- */
+/* log N(y | 0, K + (noise + jitter) I), K ExpQuad on x_dev [n, d].  Replaces
+ * gpf.fit_gp(kernel, x, noise).log_prob(y) (gp_functions.py:166-172; 3D_sin_wave.py:161-172).
+ * Blocking; result in *logprob_host. */
+int vgp_gp_logprob(int device, const double *x_dev, int64_t n, int d, const double *y_dev, double amplitude,
+                   double length_scale, double noise_variance, double jitter, double *logprob_host,
+                   void *stream);
+/* Posterior mean [t] and marginal variance [t] at xt_dev [t, d] given observations.  Replaces
+ * gpf.tf_gp_regression_model(...).mean() / .variance() (gp_functions.py:283-297). */
+int vgp_gp_regression(int device, const double *x_dev, int64_t n, int d, const double *y_dev,
+                      const double *xt_dev, int64_t t, double amplitude, double length_scale,
+                      double noise_variance, double predictive_noise_variance, double divisor_jitter,
+                      double *mean_dev, double *var_dev, void *stream);
+
+/* ---------------------------------------------------------------- variational GP (a4, a5) ------------------- */
+typedef struct vgp_vgp_terms {
+    double loss, ll, tr1, tr2, kl;
+} vgp_vgp_terms;
+/* Titsias-optimal q(u): loc [m], scale [m, m] (S = scale scale^T = Kzz Sigma Kzz).  Replaces
+ * tfd.VariationalGaussianProcess.optimal_variational_posterior
+ * (variational_Gaussian_process_example.py:68-74; main_architecture_2.py:200-206).  K_zx is generated tile by
+ * tile and consumed by the m x m SYRK; the m x N matrix is never stored. */
+int vgp_vgp_optimal_posterior(int device, const double *z_dev, int64_t m, const double *x_dev, int64_t n_obs,
+                              int d, const double *y_dev, double amplitude, double length_scale,
+                              double noise_variance, double jitter, int legacy_scale_orientation,
+                              double *loc_dev, double *scale_dev, void *stream);
+/* Negative ELBO on a minibatch.  Replaces vgp.variational_loss(observations, observation_index_points,
+ * kl_weight) (variational_Gaussian_process_example.py:96-99).  Blocking; pieces in *terms_host. */
+int vgp_vgp_loss(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                 const double *scale_dev, const double *xb_dev, const double *yb_dev, int64_t b,
+                 double amplitude, double length_scale, double noise_variance, double kl_weight, double jitter,
+                 vgp_vgp_terms *terms_host, void *stream);
+/* Predictive mean [t] / marginal variance [t].  Replaces vgp.mean() / vgp.variance()
+ * (variational_Gaussian_process_example.py:141-142; main_architecture_2.py:347-360). */
+int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                    const double *scale_dev, const double *xt_dev, int64_t t, double amplitude,
+                    double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
+                    double *var_dev, void *stream);
+
+/* ---------------------------------------------------------------- (3) greedy MI placement ------------------- */
+/* One handle holds one device's shard of the candidate set: columns [c0, c0 + nloc) of Sigma and of the
+ * precision P of the unselected set, all n rows.  Replaces the state that
+ * placement_algorithm2.py:128-145 (alg. 1) / :151-219 (alg. 2) keep in Python lists.
+ *
+ * Per selection (all kernels on `stream`, no host synchronisation):
+ *   vgp_greedy_local_best   delta_j = guard(num_j, 1/P_jj) over the shard, first strict maximum
+ *   (exchange 1: every rank's 32-byte candidate record)
+ *   vgp_greedy_select       winner over all records: max score, lowest index on exact ties
+ *   vgp_greedy_segments     w_J = (Sigma[y,J] - W^T W[:,y]) / sqrt(num_y),  p_J = P[y,J]
+ *   (exchange 2: every rank's [w_J | p_J])
+ *   vgp_greedy_apply        num_J -= w_J^2;  P[:,J] -= p p_J^T / p_y;  row/column y zeroed
+ * With one shard (c0 == 0, nloc == n) vgp_greedy_run does the whole loop inside the library. */
+typedef struct vgp_greedy vgp_greedy;
+
+typedef struct vgp_candidate {      /* exchange-1 record, 32 bytes */
+    double score;                   /* -inf when the shard has no candidate */
+    int64_t index;                  /* global candidate index, -1 when none */
+    double num;                     /* numerator sigma^2(y|A) of that candidate (incl. jitter) */
+    double pdiag;                   /* P_yy */
+} vgp_candidate;
+
+/* small: guard threshold (1e-8, placement_algorithm2.py:116,198; 1e-7 for the TF-graph variant
+ * snippets_a2.py:480); jitter: diagonal shift of Sigma_AA (0; 1e-6 for snippets_a2.py:161-163). */
+int vgp_greedy_create(vgp_greedy **handle, int device, int64_t n, int64_t c0, int64_t nloc, int64_t kmax,
+                      double small, double jitter);
+int vgp_greedy_destroy(vgp_greedy *handle);
+/* Leading dimension (elements) and device pointers of the handle-owned panels: Sigma[:, J] and P[:, J],
+ * both [n_pad, ld] with rows >= n and columns >= nloc zero-padded by the library. */
+int vgp_greedy_panels(vgp_greedy *handle, double **cov_dev, double **prec_dev, int64_t *ld, int64_t *n_pad);
+/* Single shard only: build P = Sigma^-1 from the Sigma panel already stored in the handle (potrf + potri
+ * on device) and reset the selection state.  Blocking for the status read. */
+int vgp_greedy_factor(vgp_greedy *handle, int *info_host, void *stream);
+/* Reset selection state (num = diag Sigma (+jitter), W empty, nothing taken), P taken as stored. */
+int vgp_greedy_reset(vgp_greedy *handle, void *stream);
+/* Snapshot / restore of the precision panel (bench warm-up; 8 n ld bytes of extra HBM). */
+int vgp_greedy_save_precision(vgp_greedy *handle, void *stream);
+int vgp_greedy_restore_precision(vgp_greedy *handle, void *stream);
+
+int vgp_greedy_local_best(vgp_greedy *handle, vgp_candidate *best_dev, void *stream);
+int vgp_greedy_select(vgp_greedy *handle, const vgp_candidate *records_dev, int nrecords, void *stream);
+/* seg_dev: [2, seg_stride] doubles: row 0 = w_J, row 1 = p_J (entries >= nloc are zero) */
+int vgp_greedy_segments(vgp_greedy *handle, double *seg_dev, int64_t seg_stride, void *stream);
+/* gathered_dev: [nranks, 2, seg_stride]; bounds_host[nranks + 1]: column ranges of the ranks */
+int vgp_greedy_apply(vgp_greedy *handle, const double *gathered_dev, int64_t seg_stride, int nranks,
+                     const int64_t *bounds_host, void *stream);
+/* Single shard: k further selections enqueued back to back. */
+int vgp_greedy_run(vgp_greedy *handle, int64_t k, void *stream);
+/* Results so far (blocking): indices [count], winning scores [count], relative top-2 gap is not tracked. */
+int vgp_greedy_results(vgp_greedy *handle, int64_t *count, int64_t *selection_host, double *scores_host,
+                       int64_t capacity, void *stream);
+/* Dense per-step score vectors for the steps run so far, [count, nloc] (NaN where already selected);
+ * only recorded if enabled before the run.  Lets the host replay alg. 2's lazy cache and its prints
+ * (placement_algorithm2.py:183-208). */
+int vgp_greedy_record_scores(vgp_greedy *handle, int enable);
+int vgp_greedy_step_scores(vgp_greedy *handle, double *scores_host, int64_t capacity_rows, void *stream);
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int vgp_greedy_launch_count(vgp_greedy *handle, int64_t *launches);
+
+/* One-call form of placement_algorithm_1/2(cov_vv, k) (placement_algorithm2.py:128,151) for a HOST matrix:
+ * H2D, factor, k selections, D2H.  cov_host [n, ld_host] row-major float64 (pageable or pinned).
+ * seconds_host (optional, may be NULL): [h2d, factor, select, total] wall seconds measured with CUDA events. */
+int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
+                       double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
+                       double *seconds_host);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGPOSP_H */

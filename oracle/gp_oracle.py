@@ -1,0 +1,159 @@
+"""TEST INFRASTRUCTURE ONLY -- float64 NumPy/SciPy restatement of the GP arithmetic behind the path.
+
+**Parity unpinned.**  The reference delegates this arithmetic to TensorFlow-Probability
+(`tfkern.ExponentiatedQuadratic`, `tfd.GaussianProcess`, `tfd.GaussianProcessRegressionModel`,
+`tfd.VariationalGaussianProcess`), which is neither vendored under /root/reference nor installed
+here, and the reference pins no TFP version and asserts no numeric result for these calls (SURVEY.md
+section 8c).  The functions below restate TFP's published algorithm as recorded in SURVEY.md
+Appendix A.2-A.5 and are anchored on the reference's call sites:
+
+    kernel                variational_Gaussian_process_example.py:55-57, 3D_sin_wave.py:158-159
+    exact GP log_prob     gp_functions.py:166-172 (fit_gp), 3D_sin_wave.py:161-172
+    GP regression model   gp_functions.py:283-297, 3D_sin_wave.py:262-268
+    optimal posterior     variational_Gaussian_process_example.py:68-74, main_architecture_2.py:200-206
+    VGP loss / mean       variational_Gaussian_process_example.py:83-99,141-142
+    Adam                  gp_functions.py:179-182 (tf.train.AdamOptimizer defaults)
+    softplus params       gp_functions.py:124-135, variational_Gaussian_process_example.py:47-61
+
+The one first-party NumPy statement of kernel -> Cholesky -> solve -> posterior variance in the
+reference, `plot_confidence_interval.py:17-19,26,43-51`, is reproduced by `expquad_matrix`,
+`gp_regression` (see tests/test_oracle_gp.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU baseline may import this module.
+"""
+import numpy as np
+from scipy.linalg import cholesky, solve_triangular
+
+LOG_2PI = float(np.log(2.0 * np.pi))
+DEFAULT_JITTER = 1e-6        # TFP class default; passed explicitly at main_architecture_2.py:225
+
+
+def softplus(v):
+    return np.logaddexp(0.0, v)
+
+
+def softplus_inverse(p):
+    """gp_functions.py:106-109 invert_softplus: v = log(exp(p) - 1)."""
+    return np.log(np.expm1(p))
+
+
+def sqdist(x1, x2):
+    """Direct sum of squared coordinate differences (no |x|^2+|y|^2-2xy expansion)."""
+    d = x1[:, None, :] - x2[None, :, :]
+    return np.einsum("ijk,ijk->ij", d, d)
+
+
+def expquad_matrix(x1, x2, amplitude, length_scale, diag_add=0.0):
+    """k(x,y) = a^2 exp(-|x-y|^2 / (2 l^2)); `diag_add` is added where row index == column index."""
+    k = amplitude ** 2 * np.exp(sqdist(x1, x2) * (-0.5 / length_scale ** 2))
+    if diag_add:
+        m = min(k.shape)
+        k[np.arange(m), np.arange(m)] += diag_add
+    return k
+
+
+def _chol(a):
+    return cholesky(a, lower=True, check_finite=False)
+
+
+def _fwd(l, b):
+    return solve_triangular(l, b, lower=True, check_finite=False)
+
+
+def _bwd(l, b):
+    return solve_triangular(l, b, lower=True, trans="T", check_finite=False)
+
+
+def gp_log_prob(x, y, amplitude, length_scale, noise_variance, jitter=DEFAULT_JITTER, mean=0.0):
+    """Exact-GP marginal log-likelihood: L = chol(K + (s2 + jitter) I)."""
+    n = x.shape[0]
+    l = _chol(expquad_matrix(x, x, amplitude, length_scale, noise_variance + jitter))
+    z = _fwd(l, y - mean)
+    return -0.5 * float(z @ z) - float(np.sum(np.log(np.diag(l)))) - 0.5 * n * LOG_2PI
+
+
+def gp_regression(x_obs, y_obs, x_pred, amplitude, length_scale, noise_variance,
+                  predictive_noise_variance=0.0, divisor_jitter=0.0, mean=0.0, full_cov=False):
+    """Posterior mean / (co)variance of GaussianProcessRegressionModel."""
+    l = _chol(expquad_matrix(x_obs, x_obs, amplitude, length_scale, noise_variance + divisor_jitter))
+    k_xt = expquad_matrix(x_obs, x_pred, amplitude, length_scale)
+    c = _fwd(l, k_xt)
+    post_mean = mean + c.T @ _fwd(l, y_obs - mean)
+    if full_cov:
+        cov = expquad_matrix(x_pred, x_pred, amplitude, length_scale, predictive_noise_variance) - c.T @ c
+        return post_mean, cov
+    var = amplitude ** 2 - np.sum(c * c, axis=0) + predictive_noise_variance
+    return post_mean, var
+
+
+def optimal_variational_posterior(z, x, y, amplitude, length_scale, noise_variance,
+                                  jitter=DEFAULT_JITTER, legacy_scale_orientation=False):
+    """Titsias optimum.  Returns (loc [m], scale [m,m]) with S = scale @ scale.T =
+    K_zz Sigma K_zz; `legacy_scale_orientation` returns L_Sigma^-1 K_zz (S = scale.T @ scale)."""
+    k_zz = expquad_matrix(z, z, amplitude, length_scale)
+    k_zx = expquad_matrix(z, x, amplitude, length_scale)
+    sigma_inv = k_zz + (k_zx @ k_zx.T) / noise_variance
+    sigma_inv[np.diag_indices_from(sigma_inv)] += jitter
+    l_s = _chol(sigma_inv)
+    loc = (k_zz @ _bwd(l_s, _fwd(l_s, k_zx @ y))) / noise_variance
+    scale = _fwd(l_s, k_zz)
+    return loc, (scale if legacy_scale_orientation else scale.T)
+
+
+def vgp_terms(z, q_loc, q_scale, x_b, y_b, amplitude, length_scale, noise_variance, kl_weight,
+              jitter=DEFAULT_JITTER):
+    """All pieces of the negative ELBO of SURVEY.md A.2 (dict), S = q_scale @ q_scale.T."""
+    m, b = z.shape[0], x_b.shape[0]
+    l = _chol(expquad_matrix(z, z, amplitude, length_scale, jitter))
+    k_zb = expquad_matrix(z, x_b, amplitude, length_scale)
+    alpha = _bwd(l, _fwd(l, q_loc))
+    mu_b = k_zb.T @ alpha
+    r = y_b - mu_b
+    ll = -0.5 * float(r @ r) / noise_variance - 0.5 * b * (LOG_2PI + np.log(noise_variance))
+    c = _fwd(l, k_zb)
+    d = _bwd(l, c)
+    tr1 = b * amplitude ** 2 - float(np.sum(c * c))
+    e = q_scale.T @ d
+    tr2 = float(np.sum(e * e))
+    li_a = _fwd(l, q_scale)                         # tr(Kzz^-1 S) = |L^-1 A|_F^2
+    li_mu = _fwd(l, q_loc)
+    sign, logdet_s = np.linalg.slogdet(q_scale @ q_scale.T)
+    logdet_k = 2.0 * float(np.sum(np.log(np.diag(l))))
+    kl = 0.5 * (float(np.sum(li_a * li_a)) + float(li_mu @ li_mu) - m + logdet_k - logdet_s)
+    loss = -(ll - 0.5 * (tr1 + tr2) / noise_variance - kl_weight * kl)
+    return dict(loss=loss, ll=ll, tr1=tr1, tr2=tr2, kl=kl, mu_b=mu_b, chol_kzz=l, alpha=alpha)
+
+
+def vgp_loss(*args, **kwargs):
+    return vgp_terms(*args, **kwargs)["loss"]
+
+
+def vgp_predict(z, q_loc, q_scale, x_t, amplitude, length_scale, predictive_noise_variance=0.0,
+                jitter=DEFAULT_JITTER):
+    """Predictive mean and marginal variance of the VGP at x_t (last paragraph)."""
+    l = _chol(expquad_matrix(z, z, amplitude, length_scale, jitter))
+    k_zt = expquad_matrix(z, x_t, amplitude, length_scale)
+    c = _fwd(l, k_zt)
+    d = _bwd(l, c)
+    mean = d.T @ q_loc
+    e = q_scale.T @ d
+    var = amplitude ** 2 - np.sum(c * c, axis=0) + np.sum(e * e, axis=0) + predictive_noise_variance
+    return mean, var
+
+
+class TfAdam:
+    """tf.train.AdamOptimizer update (beta1 .9, beta2 .999, eps 1e-8; 'epsilon hat' form):
+    lr_t = lr sqrt(1-b2^t)/(1-b1^t);  theta -= lr_t m / (sqrt(v) + eps)."""
+
+    def __init__(self, shape, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.m = np.zeros(shape)
+        self.v = np.zeros(shape)
+        self.t = 0
+        self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
+
+    def step(self, theta, grad):
+        self.t += 1
+        self.m = self.b1 * self.m + (1 - self.b1) * grad
+        self.v = self.b2 * self.v + (1 - self.b2) * grad * grad
+        lr_t = self.lr * np.sqrt(1 - self.b2 ** self.t) / (1 - self.b1 ** self.t)
+        return theta - lr_t * self.m / (np.sqrt(self.v) + self.eps)

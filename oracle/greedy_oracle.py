@@ -1,0 +1,283 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's greedy mutual-information placement.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / reference arm may import this
+module; no product code does.  It restates `/root/reference/placement_algorithm2.py` in two forms:
+
+* the **literal** form (``literal_*``) follows the reference line by line -- sub-matrix gathers, `pinv`,
+  first-strict-maximum scans -- and is what the golden vectors in ``tests/golden/`` were checked
+  against (the vectors themselves come from the reference's own functions, exec'd unmodified by
+  ``oracle/ref_extract.py``).  It is O(n^4) per selection and only usable for n of a few hundred;
+* the **incremental** form (``incremental_greedy``) is the algebraically identical O(n^2)-per-selection
+  restatement that the CUDA path implements: sigma^2(y|A) by a growing Cholesky panel, and
+  sigma^2(y | Abar \\ y) = 1 / (Sigma_AbarAbar^-1)_yy by rank-1 downdates of the precision.
+
+Parity status: **pinned** -- both forms reproduce every golden vector in ``tests/golden/greedy_*.json``
+(selection sequences bit-exactly, scores within 1e-10 relative).
+"""
+import numpy as np
+
+GUARD_NUMPY = 1e-8      # placement_algorithm2.py:116,198
+GUARD_TF_GRAPH = 1e-7   # snippets_a2.py:480
+JITTER_TF_GRAPH = 1e-6  # snippets_a2.py:161-163
+
+
+# --------------------------------------------------------------------------------------------------
+# literal form
+# --------------------------------------------------------------------------------------------------
+def literal_make_slice(cov_vv, rows, cols):
+    """Sub-matrix gather, placement_algorithm2.py:391-396 (the reference loops in Python)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    cols = np.asarray(cols, dtype=np.int64)
+    out = np.zeros((len(rows), len(cols)))
+    if len(rows) and len(cols):
+        out[:, :] = cov_vv[np.ix_(rows, cols)]
+    return out
+
+
+def literal_call_pinv(a):
+    """placement_algorithm2.py:399-405: reciprocal for 1x1, else SVD pseudo-inverse (rcond 1e-15)."""
+    assert a.shape[0] == a.shape[1]
+    if a.shape[0] == 1:
+        return 1 / a
+    return np.linalg.pinv(a)
+
+
+def literal_nominator(y, A, cov_vv, jitter=0.0):
+    """sigma^2(y | A), placement_algorithm2.py:371-388.  `jitter` is the TF-graph variant's diagonal
+    shift of Sigma_AA (snippets_a2.py:161-163)."""
+    A_ = [int(a) for a in A]
+    sigm_yy = literal_make_slice(cov_vv, [y], [y])
+    if len(A_) == 0:
+        return sigm_yy
+    cov_yA = literal_make_slice(cov_vv, [y], A_)
+    cov_AA = literal_make_slice(cov_vv, A_, A_)
+    cov_Ay = literal_make_slice(cov_vv, A_, [y])
+    if jitter:
+        cov_AA = cov_AA + jitter * np.eye(len(A_))
+    return sigm_yy - np.dot(np.dot(cov_yA, literal_call_pinv(cov_AA)), cov_Ay)
+
+
+def literal_denominator(y, A_hat, cov_vv, jitter=0.0):
+    """sigma^2(y | Abar \\ y), placement_algorithm2.py:408-413."""
+    rest = [int(a) for a in A_hat if int(a) != int(y)]
+    return literal_nominator(y, rest, cov_vv, jitter)
+
+
+def literal_delta(y, A, A_bar, cov_vv, small=GUARD_NUMPY, jitter=0.0):
+    """Guarded ratio, placement_algorithm2.py:113-119 / :194-203."""
+    nom = literal_nominator(y, A, cov_vv, jitter)
+    den = literal_denominator(y, A_bar, cov_vv, jitter)
+    if np.abs(den) < small or np.abs(nom) < small:
+        return 0.0
+    return float((nom / den).reshape(()))
+
+
+def literal_placement_algorithm_1(cov_vv, k, small=GUARD_NUMPY, jitter=0.0, return_scores=False):
+    """Naive greedy, placement_algorithm2.py:128-145 with argmax_ :105-125: first strict maximum,
+    running best initialised to -1."""
+    n = cov_vv.shape[0]
+    A, A_bar = [], list(range(n))
+    per_step = []
+    while len(A) < k:
+        y_st, delta_st = -1, -1
+        scores = np.full(n, np.nan)
+        for y in range(n):
+            if y in A:
+                continue
+            d = literal_delta(y, A, A_bar, cov_vv, small, jitter)
+            scores[y] = d
+            if delta_st < d:
+                delta_st, y_st = d, y
+        A.append(y_st)
+        A_bar.remove(y_st)          # raises ValueError for y_st == -1, as the reference does
+        per_step.append(scores)
+    return (A, per_step) if return_scores else A
+
+
+def literal_placement_algorithm_2(cov_vv, k, small=GUARD_NUMPY, jitter=0.0):
+    """Lazy greedy, placement_algorithm2.py:151-219 (cache starts at +inf, :164)."""
+    n = cov_vv.shape[0]
+    A, A_bar = [], list(range(n))
+    cache = [np.inf] * n
+    evaluations = []
+    while len(A) < k:
+        fresh = [False] * n
+        while True:
+            y_st, delta_st = -1, -1
+            for y in range(n):          # argmax_cache_linear, :53-67
+                if y in A:
+                    continue
+                if delta_st < cache[y]:
+                    delta_st, y_st = cache[y], y
+            if fresh[y_st]:
+                break
+            cache[y_st] = literal_delta(y_st, A, A_bar, cov_vv, small, jitter)
+            fresh[y_st] = True
+            evaluations.append((len(A), y_st, cache[y_st]))
+        A.append(y_st)
+        A_bar.remove(y_st)
+    return A, evaluations
+
+
+# --------------------------------------------------------------------------------------------------
+# incremental form (what the CUDA kernels compute)
+# --------------------------------------------------------------------------------------------------
+def spd_inverse(cov):
+    """Sigma^-1 through LAPACK potrf + potri (the same factor-then-invert route the GPU path takes)."""
+    from scipy.linalg import lapack
+    c, info = lapack.dpotrf(cov, lower=1, clean=1, overwrite_a=0)
+    if info != 0:
+        raise np.linalg.LinAlgError("covariance is not positive definite (potrf info=%d)" % info)
+    inv, info = lapack.dpotri(c, lower=1, overwrite_c=1)
+    if info != 0:
+        raise np.linalg.LinAlgError("potri info=%d" % info)
+    inv = np.tril(inv)
+    return inv + np.tril(inv, -1).T
+
+
+def guarded_scores(num, den, small):
+    """delta = 0 where |den| < small or |num| < small, else num/den (placement_algorithm2.py:116-119)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = num / den
+    bad = (np.abs(den) < small) | (np.abs(num) < small)
+    return np.where(bad, 0.0, ratio)
+
+
+def first_argmax(scores, taken):
+    """First index of the strict maximum over candidates not yet taken, running best starting at -1
+    (placement_algorithm2.py:106-123).  Returns -1 when no score exceeds -1."""
+    s = np.where(taken, -np.inf, scores)
+    y = int(np.argmax(s))               # np.argmax returns the first maximal index
+    return y if s[y] > -1 else -1
+
+
+class IncrementalState:
+    """State of the incremental greedy over a contiguous block of candidate columns [c0, c1).
+
+    One instance over [0, n) is the single-device algorithm; G instances over a partition of [0, n)
+    are the shards of the multi-GPU layout.  All updates are element-wise in
+    the column index, so the results do not depend on the partition.
+    """
+
+    def __init__(self, cov_cols, prec_cols, c0, small=GUARD_NUMPY, jitter=0.0):
+        self.c0 = int(c0)
+        self.n = cov_cols.shape[0]
+        self.nloc = cov_cols.shape[1]
+        self.cov = cov_cols                       # Sigma[:, c0:c1]   (row y = Sigma[y, c0:c1])
+        self.P = np.array(prec_cols, dtype=np.float64, order="C")   # precision panel, updated in place
+        self.small = small
+        self.jitter = jitter
+        idx = np.arange(self.nloc)
+        self.num = np.array(cov_cols[self.c0 + idx, idx], dtype=np.float64)
+        if jitter:
+            self.num = self.num + jitter          # run on Sigma + jitter*I, subtract it at scoring
+        self.W = np.zeros((0, self.nloc))         # growing conditioning panel, rows = selections
+        self.taken = np.zeros(self.nloc, dtype=bool)
+
+    def local_scores(self):
+        idx = np.arange(self.nloc)
+        pdiag = self.P[self.c0 + idx, idx]
+        with np.errstate(divide="ignore"):
+            den = 1.0 / pdiag
+        return guarded_scores(self.num - self.jitter, den - self.jitter, self.small)
+
+    def local_best(self):
+        """(score, global index, numerator) of this block's first strict maximum; index -1 if none."""
+        s = self.local_scores()
+        j = first_argmax(s, self.taken)
+        if j < 0:
+            return -np.inf, -1, 0.0
+        return float(s[j]), self.c0 + j, float(self.num[j])
+
+    def segments(self, y, num_y, w_hist_y):
+        """Row segments for the exchange: w = (Sigma[y, J] - W^T W[:, y]) / sqrt(num_y), p = P[y, J].
+        `w_hist_y` holds W[0..t-1, y] (column y of the full panel)."""
+        row = self.cov[y, :].astype(np.float64, copy=True)
+        if self.jitter and self.c0 <= y < self.c0 + self.nloc:
+            row[y - self.c0] += self.jitter
+        for s in range(self.W.shape[0]):          # fixed summation order over earlier selections
+            row -= self.W[s, :] * w_hist_y[s]
+        return row / np.sqrt(num_y), self.P[y, :].copy()
+
+    def apply(self, y, w_seg, p_full):
+        """Condition the numerators on y and drop y from the precision of the unselected set."""
+        self.W = np.vstack([self.W, w_seg[None, :]])
+        self.num = self.num - w_seg * w_seg
+        inv_pivot = 1.0 / p_full[y]
+        p_loc = p_full[self.c0:self.c0 + self.nloc]
+        self.P -= (p_full[:, None] * p_loc[None, :]) * inv_pivot
+        self.P[y, :] = 0.0                         # exact zeros instead of rounding residue
+        if self.c0 <= y < self.c0 + self.nloc:
+            self.P[:, y - self.c0] = 0.0
+            self.taken[y - self.c0] = True
+
+
+def pick_winner(candidates):
+    """Global winner among per-block (score, index, num) triples: largest score, lowest index on exact
+    ties -- what a single ascending scan with strict '<' returns (placement_algorithm2.py:121)."""
+    best = (-np.inf, -1, 0.0)
+    for c in candidates:
+        if c[1] < 0:
+            continue
+        if c[0] > best[0] or (c[0] == best[0] and c[1] < best[1]) or best[1] < 0:
+            best = c
+    return best
+
+
+def incremental_greedy(cov_vv, k, small=GUARD_NUMPY, jitter=0.0, shards=1, prec=None,
+                       return_all_scores=False):
+    """O(n^2)-per-selection greedy.  Returns (selection list, winning scores [k], per-step score
+    vectors [k, n] or None, min relative top-2 gap per step [k])."""
+    cov_vv = np.ascontiguousarray(cov_vv, dtype=np.float64)
+    n = cov_vv.shape[0]
+    if prec is None:
+        prec = spd_inverse(cov_vv + jitter * np.eye(n) if jitter else cov_vv)
+    bounds = [(n * g) // shards for g in range(shards + 1)]
+    blocks = [IncrementalState(cov_vv[:, a:b], prec[:, a:b], a, small, jitter)
+              for a, b in zip(bounds[:-1], bounds[1:])]
+    selection, win_scores, gaps = [], [], []
+    all_scores = [] if return_all_scores else None
+    w_rows = np.zeros((0, n))
+    for _ in range(k):
+        full = np.concatenate([b.local_scores() for b in blocks])
+        taken = np.concatenate([b.taken for b in blocks])
+        score, y, num_y = pick_winner([b.local_best() for b in blocks])
+        if y < 0:
+            raise ValueError("list.remove(x): x not in list")   # the reference's failure mode (:144)
+        masked = np.where(taken, -np.inf, full)
+        if all_scores is not None:
+            all_scores.append(np.where(taken, np.nan, full))
+        top2 = np.partition(masked, -2)[-2:] if n - len(selection) >= 2 else None
+        gaps.append(float((top2[1] - top2[0]) / abs(top2[1])) if top2 is not None and top2[1] != 0
+                    else np.inf)
+        segs = [b.segments(y, num_y, w_rows[:, y]) for b in blocks]
+        w_full = np.concatenate([s[0] for s in segs])
+        p_full = np.concatenate([s[1] for s in segs])
+        for b, s in zip(blocks, segs):
+            b.apply(y, s[0], p_full)
+        w_rows = np.vstack([w_rows, w_full[None, :]])
+        selection.append(y)
+        win_scores.append(score)
+    return selection, np.array(win_scores), (np.array(all_scores) if all_scores is not None else None), \
+        np.array(gaps)
+
+
+def replay_lazy_evaluations(step_scores, selection):
+    """Replay alg. 2's lazy cache (placement_algorithm2.py:157-214) on dense per-step score vectors
+    [k, n]; returns the (step, y, delta) evaluation trace it would print."""
+    k, n = step_scores.shape
+    cache = np.full(n, np.inf)
+    taken = np.zeros(n, dtype=bool)
+    trace, picks = [], []
+    for t in range(k):
+        fresh = np.zeros(n, dtype=bool)
+        while True:
+            y = first_argmax(cache, taken)
+            if fresh[y]:
+                break
+            cache[y] = step_scores[t, y]
+            fresh[y] = True
+            trace.append((t, y, float(cache[y])))
+        picks.append(y)
+        taken[y] = True
+    return picks, trace

@@ -1,0 +1,644 @@
+// (2) Dense float64 layer: DMMA GEMM + recursive Cholesky / triangular inverse / X^T X / triangular solves.
+//
+// Stands in for the LAPACK/Eigen calls the reference reaches through TensorFlow: tf.linalg.cholesky inside
+// tfd.GaussianProcess.log_prob (gp_functions.py:166-172, 3D_sin_wave.py:172), the triangular solves and
+// matmuls of the VGP loss (variational_Gaussian_process_example.py:68-74,96-99), and the (pseudo-)inverse
+// behind every greedy denominator (placement_algorithm2.py:399-413).
+//
+// Design
+//   * Every matrix is row-major with all dimensions multiples of 128 (callers pad with an identity block),
+//     so no kernel has edge cases.
+//   * All O(n^3) work funnels into ONE kernel, `gemm_kernel`: CTA tile 128x128x16, 8 warps of 64x32,
+//     float64 tensor-core MMA (mma.sync.m8n8k4.f64 -> DMMA), operands staged through a 3-deep
+//     cp.async ring in shared memory with bank-conflict-free padded layouts for both operand
+//     orientations.  tcgen05 has no f64 kind, so DMMA is the tensor path for this dtype.
+//   * Cholesky, L^-1 and L^-T L^-1 are the classic recursive (2x2 block) formulations: each level is
+//     one or two large GEMMs on rectangular off-diagonal blocks plus recursion on the diagonal blocks;
+//     128x128 diagonal blocks are handled by single-CTA shared-memory kernels.  Diagonal-block solves
+//     multiply by an explicitly inverted 128x128 block (one more GEMM call, in place).
+#include <math.h>
+
+#include "dense.cuh"
+
+namespace vgp {
+
+// =====================================================================================================
+// GEMM
+// =====================================================================================================
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, GEMM_THREADS = 256;
+constexpr int LDK = 20;    // k-contiguous operand tile  [128][LDK]   (stride = 32 B mod 128 B)
+constexpr int LDM = 132;   // k-strided   operand tile   [16][LDM]    (stride = 32 B mod 128 B)
+constexpr int TILE_DOUBLES = BM * LDK;                       // 2560 >= 16 * 132
+constexpr int GEMM_SMEM = STAGES * 2 * TILE_DOUBLES * 8;    // 122 880 B
+
+struct GemmArgs {
+    const double *a;
+    const double *b;
+    double *c;
+    int64_t lda, ldb, ldc;
+    int64_t m, n, k;
+    double alpha, beta;
+    int lower;
+    int64_t k_split;         // k range handled by one blockIdx.z slice (== k without split-K)
+    int64_t c_split_stride;  // element offset between the partial outputs of consecutive slices
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool AKC, bool BKC>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    int tm, tn;
+    if (p.lower) {
+        const int64_t b = blockIdx.x;
+        int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+        while ((int64_t)r * (r + 1) / 2 > b) --r;
+        while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
+        tm = r;
+        tn = (int)(b - (int64_t)r * (r + 1) / 2);
+    } else {
+        tn = blockIdx.x;
+        tm = blockIdx.y;
+    }
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+    const int64_t kbase = (int64_t)blockIdx.z * p.k_split;
+    const int64_t klen = p.k - kbase < p.k_split ? p.k - kbase : p.k_split;
+    const int KT = (int)(klen / BK);
+    double *cout = p.c + (int64_t)blockIdx.z * p.c_split_stride;
+
+    auto load_stage = [&](int stage, int kt) {
+        double *sa = smem + (size_t)stage * 2 * TILE_DOUBLES;
+        double *sb = sa + TILE_DOUBLES;
+        const int64_t k0 = kbase + (int64_t)kt * BK;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int c = tid + it * GEMM_THREADS;
+            if (AKC) {
+                const int row = c >> 3, kc = c & 7;
+                cp_async16(sa + row * LDK + 2 * kc, p.a + (m0 + row) * p.lda + k0 + 2 * kc);
+            } else {
+                const int kr = c >> 6, mc = c & 63;
+                cp_async16(sa + kr * LDM + 2 * mc, p.a + (k0 + kr) * p.lda + m0 + 2 * mc);
+            }
+            if (BKC) {
+                const int row = c >> 3, kc = c & 7;
+                cp_async16(sb + row * LDK + 2 * kc, p.b + (n0 + row) * p.ldb + k0 + 2 * kc);
+            } else {
+                const int kr = c >> 6, nc = c & 63;
+                cp_async16(sb + kr * LDM + 2 * nc, p.b + (k0 + kr) * p.ldb + n0 + 2 * nc);
+            }
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    load_stage(0, 0);
+    cp_async_commit();
+    if (KT > 1) load_stage(1, 1);
+    cp_async_commit();
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<1>();
+        __syncthreads();
+        if (kt + 2 < KT) load_stage((kt + 2) % STAGES, kt + 2);
+        cp_async_commit();
+        const double *sa = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
+        const double *sb = sa + TILE_DOUBLES;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                af[i] = AKC ? sa[(wm0 + 8 * i + g) * LDK + kk + t] : sa[(kk + t) * LDM + wm0 + 8 * i + g];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                bf[j] = BKC ? sb[(wn0 + 8 * j + g) * LDK + kk + t] : sb[(kk + t) * LDM + wn0 + 8 * j + g];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = m0 + wm0 + 8 * i + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double2 *dst = reinterpret_cast<double2 *>(cout + r * p.ldc + n0 + wn0 + 8 * j + 2 * t);
+            double2 o;
+            if (p.beta != 0.0) {
+                const double2 old = *dst;
+                o.x = fma(p.alpha, acc[i][j][0], p.beta * old.x);
+                o.y = fma(p.alpha, acc[i][j][1], p.beta * old.y);
+            } else {
+                o.x = p.alpha * acc[i][j][0];
+                o.y = p.alpha * acc[i][j][1];
+            }
+            *dst = o;
+        }
+    }
+}
+
+template <bool AKC, bool BKC>
+static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
+    static bool configured[64] = {};
+    int dev = 0;
+    VGP_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        VGP_CUDA(cudaFuncSetAttribute(gemm_kernel<AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        configured[dev] = true;
+    }
+    const int64_t tm = p.m / BM, tn = p.n / BN;
+    const unsigned splits = (unsigned)((p.k + p.k_split - 1) / p.k_split);
+    if (p.lower) {
+        const int64_t blocks = tm * (tm + 1) / 2;
+        gemm_kernel<AKC, BKC><<<dim3((unsigned)blocks, 1, splits), GEMM_THREADS, GEMM_SMEM, s>>>(p);
+    } else {
+        dim3 grid((unsigned)tn, (unsigned)tm, splits);
+        gemm_kernel<AKC, BKC><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(p);
+    }
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+static int gemm_dispatch(int trans_a, int trans_b, const GemmArgs &p, cudaStream_t s) {
+    // operand is k-contiguous when: A not transposed / B transposed
+    if (!trans_a && trans_b) return gemm_launch<true, true>(p, s);
+    if (!trans_a && !trans_b) return gemm_launch<true, false>(p, s);
+    if (trans_a && !trans_b) return gemm_launch<false, false>(p, s);
+    return gemm_launch<false, true>(p, s);
+}
+
+int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
+               int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, GemmTiles tiles,
+               cudaStream_t s) {
+    if (m == 0 || n == 0) return VGP_OK;
+    VGP_REQUIRE(m % BM == 0 && n % BN == 0 && k % BK == 0 && k > 0, "dense_gemm: unpadded size %lldx%lldx%lld",
+                (long long)m, (long long)n, (long long)k);
+    VGP_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0, "dense_gemm: odd leading dimension");
+    VGP_REQUIRE(((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && ((uintptr_t)c % 16) == 0,
+                "dense_gemm: operands must be 16-byte aligned");
+    VGP_REQUIRE(tiles == GEMM_FULL || m == n, "dense_gemm: lower-tile mode needs a square C");
+    VGP_REQUIRE(m / BM <= 65535, "dense_gemm: too many row tiles");
+    GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0, k, 0};
+    return gemm_dispatch(trans_a, trans_b, p, s);
+}
+
+// C = beta C + sum_z partial_z, fixed summation order
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const double *partial, int64_t stride, int splits,
+                                                            double beta, double *c, int64_t ldc, int64_t m,
+                                                            int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= m * n) return;
+    const int64_t i = e / n, j = e % n;
+    double acc = 0.0;
+    for (int z = 0; z < splits; ++z) acc += partial[(int64_t)z * stride + i * n + j];
+    c[i * ldc + j] = beta != 0.0 ? fma(beta, c[i * ldc + j], acc) : acc;
+}
+
+// Split-K form for short-and-wide products (m, n small, k huge: the m x m SYRK over all N observations).
+// `partial` holds splits * m * n doubles.
+int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
+                      int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,
+                      double *partial, cudaStream_t s) {
+    if (m == 0 || n == 0) return VGP_OK;
+    VGP_REQUIRE(m % BM == 0 && n % BN == 0 && k % BK == 0 && k > 0, "dense_gemm_splitk: unpadded size");
+    VGP_REQUIRE(splits >= 1 && partial, "dense_gemm_splitk: bad split");
+    int64_t k_split = round_up((k + splits - 1) / splits, BK);
+    const int real_splits = (int)((k + k_split - 1) / k_split);
+    GemmArgs p{a, b, partial, lda, ldb, n, m, n, k, alpha, 0.0, 0, k_split, m * n};
+    VGP_TRY(gemm_dispatch(trans_a, trans_b, p, s));
+    splitk_reduce_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, s>>>(partial, m * n, real_splits, beta, c, ldc, m, n);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+// =====================================================================================================
+// small element-wise helpers
+// =====================================================================================================
+__global__ void add_diag_kernel(double *a, int64_t ld, int64_t n, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i * ld + i] += v;
+}
+
+int dense_add_diag(double *a, int64_t ld, int64_t n, double value, cudaStream_t s) {
+    if (n == 0) return VGP_OK;
+    add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, ld, n, value);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+// a[i][j] = 0 for j > i
+__global__ void __launch_bounds__(256) zero_upper_kernel(double *a, int64_t n, int64_t ld) {
+    for (int64_t i = blockIdx.y; i < n; i += gridDim.y)
+        for (int64_t j = i + 1 + (int64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += (int64_t)gridDim.x * 256)
+            a[i * ld + j] = 0.0;
+}
+
+int dense_zero_strict_upper(double *a, int64_t n, int64_t ld, cudaStream_t s) {
+    const int64_t gx = (n + 255) / 256 < 64 ? (n + 255) / 256 : 64;
+    const int64_t gy = n < 4096 ? n : 4096;
+    zero_upper_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(a, n, ld);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+// upper = lower^T, 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) mirror_kernel(double *a, int64_t n, int64_t ld) {
+    __shared__ double tile[32][33];
+    const int64_t b = blockIdx.x;
+    int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((int64_t)r * (r + 1) / 2 > b) --r;
+    while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
+    const int ti = r, tj = (int)(b - (int64_t)r * (r + 1) / 2);   // ti >= tj
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int64_t i = (int64_t)ti * 32 + rr, j = (int64_t)tj * 32 + tx;
+        tile[rr][tx] = (i < n && j < n) ? a[i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int64_t i = (int64_t)tj * 32 + rr, j = (int64_t)ti * 32 + tx;   // transposed position
+        if (i < n && j < n && j > i) a[i * ld + j] = tile[tx][rr];
+    }
+}
+
+int dense_mirror_lower(double *a, int64_t n, int64_t ld, cudaStream_t s) {
+    const int64_t t = (n + 31) / 32;
+    const int64_t blocks = t * (t + 1) / 2;
+    VGP_REQUIRE(blocks <= 0x7fffffffLL, "mirror: matrix too large");
+    mirror_kernel<<<(unsigned)blocks, 256, 0, s>>>(a, n, ld);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+// =====================================================================================================
+// 128 x 128 diagonal-block kernels (one CTA, block resident in shared memory)
+// =====================================================================================================
+constexpr int NB = 128;
+constexpr int SLD = NB + 1;
+constexpr int BLOCK_SMEM = NB * SLD * 8;    // 132 096 B
+
+// Lower Cholesky of one diagonal block, in place; strict upper triangle zeroed.
+__global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, int *info, int row_offset) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 7, j = e & 127;
+        sm[i * SLD + j] = j <= i ? a[(int64_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < NB; ++j) {
+        const double d = sm[j * SLD + j];
+        // every thread sees the same d (written before the previous barrier)
+        if (!(d > 0.0)) {
+            if (tid == 0) atomicCAS(info, 0, row_offset + j + 1);
+        }
+        const double piv = sqrt(d);
+        const double inv = 1.0 / piv;
+        __syncthreads();
+        if (tid == 0) sm[j * SLD + j] = piv;
+        for (int i = j + 1 + tid; i < NB; i += 256) sm[i * SLD + j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: rows i > j, columns j < c <= i
+        const int rem = NB - 1 - j;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+            if (c <= i) sm[i * SLD + c] = fma(-sm[i * SLD + j], sm[c * SLD + j], sm[i * SLD + c]);
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 7, j = e & 127;
+        a[(int64_t)i * ld + j] = sm[i * SLD + j];
+    }
+}
+
+// out = inv(L) for one lower 128-block (strict upper of `out` zeroed).  `transpose` writes inv(L)^T.
+// Thread c solves L x = e_c by forward substitution.  L sits in the lower triangle of one [128][129]
+// shared array; the solution column x_k (k >= c) is kept in the unused strict upper part at [c][k + 1].
+__global__ void __launch_bounds__(128, 1) trtri_kernel(const double *l, int64_t ldl, double *out, int64_t ldo,
+                                                       int transpose) {
+    extern __shared__ __align__(16) double sm[];
+    const int c = threadIdx.x;
+    for (int e = c; e < NB * NB; e += 128) {
+        const int i = e >> 7, j = e & 127;
+        if (j <= i) sm[i * SLD + j] = l[(int64_t)i * ldl + j];
+    }
+    __syncthreads();
+    double *xc = sm + c * SLD + 1;          // xc[k] = x_k, valid for k >= c
+    for (int i = c; i < NB; ++i) {
+        double acc = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) acc = fma(-sm[i * SLD + k], xc[k], acc);
+        xc[i] = acc / sm[i * SLD + i];
+    }
+    __syncthreads();
+    for (int e = c; e < NB * NB; e += 128) {
+        const int i = e >> 7, j = e & 127;
+        // X[i][j] = x_i of column j, stored at sm[j][i + 1]
+        const int r = transpose ? j : i, q = transpose ? i : j;      // element (r, q) of inv(L)
+        out[(int64_t)i * ldo + j] = q <= r ? sm[q * SLD + r + 1] : 0.0;
+    }
+}
+
+// block = X^T X for one lower 128-block X, written as a full symmetric block.
+__global__ void __launch_bounds__(256, 1) lauum_kernel(double *x, int64_t ld) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 7, j = e & 127;
+        sm[i * SLD + j] = j <= i ? x[(int64_t)i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int i = e >> 7, j = e & 127;
+        const int k0 = i > j ? i : j;
+        double acc = 0.0;
+        for (int k = k0; k < NB; ++k) acc = fma(sm[k * SLD + i], sm[k * SLD + j], acc);
+        x[(int64_t)i * ld + j] = acc;
+    }
+}
+
+static int block_kernels_configure() {
+    static bool configured[64] = {};
+    int dev = 0;
+    VGP_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        VGP_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
+        VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
+        VGP_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
+        configured[dev] = true;
+    }
+    return VGP_OK;
+}
+
+static int block_trtri(const double *l, int64_t ldl, double *out, int64_t ldo, int transpose, cudaStream_t s) {
+    trtri_kernel<<<1, 128, BLOCK_SMEM, s>>>(l, ldl, out, ldo, transpose);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+// =====================================================================================================
+// workspace
+// =====================================================================================================
+int DenseWorkspace::ensure(int64_t nblocks) {
+    int dev = 0;
+    VGP_CUDA(cudaGetDevice(&dev));
+    if (winv && device != dev) release();
+    device = dev;
+    if (!winv) {
+        VGP_CUDA(cudaMalloc((void **)&winv, (size_t)NB * NB * 8));
+        VGP_CUDA(cudaMalloc((void **)&info, sizeof(int)));
+        VGP_CUDA(cudaMemset(info, 0, sizeof(int)));
+        VGP_TRY(block_kernels_configure());
+    }
+    if (nblocks > dinv_blocks) {
+        if (dinv) cudaFree(dinv);
+        dinv = nullptr;
+        dinv_blocks = 0;
+        VGP_CUDA(cudaMalloc((void **)&dinv, (size_t)nblocks * NB * NB * 8));
+        dinv_blocks = nblocks;
+    }
+    return VGP_OK;
+}
+
+void DenseWorkspace::release() {
+    if (winv) cudaFree(winv);
+    if (info) cudaFree(info);
+    if (dinv) cudaFree(dinv);
+    winv = nullptr;
+    info = nullptr;
+    dinv = nullptr;
+    dinv_blocks = 0;
+    device = -1;
+}
+
+static inline int64_t split(int64_t n) {
+    int64_t n1 = (n / NB / 2) * NB;
+    return n1 < NB ? NB : n1;
+}
+
+// Explicit inverse of the 128-block at `l`: from the cache filled by potrf (`dinv`, one [128][128] slab per
+// diagonal block) when there is one, else computed into ws.winv.
+static int block_inverse(const double *l, int64_t ldl, const double *dinv, DenseWorkspace &ws, cudaStream_t s,
+                         const double **w) {
+    if (dinv) {
+        *w = dinv;
+        return VGP_OK;
+    }
+    *w = ws.winv;
+    return block_trtri(l, ldl, ws.winv, NB, 0, s);
+}
+static inline const double *dinv_at(const double *dinv, int64_t rows) {
+    return dinv ? dinv + (rows / NB) * NB * NB : nullptr;
+}
+
+// =====================================================================================================
+// triangular solves (recursive), all in place on B.  `dinv`: cached inverses of L's diagonal blocks or NULL.
+// =====================================================================================================
+// X L^T = alpha B,  B [m][n]
+static int trsm_right_t(int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
+                        double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
+    if (n == NB) {
+        const double *w;
+        VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
+        return dense_gemm(0, 1, m, NB, NB, alpha, b, ldb, w, NB, 0.0, b, ldb, GEMM_FULL, s);
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    VGP_TRY(trsm_right_t(m, n1, alpha, l, ldl, dinv, b, ldb, ws, s));
+    // B2 = alpha B2 - X1 Lb^T
+    VGP_TRY(dense_gemm(0, 1, m, n2, n1, -1.0, b, ldb, l + n1 * ldl, ldl, alpha, b + n1, ldb, GEMM_FULL, s));
+    return trsm_right_t(m, n2, 1.0, l + n1 * ldl + n1, ldl, dinv_at(dinv, n1), b + n1, ldb, ws, s);
+}
+
+// X L = alpha B,  B [m][n]
+static int trsm_right_n(int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
+                        double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
+    if (n == NB) {
+        const double *w;
+        VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
+        return dense_gemm(0, 0, m, NB, NB, alpha, b, ldb, w, NB, 0.0, b, ldb, GEMM_FULL, s);
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    VGP_TRY(trsm_right_n(m, n2, alpha, l + n1 * ldl + n1, ldl, dinv_at(dinv, n1), b + n1, ldb, ws, s));
+    // B1 = alpha B1 - X2 Lb
+    VGP_TRY(dense_gemm(0, 0, m, n1, n2, -1.0, b + n1, ldb, l + n1 * ldl, ldl, alpha, b, ldb, GEMM_FULL, s));
+    return trsm_right_n(m, n1, 1.0, l, ldl, dinv, b, ldb, ws, s);
+}
+
+// L X = alpha B,  B [n][nrhs]
+static int trsm_left_n(int64_t n, int64_t nrhs, double alpha, const double *l, int64_t ldl, const double *dinv,
+                       double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
+    if (n == NB) {
+        const double *w;
+        VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
+        return dense_gemm(0, 0, NB, nrhs, NB, alpha, w, NB, b, ldb, 0.0, b, ldb, GEMM_FULL, s);
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    VGP_TRY(trsm_left_n(n1, nrhs, alpha, l, ldl, dinv, b, ldb, ws, s));
+    // B2 = alpha B2 - Lb X1
+    VGP_TRY(dense_gemm(0, 0, n2, nrhs, n1, -1.0, l + n1 * ldl, ldl, b, ldb, alpha, b + n1 * ldb, ldb, GEMM_FULL, s));
+    return trsm_left_n(n2, nrhs, 1.0, l + n1 * ldl + n1, ldl, dinv_at(dinv, n1), b + n1 * ldb, ldb, ws, s);
+}
+
+// L^T X = alpha B,  B [n][nrhs]
+static int trsm_left_t(int64_t n, int64_t nrhs, double alpha, const double *l, int64_t ldl, const double *dinv,
+                       double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
+    if (n == NB) {
+        const double *w;
+        VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
+        return dense_gemm(1, 0, NB, nrhs, NB, alpha, w, NB, b, ldb, 0.0, b, ldb, GEMM_FULL, s);
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    VGP_TRY(trsm_left_t(n2, nrhs, alpha, l + n1 * ldl + n1, ldl, dinv_at(dinv, n1), b + n1 * ldb, ldb, ws, s));
+    // B1 = alpha B1 - Lb^T X2
+    VGP_TRY(dense_gemm(1, 0, n1, nrhs, n2, -1.0, l + n1 * ldl, ldl, b + n1 * ldb, ldb, alpha, b, ldb, GEMM_FULL, s));
+    return trsm_left_t(n1, nrhs, 1.0, l, ldl, dinv, b, ldb, ws, s);
+}
+
+int dense_trsm(int side, int trans, int64_t n, int64_t nrhs, double alpha, const double *l, int64_t ldl,
+               double *b, int64_t ldb, DenseWorkspace &ws, bool use_cached_inverses, cudaStream_t s) {
+    if (n == 0 || nrhs == 0) return VGP_OK;
+    VGP_REQUIRE(n % NB == 0 && nrhs % NB == 0, "dense_trsm: unpadded size n=%lld nrhs=%lld", (long long)n,
+                (long long)nrhs);
+    VGP_TRY(ws.ensure(0));
+    const double *dinv = nullptr;
+    if (use_cached_inverses) {
+        VGP_REQUIRE(ws.dinv && ws.dinv_blocks >= n / NB, "dense_trsm: no cached diagonal-block inverses");
+        dinv = ws.dinv;
+    }
+    if (side == 0) return trans ? trsm_left_t(n, nrhs, alpha, l, ldl, dinv, b, ldb, ws, s)
+                                : trsm_left_n(n, nrhs, alpha, l, ldl, dinv, b, ldb, ws, s);
+    return trans ? trsm_right_t(nrhs, n, alpha, l, ldl, dinv, b, ldb, ws, s)
+                 : trsm_right_n(nrhs, n, alpha, l, ldl, dinv, b, ldb, ws, s);
+}
+
+// =====================================================================================================
+// Cholesky, inverse of the factor, X^T X
+// =====================================================================================================
+static int potrf_rec(double *a, int64_t n, int64_t ld, int64_t row_offset, double *dinv, DenseWorkspace &ws,
+                     cudaStream_t s) {
+    if (n == NB) {
+        potf2_kernel<<<1, 256, BLOCK_SMEM, s>>>(a, ld, ws.info, (int)row_offset);
+        VGP_LAUNCH_CHECK();
+        return block_trtri(a, ld, dinv, NB, 0, s);          // cache inv(L_ii) for every later solve
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    double *a21 = a + n1 * ld, *a22 = a21 + n1;
+    VGP_TRY(potrf_rec(a, n1, ld, row_offset, dinv, ws, s));
+    VGP_TRY(trsm_right_t(n2, n1, 1.0, a, ld, dinv, a21, ld, ws, s));                               // A21 <- A21 L11^-T
+    VGP_TRY(dense_gemm(0, 1, n2, n2, n1, -1.0, a21, ld, a21, ld, 1.0, a22, ld, GEMM_LOWER, s));    // A22 -= A21 A21^T
+    return potrf_rec(a22, n2, ld, row_offset + n1, dinv + (n1 / NB) * NB * NB, ws, s);
+}
+
+int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
+    VGP_REQUIRE(n > 0 && n % NB == 0 && ld >= n && ld % 2 == 0, "dense_potrf: unpadded size %lld (ld %lld)",
+                (long long)n, (long long)ld);
+    VGP_TRY(ws.ensure(n / NB));
+    VGP_CUDA(cudaMemsetAsync(ws.info, 0, sizeof(int), s));
+    return potrf_rec(a, n, ld, 0, ws.dinv, ws, s);
+}
+
+// copy a cached [128][128] inverse into the matrix (it already has a zero strict upper triangle)
+__global__ void __launch_bounds__(256) block_copy_kernel(const double *src, double *dst, int64_t ldd) {
+    for (int e = threadIdx.x; e < NB * NB; e += 256) dst[(int64_t)(e >> 7) * ldd + (e & 127)] = src[e];
+}
+
+static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, DenseWorkspace &ws, cudaStream_t s) {
+    if (n == NB) {
+        block_copy_kernel<<<1, 256, 0, s>>>(dinv, l, ld);
+        VGP_LAUNCH_CHECK();
+        return VGP_OK;
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    double *lb = l + n1 * ld, *lc = lb + n1;
+    VGP_TRY(trsm_right_n(n2, n1, 1.0, l, ld, dinv, lb, ld, ws, s));                     // Lb <- Lb La^-1
+    VGP_TRY(trsm_left_n(n2, n1, -1.0, lc, ld, dinv_at(dinv, n1), lb, ld, ws, s));       // Lb <- -Lc^-1 Lb
+    VGP_TRY(trtri_rec(l, n1, ld, dinv, ws, s));
+    return trtri_rec(lc, n2, ld, dinv_at(dinv, n1), ws, s);
+}
+
+// Needs the diagonal-block inverses cached by dense_potrf on the same workspace.
+int dense_trtri(double *l, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
+    VGP_REQUIRE(n > 0 && n % NB == 0, "dense_trtri: unpadded size");
+    VGP_REQUIRE(ws.dinv && ws.dinv_blocks >= n / NB, "dense_trtri: call dense_potrf on this workspace first");
+    return trtri_rec(l, n, ld, ws.dinv, ws, s);
+}
+
+// B <- X^T B for lower X [n][n] (diagonal 128-blocks have a zero strict upper triangle), B [n][ncols]
+static int trmm_left_t(int64_t n, int64_t ncols, const double *x, int64_t ldx, double *b, int64_t ldb,
+                       cudaStream_t s) {
+    if (n == NB) return dense_gemm(1, 0, NB, ncols, NB, 1.0, x, ldx, b, ldb, 0.0, b, ldb, GEMM_FULL, s);
+    const int64_t n1 = split(n), n2 = n - n1;
+    VGP_TRY(trmm_left_t(n1, ncols, x, ldx, b, ldb, s));
+    // B1 += Xb^T B2
+    VGP_TRY(dense_gemm(1, 0, n1, ncols, n2, 1.0, x + n1 * ldx, ldx, b + n1 * ldb, ldb, 1.0, b, ldb, GEMM_FULL, s));
+    return trmm_left_t(n2, ncols, x + n1 * ldx + n1, ldx, b + n1 * ldb, ldb, s);
+}
+
+static int lauum_rec(double *x, int64_t n, int64_t ld, cudaStream_t s) {
+    if (n == NB) {
+        lauum_kernel<<<1, 256, BLOCK_SMEM, s>>>(x, ld);
+        VGP_LAUNCH_CHECK();
+        return VGP_OK;
+    }
+    const int64_t n1 = split(n), n2 = n - n1;
+    double *xb = x + n1 * ld, *xc = xb + n1;
+    VGP_TRY(lauum_rec(x, n1, ld, s));                                                           // P11 = Xa^T Xa
+    VGP_TRY(dense_gemm(1, 0, n1, n1, n2, 1.0, xb, ld, xb, ld, 1.0, x, ld, GEMM_LOWER, s));      // P11 += Xb^T Xb
+    VGP_TRY(trmm_left_t(n2, n1, xc, ld, xb, ld, s));                                            // P21 = Xc^T Xb
+    return lauum_rec(xc, n2, ld, s);
+}
+
+int dense_lauum(double *x, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
+    VGP_REQUIRE(n > 0 && n % NB == 0, "dense_lauum: unpadded size");
+    VGP_TRY(ws.ensure(0));
+    return lauum_rec(x, n, ld, s);
+}
+
+int dense_read_info(DenseWorkspace &ws, int *info_host, cudaStream_t s) {
+    int info = 0;
+    VGP_CUDA(cudaMemcpyAsync(&info, ws.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGP_CUDA(cudaStreamSynchronize(s));
+    if (info_host) *info_host = info;
+    if (info != 0) {
+        set_error("matrix is not positive definite: non-positive pivot at row %d "
+                  "(the reference would take a pseudo-inverse here; this path needs an SPD input)",
+                  info - 1);
+        return VGP_ERR_NOT_PD;
+    }
+    return VGP_OK;
+}
+
+int dense_spd_inverse(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, int *info_host, cudaStream_t s) {
+    VGP_TRY(dense_potrf(a, n, ld, ws, s));
+    VGP_TRY(dense_read_info(ws, info_host, s));
+    VGP_TRY(dense_trtri(a, n, ld, ws, s));
+    VGP_TRY(dense_lauum(a, n, ld, ws, s));
+    return dense_mirror_lower(a, n, ld, s);
+}
+
+}  // namespace vgp

@@ -1,0 +1,55 @@
+// Internal interface of the dense float64 layer (dense.cu).  All matrices row-major; every dimension
+// handed to these functions is a multiple of vgp::TILE (128) -- callers pad (identity on the padding
+// diagonal), which removes every edge case from the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace vgp {
+
+struct DenseWorkspace {
+    int device = -1;
+    double *winv = nullptr;     // TILE x TILE scratch: explicit inverse of a diagonal block
+    int *info = nullptr;        // device flag: 0, or 1 + row of the first non-positive pivot
+    double *dinv = nullptr;     // [dinv_blocks][TILE][TILE]: inverses of the diagonal blocks of the last potrf
+    int64_t dinv_blocks = 0;
+    int ensure(int64_t nblocks);
+    void release();
+};
+
+enum GemmTiles { GEMM_FULL = 0, GEMM_LOWER = 1 };   // LOWER: only tiles with tile_row >= tile_col
+
+// C[m,n] = alpha op(A) op(B) + beta C.  trans_a == 0: A stored [m][k]; 1: stored [k][m].
+// trans_b == 0: B stored [k][n]; 1: stored [n][k].
+int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
+               int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, GemmTiles tiles,
+               cudaStream_t s);
+
+int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
+                      int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,
+                      double *partial, cudaStream_t s);
+
+int dense_add_diag(double *a, int64_t ld, int64_t n, double value, cudaStream_t s);
+int dense_zero_strict_upper(double *a, int64_t n, int64_t ld, cudaStream_t s);
+int dense_mirror_lower(double *a, int64_t n, int64_t ld, cudaStream_t s);
+
+// In-place lower Cholesky (strict upper triangle of off-diagonal blocks untouched, of diagonal
+// 128-blocks zeroed).  Asynchronous; failures are recorded in ws.info.
+int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s);
+// In-place inverse of the lower factor / in-place lower part of X^T X.
+int dense_trtri(double *l, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s);
+int dense_lauum(double *x, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s);
+// potrf + trtri + lauum + mirror; synchronises and reports *info_host (VGP_ERR_NOT_PD when non-zero).
+int dense_spd_inverse(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, int *info_host, cudaStream_t s);
+int dense_read_info(DenseWorkspace &ws, int *info_host, cudaStream_t s);
+
+// Triangular solves with a lower factor L [n][n]; B in place.
+//   side 0 (left):  op(L) X = alpha B,  B is [n][nrhs]
+//   side 1 (right): X op(L) = alpha B,  B is [nrhs][n]
+// use_cached_inverses: L is the factor produced by the last dense_potrf on `ws` (its diagonal-block
+// inverses are reused); otherwise each diagonal block is inverted on the fly.
+int dense_trsm(int side, int trans, int64_t n, int64_t nrhs, double alpha, const double *l, int64_t ldl,
+               double *b, int64_t ldb, DenseWorkspace &ws, bool use_cached_inverses, cudaStream_t s);
+
+int pad_identity(double *a, int64_t ld, int64_t n, int64_t n_pad, cudaStream_t s);
+
+}  // namespace vgp

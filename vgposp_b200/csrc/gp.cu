@@ -1,0 +1,524 @@
+// Exact-GP and variational-GP arithmetic on top of expquad + dense.
+//
+// Reference call sites (all delegate to TensorFlow-Probability):
+//   exact GP log_prob        gp_functions.py:166-172, 3D_sin_wave.py:161-172
+//   GP regression model      gp_functions.py:283-297, 3D_sin_wave.py:262-268
+//   optimal q(u)             variational_Gaussian_process_example.py:68-74, main_architecture_2.py:200-206
+//   variational_loss / mean  variational_Gaussian_process_example.py:83-99,141-142
+// Formulas: SURVEY.md Appendix A.2-A.4 (restated on the CPU in oracle/gp_oracle.py).
+//
+// Everything is float64.  Matrices live in 128-padded scratch (identity on the padding diagonal of every
+// factorised matrix, zeros elsewhere), so padded rows/columns contribute exact zeros to every norm.
+// Scalar reductions are two-stage with a fixed tree: results are run-to-run deterministic.
+#include <math.h>
+
+#include "dense.cuh"
+
+namespace vgp {
+
+int expquad_dispatch_public(const double *x1, int64_t n1, const double *x2, int64_t n2, int d, double amplitude,
+                            double length_scale, double diag_add, int64_t diag_col0, double *out, int64_t ld,
+                            cudaStream_t s);
+
+namespace {
+
+struct Buf {
+    double *p = nullptr;
+    int64_t rows = 0, cols = 0;
+    cudaStream_t s = nullptr;
+    int alloc(int64_t r, int64_t c, cudaStream_t stream, bool pad = true) {
+        rows = pad ? round_up(r > 0 ? r : 1, TILE) : r;
+        cols = pad ? round_up(c > 0 ? c : 1, TILE) : c;
+        s = stream;
+        VGP_CUDA(cudaMallocAsync((void **)&p, (size_t)rows * cols * 8, s));
+        VGP_CUDA(cudaMemsetAsync(p, 0, (size_t)rows * cols * 8, s));
+        return VGP_OK;
+    }
+    ~Buf() {
+        if (p) cudaFreeAsync(p, s);
+    }
+};
+
+// ---- deterministic scalar reductions ---------------------------------------------------------------
+constexpr int RED_BLOCKS = 128;
+
+struct SumSqRegion {      // sum over i < rows, j < cols of a[i][j]^2
+    const double *a;
+    int64_t ld, cols;
+    __device__ double operator()(int64_t e) const {
+        const double v = a[(e / cols) * ld + e % cols];
+        return v * v;
+    }
+};
+struct SumLogDiag {
+    const double *a;
+    int64_t ld;
+    __device__ double operator()(int64_t e) const { return log(a[e * ld + e]); }
+};
+struct SumSqDiff {        // (y - mu)^2
+    const double *y, *mu;
+    __device__ double operator()(int64_t e) const {
+        const double r = y[e] - mu[e];
+        return r * r;
+    }
+};
+struct SumSqStrided {
+    const double *a;
+    int64_t stride;
+    __device__ double operator()(int64_t e) const {
+        const double v = a[e * stride];
+        return v * v;
+    }
+};
+
+template <class F>
+__global__ void __launch_bounds__(256) reduce_kernel(F f, int64_t count, double *partials, unsigned *counter,
+                                                     double *out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < count; e += (int64_t)gridDim.x * 256) acc += f(e);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+    __threadfence();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partials + b);
+        *out = t;
+    }
+}
+
+struct Reducer {
+    double *partials = nullptr;
+    unsigned *counter = nullptr;
+    double *scal = nullptr;      // device results
+    cudaStream_t s = nullptr;
+    int init(cudaStream_t stream) {
+        s = stream;
+        VGP_CUDA(cudaMallocAsync((void **)&partials, RED_BLOCKS * 8, s));
+        VGP_CUDA(cudaMallocAsync((void **)&counter, 4, s));
+        VGP_CUDA(cudaMallocAsync((void **)&scal, 16 * 8, s));
+        VGP_CUDA(cudaMemsetAsync(counter, 0, 4, s));
+        VGP_CUDA(cudaMemsetAsync(scal, 0, 16 * 8, s));
+        return VGP_OK;
+    }
+    template <class F>
+    int run(F f, int64_t count, int slot) {
+        if (count <= 0) return VGP_OK;
+        int64_t blocks = (count + 255) / 256;
+        if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+        reduce_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(f, count, partials, counter, scal + slot);
+        VGP_LAUNCH_CHECK();
+        return VGP_OK;
+    }
+    int fetch(double *host, int count) {
+        VGP_CUDA(cudaMemcpyAsync(host, scal, (size_t)count * 8, cudaMemcpyDeviceToHost, s));
+        VGP_CUDA(cudaStreamSynchronize(s));
+        return VGP_OK;
+    }
+    ~Reducer() {
+        if (partials) cudaFreeAsync(partials, s);
+        if (counter) cudaFreeAsync(counter, s);
+        if (scal) cudaFreeAsync(scal, s);
+    }
+};
+
+// ---- small dense helpers ---------------------------------------------------------------------------
+// out[j] = sum_k a[k][j] v[k * vstride]   (thread per column, coalesced over j)
+__global__ void __launch_bounds__(256) gemv_t_kernel(const double *a, int64_t ld, int64_t rows, int64_t cols,
+                                                     const double *v, int64_t vstride, double *out) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= cols) return;
+    double acc = 0.0;
+    for (int64_t k = 0; k < rows; ++k) acc = fma(a[k * ld + j], v[k * vstride], acc);
+    out[j] = acc;
+}
+
+// out[k * ostride] (+)= scale * sum_j a[k][j] v[j]   (block per row, fixed reduction tree)
+__global__ void __launch_bounds__(256) gemv_n_kernel(const double *a, int64_t ld, int64_t cols, const double *v,
+                                                     double scale, int accumulate, double *out, int64_t ostride) {
+    __shared__ double sh[256];
+    const int64_t k = blockIdx.x;
+    double acc = 0.0;
+    for (int64_t j = threadIdx.x; j < cols; j += 256) acc = fma(a[k * ld + j], v[j], acc);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[k * ostride] = accumulate ? out[k * ostride] + scale * sh[0] : scale * sh[0];
+}
+
+// var[j] = base - sum_k c[k][j]^2 + sum_k e[k][j]^2   (e may be NULL)
+__global__ void __launch_bounds__(256) colvar_kernel(const double *c, const double *e, int64_t ld, int64_t rows,
+                                                     int64_t cols, double base, double *var) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= cols) return;
+    double sc = 0.0, se = 0.0;
+    for (int64_t k = 0; k < rows; ++k) {
+        const double v = c[k * ld + j];
+        sc = fma(v, v, sc);
+        if (e) {
+            const double w = e[k * ld + j];
+            se = fma(w, w, se);
+        }
+    }
+    var[j] = base - sc + se;
+}
+
+// dst[i][j] = a[i][j] * sa + b[i][j] * sb (+ diag on i == j < n)
+__global__ void __launch_bounds__(256) axpby_kernel(const double *a, double sa, const double *b, double sb,
+                                                    double diag, int64_t n, double *dst, int64_t ld, int64_t count) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= count) return;
+    const int64_t i = e / ld, j = e % ld;
+    double v = a[e] * sa + (b ? b[e] * sb : 0.0);
+    if (i == j && i < n) v += diag;
+    dst[e] = v;
+}
+
+// dst[j][i] = src[i][j] for a square [n][ld] matrix (out of place)
+__global__ void __launch_bounds__(256) transpose_kernel(const double *src, double *dst, int64_t n, int64_t ld) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t i0 = (int64_t)blockIdx.y * 32, j0 = (int64_t)blockIdx.x * 32;
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = (i0 + r < n && j0 + tx < n) ? src[(i0 + r) * ld + j0 + tx] : 0.0;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (j0 + r < n && i0 + tx < n) dst[(j0 + r) * ld + i0 + tx] = tile[tx][r];
+}
+
+int copy_vec_to_col0(const double *v, int64_t n, Buf &dst) {
+    VGP_CUDA(cudaMemcpy2DAsync(dst.p, (size_t)dst.cols * 8, v, 8, 8, (size_t)n, cudaMemcpyDeviceToDevice, dst.s));
+    return VGP_OK;
+}
+int copy_col0_to_vec(const Buf &src, int64_t n, double *v) {
+    VGP_CUDA(cudaMemcpy2DAsync(v, 8, src.p, (size_t)src.cols * 8, 8, (size_t)n, cudaMemcpyDeviceToDevice, src.s));
+    return VGP_OK;
+}
+int copy_matrix(const double *src, int64_t lds, int64_t r, int64_t c, Buf &dst) {
+    VGP_CUDA(cudaMemcpy2DAsync(dst.p, (size_t)dst.cols * 8, src, (size_t)lds * 8, (size_t)c * 8, (size_t)r,
+                               cudaMemcpyDeviceToDevice, dst.s));
+    return VGP_OK;
+}
+
+// K(x, x) + shift I, padded with identity, factorised in place.
+int kernel_cholesky(const double *x, int64_t n, int d, double amplitude, double length_scale, double shift, Buf &k,
+                    DenseWorkspace &ws, cudaStream_t s) {
+    VGP_TRY(k.alloc(n, n, s));
+    VGP_TRY(expquad_dispatch_public(x, n, x, n, d, amplitude, length_scale, shift, 0, k.p, k.cols, s));
+    VGP_TRY(pad_identity(k.p, k.cols, n, k.rows, s));
+    VGP_TRY(dense_potrf(k.p, k.rows, k.cols, ws, s));
+    return dense_read_info(ws, nullptr, s);
+}
+
+}  // namespace
+}  // namespace vgp
+
+using namespace vgp;
+
+extern "C" {
+
+int vgp_gp_logprob(int device, const double *x_dev, int64_t n, int d, const double *y_dev, double amplitude,
+                   double length_scale, double noise_variance, double jitter, double *logprob_host,
+                   void *stream) {
+    VGP_REQUIRE(x_dev && y_dev && logprob_host && n > 0, "bad argument");
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    DenseWorkspace ws;
+    int rc;
+    {
+        Buf k, yb;
+        Reducer red;
+        rc = red.init(s);
+        if (rc == VGP_OK) rc = kernel_cholesky(x_dev, n, d, amplitude, length_scale, noise_variance + jitter, k, ws, s);
+        if (rc == VGP_OK) rc = yb.alloc(n, 1, s);
+        if (rc == VGP_OK) rc = copy_vec_to_col0(y_dev, n, yb);
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, k.rows, yb.cols, 1.0, k.p, k.cols, yb.p, yb.cols, ws, true, s);
+        if (rc == VGP_OK) rc = red.run(SumSqStrided{yb.p, yb.cols}, n, 0);
+        if (rc == VGP_OK) rc = red.run(SumLogDiag{k.p, k.cols}, n, 1);
+        double h[2] = {0, 0};
+        if (rc == VGP_OK) rc = red.fetch(h, 2);
+        if (rc == VGP_OK) *logprob_host = -0.5 * h[0] - h[1] - 0.5 * (double)n * log(2.0 * M_PI);
+    }
+    cudaStreamSynchronize(s);
+    ws.release();
+    return rc;
+}
+
+int vgp_gp_regression(int device, const double *x_dev, int64_t n, int d, const double *y_dev,
+                      const double *xt_dev, int64_t t, double amplitude, double length_scale,
+                      double noise_variance, double predictive_noise_variance, double divisor_jitter,
+                      double *mean_dev, double *var_dev, void *stream) {
+    VGP_REQUIRE(x_dev && y_dev && xt_dev && n > 0 && t > 0, "bad argument");
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    DenseWorkspace ws;
+    int rc;
+    {
+        Buf k, yb, c;
+        rc = kernel_cholesky(x_dev, n, d, amplitude, length_scale, noise_variance + divisor_jitter, k, ws, s);
+        if (rc == VGP_OK) rc = c.alloc(n, t, s);
+        if (rc == VGP_OK)
+            rc = expquad_dispatch_public(x_dev, n, xt_dev, t, d, amplitude, length_scale, 0.0, 0, c.p, c.cols, s);
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, k.rows, c.cols, 1.0, k.p, k.cols, c.p, c.cols, ws, true, s);
+        if (rc == VGP_OK) rc = yb.alloc(n, 1, s);
+        if (rc == VGP_OK) rc = copy_vec_to_col0(y_dev, n, yb);
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, k.rows, yb.cols, 1.0, k.p, k.cols, yb.p, yb.cols, ws, true, s);
+        if (rc == VGP_OK && mean_dev) {
+            gemv_t_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(c.p, c.cols, n, t, yb.p, yb.cols, mean_dev);
+            ++g_launches;
+        }
+        if (rc == VGP_OK && var_dev) {
+            colvar_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(c.p, nullptr, c.cols, n, t,
+                                                                    amplitude * amplitude + predictive_noise_variance,
+                                                                    var_dev);
+            ++g_launches;
+        }
+        if (rc == VGP_OK) {
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) rc = cuda_fail(e, "gp_regression kernels", __FILE__, __LINE__);
+        }
+    }
+    cudaStreamSynchronize(s);
+    ws.release();
+    return rc;
+}
+
+int vgp_vgp_optimal_posterior(int device, const double *z_dev, int64_t m, const double *x_dev, int64_t n_obs,
+                              int d, const double *y_dev, double amplitude, double length_scale,
+                              double noise_variance, double jitter, int legacy_scale_orientation,
+                              double *loc_dev, double *scale_dev, void *stream) {
+    VGP_REQUIRE(z_dev && x_dev && y_dev && loc_dev && scale_dev && m > 0 && n_obs > 0, "bad argument");
+    VGP_REQUIRE(noise_variance > 0.0, "observation noise variance must be positive");
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    DenseWorkspace ws;
+    int rc = VGP_OK;
+    {
+        const int64_t mp = round_up(m, TILE);
+        const int64_t chunk = 16384;          // observations per K_zx slab: [mp][chunk] stays L2-resident
+        int sm = 148;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+        const int tiles = (int)((mp / TILE) * (mp / TILE));
+        int splits = (2 * sm + tiles - 1) / tiles;
+        if (splits > (int)(chunk / 128)) splits = (int)(chunk / 128);
+        if (splits < 1) splits = 1;
+        Buf kzz, kzx, gram, partial, v, sig, kzz2;
+        rc = kzz.alloc(m, m, s);
+        if (rc == VGP_OK) rc = kzx.alloc(m, chunk, s);
+        if (rc == VGP_OK) rc = gram.alloc(m, m, s);
+        if (rc == VGP_OK) rc = partial.alloc((int64_t)splits * mp, mp, s, false);
+        if (rc == VGP_OK) rc = v.alloc(m, 1, s);
+        if (rc == VGP_OK) rc = sig.alloc(m, m, s);
+        if (rc == VGP_OK)
+            rc = expquad_dispatch_public(z_dev, m, z_dev, m, d, amplitude, length_scale, 0.0, 0, kzz.p, kzz.cols, s);
+        for (int64_t c0 = 0; c0 < n_obs && rc == VGP_OK; c0 += chunk) {
+            const int64_t cn = n_obs - c0 < chunk ? n_obs - c0 : chunk;
+            if (cn < chunk) rc = cudaMemsetAsync(kzx.p, 0, (size_t)kzx.rows * kzx.cols * 8, s) == cudaSuccess
+                                     ? VGP_OK
+                                     : VGP_ERR_CUDA;
+            if (rc == VGP_OK)
+                rc = expquad_dispatch_public(z_dev, m, x_dev + c0 * d, cn, d, amplitude, length_scale, 0.0, -1 - n_obs,
+                                             kzx.p, kzx.cols, s);
+            // gram += K_zx K_zx^T ;  v += K_zx y
+            if (rc == VGP_OK)
+                rc = dense_gemm_splitk(0, 1, mp, mp, chunk, 1.0, kzx.p, kzx.cols, kzx.p, kzx.cols, 1.0, gram.p,
+                                       gram.cols, splits, partial.p, s);
+            if (rc == VGP_OK) {
+                gemv_n_kernel<<<(unsigned)m, 256, 0, s>>>(kzx.p, kzx.cols, cn, y_dev + c0, 1.0, 1, v.p, v.cols);
+                ++g_launches;
+            }
+        }
+        // Sigma^-1 = K_zz + gram / noise + jitter I   (padding: identity)
+        if (rc == VGP_OK) {
+            const int64_t count = sig.rows * sig.cols;
+            axpby_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(kzz.p, 1.0, gram.p, 1.0 / noise_variance,
+                                                                       jitter, m, sig.p, sig.cols, count);
+            ++g_launches;
+            rc = pad_identity(sig.p, sig.cols, m, sig.rows, s);
+        }
+        if (rc == VGP_OK) rc = dense_potrf(sig.p, sig.rows, sig.cols, ws, s);
+        if (rc == VGP_OK) rc = dense_read_info(ws, nullptr, s);
+        // loc = K_zz (L^-T L^-1 v) / noise
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, sig.rows, v.cols, 1.0, sig.p, sig.cols, v.p, v.cols, ws, true, s);
+        if (rc == VGP_OK) rc = dense_trsm(0, 1, sig.rows, v.cols, 1.0, sig.p, sig.cols, v.p, v.cols, ws, true, s);
+        if (rc == VGP_OK) {
+            // v is strided ([mp][128], column 0): gather it into a dense vector first
+            Buf vd;
+            rc = vd.alloc(mp, 1, s, false);
+            if (rc == VGP_OK) rc = copy_col0_to_vec(v, m, vd.p);
+            if (rc == VGP_OK) {
+                gemv_n_kernel<<<(unsigned)m, 256, 0, s>>>(kzz.p, kzz.cols, m, vd.p, 1.0 / noise_variance, 0, loc_dev, 1);
+                ++g_launches;
+            }
+        }
+        // scale: L^-1 K_zz (legacy) or its transpose K_zz L^-T (S = scale scale^T = K_zz Sigma K_zz)
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, sig.rows, kzz.cols, 1.0, sig.p, sig.cols, kzz.p, kzz.cols, ws, true, s);
+        if (rc == VGP_OK) {
+            if (legacy_scale_orientation) {
+                cudaError_t e = cudaMemcpy2DAsync(scale_dev, (size_t)m * 8, kzz.p, (size_t)kzz.cols * 8, (size_t)m * 8,
+                                                  (size_t)m, cudaMemcpyDeviceToDevice, s);
+                if (e != cudaSuccess) rc = cuda_fail(e, "scale copy", __FILE__, __LINE__);
+            } else {
+                rc = kzz2.alloc(m, m, s);
+                if (rc == VGP_OK) {
+                    dim3 grid((unsigned)((m + 31) / 32), (unsigned)((m + 31) / 32));
+                    transpose_kernel<<<grid, 256, 0, s>>>(kzz.p, kzz2.p, m, kzz.cols);
+                    ++g_launches;
+                    cudaError_t e = cudaMemcpy2DAsync(scale_dev, (size_t)m * 8, kzz2.p, (size_t)kzz2.cols * 8,
+                                                      (size_t)m * 8, (size_t)m, cudaMemcpyDeviceToDevice, s);
+                    if (e != cudaSuccess) rc = cuda_fail(e, "scale copy", __FILE__, __LINE__);
+                }
+            }
+        }
+        if (rc == VGP_OK) {
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) rc = cuda_fail(e, "optimal posterior kernels", __FILE__, __LINE__);
+        }
+        cudaStreamSynchronize(s);
+    }
+    ws.release();
+    return rc;
+}
+
+int vgp_vgp_loss(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                 const double *scale_dev, const double *xb_dev, const double *yb_dev, int64_t b,
+                 double amplitude, double length_scale, double noise_variance, double kl_weight, double jitter,
+                 vgp_vgp_terms *terms_host, void *stream) {
+    VGP_REQUIRE(z_dev && loc_dev && scale_dev && xb_dev && yb_dev && terms_host && m > 0 && b > 0, "bad argument");
+    VGP_REQUIRE(noise_variance > 0.0, "observation noise variance must be positive");
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    DenseWorkspace ws, ws2;
+    int rc;
+    {
+        Buf l, kzb, c, q, a, e, ssum, mu, qa;
+        Reducer red;
+        rc = red.init(s);
+        // L = chol(K_zz + jitter I)
+        if (rc == VGP_OK) rc = kernel_cholesky(z_dev, m, d, amplitude, length_scale, jitter, l, ws, s);
+        // q = L^-1 q_loc (kept for the KL), then alpha = L^-T q
+        if (rc == VGP_OK) rc = q.alloc(m, 1, s);
+        if (rc == VGP_OK) rc = copy_vec_to_col0(loc_dev, m, q);
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, l.rows, q.cols, 1.0, l.p, l.cols, q.p, q.cols, ws, true, s);
+        if (rc == VGP_OK) rc = red.run(SumSqStrided{q.p, q.cols}, m, 4);                  // |L^-1 mu|^2
+        if (rc == VGP_OK) rc = dense_trsm(0, 1, l.rows, q.cols, 1.0, l.p, l.cols, q.p, q.cols, ws, true, s);
+        // K_zb, mu_b = K_zb^T alpha, ll
+        if (rc == VGP_OK) rc = kzb.alloc(m, b, s);
+        if (rc == VGP_OK)
+            rc = expquad_dispatch_public(z_dev, m, xb_dev, b, d, amplitude, length_scale, 0.0, -1 - b, kzb.p, kzb.cols, s);
+        if (rc == VGP_OK) rc = mu.alloc(b, 1, s, false);
+        if (rc == VGP_OK) {
+            gemv_t_kernel<<<(unsigned)((b + 255) / 256), 256, 0, s>>>(kzb.p, kzb.cols, m, b, q.p, q.cols, mu.p);
+            ++g_launches;
+            rc = red.run(SumSqDiff{yb_dev, mu.p}, b, 0);                                  // |y - mu|^2
+        }
+        // C = L^-1 K_zb ; D = L^-T C ; E = q_scale^T D
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, l.rows, kzb.cols, 1.0, l.p, l.cols, kzb.p, kzb.cols, ws, true, s);
+        if (rc == VGP_OK) rc = red.run(SumSqRegion{kzb.p, kzb.cols, b}, m * b, 1);        // |C|_F^2
+        if (rc == VGP_OK) rc = dense_trsm(0, 1, l.rows, kzb.cols, 1.0, l.p, l.cols, kzb.p, kzb.cols, ws, true, s);
+        if (rc == VGP_OK) rc = a.alloc(m, m, s);
+        if (rc == VGP_OK) rc = copy_matrix(scale_dev, m, m, m, a);
+        if (rc == VGP_OK) rc = e.alloc(m, b, s);
+        if (rc == VGP_OK)
+            rc = dense_gemm(1, 0, a.cols, kzb.cols, a.rows, 1.0, a.p, a.cols, kzb.p, kzb.cols, 0.0, e.p, e.cols,
+                            GEMM_FULL, s);
+        if (rc == VGP_OK) rc = red.run(SumSqRegion{e.p, e.cols, b}, m * b, 2);            // |A^T D|_F^2
+        // KL pieces: |L^-1 A|_F^2, logdet K, logdet S (S = A A^T factorised on its own workspace)
+        if (rc == VGP_OK) rc = qa.alloc(m, m, s);
+        if (rc == VGP_OK) rc = copy_matrix(scale_dev, m, m, m, qa);
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, l.rows, qa.cols, 1.0, l.p, l.cols, qa.p, qa.cols, ws, true, s);
+        if (rc == VGP_OK) rc = red.run(SumSqRegion{qa.p, qa.cols, m}, m * m, 3);          // tr(K^-1 S)
+        if (rc == VGP_OK) rc = red.run(SumLogDiag{l.p, l.cols}, m, 5);
+        if (rc == VGP_OK) rc = ssum.alloc(m, m, s);
+        if (rc == VGP_OK)
+            rc = dense_gemm(0, 1, a.rows, a.rows, a.cols, 1.0, a.p, a.cols, a.p, a.cols, 0.0, ssum.p, ssum.cols,
+                            GEMM_FULL, s);
+        if (rc == VGP_OK) rc = pad_identity(ssum.p, ssum.cols, m, ssum.rows, s);
+        if (rc == VGP_OK) rc = dense_potrf(ssum.p, ssum.rows, ssum.cols, ws2, s);
+        if (rc == VGP_OK) rc = dense_read_info(ws2, nullptr, s);
+        if (rc == VGP_OK) rc = red.run(SumLogDiag{ssum.p, ssum.cols}, m, 6);
+        double h[8] = {0};
+        if (rc == VGP_OK) rc = red.fetch(h, 8);
+        if (rc == VGP_OK) {
+            const double log2pi = log(2.0 * M_PI);
+            vgp_vgp_terms t;
+            t.ll = -0.5 * h[0] / noise_variance - 0.5 * (double)b * (log2pi + log(noise_variance));
+            t.tr1 = (double)b * amplitude * amplitude - h[1];
+            t.tr2 = h[2];
+            t.kl = 0.5 * (h[3] + h[4] - (double)m + 2.0 * h[5] - 2.0 * h[6]);
+            t.loss = -(t.ll - 0.5 * (t.tr1 + t.tr2) / noise_variance - kl_weight * t.kl);
+            *terms_host = t;
+        }
+        cudaStreamSynchronize(s);
+    }
+    ws.release();
+    ws2.release();
+    return rc;
+}
+
+int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                    const double *scale_dev, const double *xt_dev, int64_t t, double amplitude,
+                    double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
+                    double *var_dev, void *stream) {
+    VGP_REQUIRE(z_dev && loc_dev && xt_dev && m > 0 && t > 0, "bad argument");
+    VGP_REQUIRE(!var_dev || scale_dev, "variance needs the variational scale");
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    DenseWorkspace ws;
+    int rc;
+    {
+        Buf l, kzt, c, q, a, e;
+        rc = kernel_cholesky(z_dev, m, d, amplitude, length_scale, jitter, l, ws, s);
+        if (rc == VGP_OK) rc = q.alloc(m, 1, s);
+        if (rc == VGP_OK) rc = copy_vec_to_col0(loc_dev, m, q);
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, l.rows, q.cols, 1.0, l.p, l.cols, q.p, q.cols, ws, true, s);
+        if (rc == VGP_OK) rc = dense_trsm(0, 1, l.rows, q.cols, 1.0, l.p, l.cols, q.p, q.cols, ws, true, s);
+        if (rc == VGP_OK) rc = kzt.alloc(m, t, s);
+        if (rc == VGP_OK)
+            rc = expquad_dispatch_public(z_dev, m, xt_dev, t, d, amplitude, length_scale, 0.0, -1 - t, kzt.p, kzt.cols, s);
+        if (rc == VGP_OK && mean_dev) {
+            gemv_t_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(kzt.p, kzt.cols, m, t, q.p, q.cols, mean_dev);
+            ++g_launches;
+        }
+        if (rc == VGP_OK && var_dev) {
+            rc = dense_trsm(0, 0, l.rows, kzt.cols, 1.0, l.p, l.cols, kzt.p, kzt.cols, ws, true, s);      // C
+            if (rc == VGP_OK) rc = c.alloc(m, t, s);
+            if (rc == VGP_OK) {
+                cudaError_t ce = cudaMemcpyAsync(c.p, kzt.p, (size_t)c.rows * c.cols * 8, cudaMemcpyDeviceToDevice, s);
+                if (ce != cudaSuccess) rc = cuda_fail(ce, "copy C", __FILE__, __LINE__);
+            }
+            if (rc == VGP_OK) rc = dense_trsm(0, 1, l.rows, kzt.cols, 1.0, l.p, l.cols, kzt.p, kzt.cols, ws, true, s);   // D
+            if (rc == VGP_OK) rc = a.alloc(m, m, s);
+            if (rc == VGP_OK) rc = copy_matrix(scale_dev, m, m, m, a);
+            if (rc == VGP_OK) rc = e.alloc(m, t, s);
+            if (rc == VGP_OK)
+                rc = dense_gemm(1, 0, a.cols, kzt.cols, a.rows, 1.0, a.p, a.cols, kzt.p, kzt.cols, 0.0, e.p, e.cols,
+                                GEMM_FULL, s);
+            if (rc == VGP_OK) {
+                colvar_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(
+                    c.p, e.p, c.cols, m, t, amplitude * amplitude + predictive_noise_variance, var_dev);
+                ++g_launches;
+            }
+        }
+        if (rc == VGP_OK) {
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) rc = cuda_fail(ce, "vgp_predict kernels", __FILE__, __LINE__);
+        }
+        cudaStreamSynchronize(s);
+    }
+    ws.release();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,661 @@
+// (3) Krause-style greedy mutual-information placement, incremental form.
+//
+// Reference semantics: placement_algorithm2.py:105-145 (alg. 1), :151-219 (alg. 2), :371-413
+// (nominator / denominator through pinv).  Here the per-candidate score
+//     delta_y = sigma^2(y | A) / sigma^2(y | Abar \ y)
+// is held incrementally: the numerator through a growing conditioning panel W (rows = selections,
+// num_j = Sigma_jj - sum_s W[s][j]^2), the denominator as 1 / P_jj where P is the precision of the
+// still-unselected set, downdated by the rank-1 Schur step P -= p p^T / p_y when y leaves the set.
+//
+// Data layout in HBM (one handle = one shard = columns J = [c0, c0 + nloc) of the candidate set):
+//     cov   [n_pad][ld]   Sigma[:, J]     row-major, read one row segment per selection
+//     prec  [n_pad][ld]   P[:, J]         row-major, read + written once per selection (the hot loop)
+//     wfull [kmax][n_pad] conditioning panel rows (full length: W[s][y] is needed for any later y)
+//     pfull [n_pad], ploc [ld], num [ld], taken [ld]
+// The dominant kernel is `downdate_kernel`: 16 * n_pad * ld algorithmic bytes per launch, pure
+// streaming read-modify-write with 128-bit accesses -> HBM roofline.
+#include <math.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "dense.cuh"
+
+using namespace vgp;
+
+struct vgp_greedy {
+    int device = 0;
+    int64_t n = 0, c0 = 0, nloc = 0, kmax = 0;
+    int64_t n_pad = 0, ld = 0;
+    double small_ = 0, jitter = 0;
+    double *cov = nullptr, *prec = nullptr, *prec_saved = nullptr;
+    double *num = nullptr, *wfull = nullptr, *pfull = nullptr, *ploc = nullptr, *seg = nullptr;
+    int *taken = nullptr;
+    vgp_candidate *partials = nullptr, *cur = nullptr, *best = nullptr;
+    unsigned *counter = nullptr;
+    int64_t *sel = nullptr;
+    double *sel_score = nullptr;
+    double *step_scores = nullptr;
+    int record = 0;
+    int64_t t = 0;          // selections enqueued so far
+    int64_t launches = 0;
+    int score_blocks = 0;
+    int sm_count = 148;
+    DenseWorkspace ws;
+};
+
+namespace {
+
+constexpr int MAX_RANKS = 64;
+struct Bounds {
+    int64_t b[MAX_RANKS + 1];
+    int nranks;
+};
+
+struct Cand {
+    double score;
+    int64_t idx;
+    int slot;
+};
+
+__device__ __forceinline__ bool better(double s, int64_t i, double so, int64_t io) {
+    // does (so, io) beat (s, i)?  larger score wins, lower index breaks exact ties
+    return so > s || (so == s && io < i);
+}
+
+__device__ __forceinline__ void warp_argmax(double &s, int64_t &i, int &slot) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double so = __shfl_xor_sync(0xffffffffu, s, off);
+        const int64_t io = __shfl_xor_sync(0xffffffffu, i, off);
+        const int sl = __shfl_xor_sync(0xffffffffu, slot, off);
+        if (better(s, i, so, io)) {
+            s = so;
+            i = io;
+            slot = sl;
+        }
+    }
+}
+
+// Block-wide arg-max; result valid in thread 0.
+__device__ __forceinline__ void block_argmax(double &s, int64_t &i, int &slot) {
+    __shared__ double ss[8];
+    __shared__ int64_t si[8];
+    __shared__ int sl[8];
+    warp_argmax(s, i, slot);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        ss[w] = s;
+        si[w] = i;
+        sl[w] = slot;
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        s = l < nw ? ss[l] : -INFINITY;
+        i = l < nw ? si[l] : INT64_MAX;
+        slot = l < nw ? sl[l] : -1;
+        warp_argmax(s, i, slot);
+    }
+}
+
+constexpr double NEG_INF = -INFINITY;
+
+// delta_j for every local candidate + first strict maximum (placement_algorithm2.py:105-125).
+__global__ void __launch_bounds__(256) score_kernel(const double *__restrict__ prec, int64_t ld, int64_t c0,
+                                                    int64_t nloc, const double *__restrict__ num,
+                                                    const int *__restrict__ taken, double small_, double jitter,
+                                                    vgp_candidate *partials, unsigned *counter,
+                                                    vgp_candidate *best, double *step_row) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double s = NEG_INF, nm = 0.0, pd = 0.0;
+    int64_t idx = INT64_MAX;
+    if (j < nloc) {
+        pd = prec[(c0 + j) * ld + j];
+        nm = num[j];
+        if (!taken[j]) {
+            const double den = 1.0 / pd - jitter;        // sigma^2(y | Abar \ y)
+            const double nom = nm - jitter;              // sigma^2(y | A)
+            double d = nom / den;
+            if (fabs(den) < small_ || fabs(nom) < small_) d = 0.0;    // :116-119
+            if (step_row) step_row[j] = d;
+            if (d > -1.0) {                               // running best starts at -1, strict '<' (:106,:121)
+                s = d;
+                idx = c0 + j;
+            }
+        } else if (step_row) {
+            step_row[j] = nan("");
+        }
+    }
+    __shared__ int64_t win_idx;
+    __shared__ double win_score;
+    {
+        double rs = s;
+        int64_t ri = idx;
+        int slot = 0;
+        block_argmax(rs, ri, slot);
+        if (threadIdx.x == 0) {
+            win_idx = ri;
+            win_score = rs;
+        }
+    }
+    __syncthreads();
+    if (win_idx == INT64_MAX) {
+        if (threadIdx.x == 0) partials[blockIdx.x] = vgp_candidate{NEG_INF, -1, 0.0, 0.0};
+    } else if (idx == win_idx) {
+        partials[blockIdx.x] = vgp_candidate{win_score, idx, nm, pd};
+    }
+    __threadfence();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double rs = NEG_INF;
+    int64_t ri = INT64_MAX;
+    int slot = -1;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) {
+        const vgp_candidate c = ((volatile vgp_candidate *)partials)[b].index >= 0 ? partials[b]
+                                                                                : vgp_candidate{NEG_INF, -1, 0, 0};
+        if (c.index >= 0 && better(rs, ri, c.score, c.index)) {
+            rs = c.score;
+            ri = c.index;
+            slot = b;
+        }
+    }
+    __syncthreads();
+    block_argmax(rs, ri, slot);
+    if (threadIdx.x == 0) *best = slot >= 0 ? partials[slot] : vgp_candidate{NEG_INF, -1, 0.0, 0.0};
+}
+
+// Winner over all shards' records: max score, lowest index on exact ties (single ascending scan with
+// strict '<', placement_algorithm2.py:121).
+__global__ void select_kernel(const vgp_candidate *records, int nrecords, vgp_candidate *cur, int64_t *sel,
+                              double *sel_score, int64_t t) {
+    if (threadIdx.x != 0) return;
+    vgp_candidate w{NEG_INF, -1, 0.0, 0.0};
+    for (int r = 0; r < nrecords; ++r) {
+        const vgp_candidate c = records[r];
+        if (c.index < 0) continue;
+        if (w.index < 0 || c.score > w.score || (c.score == w.score && c.index < w.index)) w = c;
+    }
+    *cur = w;
+    sel[t] = w.index;
+    sel_score[t] = w.score;
+}
+
+// w_J = (Sigma'[y, J] - sum_s W[s][J] W[s][y]) / sqrt(num_y),  p_J = P[y, J]
+__global__ void __launch_bounds__(256) segments_kernel(const double *__restrict__ cov,
+                                                       const double *__restrict__ prec, int64_t ld, int64_t c0,
+                                                       int64_t nloc, const double *__restrict__ wfull,
+                                                       int64_t n_pad, int64_t t, double jitter,
+                                                       const vgp_candidate *cur, double *seg, int64_t stride) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= stride) return;
+    const int64_t y = cur->index;
+    double w = 0.0, p = 0.0;
+    if (y >= 0 && j < nloc) {
+        double acc = cov[y * ld + j];
+        if (c0 + j == y) acc += jitter;
+        for (int64_t s = 0; s < t; ++s) acc = fma(-wfull[s * n_pad + c0 + j], wfull[s * n_pad + y], acc);
+        w = acc / sqrt(cur->num);
+        p = prec[y * ld + j];
+    }
+    seg[j] = w;
+    seg[stride + j] = p;
+}
+
+// Unpack the gathered [rank][w | p] segments into full-length rows and update the local numerators.
+__global__ void __launch_bounds__(256) unpack_kernel(const double *__restrict__ gathered, int64_t stride,
+                                                     Bounds bounds, int64_t n, int64_t n_pad, int64_t c0,
+                                                     int64_t nloc, int64_t ld, double *wrow, double *pfull,
+                                                     double *ploc, double *num, int *taken,
+                                                     const vgp_candidate *cur) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t y = cur->index;
+    if (y < 0) return;
+    if (i < n_pad) {
+        double w = 0.0, p = 0.0;
+        if (i < n) {
+            int g = 0;
+            while (g + 1 < bounds.nranks && i >= bounds.b[g + 1]) ++g;
+            const double *base = gathered + (int64_t)g * 2 * stride;
+            w = base[i - bounds.b[g]];
+            p = base[stride + i - bounds.b[g]];
+        }
+        wrow[i] = w;
+        pfull[i] = p;
+        if (i >= c0 && i < c0 + nloc) {
+            const int64_t j = i - c0;
+            num[j] = fma(-w, w, num[j]);
+            ploc[j] = p;
+            if (i == y) taken[j] = 1;
+        }
+    }
+    // zero the padding of ploc (columns nloc .. ld)
+    if (i >= nloc && i < ld) ploc[i] = 0.0;
+}
+
+// P[i][j] -= (p_i p_j) / p_y over the whole panel; row y and column y become exact zeros.
+// (p_i p_j) is formed first so the update is bitwise symmetric in (i, j) and independent of the sharding.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) downdate_kernel(double *__restrict__ prec, int64_t ld, int64_t n_rows,
+                                                       const double *__restrict__ pfull,
+                                                       const double *__restrict__ ploc, int64_t c0,
+                                                       const vgp_candidate *cur, int rows_per_block) {
+    const int64_t y = cur->index;
+    if (y < 0) return;
+    const int64_t col = (int64_t)blockIdx.x * 512 + 2 * threadIdx.x;
+    if (col >= ld) return;
+    const double inv = 1.0 / pfull[y];
+    const double pj0 = ploc[col], pj1 = ploc[col + 1];
+    const int64_t yl = y - c0;
+    const bool z0 = col == yl, z1 = col + 1 == yl;
+    for (int64_t rb = (int64_t)blockIdx.y * rows_per_block; rb < n_rows; rb += (int64_t)gridDim.y * rows_per_block) {
+        const int64_t rend = min(rb + rows_per_block, n_rows);
+        for (int64_t r = rb; r < rend; r += UNROLL) {
+            double2 v[UNROLL];
+            double pi[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (r + u < rend) {
+                    v[u] = *reinterpret_cast<const double2 *>(prec + (r + u) * ld + col);
+                    pi[u] = pfull[r + u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (r + u < rend) {
+                    double2 o;
+                    o.x = fma(-(pi[u] * pj0), inv, v[u].x);
+                    o.y = fma(-(pi[u] * pj1), inv, v[u].y);
+                    if (r + u == y) o = make_double2(0.0, 0.0);
+                    if (z0) o.x = 0.0;
+                    if (z1) o.y = 0.0;
+                    *reinterpret_cast<double2 *>(prec + (r + u) * ld + col) = o;
+                }
+            }
+        }
+    }
+}
+
+// num = diag(Sigma) (+ jitter); nothing taken
+__global__ void __launch_bounds__(256) reset_kernel(const double *__restrict__ cov, int64_t ld, int64_t c0,
+                                                    int64_t nloc, double jitter, double *num, int *taken,
+                                                    double *ploc) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= ld) return;
+    num[j] = j < nloc ? cov[(c0 + j) * ld + j] + jitter : 0.0;
+    taken[j] = j < nloc ? 0 : 1;
+    ploc[j] = 0.0;
+}
+
+// identity on the padding block of a square padded matrix: a[i][i] = 1 for i in [n, n_pad)
+__global__ void pad_identity_kernel(double *a, int64_t ld, int64_t n, int64_t n_pad) {
+    const int64_t i = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) a[i * ld + i] = 1.0;
+}
+
+int check_handle(vgp_greedy *h) {
+    if (!h) {
+        set_error("greedy handle is NULL");
+        return VGP_ERR_INVALID;
+    }
+    return VGP_OK;
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+#define H_LAUNCH_CHECK(h)      \
+    do {                       \
+        ++(h)->launches;       \
+        VGP_LAUNCH_CHECK();    \
+    } while (0)
+
+extern "C" {
+
+int vgp_greedy_create(vgp_greedy **handle, int device, int64_t n, int64_t c0, int64_t nloc, int64_t kmax,
+                      double small, double jitter) {
+    VGP_REQUIRE(handle, "handle is NULL");
+    *handle = nullptr;
+    VGP_REQUIRE(n > 0 && nloc > 0 && c0 >= 0 && c0 + nloc <= n, "bad shard [%lld, %lld) of %lld", (long long)c0,
+                (long long)(c0 + nloc), (long long)n);
+    VGP_REQUIRE(kmax > 0 && kmax <= n, "kmax %lld outside [1, n]", (long long)kmax);
+    VGP_ENTER(device);
+    vgp_greedy *h = new (std::nothrow) vgp_greedy();
+    VGP_REQUIRE(h, "out of host memory");
+    h->device = device;
+    h->n = n;
+    h->c0 = c0;
+    h->nloc = nloc;
+    h->kmax = kmax;
+    h->small_ = small;
+    h->jitter = jitter;
+    h->n_pad = round_up(n, TILE);
+    h->ld = (c0 == 0 && nloc == n) ? h->n_pad : round_up(nloc, TILE);
+    h->score_blocks = (int)((nloc + 255) / 256);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    const size_t panel = (size_t)h->n_pad * h->ld * sizeof(double);
+    struct {
+        void **p;
+        size_t bytes;
+    } allocs[] = {
+        {(void **)&h->cov, panel},
+        {(void **)&h->prec, panel},
+        {(void **)&h->num, (size_t)h->ld * 8},
+        {(void **)&h->ploc, (size_t)h->ld * 8},
+        {(void **)&h->taken, (size_t)h->ld * 4},
+        {(void **)&h->wfull, (size_t)kmax * h->n_pad * 8},
+        {(void **)&h->pfull, (size_t)h->n_pad * 8},
+        {(void **)&h->seg, (size_t)2 * h->n_pad * 8},
+        {(void **)&h->partials, (size_t)h->score_blocks * sizeof(vgp_candidate)},
+        {(void **)&h->cur, sizeof(vgp_candidate)},
+        {(void **)&h->best, sizeof(vgp_candidate)},
+        {(void **)&h->counter, sizeof(unsigned)},
+        {(void **)&h->sel, (size_t)kmax * 8},
+        {(void **)&h->sel_score, (size_t)kmax * 8},
+    };
+    for (auto &a : allocs) {
+        e = cudaMalloc(a.p, a.bytes);
+        if (e != cudaSuccess) {
+            int rc = cuda_fail(e, "cudaMalloc (greedy state)", __FILE__, __LINE__);
+            vgp_greedy_destroy(h);
+            return rc;
+        }
+    }
+    cudaMemset(h->cov, 0, panel);
+    cudaMemset(h->prec, 0, panel);
+    cudaMemset(h->counter, 0, sizeof(unsigned));
+    cudaMemset(h->pfull, 0, (size_t)h->n_pad * 8);
+    cudaMemset(h->wfull, 0, (size_t)kmax * h->n_pad * 8);
+    cudaMemset(h->sel, 0xff, (size_t)kmax * 8);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "greedy state init", __FILE__, __LINE__);
+        vgp_greedy_destroy(h);
+        return rc;
+    }
+    *handle = h;
+    return VGP_OK;
+}
+
+int vgp_greedy_destroy(vgp_greedy *h) {
+    if (!h) return VGP_OK;
+    VGP_ENTER(h->device);
+    void *ptrs[] = {h->cov, h->prec, h->prec_saved, h->num, h->ploc, h->taken, h->wfull, h->pfull, h->seg,
+                    h->partials, h->cur, h->best, h->counter, h->sel, h->sel_score, h->step_scores};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    h->ws.release();
+    delete h;
+    return VGP_OK;
+}
+
+int vgp_greedy_panels(vgp_greedy *h, double **cov_dev, double **prec_dev, int64_t *ld, int64_t *n_pad) {
+    VGP_TRY(check_handle(h));
+    if (cov_dev) *cov_dev = h->cov;
+    if (prec_dev) *prec_dev = h->prec;
+    if (ld) *ld = h->ld;
+    if (n_pad) *n_pad = h->n_pad;
+    return VGP_OK;
+}
+
+int vgp_greedy_reset(vgp_greedy *h, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    reset_kernel<<<(unsigned)((h->ld + 255) / 256), 256, 0, s>>>(h->cov, h->ld, h->c0, h->nloc, h->jitter, h->num,
+                                                               h->taken, h->ploc);
+    H_LAUNCH_CHECK(h);
+    VGP_CUDA(cudaMemsetAsync(h->sel, 0xff, (size_t)h->kmax * 8, s));
+    h->t = 0;
+    return VGP_OK;
+}
+
+int vgp_greedy_factor(vgp_greedy *h, int *info_host, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(h->c0 == 0 && h->nloc == h->n, "vgp_greedy_factor needs a single shard holding all columns");
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t panel = (size_t)h->n_pad * h->ld * sizeof(double);
+    VGP_CUDA(cudaMemcpyAsync(h->prec, h->cov, panel, cudaMemcpyDeviceToDevice, s));
+    if (h->jitter != 0.0) {
+        VGP_TRY(dense_add_diag(h->prec, h->ld, h->n, h->jitter, s));
+        ++h->launches;
+    }
+    if (h->n_pad > h->n) {
+        const int64_t extra = h->n_pad - h->n;
+        pad_identity_kernel<<<(unsigned)((extra + 127) / 128), 128, 0, s>>>(h->prec, h->ld, h->n, h->n_pad);
+        H_LAUNCH_CHECK(h);
+    }
+    const int64_t before = g_launches;
+    int rc = dense_spd_inverse(h->prec, h->n_pad, h->ld, h->ws, info_host, s);
+    h->launches += g_launches - before;
+    VGP_TRY(rc);
+    return vgp_greedy_reset(h, stream);
+}
+
+int vgp_greedy_save_precision(vgp_greedy *h, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_ENTER(h->device);
+    const size_t panel = (size_t)h->n_pad * h->ld * sizeof(double);
+    if (!h->prec_saved) VGP_CUDA(cudaMalloc((void **)&h->prec_saved, panel));
+    VGP_CUDA(cudaMemcpyAsync(h->prec_saved, h->prec, panel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_greedy_restore_precision(vgp_greedy *h, void *stream) {
+    VGP_TRY(check_handle(h));
+    if (!h->prec_saved) {
+        set_error("no saved precision panel");
+        return VGP_ERR_STATE;
+    }
+    VGP_ENTER(h->device);
+    const size_t panel = (size_t)h->n_pad * h->ld * sizeof(double);
+    VGP_CUDA(cudaMemcpyAsync(h->prec, h->prec_saved, panel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return vgp_greedy_reset(h, stream);
+}
+
+int vgp_greedy_local_best(vgp_greedy *h, vgp_candidate *best_dev, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(best_dev, "best_dev is NULL");
+    if (h->t >= h->kmax) {
+        set_error("greedy handle already holds kmax = %lld selections", (long long)h->kmax);
+        return VGP_ERR_STATE;
+    }
+    VGP_ENTER(h->device);
+    double *row = (h->record && h->step_scores) ? h->step_scores + h->t * h->nloc : nullptr;
+    score_kernel<<<h->score_blocks, 256, 0, (cudaStream_t)stream>>>(h->prec, h->ld, h->c0, h->nloc, h->num, h->taken,
+                                                                    h->small_, h->jitter, h->partials, h->counter,
+                                                                    best_dev, row);
+    H_LAUNCH_CHECK(h);
+    return VGP_OK;
+}
+
+int vgp_greedy_select(vgp_greedy *h, const vgp_candidate *records_dev, int nrecords, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(records_dev && nrecords > 0, "no candidate records");
+    VGP_ENTER(h->device);
+    select_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(records_dev, nrecords, h->cur, h->sel, h->sel_score, h->t);
+    H_LAUNCH_CHECK(h);
+    return VGP_OK;
+}
+
+int vgp_greedy_segments(vgp_greedy *h, double *seg_dev, int64_t seg_stride, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(seg_dev && seg_stride >= h->nloc, "segment buffer too small");
+    VGP_ENTER(h->device);
+    segments_kernel<<<(unsigned)((seg_stride + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        h->cov, h->prec, h->ld, h->c0, h->nloc, h->wfull, h->n_pad, h->t, h->jitter, h->cur, seg_dev, seg_stride);
+    H_LAUNCH_CHECK(h);
+    return VGP_OK;
+}
+
+int vgp_greedy_apply(vgp_greedy *h, const double *gathered_dev, int64_t seg_stride, int nranks,
+                     const int64_t *bounds_host, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(gathered_dev && bounds_host, "NULL argument");
+    VGP_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS, "nranks %d outside [1, %d]", nranks, MAX_RANKS);
+    VGP_REQUIRE(bounds_host[0] == 0 && bounds_host[nranks] == h->n, "bounds do not cover [0, n)");
+    for (int g = 0; g < nranks; ++g)
+        VGP_REQUIRE(bounds_host[g + 1] - bounds_host[g] <= seg_stride && bounds_host[g + 1] >= bounds_host[g],
+                    "rank %d segment does not fit seg_stride", g);
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    Bounds b;
+    b.nranks = nranks;
+    for (int g = 0; g <= nranks; ++g) b.b[g] = bounds_host[g];
+    const int64_t span = h->n_pad > h->ld ? h->n_pad : h->ld;
+    unpack_kernel<<<(unsigned)((span + 255) / 256), 256, 0, s>>>(gathered_dev, seg_stride, b, h->n, h->n_pad, h->c0,
+                                                               h->nloc, h->ld, h->wfull + h->t * h->n_pad, h->pfull,
+                                                               h->ploc, h->num, h->taken, h->cur);
+    H_LAUNCH_CHECK(h);
+    static const int rows_per_block = env_int("VGP_DOWNDATE_ROWS", 32);
+    static const int waves = env_int("VGP_DOWNDATE_WAVES", 4);
+    static const int unroll = env_int("VGP_DOWNDATE_UNROLL", 4);
+    const unsigned gx = (unsigned)((h->ld + 511) / 512);
+    const int64_t row_tiles = (h->n_pad + rows_per_block - 1) / rows_per_block;
+    int64_t gy = ((int64_t)h->sm_count * 8 * waves + gx - 1) / gx;
+    if (gy > row_tiles) gy = row_tiles;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    dim3 grid(gx, (unsigned)gy);
+    if (unroll >= 8)
+        downdate_kernel<8><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
+    else if (unroll >= 4)
+        downdate_kernel<4><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
+    else
+        downdate_kernel<2><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
+    H_LAUNCH_CHECK(h);
+    ++h->t;
+    return VGP_OK;
+}
+
+int vgp_greedy_run(vgp_greedy *h, int64_t k, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(h->c0 == 0 && h->nloc == h->n, "vgp_greedy_run needs a single shard; drive shards step by step");
+    VGP_REQUIRE(k >= 0 && h->t + k <= h->kmax, "k = %lld exceeds kmax = %lld (already %lld)", (long long)k,
+                (long long)h->kmax, (long long)h->t);
+    const int64_t bounds[2] = {0, h->n};
+    for (int64_t i = 0; i < k; ++i) {
+        VGP_TRY(vgp_greedy_local_best(h, h->best, stream));
+        VGP_TRY(vgp_greedy_select(h, h->best, 1, stream));
+        VGP_TRY(vgp_greedy_segments(h, h->seg, h->n_pad, stream));
+        VGP_TRY(vgp_greedy_apply(h, h->seg, h->n_pad, 1, bounds, stream));
+    }
+    return VGP_OK;
+}
+
+int vgp_greedy_results(vgp_greedy *h, int64_t *count, int64_t *selection_host, double *scores_host,
+                       int64_t capacity, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t c = h->t < capacity ? h->t : capacity;
+    if (count) *count = h->t;
+    if (selection_host && c > 0)
+        VGP_CUDA(cudaMemcpyAsync(selection_host, h->sel, (size_t)c * 8, cudaMemcpyDeviceToHost, s));
+    if (scores_host && c > 0)
+        VGP_CUDA(cudaMemcpyAsync(scores_host, h->sel_score, (size_t)c * 8, cudaMemcpyDeviceToHost, s));
+    VGP_CUDA(cudaStreamSynchronize(s));
+    return VGP_OK;
+}
+
+int vgp_greedy_record_scores(vgp_greedy *h, int enable) {
+    VGP_TRY(check_handle(h));
+    VGP_ENTER(h->device);
+    if (enable && !h->step_scores)
+        VGP_CUDA(cudaMalloc((void **)&h->step_scores, (size_t)h->kmax * h->nloc * 8));
+    h->record = enable ? 1 : 0;
+    return VGP_OK;
+}
+
+int vgp_greedy_step_scores(vgp_greedy *h, double *scores_host, int64_t capacity_rows, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(scores_host, "scores_host is NULL");
+    if (!h->step_scores) {
+        set_error("score recording was not enabled");
+        return VGP_ERR_STATE;
+    }
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t rows = h->t < capacity_rows ? h->t : capacity_rows;
+    if (rows > 0)
+        VGP_CUDA(cudaMemcpyAsync(scores_host, h->step_scores, (size_t)rows * h->nloc * 8, cudaMemcpyDeviceToHost, s));
+    VGP_CUDA(cudaStreamSynchronize(s));
+    return VGP_OK;
+}
+
+int vgp_greedy_launch_count(vgp_greedy *h, int64_t *launches) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(launches, "launches is NULL");
+    *launches = h->launches;
+    return VGP_OK;
+}
+
+int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
+                       double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
+                       double *seconds_host) {
+    VGP_REQUIRE(cov_host && selection_host, "NULL argument");
+    VGP_REQUIRE(n > 0 && ld_host >= n && k > 0 && k <= n, "bad sizes n=%lld ld=%lld k=%lld", (long long)n,
+                (long long)ld_host, (long long)k);
+    VGP_ENTER(device);
+    vgp_greedy *h = nullptr;
+    VGP_TRY(vgp_greedy_create(&h, device, n, 0, n, k, small, jitter));
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[4];
+    for (auto &e : ev) cudaEventCreate(&e);
+    int rc = VGP_OK;
+    auto fail = [&](int code) {
+        for (auto &e : ev) cudaEventDestroy(e);
+        vgp_greedy_destroy(h);
+        return code;
+    };
+    cudaEventRecord(ev[0], s);
+    cudaError_t ce = cudaMemcpy2DAsync(h->cov, (size_t)h->ld * 8, cov_host, (size_t)ld_host * 8, (size_t)n * 8,
+                                       (size_t)n, cudaMemcpyHostToDevice, s);
+    if (ce != cudaSuccess) return fail(cuda_fail(ce, "H2D of cov_vv", __FILE__, __LINE__));
+    cudaEventRecord(ev[1], s);
+    int info = 0;
+    rc = vgp_greedy_factor(h, &info, s);
+    if (rc != VGP_OK) return fail(rc);
+    cudaEventRecord(ev[2], s);
+    if (step_scores_host) {
+        rc = vgp_greedy_record_scores(h, 1);
+        if (rc != VGP_OK) return fail(rc);
+    }
+    rc = vgp_greedy_run(h, k, s);
+    if (rc != VGP_OK) return fail(rc);
+    int64_t count = 0;
+    rc = vgp_greedy_results(h, &count, selection_host, scores_host, k, s);
+    if (rc != VGP_OK) return fail(rc);
+    if (step_scores_host) {
+        rc = vgp_greedy_step_scores(h, step_scores_host, k, s);
+        if (rc != VGP_OK) return fail(rc);
+    }
+    cudaEventRecord(ev[3], s);
+    ce = cudaEventSynchronize(ev[3]);
+    if (ce != cudaSuccess) return fail(cuda_fail(ce, "placement", __FILE__, __LINE__));
+    if (seconds_host) {
+        float ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        seconds_host[0] = ms * 1e-3;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]);
+        seconds_host[1] = ms * 1e-3;
+        cudaEventElapsedTime(&ms, ev[2], ev[3]);
+        seconds_host[2] = ms * 1e-3;
+        cudaEventElapsedTime(&ms, ev[0], ev[3]);
+        seconds_host[3] = ms * 1e-3;
+    }
+    return fail(VGP_OK);
+}
+
+}  // extern "C"

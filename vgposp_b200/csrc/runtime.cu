@@ -1,0 +1,232 @@
+// Runtime part of the C-ABI: errors, memory, streams, events, DLPack views.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vgp {
+
+static thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    return e == cudaErrorMemoryAllocation ? VGP_ERR_NOMEM : VGP_ERR_CUDA;
+}
+
+DeviceGuard::DeviceGuard(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDevice (no CUDA device? this library has no CPU fallback)", __FILE__, __LINE__);
+        prev = -1;
+        return;
+    }
+    if (prev != device) {
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) {
+            cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+            return;
+        }
+    }
+    ok = true;
+}
+
+DeviceGuard::~DeviceGuard() {
+    if (ok && prev >= 0) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+}
+
+}  // namespace vgp
+
+using namespace vgp;
+
+extern "C" {
+
+int vgp_abi_version(void) { return VGP_ABI_VERSION; }
+
+const char *vgp_last_error(void) { return g_error.c_str(); }
+
+int vgp_device_count(int *count) {
+    VGP_REQUIRE(count, "count is NULL");
+    *count = 0;
+    VGP_CUDA(cudaGetDeviceCount(count));
+    return VGP_OK;
+}
+
+int vgp_device_info(int device, char *name, int len, int *sm_count, size_t *total_bytes, size_t *free_bytes) {
+    VGP_ENTER(device);
+    cudaDeviceProp prop;
+    VGP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (name && len > 0) {
+        strncpy(name, prop.name, len - 1);
+        name[len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    size_t f = 0, t = 0;
+    VGP_CUDA(cudaMemGetInfo(&f, &t));
+    if (total_bytes) *total_bytes = t;
+    if (free_bytes) *free_bytes = f;
+    return VGP_OK;
+}
+
+int vgp_malloc(int device, size_t bytes, void **ptr_dev) {
+    VGP_REQUIRE(ptr_dev, "ptr is NULL");
+    VGP_ENTER(device);
+    *ptr_dev = nullptr;
+    VGP_CUDA(cudaMalloc(ptr_dev, bytes ? bytes : 1));
+    return VGP_OK;
+}
+
+int vgp_free(int device, void *ptr_dev) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaFree(ptr_dev));
+    return VGP_OK;
+}
+
+int vgp_host_alloc(size_t bytes, void **ptr_host) {
+    VGP_REQUIRE(ptr_host, "ptr is NULL");
+    *ptr_host = nullptr;
+    VGP_CUDA(cudaHostAlloc(ptr_host, bytes ? bytes : 1, cudaHostAllocDefault));
+    return VGP_OK;
+}
+
+int vgp_host_free(void *ptr_host) {
+    VGP_CUDA(cudaFreeHost(ptr_host));
+    return VGP_OK;
+}
+
+int vgp_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_memcpy_d2d(int device, void *dst_dev, const void *src_dev, size_t bytes, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_memcpy2d_h2d(int device, void *dst_dev, size_t dpitch, const void *src_host, size_t spitch,
+                     size_t width_bytes, size_t rows, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaMemcpy2DAsync(dst_dev, dpitch, src_host, spitch, width_bytes, rows, cudaMemcpyHostToDevice,
+                               (cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_memcpy2d_d2h(int device, void *dst_host, size_t dpitch, const void *src_dev, size_t spitch,
+                     size_t width_bytes, size_t rows, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaMemcpy2DAsync(dst_host, dpitch, src_dev, spitch, width_bytes, rows, cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_memset(int device, void *dst_dev, int value, size_t bytes, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaMemsetAsync(dst_dev, value, bytes, (cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_stream_create(int device, void **stream) {
+    VGP_REQUIRE(stream, "stream is NULL");
+    VGP_ENTER(device);
+    cudaStream_t s;
+    VGP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return VGP_OK;
+}
+
+int vgp_stream_destroy(int device, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_stream_sync(int device, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return VGP_OK;
+}
+
+int vgp_event_record(int device, void *stream, void **event) {
+    VGP_REQUIRE(event, "event is NULL");
+    VGP_ENTER(device);
+    cudaEvent_t ev;
+    VGP_CUDA(cudaEventCreate(&ev));
+    VGP_CUDA(cudaEventRecord(ev, (cudaStream_t)stream));
+    *event = (void *)ev;
+    return VGP_OK;
+}
+
+int vgp_event_elapsed_ms(int device, void *start_event, void *stop_event, float *ms) {
+    VGP_REQUIRE(start_event && stop_event && ms, "NULL argument");
+    VGP_ENTER(device);
+    VGP_CUDA(cudaEventSynchronize((cudaEvent_t)stop_event));
+    VGP_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start_event, (cudaEvent_t)stop_event));
+    cudaEventDestroy((cudaEvent_t)start_event);
+    cudaEventDestroy((cudaEvent_t)stop_event);
+    return VGP_OK;
+}
+
+// ---- DLPack (dlpack.h v0.x layout, restated here so that no external header is needed) -------------
+struct DLDevice_ { int32_t device_type; int32_t device_id; };
+struct DLDataType_ { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor_ {
+    void *data;
+    DLDevice_ device;
+    int32_t ndim;
+    DLDataType_ dtype;
+    int64_t *shape;
+    int64_t *strides;
+    uint64_t byte_offset;
+};
+struct DLManagedTensor_ {
+    DLTensor_ dl_tensor;
+    void *manager_ctx;
+    void (*deleter)(DLManagedTensor_ *);
+};
+
+int vgp_dlpack_view(const void *dl_managed_tensor, vgp_tensor_view *out) {
+    VGP_REQUIRE(dl_managed_tensor && out, "NULL argument");
+    const DLTensor_ &t = ((const DLManagedTensor_ *)dl_managed_tensor)->dl_tensor;
+    VGP_REQUIRE(t.ndim >= 0 && t.ndim <= 8, "DLPack tensor rank %d not supported", t.ndim);
+    VGP_REQUIRE(t.dtype.lanes == 1, "vector dtypes not supported");
+    memset(out, 0, sizeof *out);
+    out->data = (char *)t.data + t.byte_offset;
+    out->device_type = t.device.device_type;
+    out->device_id = t.device.device_id;
+    out->ndim = t.ndim;
+    out->dtype_code = t.dtype.code;
+    out->dtype_bits = t.dtype.bits;
+    int64_t expect = 1;
+    int contiguous = 1;
+    for (int i = t.ndim - 1; i >= 0; --i) {
+        out->shape[i] = t.shape[i];
+        out->strides[i] = t.strides ? t.strides[i] : expect;
+        if (t.shape[i] > 1 && out->strides[i] != expect) contiguous = 0;
+        expect *= t.shape[i];
+    }
+    out->contiguous = contiguous;
+    return VGP_OK;
+}
+
+}  // extern "C"
