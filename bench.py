@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- greedy mutual-information placement throughput (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on; fits one GPU):
+    synthetic 3-D point cloud, n = 50 000 candidates in [-2,2]^3, ExpQuad covariance a = 1, l = 0.136,
+    nugget 1e-2, k = 100 selections.
+A "step" is one greedy selection: score + arg-max, numerator update, rank-1 precision downdate of the
+panel this rank owns.  `value` = selections/s with Sigma and P resident in HBM (the O(n^3) inverse that seeds
+P is setup and is reported separately as `setup_s`); `e2e` = the same selections/s through the one-call C-ABI
+`vgp_placement_host` with the covariance in pinned HOST memory (H2D + inverse + k selections + D2H inside
+the timed region).
+
+One JSON line on stdout (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FULL = 50000
+K_FULL = 100
+SEED = 20261018 + 3
+
+
+def workload(n):
+    rng = np.random.default_rng(SEED)
+    x = rng.uniform(-2.0, 2.0, (n, 3))
+    length_scale = 0.5 * (1000.0 / n) ** (1.0 / 3.0)
+    return x, 1.0, length_scale, 1e-2
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Polls NVML (SM clock, throttle reasons) every 100 ms on a side thread while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, device):
+        self.samples, self.reasons, self.max_mhz, self.err = [], set(), None, None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device])
+                except Exception:
+                    idx = device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:        # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                    if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as e:    # noqa: BLE001
+                self.err = repr(e)
+                return
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv:
+            self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": self.err or "no samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port (C/OpenMP + LAPACK) on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_greedy(n_full, n_sample, steps, warmup):
+    """The incremental oracle run for real on the first n_sample points of the same cloud; per-selection
+    cost is O(n^2) HBM/DRAM streaming, so selections/s at n_full = measured * (n_sample / n_full)^2."""
+    from oracle import greedy_oracle as go
+    from oracle import gp_oracle as gpo
+    x, amp, _, nugget = workload(n_full)
+    xs = x[:n_sample]
+    ls = 0.5 * (1000.0 / n_sample) ** (1.0 / 3.0)          # same neighbour density as the full workload
+    t0 = time.perf_counter()
+    cov = np.empty((n_sample, n_sample))
+    for i in range(0, n_sample, 1024):                      # blocked: bounded temporary
+        cov[i:i + 1024] = gpo.expquad_matrix(xs[i:i + 1024], xs, amp, ls)
+    cov[np.diag_indices(n_sample)] += nugget
+    build_s = time.perf_counter() - t0
+    tm = {}
+    sel, _ = go.incremental_greedy_c(cov, warmup + steps, timings=tm)
+    per_step = float(np.mean(tm["steps_s"][warmup:]))
+    scale = (n_sample / n_full) ** 2
+    cores = os.cpu_count() or 1
+    threads = int(os.environ.get("OMP_NUM_THREADS", cores))
+    return {
+        "value": scale / per_step, "unit": "selections/s", "cores": threads, "kind": "port",
+        "sample": "incremental oracle (C/OpenMP step + LAPACK inverse) run for real at n=%d of the same cloud, "
+                  "%d selections after %d warm-up; per-selection time scaled by (n/%d)^2 to n=%d; setup "
+                  "(inverse %.1f s, kernel build %.1f s at the sample size) excluded like `value`"
+                  % (n_sample, steps, warmup, n_sample, n_full, tm["setup_s"], build_s),
+        "ms_per_step_sample": per_step * 1e3, "ms_per_step_scaled": per_step * 1e3 / scale,
+        "host": {"cpu_count": cores, "omp_threads": threads},
+    }
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_sample = int(os.environ.get("VGP_BENCH_CPU_N", 8192))
+    base = cpu_greedy(args.n, n_sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "greedy_mi_selections_per_s", "value": base["value"],
+        "unit": "selections/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": base["ms_per_step_scaled"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "selections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference arm = CPU restatement of the reference's greedy (oracle/, pinned to the reference's "
+                "own golden vectors); the literal reference is O(n^4)/selection and Python-only "
+                "(0.063 selections/s at n=400, BASELINE.md) and cannot run at this size",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args):
+    _, amp, ls, nugget = workload(args.n)
+    return {"workload": "greedy_mi_placement_n%d_k%d_expquad_cloud" % (args.n, args.k), "n": args.n, "k": args.k,
+            "amplitude": amp, "length_scale": round(ls, 6), "nugget": nugget, "seed": SEED,
+            "parallelism": "column-panel shards x%d" % args.gpus,
+            "l2": "inputs larger than L2: every step streams the %.1f GB precision panel"
+                  % (8.0 * args.n * args.n / args.gpus / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from vgposp_b200 import _ffi, greedy
+    from vgposp_b200._ffi import call
+
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    n, k = args.n, args.k
+    x, amp, ls, nugget = workload(n)
+    stream = torch.cuda.current_stream().cuda_stream
+    bounds = greedy.shard_bounds(n, world)
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if \
+        os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak, peak_kind = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    def ev():
+        e = ctypes.c_void_p()
+        call("vgp_event_record", dev, stream, ctypes.byref(e))
+        return e
+
+    def elapsed(a, b):
+        ms = ctypes.c_float()
+        call("vgp_event_elapsed_ms", dev, a, b, ctypes.byref(ms))
+        return ms.value
+
+    # ---- setup: Sigma panel from coordinates, P = Sigma^-1 (untimed, reported) -----------------------
+    xd = _ffi.DeviceArray.from_host(x, dev)
+    shard = greedy.GreedyShard(n, c0, c1, max(k, args.steps + args.warmup), dev, stream=stream)
+    e0 = ev()
+    shard.build_cov_expquad(xd.ptr, 3, amp, ls, nugget)
+    e1 = ev()
+    build_ms = elapsed(e0, e1)
+    t0 = time.perf_counter()
+    if world == 1:
+        shard.factor()
+    else:
+        # round 1: every rank inverts the full matrix (replicated setup), then keeps its column panel
+        n_pad = shard.n_pad
+        full = _ffi.DeviceArray((n_pad, n_pad), np.float64, dev).zero_(stream)
+        call("vgp_expquad_matrix", dev, xd.ptr, n, xd.ptr, n, 3, amp, ls, nugget, 0, full.ptr, n_pad, stream)
+        if n_pad > n:
+            ones = np.ones(n_pad - n)
+            call("vgp_memcpy2d_h2d", dev, full.ptr + (n * n_pad + n) * 8, (n_pad + 1) * 8, ones.ctypes.data, 8, 8,
+                 n_pad - n, stream)
+        info = ctypes.c_int(0)
+        call("vgp_spd_inverse", dev, full.ptr, n_pad, n_pad, ctypes.byref(info), stream)
+        shard.load_prec_device(full.ptr, n_pad)
+        shard.reset()
+        shard.sync()
+        full.free()
+    shard.sync()
+    factor_s = time.perf_counter() - t0
+    shard.save_precision()
+
+    if world > 1:
+        def make_buffer(m):
+            return torch.zeros(m, dtype=torch.float64, device="cuda:%d" % dev)
+
+        def all_gather(dst, src):
+            dist.all_gather_into_tensor(dst, src)
+        driver = greedy.ShardedGreedy(shard, n, rank, world, make_buffer, all_gather)
+        run_steps = driver.run
+    else:
+        run_steps = shard.run
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then restore the precision so that the timed region is selections 1..K -------------
+    run_steps(args.warmup)
+    shard.sync()
+    shard.restore_precision()
+    call("vgp_greedy_profile", shard.handle, 1)
+    launches0 = shard.launch_count()
+    barrier()
+    with ClockSampler(dev) as clocks:
+        a = ev()
+        run_steps(args.steps)
+        b = ev()
+        ms = elapsed(a, b)
+        barrier()
+    launches = shard.launch_count() - launches0
+    kms, kcount = ctypes.c_double(), ctypes.c_int64()
+    call("vgp_greedy_profile_read", shard.handle, ctypes.byref(kms), ctypes.byref(kcount))
+    call("vgp_greedy_profile", shard.handle, 0)
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sel, scores = shard.results()
+    gaps_ok = bool(np.all(np.diff(scores) <= 1e-12 * np.abs(scores[:-1]))) if len(scores) > 1 else True
+
+    # ---- e2e: host covariance in pinned memory through the one-call C-ABI -----------------------------
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        e2e = measure_e2e(args, shard, dev, sel)
+    elif world > 1:
+        e2e = {"value": None, "unit": "selections/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "note": "round 1 measures the host-buffer path at N=1 only (vgp_placement_host is single-device)"}
+    shard.close()
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    nloc = c1 - c0
+    algo_bytes = 16.0 * n * nloc
+    kernel_ms = kms.value / max(kcount.value, 1)
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    line = {
+        "metric": "greedy_mi_selections_per_s", "value": args.steps / (ms * 1e-3), "unit": "selections/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args),
+        "roofline": {"bound": "hbm", "kernel": "downdate_kernel", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                     "peak_kind": "%s copy bandwidth (MEASURED_PEAKS.json)" % peak_kind, "traffic": None,
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": kernel_ms,
+                     "kernel_launches_timed": kcount.value,
+                     "kernel_share_of_step": kms.value / ms if ms > 0 else None},
+        "clocks": clocks.summary(),
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "setup_s": {"expquad_panel_build": build_ms * 1e-3, "inverse_potrf_potri": factor_s,
+                    "expquad_GBps": 8.0 * n * nloc / (build_ms * 1e-3) / 1e9 if build_ms > 0 else None,
+                    "inverse_tflops": (float(n) ** 3) / factor_s / 1e12 if factor_s > 0 else None},
+        "selection_head": [int(s) for s in sel[:8]], "scores_non_increasing": gaps_ok,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_greedy(n, int(os.environ.get("VGP_BENCH_CPU_N", 8192)), 20, 2)
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def measure_e2e(args, shard, dev, expect_sel):
+    """k selections through vgp_placement_host with Sigma in pinned host memory."""
+    from vgposp_b200._ffi import call
+    import psutil
+    n, k = args.n, args.k
+    nbytes = 8 * n * n
+    if psutil.virtual_memory().available < nbytes * 1.3 + (8 << 30):
+        return {"value": None, "unit": "selections/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                "note": "host has less than %.0f GB available for the pinned covariance" % (nbytes * 1.3 / 1e9)}
+    host = ctypes.c_void_p()
+    call("vgp_host_alloc", nbytes, ctypes.byref(host))
+    try:
+        # fill the host matrix from the device panel (outside the timed region)
+        call("vgp_memcpy2d_d2h", dev, host, n * 8, shard.cov_ptr, shard.ld * 8, n * 8, n, shard.stream)
+        shard.sync()
+        shard.close()                       # free the 3 panels before the one-call path allocates its own
+        sel = np.full(k, -1, dtype=np.int64)
+        sc = np.zeros(k)
+        secs = np.zeros(4)
+        t0 = time.perf_counter()
+        call("vgp_placement_host", dev, host, n, n, k, 1e-8, 0.0, sel.ctypes.data, sc.ctypes.data, None,
+             secs.ctypes.data)
+        wall = time.perf_counter() - t0
+    finally:
+        call("vgp_host_free", host)
+    same = bool(np.array_equal(sel[:len(expect_sel)], expect_sel[:k]))
+    return {"value": k / secs[3], "unit": "selections/s", "h2d_bytes_per_step": nbytes / k, "d2h_bytes_per_step": 16,
+            "seconds": {"h2d": secs[0], "inverse": secs[1], "selections_and_d2h": secs[2], "total_events": secs[3],
+                        "total_wall": wall},
+            "k": k, "selection_equals_resident_run": same,
+            "api": "vgp_placement_host == vgposp_b200.placement_algorithm2.placement_algorithm_1(cov_vv, k)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=K_FULL)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_FULL, help="candidate count (default: the BASELINE workload)")
+    ap.add_argument("--k", type=int, default=None, help="selections of the e2e call (default: --steps)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.k is None:
+        args.k = args.steps
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (see the module docstring)")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,8 @@ int vgp_memcpy2d_h2d(int device, void *dst_dev, size_t dpitch, const void *src_h
                      size_t width_bytes, size_t rows, void *stream);
 int vgp_memcpy2d_d2h(int device, void *dst_host, size_t dpitch, const void *src_dev, size_t spitch,
                      size_t width_bytes, size_t rows, void *stream);
+int vgp_memcpy2d_d2d(int device, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch,
+                     size_t width_bytes, size_t rows, void *stream);
 int vgp_memset(int device, void *dst_dev, int value, size_t bytes, void *stream);
 int vgp_stream_create(int device, void **stream);
 int vgp_stream_destroy(int device, void *stream);
@@ -106,7 +108,9 @@ int vgp_dgemm(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_
  * *info_host = 0, or 1 + index of the first non-positive pivot (then returns VGP_ERR_NOT_PD). */
 int vgp_potrf(int device, double *a_dev, int64_t n, int64_t lda, int *info_host, void *stream);
 /* Full symmetric inverse of an SPD matrix, in place (potrf + trtri + lauum + mirror).  Replaces the
- * pseudo-inverses of placement_algorithm2.py:399-405 on the well-conditioned inputs where pinv == inv. */
+ * pseudo-inverses of placement_algorithm2.py:399-405 on the well-conditioned inputs where pinv == inv.
+ * When n is a multiple of 128, lda is even and a_dev is 16-byte aligned the matrix is processed where it
+ * lies; otherwise through a padded copy (8 n^2 bytes of scratch). */
 int vgp_spd_inverse(int device, double *a_dev, int64_t n, int64_t lda, int *info_host, void *stream);
 /* Triangular solves with the lower factor: side 0: op(L) X = B (B is [n, nrhs]), side 1: X op(L) = B
  * (B is [nrhs, n]); trans 0: op(L) = L, 1: op(L) = L^T.  In place on B.  Replaces
@@ -211,6 +215,11 @@ int vgp_greedy_record_scores(vgp_greedy *handle, int enable);
 int vgp_greedy_step_scores(vgp_greedy *handle, double *scores_host, int64_t capacity_rows, void *stream);
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int vgp_greedy_launch_count(vgp_greedy *handle, int64_t *launches);
+
+/* Timing of the dominant kernel (the precision downdate): when enabled, every downdate launch is bracketed by
+ * CUDA events on its stream; profile_read returns their summed duration and count (blocking). */
+int vgp_greedy_profile(vgp_greedy *handle, int enable);
+int vgp_greedy_profile_read(vgp_greedy *handle, double *total_ms, int64_t *launches);
 
 /* One-call form of placement_algorithm_1/2(cov_vv, k) (placement_algorithm2.py:128,151) for a HOST matrix:
  * H2D, factor, k selections, D2H.  cov_host [n, ld_host] row-major float64 (pageable or pinned).

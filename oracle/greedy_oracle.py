@@ -281,3 +281,72 @@ def replay_lazy_evaluations(step_scores, selection):
         picks.append(y)
         taken[y] = True
     return picks, trace
+
+
+# --------------------------------------------------------------------------------------------------
+# C/OpenMP form of the same step (oracle/greedy_step.c) -- CPU baseline for bench.py
+# --------------------------------------------------------------------------------------------------
+def _load_c():
+    import ctypes
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libgreedy_oracle.so")
+    if not os.path.exists(path):
+        try:
+            from . import build_oracle
+            build_oracle.build()
+        except Exception:
+            return None
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError:
+        return None
+    i64, dbl, vp = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
+    lib.oracle_scores.restype = i64
+    lib.oracle_scores.argtypes = [vp, i64, i64, i64, vp, vp, dbl, dbl, vp, ctypes.POINTER(dbl)]
+    lib.oracle_segments.restype = None
+    lib.oracle_segments.argtypes = [vp, vp, i64, i64, i64, vp, i64, i64, dbl, i64, dbl, vp, vp]
+    lib.oracle_apply.restype = None
+    lib.oracle_apply.argtypes = [vp, i64, i64, i64, i64, vp, vp, i64, vp, vp]
+    return lib
+
+
+def incremental_greedy_c(cov_vv, k, small=GUARD_NUMPY, jitter=0.0, prec=None, timings=None):
+    """Single-block incremental greedy with the per-step work in C/OpenMP.  Returns (selection, scores).
+    `timings`, if a dict, receives 'setup_s' (inverse) and 'steps_s' (list of per-selection seconds)."""
+    import ctypes
+    import time
+    lib = _load_c()
+    if lib is None:
+        sel, sc, _, _ = incremental_greedy(cov_vv, k, small, jitter, prec=prec)
+        return sel, sc
+    cov = np.ascontiguousarray(cov_vv, dtype=np.float64)
+    n = cov.shape[0]
+    t0 = time.perf_counter()
+    if prec is None:
+        prec = spd_inverse(cov + jitter * np.eye(n) if jitter else cov)
+    P = np.ascontiguousarray(prec, dtype=np.float64).copy()
+    if timings is not None:
+        timings["setup_s"] = time.perf_counter() - t0
+        timings["steps_s"] = []
+    num = np.ascontiguousarray(np.diag(cov) + jitter)
+    taken = np.zeros(n, dtype=np.uint8)
+    wfull = np.zeros((k, n))
+    scores = np.empty(n)
+    w_seg, p_seg = np.empty(n), np.empty(n)
+    selection, win = [], []
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+    for t in range(k):
+        t1 = time.perf_counter()
+        bs = ctypes.c_double(0.0)
+        y = lib.oracle_scores(ptr(P), n, 0, n, ptr(num), ptr(taken), small, jitter, ptr(scores), ctypes.byref(bs))
+        if y < 0:
+            raise ValueError("list.remove(x): x not in list")
+        lib.oracle_segments(ptr(cov), ptr(P), n, 0, n, ptr(wfull), n, t, jitter, y, float(num[y]), ptr(w_seg),
+                            ptr(p_seg))
+        wfull[t] = w_seg
+        lib.oracle_apply(ptr(P), n, n, 0, n, ptr(w_seg), ptr(p_seg), y, ptr(num), ptr(taken))
+        selection.append(int(y))
+        win.append(bs.value)
+        if timings is not None:
+            timings["steps_s"].append(time.perf_counter() - t1)
+    return selection, np.array(win)

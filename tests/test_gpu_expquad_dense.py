@@ -1,0 +1,139 @@
+"""GPU parity: ExpQuad builder and the dense float64 layer, through the C-ABI, against NumPy/SciPy."""
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import gp_oracle as gpo
+from vgposp_b200 import _ffi
+
+pytestmark = pytest.mark.gpu
+D = 0
+
+
+def dev(a):
+    return _ffi.DeviceArray.from_host(np.ascontiguousarray(a, dtype=np.float64), D)
+
+
+def expquad(x1, x2, amp, ls, diag_add=0.0, diag_col0=0, ld=None, same=False):
+    n1, n2 = x1.shape[0], x2.shape[0]
+    ld = ld or n2
+    d1 = dev(x1)
+    d2 = d1 if same else dev(x2)
+    out = _ffi.DeviceArray((n1, ld), np.float64, D).zero_()
+    _ffi.call("vgp_expquad_matrix", D, d1.ptr, n1, d2.ptr, n2, x1.shape[1], amp, ls, diag_add, diag_col0, out.ptr, ld,
+              None)
+    return out.to_host()[:, :n2]
+
+
+@pytest.mark.parametrize("n1,n2,d", [(1, 1, 3), (5, 7, 1), (33, 1030, 3), (513, 77, 5), (300, 300, 8), (129, 640, 2)])
+def test_expquad_rectangular(n1, n2, d):
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    x1, x2 = rng.uniform(-2, 2, (n1, d)), rng.uniform(-2, 2, (n2, d))
+    got = expquad(x1, x2, 1.3, 0.45)
+    want = gpo.expquad_matrix(x1, x2, 1.3, 0.45)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-300)      # float64, tolerance 1e-9 in north_star
+
+
+@pytest.mark.parametrize("n", [128, 130, 191, 1000, 2049])
+def test_expquad_symmetric_path(n):
+    x = np.random.default_rng(n).uniform(-2, 2, (n, 3))
+    got = expquad(x, x, 1.0, 0.5, diag_add=1e-2, same=True, ld=n + (n % 2))
+    want = gpo.expquad_matrix(x, x, 1.0, 0.5, diag_add=1e-2)
+    np.testing.assert_allclose(got, want, rtol=1e-13)
+    assert np.array_equal(got, got.T)                                   # mirrored tiles: bitwise symmetric
+
+
+def test_expquad_odd_ld_and_panel_diagonal():
+    x = np.random.default_rng(5).uniform(-2, 2, (200, 3))
+    got = expquad(x, x[60:131], 1.1, 0.3, diag_add=0.25, diag_col0=60, ld=73)
+    want = gpo.expquad_matrix(x, x, 1.1, 0.3, diag_add=0.25)[:, 60:131]
+    np.testing.assert_allclose(got, want, rtol=1e-13)
+
+
+def test_expquad_empty_and_bad_arguments():
+    out = _ffi.DeviceArray((4,), np.float64, D)
+    _ffi.call("vgp_expquad_matrix", D, out.ptr, 0, out.ptr, 4, 3, 1.0, 1.0, 0.0, 0, out.ptr, 4, None)   # n1 == 0: no-op
+    with pytest.raises(_ffi.VgpError):
+        _ffi.call("vgp_expquad_matrix", D, out.ptr, 1, out.ptr, 1, 9, 1.0, 1.0, 0.0, 0, out.ptr, 1, None)
+
+
+def gemm(ta, tb, a, b, c=None, alpha=1.0, beta=0.0):
+    m = a.shape[1] if ta else a.shape[0]
+    k = a.shape[0] if ta else a.shape[1]
+    n = b.shape[0] if tb else b.shape[1]
+    da, db = dev(a), dev(b)
+    dc = dev(c) if c is not None else _ffi.DeviceArray((m, n), np.float64, D).zero_()
+    _ffi.call("vgp_dgemm", D, ta, tb, m, n, k, alpha, da.ptr, a.shape[1], db.ptr, b.shape[1], beta, dc.ptr, n, None)
+    return dc.to_host()
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 384, 512), (100, 37, 59), (1, 1, 1), (300, 129, 1000)])
+def test_dgemm_all_layouts(ta, tb, m, n, k):
+    rng = np.random.default_rng(m + 7 * n + 13 * k)
+    a = rng.standard_normal((k, m) if ta else (m, k))
+    b = rng.standard_normal((n, k) if tb else (k, n))
+    c = rng.standard_normal((m, n))
+    got = gemm(ta, tb, a, b, c, alpha=-0.7, beta=1.5)
+    want = -0.7 * ((a.T if ta else a) @ (b.T if tb else b)) + 1.5 * c
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12 * np.sqrt(k))
+
+
+def spd(n, seed):
+    x = np.random.default_rng(seed).uniform(-2, 2, (n, 3))
+    return gpo.expquad_matrix(x, x, 1.0, 0.5 * (1000.0 / max(n, 1000)) ** (1 / 3), diag_add=1e-2)
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 256, 640, 1000, 2500])
+def test_potrf_matches_lapack(n):
+    a = spd(n, n)
+    marker = np.triu(np.full((n, n), 7.0), 1)
+    d = dev(np.tril(a) + marker)                      # strict upper triangle must come back untouched
+    info = ctypes.c_int(-1)
+    _ffi.call("vgp_potrf", D, d.ptr, n, n, ctypes.byref(info), None)
+    got = d.to_host()
+    want = np.linalg.cholesky(a)
+    assert info.value == 0
+    np.testing.assert_allclose(np.tril(got), want, rtol=1e-9, atol=1e-13)      # factors within 1e-9 relative
+    np.testing.assert_array_equal(np.triu(got, 1), marker)
+    np.testing.assert_allclose(np.tril(got) @ np.tril(got).T, a, rtol=1e-12, atol=1e-14)
+
+
+def test_potrf_reports_not_positive_definite():
+    a = spd(300, 1)
+    a[200, 200] = -1.0
+    d = dev(a)
+    info = ctypes.c_int(0)
+    with pytest.raises(_ffi.NotPositiveDefiniteError):
+        _ffi.call("vgp_potrf", D, d.ptr, 300, 300, ctypes.byref(info), None)
+    assert info.value == 201                          # 1 + first failing row
+
+
+@pytest.mark.parametrize("n", [1, 3, 128, 200, 384, 1000, 2304])
+def test_spd_inverse(n):
+    a = spd(n, 100 + n)
+    d = dev(a)
+    info = ctypes.c_int(0)
+    _ffi.call("vgp_spd_inverse", D, d.ptr, n, n, ctypes.byref(info), None)
+    got = d.to_host()
+    want = np.linalg.inv(a)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
+    assert np.array_equal(got, got.T)
+    np.testing.assert_allclose(got @ a, np.eye(n), atol=1e-10)
+
+
+@pytest.mark.parametrize("side,trans", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("n,nrhs", [(128, 128), (300, 5), (640, 257), (1, 3)])
+def test_trsm(side, trans, n, nrhs):
+    l = np.linalg.cholesky(spd(n, 7 * n))
+    rng = np.random.default_rng(n + nrhs)
+    b = rng.standard_normal((n, nrhs) if side == 0 else (nrhs, n))
+    dl, db = dev(l + np.triu(np.full((n, n), 9.0), 1)), dev(b)      # garbage above the diagonal must be ignored
+    _ffi.call("vgp_trsm", D, side, trans, n, nrhs, dl.ptr, n, db.ptr, b.shape[1], None)
+    got = db.to_host()
+    op = l.T if trans else l
+    want = sla.solve_triangular(op, b, lower=not trans) if side == 0 else \
+        sla.solve_triangular(op.T, b.T, lower=bool(trans)).T
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11 * np.abs(want).max())

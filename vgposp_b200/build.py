@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 2)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))

@@ -79,6 +79,9 @@ int vgp_dgemm(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_
     VGP_REQUIRE(lda >= ac && ldb >= bc && ldc >= n, "leading dimension too small");
     VGP_ENTER(device);
     cudaStream_t s = (cudaStream_t)stream;
+    if (m % TILE == 0 && n % TILE == 0 && k % 16 == 0 && k > 0 && lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0 &&
+        ((uintptr_t)a_dev % 16) == 0 && ((uintptr_t)b_dev % 16) == 0 && ((uintptr_t)c_dev % 16) == 0)
+        return dense_gemm(trans_a, trans_b, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, GEMM_FULL, s);
     Padded pa, pb, pc;
     VGP_TRY(pa.alloc(ar, ac, s));
     VGP_TRY(pb.alloc(br, bc, s));
@@ -120,6 +123,13 @@ int vgp_spd_inverse(int device, double *a_dev, int64_t n, int64_t lda, int *info
     VGP_REQUIRE(a_dev, "NULL pointer");
     VGP_ENTER(device);
     cudaStream_t s = (cudaStream_t)stream;
+    if (n % TILE == 0 && lda % 2 == 0 && ((uintptr_t)a_dev % 16) == 0) {      // in place, no scratch copy
+        DenseWorkspace ws;
+        int rc = dense_spd_inverse(a_dev, n, lda, ws, info_host, s);
+        cudaStreamSynchronize(s);
+        ws.release();
+        return rc;
+    }
     Padded pa;
     VGP_TRY(pa.alloc(n, n, s));
     VGP_TRY(pa.load(a_dev, lda, n, n));

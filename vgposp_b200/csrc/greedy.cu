@@ -17,6 +17,8 @@
 #include <math.h>
 
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "dense.cuh"
@@ -42,6 +44,8 @@ struct vgp_greedy {
     int score_blocks = 0;
     int sm_count = 148;
     DenseWorkspace ws;
+    int profile = 0;                                    // CUDA events around every downdate launch
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
 namespace {
@@ -156,17 +160,27 @@ __global__ void __launch_bounds__(256) score_kernel(const double *__restrict__ p
     int64_t ri = INT64_MAX;
     int slot = -1;
     for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) {
-        const vgp_candidate c = ((volatile vgp_candidate *)partials)[b].index >= 0 ? partials[b]
-                                                                                : vgp_candidate{NEG_INF, -1, 0, 0};
-        if (c.index >= 0 && better(rs, ri, c.score, c.index)) {
-            rs = c.score;
-            ri = c.index;
+        // other CTAs' partials: read through L2 (written before their fence + counter increment)
+        const double cs = __ldcg(&partials[b].score);
+        const int64_t ci = __ldcg((const long long *)&partials[b].index);
+        if (ci >= 0 && better(rs, ri, cs, ci)) {
+            rs = cs;
+            ri = ci;
             slot = b;
         }
     }
     __syncthreads();
     block_argmax(rs, ri, slot);
-    if (threadIdx.x == 0) *best = slot >= 0 ? partials[slot] : vgp_candidate{NEG_INF, -1, 0.0, 0.0};
+    if (threadIdx.x == 0) {
+        vgp_candidate w{NEG_INF, -1, 0.0, 0.0};
+        if (slot >= 0) {
+            w.score = rs;
+            w.index = ri;
+            w.num = __ldcg(&partials[slot].num);
+            w.pdiag = __ldcg(&partials[slot].pdiag);
+        }
+        *best = w;
+    }
 }
 
 // Winner over all shards' records: max score, lowest index on exact ties (single ascending scan with
@@ -528,6 +542,12 @@ int vgp_greedy_apply(vgp_greedy *h, const double *gathered_dev, int64_t seg_stri
     if (gy > 65535) gy = 65535;
     if (gy < 1) gy = 1;
     dim3 grid(gx, (unsigned)gy);
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (h->profile) {
+        VGP_CUDA(cudaEventCreate(&pe0));
+        VGP_CUDA(cudaEventCreate(&pe1));
+        VGP_CUDA(cudaEventRecord(pe0, s));
+    }
     if (unroll >= 8)
         downdate_kernel<8><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
     else if (unroll >= 4)
@@ -535,7 +555,39 @@ int vgp_greedy_apply(vgp_greedy *h, const double *gathered_dev, int64_t seg_stri
     else
         downdate_kernel<2><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
     H_LAUNCH_CHECK(h);
+    if (h->profile) {
+        VGP_CUDA(cudaEventRecord(pe1, s));
+        h->prof_events.emplace_back(pe0, pe1);
+    }
     ++h->t;
+    return VGP_OK;
+}
+
+int vgp_greedy_profile(vgp_greedy *h, int enable) {
+    VGP_TRY(check_handle(h));
+    VGP_ENTER(h->device);
+    for (auto &pr : h->prof_events) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    h->prof_events.clear();
+    h->profile = enable ? 1 : 0;
+    return VGP_OK;
+}
+
+int vgp_greedy_profile_read(vgp_greedy *h, double *total_ms, int64_t *launches) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(total_ms && launches, "NULL argument");
+    VGP_ENTER(h->device);
+    double sum = 0.0;
+    for (auto &pr : h->prof_events) {
+        float ms = 0.f;
+        VGP_CUDA(cudaEventSynchronize(pr.second));
+        VGP_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = (int64_t)h->prof_events.size();
     return VGP_OK;
 }
 

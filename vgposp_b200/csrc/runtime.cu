@@ -140,6 +140,14 @@ int vgp_memcpy2d_d2h(int device, void *dst_host, size_t dpitch, const void *src_
     return VGP_OK;
 }
 
+int vgp_memcpy2d_d2d(int device, void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch,
+                     size_t width_bytes, size_t rows, void *stream) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaMemcpy2DAsync(dst_dev, dpitch, src_dev, spitch, width_bytes, rows, cudaMemcpyDeviceToDevice,
+                               (cudaStream_t)stream));
+    return VGP_OK;
+}
+
 int vgp_memset(int device, void *dst_dev, int value, size_t bytes, void *stream) {
     VGP_ENTER(device);
     VGP_CUDA(cudaMemsetAsync(dst_dev, value, bytes, (cudaStream_t)stream));

@@ -1,0 +1,224 @@
+"""Host side of the greedy mutual-information placement: handle wrapper and the sharded step protocol.
+
+`GreedyShard` wraps one `vgp_greedy` handle (one device, columns [c0, c1) of the candidate set).
+`ShardedGreedy` runs the per-selection protocol of include/vgposp.h over any number of ranks; the only
+data-path collectives are two small all-gathers per selection:
+
+    exchange 1   32 bytes per rank   (score, index, numerator, P_yy) of each rank's local winner
+    exchange 2   16 n/G bytes/rank   [w_J | p_J] row segments of the winner
+
+The local arithmetic sits behind a small engine interface (`local_best / select / segments / apply`) so
+that the protocol can be exercised on CPU with world_size 2 over gloo (tests inject an oracle-backed
+engine); the product engine is `GreedyShard`, i.e. the CUDA library.
+
+Reference semantics: placement_algorithm2.py:128-145 (alg. 1), :151-219 (alg. 2).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import call, c_i64, c_int, c_vp
+
+GUARD_NUMPY = 1e-8        # placement_algorithm2.py:116,198
+GUARD_TF_GRAPH = 1e-7     # snippets_a2.py:480
+JITTER_TF_GRAPH = 1e-6    # snippets_a2.py:161-163
+
+
+def _ptr(x):
+    """Device address of an int, a torch tensor (`data_ptr()`) or a DeviceArray (`ptr`)."""
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x.ptr
+
+
+def shard_bounds(n, world):
+    """Contiguous column ranges of the ranks: bounds[g] .. bounds[g + 1]."""
+    return [(n * g) // world for g in range(world + 1)]
+
+
+class GreedyShard:
+    """One device's shard: owns the Sigma[:, J] and P[:, J] panels and the incremental state."""
+
+    def __init__(self, n, c0, c1, kmax, device=0, small=GUARD_NUMPY, jitter=0.0, stream=None):
+        _ffi.require_device(device)
+        self.n, self.c0, self.c1, self.kmax = int(n), int(c0), int(c1), int(kmax)
+        self.nloc = self.c1 - self.c0
+        self.device, self.stream = device, stream
+        h = c_vp()
+        call("vgp_greedy_create", ctypes.byref(h), device, self.n, self.c0, self.nloc, self.kmax,
+             float(small), float(jitter))
+        self.handle = h.value
+        cov, prec, ld, n_pad = c_vp(), c_vp(), c_i64(), c_i64()
+        call("vgp_greedy_panels", self.handle, ctypes.byref(cov), ctypes.byref(prec), ctypes.byref(ld),
+             ctypes.byref(n_pad))
+        self.cov_ptr, self.prec_ptr, self.ld, self.n_pad = cov.value, prec.value, ld.value, n_pad.value
+        self.single = self.c0 == 0 and self.nloc == self.n
+
+    # ---- loading -----------------------------------------------------------------------------------
+    def load_cov_host(self, cov_vv):
+        """H2D of this shard's column panel of a host matrix [n, n] (any row stride)."""
+        a = np.asarray(cov_vv)
+        if a.dtype != np.float64 or a.strides[1] != 8:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == (self.n, self.n), "cov_vv must be [n, n]"
+        call("vgp_memcpy2d_h2d", self.device, self.cov_ptr, self.ld * 8, a.ctypes.data + self.c0 * 8,
+             a.strides[0], self.nloc * 8, self.n, self.stream)
+        call("vgp_stream_sync", self.device, self.stream)
+
+    def load_prec_host(self, prec):
+        a = np.ascontiguousarray(prec, dtype=np.float64)
+        assert a.shape == (self.n, self.n)
+        call("vgp_memcpy2d_h2d", self.device, self.prec_ptr, self.ld * 8, a.ctypes.data + self.c0 * 8,
+             a.strides[0], self.nloc * 8, self.n, self.stream)
+        call("vgp_stream_sync", self.device, self.stream)
+
+    def load_prec_device(self, full_ptr, full_ld):
+        """Copy columns [c0, c1) of a device-resident full precision matrix [n, full_ld] into the panel."""
+        call("vgp_memcpy2d_d2d", self.device, self.prec_ptr, self.ld * 8, full_ptr + self.c0 * 8, full_ld * 8,
+             self.nloc * 8, self.n, self.stream)
+
+    def build_cov_expquad(self, x_dev_ptr, d, amplitude, length_scale, nugget):
+        """Sigma[:, J] = K_expquad(X, X[J]) + nugget on the global diagonal, written into the panel."""
+        call("vgp_expquad_matrix", self.device, x_dev_ptr, self.n, x_dev_ptr + self.c0 * d * 8, self.nloc, d,
+             float(amplitude), float(length_scale), float(nugget), self.c0, self.cov_ptr, self.ld, self.stream)
+
+    def factor(self):
+        """P = Sigma^-1 on device (single shard only)."""
+        info = c_int(0)
+        call("vgp_greedy_factor", self.handle, ctypes.byref(info), self.stream)
+
+    def reset(self):
+        call("vgp_greedy_reset", self.handle, self.stream)
+
+    def save_precision(self):
+        call("vgp_greedy_save_precision", self.handle, self.stream)
+
+    def restore_precision(self):
+        call("vgp_greedy_restore_precision", self.handle, self.stream)
+
+    def record_scores(self, enable=True):
+        call("vgp_greedy_record_scores", self.handle, 1 if enable else 0)
+
+    # ---- engine interface (device pointers in, device pointers out) ---------------------------------
+    def local_best(self, rec):
+        call("vgp_greedy_local_best", self.handle, _ptr(rec), self.stream)
+
+    def select(self, recs, nrecords):
+        call("vgp_greedy_select", self.handle, _ptr(recs), nrecords, self.stream)
+
+    def segments(self, seg, seg_stride):
+        call("vgp_greedy_segments", self.handle, _ptr(seg), seg_stride, self.stream)
+
+    def apply(self, gathered, seg_stride, bounds):
+        arr = (c_i64 * len(bounds))(*bounds)
+        call("vgp_greedy_apply", self.handle, _ptr(gathered), seg_stride, len(bounds) - 1, arr, self.stream)
+
+    def run(self, k):
+        call("vgp_greedy_run", self.handle, int(k), self.stream)
+
+    # ---- results -----------------------------------------------------------------------------------
+    def results(self):
+        count = c_i64(0)
+        sel = np.full(self.kmax, -1, dtype=np.int64)
+        sc = np.zeros(self.kmax, dtype=np.float64)
+        call("vgp_greedy_results", self.handle, ctypes.byref(count), sel.ctypes.data, sc.ctypes.data, self.kmax,
+             self.stream)
+        return sel[:count.value], sc[:count.value]
+
+    def step_scores(self):
+        sel, _ = self.results()
+        out = np.empty((len(sel), self.nloc), dtype=np.float64)
+        if len(sel):
+            call("vgp_greedy_step_scores", self.handle, out.ctypes.data, len(sel), self.stream)
+        return out
+
+    def launch_count(self):
+        c = c_i64(0)
+        call("vgp_greedy_launch_count", self.handle, ctypes.byref(c))
+        return c.value
+
+    def sync(self):
+        call("vgp_stream_sync", self.device, self.stream)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            call("vgp_greedy_destroy", self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def check_selection(sel):
+    """The reference crashes with `ValueError: list.remove(x): x not in list` when no candidate scores above
+    -1 (placement_algorithm2.py:144 after argmax_ returned -1); keep that failure mode."""
+    if len(sel) and (np.asarray(sel) < 0).any():
+        raise ValueError("list.remove(x): x not in list")
+
+
+def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_scores=False):
+    """placement_algorithm_1/2(cov_vv, k) for a host matrix on one device: one C-ABI call
+    (H2D, potrf+potri, k selections, D2H).  Returns (selection, scores, step_scores or None, seconds)."""
+    _ffi.require_device(device)
+    a = np.asarray(cov_vv)
+    if a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("cov_vv must be a square matrix, got shape %r" % (a.shape,))
+    if a.dtype != np.float64 or a.strides[1] != 8 or a.strides[0] % 8:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    k = int(k)
+    if k <= 0:
+        return np.zeros(0, np.int64), np.zeros(0), (np.zeros((0, n)) if want_step_scores else None), np.zeros(4)
+    if k > n:
+        raise ValueError("list.remove(x): x not in list")     # the reference runs out of candidates (:144)
+    sel = np.full(k, -1, dtype=np.int64)
+    sc = np.zeros(k)
+    steps = np.empty((k, n)) if want_step_scores else None
+    secs = np.zeros(4)
+    call("vgp_placement_host", device, a.ctypes.data, n, a.strides[0] // 8, k, float(small), float(jitter),
+         sel.ctypes.data, sc.ctypes.data, steps.ctypes.data if want_step_scores else None, secs.ctypes.data)
+    check_selection(sel)
+    return sel, sc, steps, secs
+
+
+class ShardedGreedy:
+    """The per-selection protocol over `world` ranks.  `engine` provides the local arithmetic, `comm`
+    the two all-gathers; buffers are torch tensors on the engine's device (cuda with NCCL, cpu with gloo)."""
+
+    def __init__(self, engine, n, rank, world, make_buffer, all_gather):
+        self.engine, self.n, self.rank, self.world = engine, int(n), int(rank), int(world)
+        self.bounds = shard_bounds(self.n, self.world)
+        self.stride = max(b - a for a, b in zip(self.bounds[:-1], self.bounds[1:]))
+        self.stride += self.stride % 2                      # keep segments 16-byte aligned
+        self.all_gather = all_gather
+        self.rec = make_buffer(4)                           # vgp_candidate viewed as 4 x 8 bytes
+        self.recs = make_buffer(4 * self.world)
+        self.seg = make_buffer(2 * self.stride)
+        self.segs = make_buffer(2 * self.stride * self.world)
+
+    def step(self):
+        e = self.engine
+        e.local_best(self.rec)
+        if self.world > 1:
+            self.all_gather(self.recs, self.rec)
+            recs = self.recs
+        else:
+            recs = self.rec
+        e.select(recs, self.world)
+        e.segments(self.seg, self.stride)
+        if self.world > 1:
+            self.all_gather(self.segs, self.seg)
+            segs = self.segs
+        else:
+            segs = self.seg
+        e.apply(segs, self.stride, self.bounds)
+
+    def run(self, k):
+        for _ in range(int(k)):
+            self.step()
