@@ -157,6 +157,29 @@ int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const dou
                     double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
                     double *var_dev, void *stream);
 
+/* ---------------------------------------------------------------- VGP training step (a4-a7) ---------------- */
+/* Reference-faithful ELBO training (variational_Gaussian_process_example.py:47-102): amplitude = softplus(v[0]),
+ * length_scale = offset + softplus(v[1]), noise = softplus(v[2]); (loc, scale) are the Titsias optimum over ALL
+ * n_obs observations and are re-derived from the trainable parameters every step; the loss is the minibatch
+ * variational_loss with kl_weight = batch / n_obs; tf.train.AdamOptimizer(learning_rate) (beta1 .9, beta2 .999,
+ * eps 1e-8) updates (v, Z).  The gradient is hand-derived (csrc/elbo.cu).  x_dev [n_obs, d] and y_dev [n_obs] are
+ * borrowed for the lifetime of the handle; z_init_host [m, d]. */
+typedef struct vgp_elbo vgp_elbo;
+int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const double *y_dev, int64_t n_obs, int d,
+                    const double *z_init_host, int64_t m, int64_t batch, double v_amplitude, double v_length_scale,
+                    double v_noise, double length_scale_offset, double jitter, double learning_rate);
+int vgp_elbo_destroy(vgp_elbo *handle);
+/* Loss and gradient at the current parameters (blocking).  grads_host[3] = d loss / d v; gradz_host [m, d] and
+ * terms_host are optional. */
+int vgp_elbo_loss_grad(vgp_elbo *handle, const double *xb_dev, const double *yb_dev, double *loss_host,
+                       double *grads_host, double *gradz_host, vgp_vgp_terms *terms_host, void *stream);
+/* One training step: loss + gradient + Adam update; *loss_host is the loss before the update (what
+ * sess.run([train_op, loss]) returns, :123-125). */
+int vgp_elbo_step(vgp_elbo *handle, const double *xb_dev, const double *yb_dev, double *loss_host, void *stream);
+int vgp_elbo_get_params(vgp_elbo *handle, double *v3_host, double *z_host, void *stream);
+int vgp_elbo_set_params(vgp_elbo *handle, const double *v3_host, const double *z_host, void *stream);
+int vgp_elbo_launch_count(vgp_elbo *handle, int64_t *launches);
+
 /* ---------------------------------------------------------------- (3) greedy MI placement ------------------- */
 /* One handle holds one device's shard of the candidate set: columns [c0, c0 + nloc) of Sigma and of the
  * precision P of the unselected set, all n rows.  Replaces the state that

@@ -1,0 +1,101 @@
+"""GPU parity: the VGP training step (loss, hand-derived gradient, Adam update) against torch autograd of the CPU
+restatement (oracle/gp_oracle_torch.py; TFP semantics, parity unpinned).  Tolerances: loss 1e-9 relative;
+gradients 1e-6 relative to the gradient's scale (they pass through three m x m inverses with cond up to 1e8)."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as gpo
+from oracle import gp_oracle_torch as gt
+import vgposp_b200.gp_functions as gpf
+
+pytestmark = pytest.mark.gpu
+
+
+def problem(n, m, b, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-2, 2, (n, d))
+    y = np.sin(x[:, 0]) * np.sin(x[:, 1 % d]) + 0.1 + 0.1 * rng.standard_normal(n)
+    z = rng.uniform(-2, 2, (m, d))
+    idx = rng.integers(n, size=b)
+    return x, y, z, idx
+
+
+@pytest.mark.parametrize("n,m,b,d", [(600, 24, 64, 3), (1000, 32, 64, 3), (3000, 100, 300, 2), (5000, 130, 256, 3)])
+def test_loss_and_gradient_match_autograd(n, m, b, d):
+    x, y, z, idx = problem(n, m, b, d, n + m)
+    tr = gpf.VgpTrainer(x, y, z, b)
+    loss, g, gz, terms = tr.loss_and_grad(x[idx], y[idx])
+    want_loss, want = gt.loss_and_grads(0.54, 0.54, 0.54, z, x, y, x[idx], y[idx])
+    assert loss == pytest.approx(want_loss, rel=1e-9)
+    for i in range(3):
+        assert g[i] == pytest.approx(float(want[i]), rel=1e-6, abs=1e-8 * abs(want_loss))
+    np.testing.assert_allclose(gz, want[3], rtol=1e-5, atol=1e-6 * np.abs(want[3]).max())
+    # the pieces agree with the forward-only entry point and with the NumPy oracle
+    amp, ls, noise = gpo.softplus(0.54), 1e-5 + gpo.softplus(0.54), gpo.softplus(0.54)
+    loc, scale = gpo.optimal_variational_posterior(z, x, y, amp, ls, noise)
+    ref = gpo.vgp_terms(z, loc, scale, x[idx], y[idx], amp, ls, noise, b / n)
+    for key in ("ll", "tr1", "tr2", "kl"):
+        assert terms[key] == pytest.approx(ref[key], rel=1e-8, abs=1e-9 * abs(want_loss)), key
+    tr.close()
+
+
+def test_training_steps_follow_tf_adam():
+    n, m, b, d = 800, 20, 64, 3
+    x, y, z, _ = problem(n, m, b, d, 5)
+    tr = gpf.VgpTrainer(x, y, z, b, learning_rate=0.01)
+    params = [np.array(0.54), np.array(0.54), np.array(0.54), z.copy()]
+    opt = gt.TfAdamTorch([p.shape for p in params], lr=0.01)
+    rng = np.random.default_rng(0)
+    for it in range(5):
+        idx = rng.integers(n, size=b)                        # variational_Gaussian_process_example.py:119
+        loss = tr.step(x[idx], y[idx])
+        want_loss, grads = gt.loss_and_grads(params[0], params[1], params[2], params[3], x, y, x[idx], y[idx])
+        assert loss == pytest.approx(want_loss, rel=1e-7), it
+        params = opt.step(params, grads)
+        v, zz = tr.variables()
+        np.testing.assert_allclose(v, [float(p) for p in params[:3]], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(zz, params[3], rtol=1e-6, atol=1e-8)
+    assert tr.launch_count() > 100
+    tr.close()
+
+
+def test_loss_decreases_and_prediction_tracks_the_field():
+    n, m, b = 4000, 64, 256
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-2, 2, (n, 2))
+    f = lambda p: np.sin(p[:, 0]) * np.sin(p[:, 1]) + 0.1     # noqa: E731  (3D_sin_wave.py:96-103)
+    y = f(x) + 0.05 * rng.standard_normal(n)
+    z = rng.uniform(-2, 2, (m, 2))
+    tr = gpf.VgpTrainer(x, y, z, b, learning_rate=0.05)
+    losses = []
+    for it in range(60):
+        idx = rng.integers(n, size=b)
+        losses.append(tr.step(x[idx], y[idx]))
+    assert np.mean(losses[-10:]) < np.mean(losses[:10]) - 50
+    xt = rng.uniform(-1.8, 1.8, (500, 2))
+    mean = tr.vgp(xt).mean()
+    assert np.sqrt(np.mean((mean - f(xt)) ** 2)) < 0.05
+    amp, ls, noise, _ = tr.parameters()
+    assert noise < 0.2 and 0.3 < ls < 3.0
+    tr.close()
+
+
+def test_config3_shape_runs_and_is_finite():
+    """BASELINE configs[2] shape at reduced N (m = 512, B = 4096): finite loss, gradient matches a central
+    finite difference of the device loss in v_length_scale."""
+    n, m, b = 20000, 512, 4096
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-2, 2, (n, 3))
+    y = np.sum(np.sin(2 * np.pi * x), axis=1) + 0.1 * rng.standard_normal(n)      # gp_functions.py:78-95
+    z = rng.uniform(-2, 2, (m, 3))
+    idx = rng.integers(n, size=b)
+    tr = gpf.VgpTrainer(x, y, z, b)
+    loss, g, gz, _ = tr.loss_and_grad(x[idx], y[idx])
+    assert np.isfinite(loss) and np.all(np.isfinite(g)) and np.all(np.isfinite(gz))
+    h = 1e-5
+    tr.assign(v=[0.54, 0.54 + h, 0.54])
+    lp = tr.loss_and_grad(x[idx], y[idx])[0]
+    tr.assign(v=[0.54, 0.54 - h, 0.54])
+    lm = tr.loss_and_grad(x[idx], y[idx])[0]
+    assert g[1] == pytest.approx((lp - lm) / (2 * h), rel=1e-4)
+    tr.close()

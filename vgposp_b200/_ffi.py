@@ -78,6 +78,14 @@ SIGNATURES = {
                      P(VgpTerms), c_vp],
     "vgp_vgp_predict": [c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp,
                         c_vp],
+    "vgp_elbo_create": [P(c_vp), c_int, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl,
+                        c_dbl],
+    "vgp_elbo_destroy": [c_vp],
+    "vgp_elbo_loss_grad": [c_vp, c_vp, c_vp, P(c_dbl), c_vp, c_vp, P(VgpTerms), c_vp],
+    "vgp_elbo_step": [c_vp, c_vp, c_vp, P(c_dbl), c_vp],
+    "vgp_elbo_get_params": [c_vp, c_vp, c_vp, c_vp],
+    "vgp_elbo_set_params": [c_vp, c_vp, c_vp, c_vp],
+    "vgp_elbo_launch_count": [c_vp, P(c_i64)],
     "vgp_greedy_create": [P(c_vp), c_int, c_i64, c_i64, c_i64, c_i64, c_dbl, c_dbl],
     "vgp_greedy_destroy": [c_vp],
     "vgp_greedy_panels": [c_vp, P(c_vp), P(c_vp), P(c_i64), P(c_i64)],

@@ -28,9 +28,8 @@
 
 #include "gp_common.cuh"
 
-using namespace vgp;
-
-namespace {
+namespace vgp {
+namespace elbo_detail {
 
 constexpr int MAXT = 12;
 struct LinComb {                       // out = sum_t c_t * (T_t ? A_t^T : A_t) + sum_r c_r * a_r b_r^T
@@ -171,7 +170,11 @@ enum VecId { V_, VB_, U_, KU_, MU_, AL_, GBAL_, ALBAR_, QA_, MUBAR_, UBAR_, VBAR
 enum Scal { S_YY, S_ALVB, S_ALGBAL, S_TRQGB, S_TRSR, S_TRQS, S_MUAL, S_LDK, S_LDKT, S_LDM, S_MUBKU, S_TRMBG, S_ACC0,
             S_ACC1, S_N };
 
-}  // namespace
+}  // namespace elbo_detail
+}  // namespace vgp
+
+using namespace vgp;
+using namespace vgp::elbo_detail;
 
 struct vgp_elbo {
     int device = 0;
@@ -193,7 +196,8 @@ struct vgp_elbo {
     double *vec(int id) const { return vecs + (size_t)id * mp; }
 };
 
-namespace {
+namespace vgp {
+namespace elbo_detail {
 
 template <int D>
 int launch_kernback(vgp_elbo *h, const double *w, const double *kmat, int64_t ld, const double *x2, int64_t n2,
@@ -417,7 +421,8 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     return VGP_OK;
 }
 
-}  // namespace
+}  // namespace elbo_detail
+}  // namespace vgp
 
 extern "C" {
 

@@ -348,3 +348,100 @@ class VariationalGaussianProcess:
 
     def stddev(self):
         return np.sqrt(self.variance())
+
+
+# --------------------------------------------------------------------------------------------------
+# VGP training (a6, a7 for the variational path)
+# --------------------------------------------------------------------------------------------------
+class VgpTrainer:
+    """The training graph of variational_Gaussian_process_example.py:46-104 as one object:
+
+        trainer = VgpTrainer(x_train, y_train, inducing_init, batch_size)      # graph(...)
+        loss = trainer.step(x_batch, y_batch)                                  # sess.run([train_op, loss], feed)
+
+    amplitude = softplus(v_a), length_scale = 1e-5 + softplus(v_l), noise = softplus(v_s), all initialised at
+    v = 0.54 (:47-61); (loc, scale) follow the parameters through `optimal_variational_posterior` over the full
+    training set (:68-74); Adam(0.01) with TF's update rule (:101-102).  Loss, gradient and update run on device.
+    """
+
+    def __init__(self, x_train, y_train, inducing_index_points, batch_size, v_amplitude=0.54, v_length_scale=0.54,
+                 v_noise=0.54, length_scale_offset=1e-5, jitter=DEFAULT_JITTER, learning_rate=0.01):
+        self._x, self._y = _points(x_train), _vector(y_train)          # kept alive: the handle borrows them
+        z = np.ascontiguousarray(np.asarray(inducing_index_points, dtype=np.float64))
+        if z.ndim == 1:
+            z = z[:, None]
+        self.n, self.d = self._x.shape
+        self.m, self.batch = z.shape[0], int(batch_size)
+        assert z.shape[1] == self.d
+        h = ctypes.c_void_p()
+        call("vgp_elbo_create", ctypes.byref(h), DEVICE, self._x.ptr, self._y.ptr, self.n, self.d, z.ctypes.data,
+             self.m, self.batch, float(v_amplitude), float(v_length_scale), float(v_noise),
+             float(length_scale_offset), float(jitter), float(learning_rate))
+        self.handle = h.value
+        self.length_scale_offset, self.jitter = length_scale_offset, jitter
+
+    def _batch(self, xb, yb):
+        xb, yb = _points(xb), _vector(yb)
+        assert xb.shape == (self.batch, self.d) and yb.size == self.batch, "minibatch shape is fixed at construction"
+        return xb, yb
+
+    def loss_and_grad(self, x_batch, y_batch):
+        """(loss, d loss / d (v_a, v_l, v_s), d loss / d Z [m, d], terms dict) at the current parameters."""
+        xb, yb = self._batch(x_batch, y_batch)
+        loss, g = ctypes.c_double(), np.zeros(3)
+        gz = np.zeros((self.m, self.d))
+        terms = _ffi.VgpTerms()
+        call("vgp_elbo_loss_grad", self.handle, xb.ptr, yb.ptr, ctypes.byref(loss), g.ctypes.data, gz.ctypes.data,
+             ctypes.byref(terms), None)
+        return loss.value, g, gz, {k: getattr(terms, k) for k, _ in terms._fields_}
+
+    def step(self, x_batch, y_batch):
+        xb, yb = self._batch(x_batch, y_batch)
+        loss = ctypes.c_double()
+        call("vgp_elbo_step", self.handle, xb.ptr, yb.ptr, ctypes.byref(loss), None)
+        return loss.value
+
+    def step_device(self, xb_ptr, yb_ptr):
+        loss = ctypes.c_double()
+        call("vgp_elbo_step", self.handle, xb_ptr, yb_ptr, ctypes.byref(loss), None)
+        return loss.value
+
+    def variables(self):
+        v, z = np.zeros(3), np.zeros((self.m, self.d))
+        call("vgp_elbo_get_params", self.handle, v.ctypes.data, z.ctypes.data, None)
+        return v, z
+
+    def assign(self, v=None, z=None):
+        vp = None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+        zp = None if z is None else np.ascontiguousarray(z, dtype=np.float64)
+        call("vgp_elbo_set_params", self.handle, None if vp is None else vp.ctypes.data,
+             None if zp is None else zp.ctypes.data, None)
+
+    def parameters(self):
+        """Constrained (amplitude, length_scale, observation_noise_variance) and Z."""
+        v, z = self.variables()
+        return float(softplus(v[0])), float(self.length_scale_offset + softplus(v[1])), float(softplus(v[2])), z
+
+    def vgp(self, index_points=None):
+        """The VariationalGaussianProcess at the current parameters (for `.mean()` etc., :141-142)."""
+        amp, ls, noise, z = self.parameters()
+        k = ExponentiatedQuadratic(amp, ls)
+        loc, scale = VariationalGaussianProcess.optimal_variational_posterior(k, z, self._x, self._y, noise,
+                                                                              jitter=self.jitter, as_device=True)
+        return VariationalGaussianProcess(k, index_points, z, loc, scale, noise, jitter=self.jitter)
+
+    def launch_count(self):
+        c = ctypes.c_int64(0)
+        call("vgp_elbo_launch_count", self.handle, ctypes.byref(c))
+        return c.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            call("vgp_elbo_destroy", self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
