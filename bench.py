@@ -126,8 +126,15 @@ def cpu_greedy(n_full, n_sample, steps, warmup):
     scale = (n_sample / n_full) ** 2
     cores = os.cpu_count() or 1
     threads = int(os.environ.get("OMP_NUM_THREADS", cores))
+    k_call = K_FULL
+    setup_scaled = tm["setup_s"] * (n_full / n_sample) ** 3          # potrf + potri are O(n^3)
+    whole_call = k_call / (setup_scaled + k_call * per_step / scale)
     return {
         "value": scale / per_step, "unit": "selections/s", "cores": threads, "kind": "port",
+        "whole_call_value": whole_call,
+        "whole_call_note": "k=%d selections / (inverse %.1f s scaled by (n/%d)^3 = %.0f s + k scaled steps): the CPU "
+                           "counterpart of `e2e` (setup inside the timed region)" % (k_call, tm["setup_s"], n_sample,
+                                                                                    setup_scaled),
         "sample": "incremental oracle (C/OpenMP step + LAPACK inverse) run for real at n=%d of the same cloud, "
                   "%d selections after %d warm-up; per-selection time scaled by (n/%d)^2 to n=%d; setup "
                   "(inverse %.1f s, kernel build %.1f s at the sample size) excluded like `value`"
@@ -142,14 +149,21 @@ def run_reference(args, rank, world):
         return
     n_sample = int(os.environ.get("VGP_BENCH_CPU_N", 8192))
     base = cpu_greedy(args.n, n_sample, args.steps, args.warmup)
+    # The reference's public call is placement_algorithm_2(cov_vv, k) on a host matrix: setup + k selections.
+    # That whole call is what our `e2e` times, so it is this arm's value; the steps-only rate (the counterpart
+    # of our `value`, P already resident) is reported beside it.
+    whole = base["whole_call_value"]
+    base = dict(base, steps_only_value=base["value"], value=whole)
     line = {
-        "impl": "reference", "metric": "greedy_mi_selections_per_s", "value": base["value"],
+        "impl": "reference", "metric": "greedy_mi_selections_per_s", "value": whole,
         "unit": "selections/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": base["ms_per_step_scaled"], "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 / whole, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args),
         "cpu_baseline": base,
-        "e2e": {"value": base["value"], "unit": "selections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "steps_only": {"value": base["steps_only_value"], "unit": "selections/s",
+                       "ms_per_step": base["ms_per_step_scaled"]},
+        "e2e": {"value": whole, "unit": "selections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference arm = CPU restatement of the reference's greedy (oracle/, pinned to the reference's "
                 "own golden vectors); the literal reference is O(n^4)/selection and Python-only "

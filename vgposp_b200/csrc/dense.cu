@@ -302,84 +302,173 @@ constexpr int NB = 128;
 constexpr int SLD = NB + 1;
 constexpr int BLOCK_SMEM = NB * SLD * 8;    // 132 096 B
 
-// Lower Cholesky of one diagonal block, in place; strict upper triangle zeroed.
+// The three diagonal-block kernels share one register layout: 256 threads as a 16 x 16 grid, thread (ti, tc)
+// owns the 8 x 8 cyclic sub-tile {(ti + 16 r, tc + 16 s)} of the 128 x 128 block in registers.  The cyclic
+// distribution keeps triangular work balanced; per elimination step a thread reads 16 values from shared
+// memory (broadcast / conflict-free) and issues 64 FMAs.
+
+// Lower Cholesky of one diagonal block, in place; strict upper triangle zeroed.  Right-looking, the pivot
+// column travels through a double-buffered 128-entry shared array: one barrier per column.
 __global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, int *info, int row_offset) {
-    extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int i = e >> 7, j = e & 127;
-        sm[i * SLD + j] = j <= i ? a[(int64_t)i * ld + j] : 0.0;
-    }
-    __syncthreads();
-    for (int j = 0; j < NB; ++j) {
-        const double d = sm[j * SLD + j];
-        // every thread sees the same d (written before the previous barrier)
-        if (!(d > 0.0)) {
-            if (tid == 0) atomicCAS(info, 0, row_offset + j + 1);
+    __shared__ double colbuf[2][NB];
+    const int ti = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    double v[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int i = ti + 16 * r, c = tc + 16 * s;
+            v[r][s] = c <= i ? a[(int64_t)i * ld + c] : 0.0;
         }
+#pragma unroll 1
+    for (int j = 0; j < NB; ++j) {
+        const int jb = j & 1, sj = j >> 4, tcj = j & 15;
+        if (tc == tcj) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = ti + 16 * r;
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    if (s == sj && i >= j) colbuf[jb][i] = v[r][s];
+            }
+        }
+        __syncthreads();
+        const double d = colbuf[jb][j];
+        if (!(d > 0.0) && threadIdx.x == 0) atomicCAS(info, 0, row_offset + j + 1);
         const double piv = sqrt(d);
         const double inv = 1.0 / piv;
-        __syncthreads();
-        if (tid == 0) sm[j * SLD + j] = piv;
-        for (int i = j + 1 + tid; i < NB; i += 256) sm[i * SLD + j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: rows i > j, columns j < c <= i
-        const int rem = NB - 1 - j;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int i = j + 1 + e / rem, c = j + 1 + e % rem;
-            if (c <= i) sm[i * SLD + c] = fma(-sm[i * SLD + j], sm[c * SLD + j], sm[i * SLD + c]);
+        double lr[8], lc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = ti + 16 * r;
+            lr[r] = i > j ? colbuf[jb][i] * inv : 0.0;
         }
-        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int c = tc + 16 * s;
+            lc[s] = c > j ? colbuf[jb][c] * inv : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int s = 0; s < 8; ++s) v[r][s] = fma(-lr[r], lc[s], v[r][s]);
+        if (tc == tcj) {        // column j is final: store L[i][j]
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = ti + 16 * r;
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    if (s == sj) {
+                        if (i > j) v[r][s] = lr[r];
+                        else if (i == j) v[r][s] = piv;
+                    }
+            }
+        }
     }
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int i = e >> 7, j = e & 127;
-        a[(int64_t)i * ld + j] = sm[i * SLD + j];
-    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int i = ti + 16 * r, c = tc + 16 * s;
+            a[(int64_t)i * ld + c] = c <= i ? v[r][s] : 0.0;
+        }
 }
 
-// out = inv(L) for one lower 128-block (strict upper of `out` zeroed).  `transpose` writes inv(L)^T.
-// Thread c solves L x = e_c by forward substitution.  L sits in the lower triangle of one [128][129]
-// shared array; the solution column x_k (k >= c) is kept in the unused strict upper part at [c][k + 1].
-__global__ void __launch_bounds__(128, 1) trtri_kernel(const double *l, int64_t ldl, double *out, int64_t ldo,
+// out = inv(L) for one lower 128-block (strict upper of `out` zeroed); `transpose` writes inv(L)^T.
+// Forward substitution on the identity, all 128 right-hand sides at once: after row k of X is final, every
+// later row gets the rank-1 correction  B[i][:] -= L[i][k] X[k][:].  L sits in shared memory, B/X in registers.
+__global__ void __launch_bounds__(256, 1) trtri_kernel(const double *l, int64_t ldl, double *out, int64_t ldo,
                                                        int transpose) {
-    extern __shared__ __align__(16) double sm[];
-    const int c = threadIdx.x;
-    for (int e = c; e < NB * NB; e += 128) {
+    extern __shared__ __align__(16) double sm[];          // L, [128][129]
+    __shared__ double rowbuf[2][NB];
+    const int ti = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    for (int e = threadIdx.x; e < NB * NB; e += 256) {
         const int i = e >> 7, j = e & 127;
-        if (j <= i) sm[i * SLD + j] = l[(int64_t)i * ldl + j];
+        sm[i * SLD + j] = j <= i ? l[(int64_t)i * ldl + j] : 0.0;
     }
+    double x[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) x[r][s] = (ti + 16 * r == tc + 16 * s) ? 1.0 : 0.0;
     __syncthreads();
-    double *xc = sm + c * SLD + 1;          // xc[k] = x_k, valid for k >= c
-    for (int i = c; i < NB; ++i) {
-        double acc = (i == c) ? 1.0 : 0.0;
-        for (int k = c; k < i; ++k) acc = fma(-sm[i * SLD + k], xc[k], acc);
-        xc[i] = acc / sm[i * SLD + i];
+#pragma unroll 1
+    for (int k = 0; k < NB; ++k) {
+        const int kb = k & 1, rk = k >> 4, tik = k & 15;
+        if (ti == tik) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    if (r == rk) rowbuf[kb][tc + 16 * s] = x[r][s];
+        }
+        __syncthreads();
+        const double dinv = 1.0 / sm[k * SLD + k];
+        double xr[8], lk[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) xr[s] = rowbuf[kb][tc + 16 * s] * dinv;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = ti + 16 * r;
+            lk[r] = i > k ? sm[i * SLD + k] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int s = 0; s < 8; ++s) x[r][s] = fma(-lk[r], xr[s], x[r][s]);
+        if (ti == tik) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    if (r == rk) x[r][s] = xr[s];
+        }
     }
-    __syncthreads();
-    for (int e = c; e < NB * NB; e += 128) {
-        const int i = e >> 7, j = e & 127;
-        // X[i][j] = x_i of column j, stored at sm[j][i + 1]
-        const int r = transpose ? j : i, q = transpose ? i : j;      // element (r, q) of inv(L)
-        out[(int64_t)i * ldo + j] = q <= r ? sm[q * SLD + r + 1] : 0.0;
-    }
+    // `out` may alias `l`: every thread finished reading L from global memory before the first barrier
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int i = ti + 16 * r, c = tc + 16 * s;
+            const double val = c <= i ? x[r][s] : 0.0;
+            if (!transpose) {
+                out[(int64_t)i * ldo + c] = val;
+            } else {
+                out[(int64_t)c * ldo + i] = val;        // inv(L)^T: upper triangular, zero strict lower
+            }
+        }
 }
 
 // block = X^T X for one lower 128-block X, written as a full symmetric block.
 __global__ void __launch_bounds__(256, 1) lauum_kernel(double *x, int64_t ld) {
     extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NB * NB; e += 256) {
+    const int ti = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    for (int e = threadIdx.x; e < NB * NB; e += 256) {
         const int i = e >> 7, j = e & 127;
         sm[i * SLD + j] = j <= i ? x[(int64_t)i * ld + j] : 0.0;
     }
     __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int i = e >> 7, j = e & 127;
-        const int k0 = i > j ? i : j;
-        double acc = 0.0;
-        for (int k = k0; k < NB; ++k) acc = fma(sm[k * SLD + i], sm[k * SLD + j], acc);
-        x[(int64_t)i * ld + j] = acc;
+    double p[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) p[r][s] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < NB; ++k) {
+        double xi[8], xc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) xi[r] = sm[k * SLD + ti + 16 * r];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) xc[s] = sm[k * SLD + tc + 16 * s];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int s = 0; s < 8; ++s) p[r][s] = fma(xi[r], xc[s], p[r][s]);
     }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) x[(int64_t)(ti + 16 * r) * ld + tc + 16 * s] = p[r][s];
 }
 
 static int block_kernels_configure() {
@@ -387,8 +476,7 @@ static int block_kernels_configure() {
     int dev = 0;
     VGP_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        VGP_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
-        VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
+                VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
         VGP_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
         configured[dev] = true;
     }
@@ -396,7 +484,7 @@ static int block_kernels_configure() {
 }
 
 static int block_trtri(const double *l, int64_t ldl, double *out, int64_t ldo, int transpose, cudaStream_t s) {
-    trtri_kernel<<<1, 128, BLOCK_SMEM, s>>>(l, ldl, out, ldo, transpose);
+    trtri_kernel<<<1, 256, BLOCK_SMEM, s>>>(l, ldl, out, ldo, transpose);
     VGP_LAUNCH_CHECK();
     return VGP_OK;
 }
@@ -542,7 +630,7 @@ int dense_trsm(int side, int trans, int64_t n, int64_t nrhs, double alpha, const
 static int potrf_rec(double *a, int64_t n, int64_t ld, int64_t row_offset, double *dinv, DenseWorkspace &ws,
                      cudaStream_t s) {
     if (n == NB) {
-        potf2_kernel<<<1, 256, BLOCK_SMEM, s>>>(a, ld, ws.info, (int)row_offset);
+        potf2_kernel<<<1, 256, 0, s>>>(a, ld, ws.info, (int)row_offset);
         VGP_LAUNCH_CHECK();
         return block_trtri(a, ld, dinv, NB, 0, s);          // cache inv(L_ii) for every later solve
     }
