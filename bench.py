@@ -172,11 +172,28 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(n, nloc):
+    """Per-launch DRAM bytes of the downdate kernel from the committed `ncu --set full` capture of this same
+    configuration (profiles/*_traffic.json); None when no capture matches (n, nloc)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(path))
+        except Exception:      # noqa: BLE001
+            continue
+        if d.get("n") == n and d.get("nloc") == nloc:
+            return d["traffic_bytes_per_launch"], os.path.basename(path)
+    return None, None
+
+
 def config_dict(args):
     _, amp, ls, nugget = workload(args.n)
     return {"workload": "greedy_mi_placement_n%d_k%d_expquad_cloud" % (args.n, args.k), "n": args.n, "k": args.k,
             "amplitude": amp, "length_scale": round(ls, 6), "nugget": nugget, "seed": SEED,
             "parallelism": "column-panel shards x%d" % args.gpus,
+            "exchange": ("none" if args.gpus == 1 else
+                         ("peer-memory mailboxes over NVLink (in-kernel)" if args.exchange == "peer"
+                          else "2 NCCL all-gathers per selection")),
             "l2": "inputs larger than L2: every step streams the %.1f GB precision panel"
                   % (8.0 * args.n * args.n / args.gpus / 1e9)}
 
@@ -244,7 +261,12 @@ def run_ours(args, rank, world, local_rank):
     factor_s = time.perf_counter() - t0
     shard.save_precision()
 
-    if world > 1:
+    if world > 1 and args.exchange == "peer":
+        # the two per-selection exchanges are stores into the peers' mailboxes over NVLink (CUDA IPC), signalled
+        # with release/acquire flags inside the kernels: no collective launch, k selections enqueued at once
+        greedy.connect_peers_torch(shard, rank, world, dist, "cuda:%d" % dev)
+        run_steps = shard.run_peer
+    elif world > 1:
         def make_buffer(m):
             return torch.zeros(m, dtype=torch.float64, device="cuda:%d" % dev)
 
@@ -275,6 +297,8 @@ def run_ours(args, rank, world, local_rank):
         ms = elapsed(a, b)
         barrier()
     launches = shard.launch_count() - launches0
+    if world > 1 and args.exchange == "peer":
+        shard.comm_status()                 # raises if any wait on a peer's flag timed out
     kms, kcount = ctypes.c_double(), ctypes.c_int64()
     call("vgp_greedy_profile_read", shard.handle, ctypes.byref(kms), ctypes.byref(kcount))
     call("vgp_greedy_profile", shard.handle, 0)
@@ -302,6 +326,7 @@ def run_ours(args, rank, world, local_rank):
     algo_bytes = 16.0 * n * nloc
     kernel_ms = kms.value / max(kcount.value, 1)
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    traffic, traffic_src = ncu_traffic(n, nloc)
     line = {
         "metric": "greedy_mi_selections_per_s", "value": args.steps / (ms * 1e-3), "unit": "selections/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -309,7 +334,8 @@ def run_ours(args, rank, world, local_rank):
         "config": config_dict(args),
         "roofline": {"bound": "hbm", "kernel": "downdate_kernel", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                     "peak_kind": "%s copy bandwidth (MEASURED_PEAKS.json)" % peak_kind, "traffic": None,
+                     "peak_kind": "%s copy bandwidth (MEASURED_PEAKS.json)" % peak_kind, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": kernel_ms,
                      "kernel_launches_timed": kcount.value,
                      "kernel_share_of_step": kms.value / ms if ms > 0 else None},
@@ -444,6 +470,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_FULL, help="candidate count (default: the BASELINE workload)")
     ap.add_argument("--k", type=int, default=None, help="selections of the e2e call (default: --steps)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: per-selection exchange through peer-memory mailboxes (default) or two NCCL all-gathers")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-elbo", action="store_true")

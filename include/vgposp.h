@@ -228,6 +228,25 @@ int vgp_greedy_apply(vgp_greedy *handle, const double *gathered_dev, int64_t seg
                      const int64_t *bounds_host, void *stream);
 /* Single shard: k further selections enqueued back to back. */
 int vgp_greedy_run(vgp_greedy *handle, int64_t k, void *stream);
+
+/* Peer-memory exchange for the shards of ONE box (the reference has no counterpart -- its
+ * loop is single-process Python, placement_algorithm2.py:128-145).  Instead of two collective launches per
+ * selection, each rank's kernels store their 32-byte candidate record and their [w_J | p_J] segment straight into
+ * every peer's mailbox over NVLink/NVSwitch and signal with system-scope release/acquire flags; the consuming
+ * kernels wait on those flags.  No host synchronisation: vgp_greedy_run_peer enqueues k selections at once.
+ *   comm_create   allocate this rank's mailbox (bounds_host[nranks + 1] = column ranges of all ranks);
+ *                 ipc_handle_out (64 bytes, may be NULL) receives its cudaIpcMemHandle_t for other processes,
+ *                 mailbox_dev_out (may be NULL) its device address for handles of the same process;
+ *   comm_connect  peers: kind 0 = void *[nranks] device pointers (same process), kind 1 = nranks x 64 bytes of
+ *                 IPC handles in rank order (cudaIpcOpenMemHandle, peer access enabled lazily).  All ranks must
+ *                 have connected (a host barrier) before any of them runs;
+ *   run_peer      k further selections; every rank must request the same k;
+ *   comm_status   blocking; VGP_ERR_STATE if a wait timed out (~10 s without the peer's flag). */
+int vgp_greedy_comm_create(vgp_greedy *handle, int rank, int nranks, const int64_t *bounds_host,
+                           void *ipc_handle_out, void **mailbox_dev_out);
+int vgp_greedy_comm_connect(vgp_greedy *handle, const void *peers, int kind);
+int vgp_greedy_run_peer(vgp_greedy *handle, int64_t k, void *stream);
+int vgp_greedy_comm_status(vgp_greedy *handle, int *error_host, void *stream);
 /* Results so far (blocking): indices [count], winning scores [count], relative top-2 gap is not tracked. */
 int vgp_greedy_results(vgp_greedy *handle, int64_t *count, int64_t *selection_host, double *scores_host,
                        int64_t capacity, void *stream);

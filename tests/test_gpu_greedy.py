@@ -1,7 +1,8 @@
 """GPU parity: greedy MI placement through the C-ABI and the drop-in module, against the golden vectors from the
 reference's own code, the CPU oracle on seeded inputs, and size-independent properties at larger n."""
-import io
 import contextlib
+import ctypes
+import io
 
 import numpy as np
 import pytest
@@ -200,3 +201,69 @@ def test_save_restore_precision_replays_identically():
     np.testing.assert_array_equal(first[1], second[1])
     assert shard.launch_count() > 8 * 4
     shard.close()
+
+
+def run_shards_peer(cov, k, world, chunk=1):
+    """G shards on ONE device, each on its own stream, exchanging through the peer-memory mailboxes
+    (same-process pointers): the kernels of one shard wait for the flags the other shards' kernels set."""
+    n = cov.shape[0]
+    prec = go.spd_inverse(cov)
+    bounds = greedy.shard_bounds(n, world)
+    shards, streams = [], []
+    for g in range(world):
+        st = _ffi.c_vp()
+        _ffi.call("vgp_stream_create", D, ctypes.byref(st))
+        streams.append(st)
+        s = greedy.GreedyShard(n, bounds[g], bounds[g + 1], k, D, stream=st)
+        s.load_cov_host(cov)
+        s.load_prec_host(prec)
+        s.reset()
+        s.sync()
+        shards.append(s)
+    boxes = [s.comm_create(g, world, bounds)[1] for g, s in enumerate(shards)]
+    for s in shards:
+        s.comm_connect_pointers(boxes)
+    done = 0
+    while done < k:                      # interleaved so that no stream's queue has to drain for another to start
+        step = min(chunk, k - done)
+        for s in shards:
+            s.run_peer(step)
+        done += step
+    out = []
+    for s in shards:
+        s.comm_status()
+        out.append(s.results())
+    for s, st in zip(shards, streams):
+        s.close()
+        _ffi.call("vgp_stream_destroy", D, st)
+    return out
+
+
+@pytest.mark.parametrize("world,chunk", [(2, 1), (3, 2), (4, 1)])
+def test_peer_exchange_equals_single_shard(world, chunk):
+    cov = cloud_cov(700, 11)
+    k = 9
+    single_sel, single_scores, _, _ = greedy.place_single(cov, k, D)
+    out = run_shards_peer(cov, k, world, chunk)
+    ref = run_shards(cov, k, world)
+    for (sel, scores), (rsel, rscores) in zip(out, ref):
+        np.testing.assert_array_equal(sel, single_sel)
+        np.testing.assert_array_equal(scores, rscores)                    # same bits as the all-gather protocol
+
+
+@pytest.mark.timeout(300)
+def test_peer_exchange_two_processes_ipc():
+    """Two ranks, one process per GPU, mailboxes mapped through CUDA IPC (needs two devices)."""
+    import os
+    import subprocess
+    import sys
+    cnt = _ffi.c_int(0)
+    _ffi.call("vgp_device_count", ctypes.byref(cnt))
+    if cnt.value < 2:
+        pytest.skip("needs two CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "peer_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=root)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "PEER_WORKER_OK" in res.stdout

@@ -98,6 +98,10 @@ SIGNATURES = {
     "vgp_greedy_segments": [c_vp, c_vp, c_i64, c_vp],
     "vgp_greedy_apply": [c_vp, c_vp, c_i64, c_int, P(c_i64), c_vp],
     "vgp_greedy_run": [c_vp, c_i64, c_vp],
+    "vgp_greedy_comm_create": [c_vp, c_int, c_int, P(c_i64), c_vp, P(c_vp)],
+    "vgp_greedy_comm_connect": [c_vp, c_vp, c_int],
+    "vgp_greedy_run_peer": [c_vp, c_i64, c_vp],
+    "vgp_greedy_comm_status": [c_vp, P(c_int), c_vp],
     "vgp_greedy_results": [c_vp, P(c_i64), c_vp, c_vp, c_i64, c_vp],
     "vgp_greedy_record_scores": [c_vp, c_int],
     "vgp_greedy_step_scores": [c_vp, c_vp, c_i64, c_vp],

@@ -207,32 +207,37 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
     return gemm_dispatch(trans_a, trans_b, p, s);
 }
 
-// C = beta C + sum_z partial_z, fixed summation order
+// C = beta C + sum_z partial_z, fixed summation order; `lower`: only tiles with tile_row >= tile_col were computed
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const double *partial, int64_t stride, int splits,
                                                             double beta, double *c, int64_t ldc, int64_t m,
-                                                            int64_t n) {
+                                                            int64_t n, int lower) {
     const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (e >= m * n) return;
     const int64_t i = e / n, j = e % n;
+    if (lower && i / BM < j / BN) return;
     double acc = 0.0;
     for (int z = 0; z < splits; ++z) acc += partial[(int64_t)z * stride + i * n + j];
     c[i * ldc + j] = beta != 0.0 ? fma(beta, c[i * ldc + j], acc) : acc;
 }
 
 // Split-K form for short-and-wide products (m, n small, k huge: the m x m SYRK over all N observations).
-// `partial` holds splits * m * n doubles.
+// `partial` holds splits * m * n doubles.  tiles == GEMM_LOWER (square C, symmetric product A A^T): only the
+// lower tiles are computed and the strict upper triangle of C is filled by mirroring (beta must be 0).
 int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                       int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,
-                      double *partial, cudaStream_t s) {
+                      double *partial, cudaStream_t s, GemmTiles tiles) {
     if (m == 0 || n == 0) return VGP_OK;
     VGP_REQUIRE(m % BM == 0 && n % BN == 0 && k % BK == 0 && k > 0, "dense_gemm_splitk: unpadded size");
     VGP_REQUIRE(splits >= 1 && partial, "dense_gemm_splitk: bad split");
+    VGP_REQUIRE(tiles == GEMM_FULL || (m == n && beta == 0.0), "dense_gemm_splitk: lower mode needs square C, beta 0");
     int64_t k_split = round_up((k + splits - 1) / splits, BK);
     const int real_splits = (int)((k + k_split - 1) / k_split);
-    GemmArgs p{a, b, partial, lda, ldb, n, m, n, k, alpha, 0.0, 0, k_split, m * n};
+    GemmArgs p{a, b, partial, lda, ldb, n, m, n, k, alpha, 0.0, tiles == GEMM_LOWER ? 1 : 0, k_split, m * n};
     VGP_TRY(gemm_dispatch(trans_a, trans_b, p, s));
-    splitk_reduce_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, s>>>(partial, m * n, real_splits, beta, c, ldc, m, n);
+    splitk_reduce_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, s>>>(partial, m * n, real_splits, beta, c, ldc, m, n,
+                                                                        tiles == GEMM_LOWER ? 1 : 0);
     VGP_LAUNCH_CHECK();
+    if (tiles == GEMM_LOWER) return dense_mirror_lower(c, m, ldc, s);
     return VGP_OK;
 }
 

@@ -26,7 +26,7 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
 
 int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                       int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,
-                      double *partial, cudaStream_t s);
+                      double *partial, cudaStream_t s, GemmTiles tiles = GEMM_FULL);
 
 int dense_add_diag(double *a, int64_t ld, int64_t n, double value, cudaStream_t s);
 int dense_zero_strict_upper(double *a, int64_t n, int64_t ld, cudaStream_t s);

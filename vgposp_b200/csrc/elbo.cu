@@ -295,9 +295,9 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(expquad_dispatch_public(h->z, m, h->x, n, h->d, a, l, 0.0, -1 - n, h->kzx, h->np_, s));
     VGP_TRY(expquad_dispatch_public(h->z, m, xb, b, h->d, a, l, 0.0, -1 - b, h->kzb, h->bp, s));
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->np_, 1.0, h->kzx, h->np_, h->kzx, h->np_, 0.0, M(G_), mp, h->splits_n,
-                              h->partial, s));
+                              h->partial, s, GEMM_LOWER));
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->bp, 1.0, h->kzb, h->bp, h->kzb, h->bp, 0.0, M(GB_), mp, h->splits_b,
-                              h->partial, s));
+                              h->partial, s, GEMM_LOWER));
     VGP_TRY(matvec(h->kzx, h->np_, m, n, h->y, 1.0, V(V_), s));
     VGP_TRY(matvec(h->kzb, h->bp, m, b, yb, 1.0, V(VB_), s));
     VGP_TRY(red.run(DotVec{yb, yb}, b, S_YY));
@@ -453,9 +453,11 @@ int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const do
     h->lr = learning_rate;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
-    const int tiles = (int)((h->mp / TILE) * (h->mp / TILE));
+    // the two Gram matrices are symmetric: only the lower tiles are computed; split K so that the CTAs fill
+    // (just under) two waves of the SMs
+    const int tiles = (int)((h->mp / TILE) * (h->mp / TILE + 1) / 2);
     auto pick = [&](int64_t k) {
-        int s = (2 * sm + tiles - 1) / tiles;
+        int s = (2 * sm) / tiles;
         const int64_t maxs = k / 256 > 0 ? k / 256 : 1;
         if (s > maxs) s = (int)maxs;
         return s < 1 ? 1 : s;

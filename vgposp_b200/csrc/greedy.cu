@@ -15,6 +15,7 @@
 // The dominant kernel is `downdate_kernel`: 16 * n_pad * ld algorithmic bytes per launch, pure
 // streaming read-modify-write with 128-bit accesses -> HBM roofline.
 #include <math.h>
+#include <string.h>
 
 #include <new>
 #include <utility>
@@ -46,6 +47,15 @@ struct vgp_greedy {
     DenseWorkspace ws;
     int profile = 0;                                    // CUDA events around every downdate launch
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    // peer-memory exchange (one box, NVLink): every rank owns a mailbox its peers store into
+    char *mailbox = nullptr;                            // this rank's mailbox (plain cudaMalloc: IPC-exportable)
+    size_t mailbox_bytes = 0;
+    int comm_rank = -1, comm_nranks = 0, comm_ipc = 0;
+    int64_t comm_stride = 0;
+    int64_t comm_bounds[65] = {0};
+    char *peer_mb[64] = {nullptr};                      // peers' mailboxes mapped into this process
+    unsigned *counter2 = nullptr;
+    unsigned long long epoch = 0;                       // exchange sequence number, never reset
 };
 
 namespace {
@@ -294,6 +304,155 @@ __global__ void __launch_bounds__(256) downdate_kernel(double *__restrict__ prec
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Peer-memory exchange: the two small per-selection exchanges are done by the kernels
+// themselves with stores into the peers' mailboxes over NVLink/NVSwitch and system-scope release/acquire flags --
+// no collective launch, no host involvement; k selections are enqueued back to back on every rank.
+//
+// Mailbox of one rank (written by its peers, read by its own kernels):
+//   [0, 512)        rec_flag[64]   u64: exchange sequence number of the record stored by rank q
+//   [512, 1024)     seg_flag[64]   u64: same for the [w_J | p_J] segment of rank q
+//   [1024, 1032)    error          int: set when a wait timed out
+//   [2048, 6144)    recs[2][64]    vgp_candidate, double-buffered by sequence parity
+//   [8192, ...)     segs[2][nranks][2][stride] doubles
+// ------------------------------------------------------------------------------------------------------------
+constexpr size_t MB_REC_FLAG = 0, MB_SEG_FLAG = 512, MB_ERROR = 1024, MB_RECS = 2048, MB_SEGS = 8192;
+constexpr long long SPIN_LIMIT_CYCLES = 20000000000LL;      // ~10 s at 1.9 GHz: a dead peer fails the run, no hang
+
+struct PeerTable {
+    char *mb[MAX_RANKS];
+    int nranks, rank;
+    int64_t stride;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ vgp_candidate *mb_rec(char *mb, unsigned long long seq, int r) {
+    return reinterpret_cast<vgp_candidate *>(mb + MB_RECS) + (seq & 1) * MAX_RANKS + r;
+}
+__device__ __forceinline__ double *mb_seg(char *mb, unsigned long long seq, int nranks, int64_t stride, int r) {
+    return reinterpret_cast<double *>(mb + MB_SEGS) + ((int64_t)(seq & 1) * nranks + r) * 2 * stride;
+}
+// Thread q < nranks waits until rank q's flag in the local mailbox reaches `seq`.
+__device__ __forceinline__ void wait_flags(char *mb, size_t flag_off, int nranks, unsigned long long seq) {
+    if ((int)threadIdx.x < nranks) {
+        const unsigned long long *f = reinterpret_cast<const unsigned long long *>(mb + flag_off) + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < seq) {
+            if (clock64() - t0 > SPIN_LIMIT_CYCLES) {
+                atomicExch(reinterpret_cast<int *>(mb + MB_ERROR), 1 + (int)threadIdx.x);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Publish this rank's local winner to every rank's mailbox (one thread per destination).
+__global__ void publish_record_kernel(PeerTable pt, unsigned long long seq, const vgp_candidate *best) {
+    const int q = threadIdx.x;
+    if (q >= pt.nranks) return;
+    *mb_rec(pt.mb[q], seq, pt.rank) = *best;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long *>(pt.mb[q] + MB_REC_FLAG) + pt.rank, seq);
+}
+
+// Exchange 1 (receive) + winner rule + this rank's segments + exchange 2 (send).
+__global__ void __launch_bounds__(256) exchange_kernel(PeerTable pt, unsigned long long seq,
+                                                       const double *__restrict__ cov, const double *__restrict__ prec,
+                                                       int64_t ld, int64_t c0, int64_t nloc,
+                                                       const double *__restrict__ wfull, int64_t n_pad, int64_t t,
+                                                       double jitter, vgp_candidate *cur, int64_t *sel,
+                                                       double *sel_score, unsigned *counter) {
+    char *me = pt.mb[pt.rank];
+    wait_flags(me, MB_REC_FLAG, pt.nranks, seq);
+    __shared__ vgp_candidate win;
+    if (threadIdx.x == 0) {
+        vgp_candidate w{NEG_INF, -1, 0.0, 0.0};
+        for (int r = 0; r < pt.nranks; ++r) {
+            const vgp_candidate *src = mb_rec(me, seq, r);
+            vgp_candidate c;
+            c.score = __ldcg(&src->score);
+            c.index = __ldcg((const long long *)&src->index);
+            c.num = __ldcg(&src->num);
+            c.pdiag = __ldcg(&src->pdiag);
+            if (c.index < 0) continue;
+            if (w.index < 0 || c.score > w.score || (c.score == w.score && c.index < w.index)) w = c;
+        }
+        win = w;
+        if (blockIdx.x == 0) {
+            *cur = w;
+            sel[t] = w.index;
+            sel_score[t] = w.score;
+        }
+    }
+    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j < pt.stride) {
+        const int64_t y = win.index;
+        double w = 0.0, p = 0.0;
+        if (y >= 0 && j < nloc) {
+            double acc = cov[y * ld + j];
+            if (c0 + j == y) acc += jitter;
+            for (int64_t s = 0; s < t; ++s) acc = fma(-wfull[s * n_pad + c0 + j], wfull[s * n_pad + y], acc);
+            w = acc / sqrt(win.num);
+            p = prec[y * ld + j];
+        }
+        for (int q = 0; q < pt.nranks; ++q) {
+            double *dst = mb_seg(pt.mb[q], seq, pt.nranks, pt.stride, pt.rank);
+            dst[j] = w;
+            dst[pt.stride + j] = p;
+        }
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last && (int)threadIdx.x < pt.nranks) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long *>(pt.mb[threadIdx.x] + MB_SEG_FLAG) + pt.rank, seq);
+    }
+}
+
+// Exchange 2 (receive): unpack_kernel reading the local mailbox once every rank's segment has arrived.
+__global__ void __launch_bounds__(256) unpack_peer_kernel(PeerTable pt, unsigned long long seq, Bounds bounds,
+                                                          int64_t n, int64_t n_pad, int64_t c0, int64_t nloc,
+                                                          int64_t ld, double *wrow, double *pfull, double *ploc,
+                                                          double *num, int *taken, const vgp_candidate *cur) {
+    char *me = pt.mb[pt.rank];
+    wait_flags(me, MB_SEG_FLAG, pt.nranks, seq);
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t y = cur->index;
+    if (y < 0) return;
+    if (i < n_pad) {
+        double w = 0.0, p = 0.0;
+        if (i < n) {
+            int g = 0;
+            while (g + 1 < bounds.nranks && i >= bounds.b[g + 1]) ++g;
+            const double *base = mb_seg(me, seq, pt.nranks, pt.stride, g);
+            w = __ldcg(base + (i - bounds.b[g]));
+            p = __ldcg(base + pt.stride + (i - bounds.b[g]));
+        }
+        wrow[i] = w;
+        pfull[i] = p;
+        if (i >= c0 && i < c0 + nloc) {
+            const int64_t j = i - c0;
+            num[j] = fma(-w, w, num[j]);
+            ploc[j] = p;
+            if (i == y) taken[j] = 1;
+        }
+    }
+    if (i >= nloc && i < ld) ploc[i] = 0.0;
+}
+
 // num = diag(Sigma) (+ jitter); nothing taken
 __global__ void __launch_bounds__(256) reset_kernel(const double *__restrict__ cov, int64_t ld, int64_t c0,
                                                     int64_t nloc, double jitter, double *num, int *taken,
@@ -331,6 +490,38 @@ int env_int(const char *name, int dflt) {
         ++(h)->launches;       \
         VGP_LAUNCH_CHECK();    \
     } while (0)
+
+// The dominant kernel: one streaming read-modify-write pass over the local precision panel.
+static int launch_downdate(vgp_greedy *h, cudaStream_t s) {
+    static const int rows_per_block = env_int("VGP_DOWNDATE_ROWS", 32);
+    static const int waves = env_int("VGP_DOWNDATE_WAVES", 4);
+    static const int unroll = env_int("VGP_DOWNDATE_UNROLL", 4);
+    const unsigned gx = (unsigned)((h->ld + 511) / 512);
+    const int64_t row_tiles = (h->n_pad + rows_per_block - 1) / rows_per_block;
+    int64_t gy = ((int64_t)h->sm_count * 8 * waves + gx - 1) / gx;
+    if (gy > row_tiles) gy = row_tiles;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    dim3 grid(gx, (unsigned)gy);
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (h->profile) {
+        VGP_CUDA(cudaEventCreate(&pe0));
+        VGP_CUDA(cudaEventCreate(&pe1));
+        VGP_CUDA(cudaEventRecord(pe0, s));
+    }
+    if (unroll >= 8)
+        downdate_kernel<8><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
+    else if (unroll >= 4)
+        downdate_kernel<4><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
+    else
+        downdate_kernel<2><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
+    H_LAUNCH_CHECK(h);
+    if (h->profile) {
+        VGP_CUDA(cudaEventRecord(pe1, s));
+        h->prof_events.emplace_back(pe0, pe1);
+    }
+    return VGP_OK;
+}
 
 extern "C" {
 
@@ -408,6 +599,11 @@ int vgp_greedy_destroy(vgp_greedy *h) {
                     h->partials, h->cur, h->best, h->counter, h->sel, h->sel_score, h->step_scores};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (h->comm_ipc)
+        for (int q = 0; q < h->comm_nranks; ++q)
+            if (q != h->comm_rank && h->peer_mb[q]) cudaIpcCloseMemHandle(h->peer_mb[q]);
+    if (h->mailbox) cudaFree(h->mailbox);
+    if (h->counter2) cudaFree(h->counter2);
     h->ws.release();
     delete h;
     return VGP_OK;
@@ -532,33 +728,7 @@ int vgp_greedy_apply(vgp_greedy *h, const double *gathered_dev, int64_t seg_stri
                                                                h->nloc, h->ld, h->wfull + h->t * h->n_pad, h->pfull,
                                                                h->ploc, h->num, h->taken, h->cur);
     H_LAUNCH_CHECK(h);
-    static const int rows_per_block = env_int("VGP_DOWNDATE_ROWS", 32);
-    static const int waves = env_int("VGP_DOWNDATE_WAVES", 4);
-    static const int unroll = env_int("VGP_DOWNDATE_UNROLL", 4);
-    const unsigned gx = (unsigned)((h->ld + 511) / 512);
-    const int64_t row_tiles = (h->n_pad + rows_per_block - 1) / rows_per_block;
-    int64_t gy = ((int64_t)h->sm_count * 8 * waves + gx - 1) / gx;
-    if (gy > row_tiles) gy = row_tiles;
-    if (gy > 65535) gy = 65535;
-    if (gy < 1) gy = 1;
-    dim3 grid(gx, (unsigned)gy);
-    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (h->profile) {
-        VGP_CUDA(cudaEventCreate(&pe0));
-        VGP_CUDA(cudaEventCreate(&pe1));
-        VGP_CUDA(cudaEventRecord(pe0, s));
-    }
-    if (unroll >= 8)
-        downdate_kernel<8><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
-    else if (unroll >= 4)
-        downdate_kernel<4><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
-    else
-        downdate_kernel<2><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
-    H_LAUNCH_CHECK(h);
-    if (h->profile) {
-        VGP_CUDA(cudaEventRecord(pe1, s));
-        h->prof_events.emplace_back(pe0, pe1);
-    }
+    VGP_TRY(launch_downdate(h, s));
     ++h->t;
     return VGP_OK;
 }
@@ -602,6 +772,128 @@ int vgp_greedy_run(vgp_greedy *h, int64_t k, void *stream) {
         VGP_TRY(vgp_greedy_select(h, h->best, 1, stream));
         VGP_TRY(vgp_greedy_segments(h, h->seg, h->n_pad, stream));
         VGP_TRY(vgp_greedy_apply(h, h->seg, h->n_pad, 1, bounds, stream));
+    }
+    return VGP_OK;
+}
+
+// ---- peer-memory exchange --------------------------------------------------------------------------------
+int vgp_greedy_comm_create(vgp_greedy *h, int rank, int nranks, const int64_t *bounds_host, void *ipc_handle_out,
+                           void **mailbox_dev_out) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(nranks >= 1 && nranks <= MAX_RANKS && rank >= 0 && rank < nranks, "bad rank %d of %d", rank, nranks);
+    VGP_REQUIRE(bounds_host && bounds_host[0] == 0 && bounds_host[nranks] == h->n, "bounds do not cover [0, n)");
+    VGP_REQUIRE(bounds_host[rank] == h->c0 && bounds_host[rank + 1] == h->c0 + h->nloc,
+                "bounds[%d] do not match this handle's shard", rank);
+    if (h->mailbox) {
+        set_error("the handle already has a mailbox");
+        return VGP_ERR_STATE;
+    }
+    VGP_ENTER(h->device);
+    int64_t stride = 0;
+    for (int g = 0; g < nranks; ++g) {
+        VGP_REQUIRE(bounds_host[g + 1] >= bounds_host[g], "bounds not monotone");
+        if (bounds_host[g + 1] - bounds_host[g] > stride) stride = bounds_host[g + 1] - bounds_host[g];
+    }
+    stride = round_up(stride, 2);
+    h->comm_rank = rank;
+    h->comm_nranks = nranks;
+    h->comm_stride = stride;
+    for (int g = 0; g <= nranks; ++g) h->comm_bounds[g] = bounds_host[g];
+    h->mailbox_bytes = MB_SEGS + (size_t)2 * nranks * 2 * stride * 8;
+    VGP_CUDA(cudaMalloc((void **)&h->mailbox, h->mailbox_bytes));
+    VGP_CUDA(cudaMemset(h->mailbox, 0, h->mailbox_bytes));
+    if (!h->counter2) {
+        VGP_CUDA(cudaMalloc((void **)&h->counter2, sizeof(unsigned)));
+        VGP_CUDA(cudaMemset(h->counter2, 0, sizeof(unsigned)));
+    }
+    VGP_CUDA(cudaDeviceSynchronize());
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t ipc;
+        VGP_CUDA(cudaIpcGetMemHandle(&ipc, h->mailbox));
+        memcpy(ipc_handle_out, &ipc, sizeof ipc);
+    }
+    if (mailbox_dev_out) *mailbox_dev_out = h->mailbox;
+    return VGP_OK;
+}
+
+int vgp_greedy_comm_connect(vgp_greedy *h, const void *peers, int kind) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(peers, "peers is NULL");
+    if (!h->mailbox) {
+        set_error("vgp_greedy_comm_create first");
+        return VGP_ERR_STATE;
+    }
+    VGP_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (device pointers) or 1 (IPC handles)");
+    VGP_ENTER(h->device);
+    for (int q = 0; q < h->comm_nranks; ++q) {
+        if (q == h->comm_rank) {
+            h->peer_mb[q] = h->mailbox;
+        } else if (kind == 0) {
+            h->peer_mb[q] = (char *)((void *const *)peers)[q];
+            VGP_REQUIRE(h->peer_mb[q], "peer %d mailbox pointer is NULL", q);
+        } else {
+            cudaIpcMemHandle_t ipc;
+            memcpy(&ipc, (const char *)peers + (size_t)q * sizeof ipc, sizeof ipc);
+            void *ptr = nullptr;
+            VGP_CUDA(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_mb[q] = (char *)ptr;
+        }
+    }
+    h->comm_ipc = kind;
+    return VGP_OK;
+}
+
+int vgp_greedy_run_peer(vgp_greedy *h, int64_t k, void *stream) {
+    VGP_TRY(check_handle(h));
+    if (!h->mailbox || !h->peer_mb[h->comm_rank]) {
+        set_error("vgp_greedy_comm_create / vgp_greedy_comm_connect first");
+        return VGP_ERR_STATE;
+    }
+    VGP_REQUIRE(k >= 0 && h->t + k <= h->kmax, "k = %lld exceeds kmax = %lld (already %lld)", (long long)k,
+                (long long)h->kmax, (long long)h->t);
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PeerTable pt;
+    for (int q = 0; q < MAX_RANKS; ++q) pt.mb[q] = q < h->comm_nranks ? h->peer_mb[q] : nullptr;
+    pt.nranks = h->comm_nranks;
+    pt.rank = h->comm_rank;
+    pt.stride = h->comm_stride;
+    Bounds b;
+    b.nranks = h->comm_nranks;
+    for (int g = 0; g <= h->comm_nranks; ++g) b.b[g] = h->comm_bounds[g];
+    const int64_t span = h->n_pad > h->ld ? h->n_pad : h->ld;
+    for (int64_t i = 0; i < k; ++i) {
+        const unsigned long long seq = ++h->epoch;
+        VGP_TRY(vgp_greedy_local_best(h, h->best, stream));
+        publish_record_kernel<<<1, MAX_RANKS, 0, s>>>(pt, seq, h->best);
+        H_LAUNCH_CHECK(h);
+        exchange_kernel<<<(unsigned)((h->comm_stride + 255) / 256), 256, 0, s>>>(
+            pt, seq, h->cov, h->prec, h->ld, h->c0, h->nloc, h->wfull, h->n_pad, h->t, h->jitter, h->cur, h->sel,
+            h->sel_score, h->counter2);
+        H_LAUNCH_CHECK(h);
+        unpack_peer_kernel<<<(unsigned)((span + 255) / 256), 256, 0, s>>>(pt, seq, b, h->n, h->n_pad, h->c0, h->nloc,
+                                                                        h->ld, h->wfull + h->t * h->n_pad, h->pfull,
+                                                                        h->ploc, h->num, h->taken, h->cur);
+        H_LAUNCH_CHECK(h);
+        VGP_TRY(launch_downdate(h, s));
+        ++h->t;
+    }
+    return VGP_OK;
+}
+
+int vgp_greedy_comm_status(vgp_greedy *h, int *error_host, void *stream) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(error_host, "error_host is NULL");
+    *error_host = 0;
+    if (!h->mailbox) return VGP_OK;
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    VGP_CUDA(cudaMemcpyAsync(error_host, h->mailbox + MB_ERROR, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VGP_CUDA(cudaStreamSynchronize(s));
+    if (*error_host != 0) {
+        set_error("peer exchange timed out waiting for rank %d (a peer died or ran a different number of steps)",
+                  *error_host - 1);
+        return VGP_ERR_STATE;
     }
     return VGP_OK;
 }

@@ -23,6 +23,21 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return e == cudaErrorMemoryAllocation ? VGP_ERR_NOMEM : VGP_ERR_CUDA;
 }
 
+// Scratch buffers come from the device's stream-ordered pool (cudaMallocAsync).  By default the pool hands its
+// memory back to the driver at every synchronisation, so each blocking call would re-map its scratch; keep up to
+// 2 GB cached (large one-off scratch, e.g. a padded copy of a covariance matrix, still goes back).
+static void keep_pool_memory(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long threshold = 2ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
 DeviceGuard::DeviceGuard(int device) {
     cudaError_t e = cudaGetDevice(&prev);
     if (e != cudaSuccess) {
@@ -37,6 +52,7 @@ DeviceGuard::DeviceGuard(int device) {
             return;
         }
     }
+    keep_pool_memory(device);
     ok = true;
 }
 

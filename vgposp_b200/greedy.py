@@ -119,6 +119,34 @@ class GreedyShard:
     def run(self, k):
         call("vgp_greedy_run", self.handle, int(k), self.stream)
 
+    # ---- peer-memory exchange (one box, NVLink; replaces the two all-gathers per selection) ---------
+    def comm_create(self, rank, nranks, bounds):
+        """Allocate this shard's mailbox.  Returns (ipc_handle bytes [64], mailbox device address)."""
+        arr = (c_i64 * len(bounds))(*bounds)
+        ipc = (ctypes.c_ubyte * 64)()
+        mb = c_vp()
+        call("vgp_greedy_comm_create", self.handle, int(rank), int(nranks), arr, ctypes.cast(ipc, c_vp),
+             ctypes.byref(mb))
+        return bytes(ipc), mb.value
+
+    def comm_connect_pointers(self, mailboxes):
+        """Peers are handles of this process: their mailbox device addresses in rank order."""
+        arr = (c_vp * len(mailboxes))(*mailboxes)
+        call("vgp_greedy_comm_connect", self.handle, ctypes.cast(arr, c_vp), 0)
+
+    def comm_connect_ipc(self, handles):
+        """Peers are other processes: their 64-byte IPC handles in rank order."""
+        blob = b"".join(handles)
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        call("vgp_greedy_comm_connect", self.handle, ctypes.cast(buf, c_vp), 1)
+
+    def run_peer(self, k):
+        call("vgp_greedy_run_peer", self.handle, int(k), self.stream)
+
+    def comm_status(self):
+        err = c_int(0)
+        call("vgp_greedy_comm_status", self.handle, ctypes.byref(err), self.stream)
+
     # ---- results -----------------------------------------------------------------------------------
     def results(self):
         count = c_i64(0)
@@ -185,6 +213,20 @@ def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_s
          sel.ctypes.data, sc.ctypes.data, steps.ctypes.data if want_step_scores else None, secs.ctypes.data)
     check_selection(sel)
     return sel, sc, steps, secs
+
+
+def connect_peers_torch(shard, rank, world, dist, device):
+    """Give `shard` a mailbox and map every other rank's (one process per GPU, same box): the 64-byte IPC
+    handles travel through one all-gather of `dist` (torch.distributed, any backend) -- plumbing, not data path."""
+    import torch
+    bounds = shard_bounds(shard.n, world)
+    ipc, _ = shard.comm_create(rank, world, bounds)
+    mine = torch.tensor(list(ipc), dtype=torch.uint8, device=device)
+    everyone = torch.empty(64 * world, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(everyone, mine)
+    blob = bytes(everyone.cpu().tolist())
+    shard.comm_connect_ipc([blob[64 * q:64 * (q + 1)] for q in range(world)])
+    dist.barrier()                       # nobody stores into a mailbox that is not mapped and zeroed yet
 
 
 class ShardedGreedy:
