@@ -366,6 +366,7 @@ def measure_elbo(dev, with_cpu, n=200000, m=512, b=4096, steps=10, warmup=3):
     512 x 512 x 200k SYRK forward plus the same GEMM shape backward."""
     import torch
     import vgposp_b200.gp_functions as gpf
+    from vgposp_b200._ffi import call
     rng = np.random.default_rng(SEED + 1)
     x = rng.uniform(-2.0, 2.0, (n, 3))
     y = np.sum(np.sin(2 * np.pi * x), axis=1) + 0.1 * rng.standard_normal(n)        # gp_functions.py:78-95
@@ -377,14 +378,19 @@ def measure_elbo(dev, with_cpu, n=200000, m=512, b=4096, steps=10, warmup=3):
     yb = torch.empty((b,), dtype=torch.float64, device="cuda:%d" % dev)
     xt = torch.as_tensor(x, device=xb.device)
     yt = torch.as_tensor(y, device=xb.device)
-    losses = []
+    losses, dev_ms = [], []
 
     def one():
         idx = torch.as_tensor(rng.integers(n, size=b), device=xb.device)              # :119
         xb.copy_(xt[idx])
         yb.copy_(yt[idx])
         torch.cuda.synchronize()
+        e0, e1, ms = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_float()
+        call("vgp_event_record", dev, None, ctypes.byref(e0))
         losses.append(tr.step_device(xb.data_ptr(), yb.data_ptr()))
+        call("vgp_event_record", dev, None, ctypes.byref(e1))
+        call("vgp_event_elapsed_ms", dev, e0, e1, ctypes.byref(ms))
+        dev_ms.append(ms.value)
 
     for _ in range(warmup):
         one()
@@ -400,6 +406,7 @@ def measure_elbo(dev, with_cpu, n=200000, m=512, b=4096, steps=10, warmup=3):
     flop = 2.0 * mp * mp * n * 2 + 2.0 * mp * mp * b * 2 + 26 * 2.0 * mp ** 3
     out = {"metric": "vgp_elbo_steps_per_s", "value": 1.0 / dt, "unit": "steps/s", "ms_per_step": dt * 1e3,
            "config": {"workload": "vgp_elbo_train_N%d_m%d_B%d_f64_reference_faithful" % (n, m, b), "d": 3},
+           "device_ms_per_step": float(np.mean(dev_ms[-steps:])),
            "flop_per_step": flop, "tflops": flop / dt / 1e12, "launches_per_step": launches,
            "loss_first_last": [losses[0], losses[-1]], "roofline_bound": "fp64 tensor pipe (DMMA)",
            "fp64_peak_tflops_cublas_dgemm_measured": 35.5}

@@ -807,6 +807,17 @@ int vgp_greedy_comm_create(vgp_greedy *h, int rank, int nranks, const int64_t *b
         VGP_CUDA(cudaMemset(h->counter2, 0, sizeof(unsigned)));
     }
     VGP_CUDA(cudaDeviceSynchronize());
+    {   // Load every kernel of the exchange loop now: with lazy module loading a first launch can wait for the
+        // device to drain, which must not happen while one of these kernels is spinning on a peer's flag.
+        cudaFuncAttributes fa;
+        VGP_CUDA(cudaFuncGetAttributes(&fa, score_kernel));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, publish_record_kernel));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, exchange_kernel));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, unpack_peer_kernel));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, downdate_kernel<2>));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, downdate_kernel<4>));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, downdate_kernel<8>));
+    }
     if (ipc_handle_out) {
         cudaIpcMemHandle_t ipc;
         VGP_CUDA(cudaIpcGetMemHandle(&ipc, h->mailbox));
