@@ -239,24 +239,28 @@ def run_ours(args, rank, world, local_rank):
     shard.build_cov_expquad(xd.ptr, 3, amp, ls, nugget)
     e1 = ev()
     build_ms = elapsed(e0, e1)
+    dist_stats = None
     t0 = time.perf_counter()
     if world == 1:
         shard.factor()
     else:
-        # round 1: every rank inverts the full matrix (replicated setup), then keeps its column panel
-        n_pad = shard.n_pad
-        full = _ffi.DeviceArray((n_pad, n_pad), np.float64, dev).zero_(stream)
-        call("vgp_expquad_matrix", dev, xd.ptr, n, xd.ptr, n, 3, amp, ls, nugget, 0, full.ptr, n_pad, stream)
-        if n_pad > n:
-            ones = np.ones(n_pad - n)
-            call("vgp_memcpy2d_h2d", dev, full.ptr + (n * n_pad + n) * 8, (n_pad + 1) * 8, ones.ctypes.data, 8, 8,
-                 n_pad - n, stream)
-        info = ctypes.c_int(0)
-        call("vgp_spd_inverse", dev, full.ptr, n_pad, n_pad, ctypes.byref(info), stream)
-        shard.load_prec_device(full.ptr, n_pad)
+        # distributed setup: every rank holds a replica, GEMM tiles are split over the ranks and stored into all
+        # replicas by the GEMM epilogues over NVLink (csrc/dist.cu); each rank then keeps its column panel
+        from vgposp_b200.dist_inverse import DistInverse
+        inv = DistInverse(n, rank, world, dev, stream=stream)
+        inv.connect_torch(dist, "cuda:%d" % dev)
+        inv.fill_padding()
+        inv.build_expquad(xd.ptr, 3, amp, ls, nugget)
+        shard.sync()
+        dist.barrier()
+        t0 = time.perf_counter()
+        inv.invert()
+        dist_stats = inv.stats()
+        factor_only_s = time.perf_counter() - t0
+        shard.load_prec_device(inv.ptr, inv.ld)
         shard.reset()
         shard.sync()
-        full.free()
+        inv.close()
     shard.sync()
     factor_s = time.perf_counter() - t0
     shard.save_precision()
@@ -313,9 +317,8 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     if world == 1 and not args.no_e2e:
         e2e = measure_e2e(args, shard, dev, sel)
-    elif world > 1:
-        e2e = {"value": None, "unit": "selections/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-               "note": "round 1 measures the host-buffer path at N=1 only (vgp_placement_host is single-device)"}
+    elif world > 1 and not args.no_e2e:
+        e2e = measure_e2e_sharded(args, shard, rank, world, dev, dist, sel)
     shard.close()
 
     if rank != 0:
@@ -344,7 +347,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "setup_s": {"expquad_panel_build": build_ms * 1e-3, "inverse_potrf_potri": factor_s,
                     "expquad_GBps": 8.0 * n * nloc / (build_ms * 1e-3) / 1e9 if build_ms > 0 else None,
-                    "inverse_tflops": (float(n) ** 3) / factor_s / 1e12 if factor_s > 0 else None},
+                    "inverse_tflops": (float(n) ** 3) / factor_s / 1e12 if factor_s > 0 else None,
+                    "inverse_distribution": dist_stats},
         "selection_head": [int(s) for s in sel[:8]], "scores_non_increasing": gaps_ok,
     }
     if world == 1 and not args.no_cpu:
@@ -467,6 +471,47 @@ def measure_e2e(args, shard, dev, expect_sel):
                         "total_wall": wall},
             "k": k, "selection_equals_resident_run": same,
             "api": "vgp_placement_host == vgposp_b200.placement_algorithm2.placement_algorithm_1(cov_vv, k)"}
+
+
+def measure_e2e_sharded(args, shard, rank, world, dev, dist, expect_sel):
+    """N > 1: every rank holds its ROW slab of Sigma in pinned host memory (n/G x n); one call to
+    vgposp_b200.greedy.place_sharded per rank does H2D, NVLink push, distributed inverse, k selections, D2H."""
+    import torch
+    from vgposp_b200 import greedy
+    from vgposp_b200._ffi import call
+    n, k = args.n, args.k
+    bounds = greedy.shard_bounds(n, world)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    rows = r1 - r0
+    host = ctypes.c_void_p()
+    call("vgp_host_alloc", rows * n * 8, ctypes.byref(host))
+    try:
+        # Sigma is symmetric: this rank's row slab is the transpose of its column panel (outside the timed region)
+        panel = np.empty((n, rows))
+        call("vgp_memcpy2d_d2h", dev, panel.ctypes.data, rows * 8, shard.cov_ptr, shard.ld * 8, rows * 8, n,
+             shard.stream)
+        shard.sync()
+        shard.close()
+        slab = np.ctypeslib.as_array(ctypes.cast(host, ctypes.POINTER(ctypes.c_double)), shape=(rows, n))
+        np.copyto(slab, panel.T)
+        del panel
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        sel, sc, secs = greedy.place_sharded(slab, n, k, rank, world, dist, dev, stream=shard.stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    finally:
+        call("vgp_host_free", host)
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda:%d" % dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    same = bool(np.array_equal(sel[:len(expect_sel)], expect_sel[:k]))
+    return {"value": k / wall, "unit": "selections/s", "h2d_bytes_per_step": 8.0 * n * n / k, "d2h_bytes_per_step": 16,
+            "seconds": dict(secs, total_wall_max_over_ranks=wall), "k": k, "selection_equals_resident_run": same,
+            "api": "vgposp_b200.greedy.place_sharded(row_slab, n, k, rank, world, torch.distributed, device): one "
+                   "process per GPU; allocation, IPC connect, H2D, NVLink push, distributed inverse, selections, D2H "
+                   "all inside the timed region (host wall clock, max over ranks)"}
 
 
 def main():

@@ -270,6 +270,27 @@ int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld
                        double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
                        double *seconds_host);
 
+/* ---------------------------------------------------------------- distributed SPD inverse (setup, 8e) ------- */
+/* P = Sigma^-1 over the GPUs of one box, one rank per GPU (process or thread).  Stands for the same pseudo-inverses
+ * as vgp_spd_inverse (placement_algorithm2.py:399-413) when the candidate set is sharded.  Every rank holds a
+ * full replica [n_pad][n_pad] (n_pad = n rounded up to 128, ld = n_pad) that the caller fills identically on all
+ * ranks (or on one rank followed by vgp_dist_push_rows + vgp_dist_barrier); the large GEMMs of potrf / trtri /
+ * lauum are split by output tile over the ranks and each finished tile is stored into every replica by the GEMM
+ * epilogue itself (peer stores over NVLink) -- the result in every replica is bitwise the single-GPU one.
+ *   create    allocates replica + barrier words; ipc_out (128 bytes, may be NULL) = their two cudaIpcMemHandle_t,
+ *             ptrs_out (void *[2], may be NULL) = their device addresses for ranks of the same process;
+ *   connect   peers: kind 0 = void *[nranks][2] device pointers, kind 1 = nranks x 128 bytes of IPC handles;
+ *   spd_inverse  collective (every rank calls it); blocking; the padding diagonal must hold ones. */
+typedef struct vgp_dist vgp_dist;
+int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t n, void *ipc_out, void **ptrs_out);
+int vgp_dist_destroy(vgp_dist *handle);
+int vgp_dist_matrix(vgp_dist *handle, double **matrix_dev, int64_t *ld);
+int vgp_dist_connect(vgp_dist *handle, const void *peers, int kind);
+int vgp_dist_push_rows(vgp_dist *handle, int64_t row0, int64_t row1, void *stream);
+int vgp_dist_barrier(vgp_dist *handle, void *stream);
+int vgp_dist_spd_inverse(vgp_dist *handle, int *info_host, void *stream);
+int vgp_dist_stats(vgp_dist *handle, int64_t *distributed_gemms, int64_t *barriers);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

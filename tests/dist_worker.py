@@ -1,0 +1,68 @@
+"""Launched by tests/test_gpu_dist_inverse.py under torch.distributed.run with two ranks (one per GPU): the
+distributed inverse across processes (replicas mapped through CUDA IPC), then the sharded greedy seeded from it."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle import greedy_oracle as go
+    from vgposp_b200 import _ffi, greedy
+    from vgposp_b200.dist_inverse import DistInverse
+    os.environ["VGP_DIST_MIN_TILES"] = "2"
+    os.environ["VGP_DIST_MIN_K"] = "256"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, k = 2500, 10
+    x = np.random.default_rng(9).uniform(-2, 2, (n, 3))
+    ls = 0.5 * (1000.0 / n) ** (1 / 3)
+    d = x[:, None, :] - x[None, :, :]
+    cov = np.exp(-np.einsum("ijk,ijk->ij", d, d) / (2 * ls * ls)) + 1e-2 * np.eye(n)
+    stream = torch.cuda.current_stream().cuda_stream
+    inv = DistInverse(n, rank, world, local, stream=stream)
+    inv.connect_torch(dist, "cuda:%d" % local)
+    inv.fill_padding()
+    bounds = greedy.shard_bounds(n, world)
+    inv.load_host(cov, bounds[rank], bounds[rank + 1])          # each rank uploads its row slab only
+    inv.push_rows(bounds[rank], bounds[rank + 1])
+    inv.invert()
+    assert inv.stats()["distributed_gemms"] > 0
+    got = inv.to_host()
+    # single-device inverse on this rank for the bitwise comparison
+    full = _ffi.DeviceArray.from_host(cov, local)
+    info = ctypes.c_int(0)
+    _ffi.call("vgp_spd_inverse", local, full.ptr, n, n, ctypes.byref(info), None)
+    want = full.to_host()
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_allclose(got @ cov, np.eye(n), atol=1e-9)
+    # seed the sharded greedy from the replica
+    shard = greedy.GreedyShard(n, bounds[rank], bounds[rank + 1], k, local, stream=stream)
+    shard.load_cov_host(cov)
+    shard.load_prec_device(inv.ptr, inv.ld)
+    shard.reset()
+    shard.sync()
+    greedy.connect_peers_torch(shard, rank, world, dist, "cuda:%d" % local)
+    shard.run_peer(k)
+    shard.comm_status()
+    sel, scores = shard.results()
+    want_sel, want_scores = go.incremental_greedy_c(cov, k)
+    assert [int(s) for s in sel] == want_sel, (rank, sel, want_sel)
+    np.testing.assert_allclose(scores, want_scores, rtol=1e-9)
+    dist.barrier()
+    shard.close()
+    inv.close()
+    if rank == 0:
+        print("DIST_WORKER_OK", [int(s) for s in sel], flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""GPU parity: the distributed SPD inverse (csrc/dist.cu) -- GEMM tiles split over ranks, every finished tile stored
+into all replicas by the GEMM epilogue -- must equal the single-device inverse bit for bit and NumPy's inverse to
+1e-9 (the pseudo-inverses of placement_algorithm2.py:399-413 on an SPD input)."""
+import ctypes
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from vgposp_b200 import _ffi
+from vgposp_b200.dist_inverse import DistInverse
+
+pytestmark = pytest.mark.gpu
+D = 0
+
+
+def spd(n, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-2, 2, (n, 3))
+    d = x[:, None, :] - x[None, :, :]
+    ls = 0.5 * (1000.0 / n) ** (1 / 3)
+    return np.exp(-np.einsum("ijk,ijk->ij", d, d) / (2 * ls * ls)) + 1e-2 * np.eye(n)
+
+
+def single_inverse(a):
+    n = a.shape[0]
+    d = _ffi.DeviceArray.from_host(a, D)
+    info = ctypes.c_int(0)
+    _ffi.call("vgp_spd_inverse", D, d.ptr, n, n, ctypes.byref(info), None)
+    out = d.to_host()
+    d.free()
+    return out
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("n,world", [(1000, 2), (1664, 3), (2050, 4)])
+def test_ranks_as_threads_one_device(n, world, monkeypatch):
+    """G ranks as threads of this process on one device (each with its own stream and replica)."""
+    monkeypatch.setenv("VGP_DIST_MIN_TILES", "2")
+    monkeypatch.setenv("VGP_DIST_MIN_K", "256")
+    a = spd(n, n)
+    want = single_inverse(a)
+    streams = []
+    for _ in range(world):
+        s = ctypes.c_void_p()
+        _ffi.call("vgp_stream_create", D, ctypes.byref(s))
+        streams.append(s)
+    ranks = [DistInverse(n, r, world, D, stream=streams[r]) for r in range(world)]
+    for r in ranks:
+        r.connect_pointers([q.pointers for q in ranks])
+        r.fill_padding()
+    # rank r uploads only its row slab and pushes it to the other replicas
+    bounds = [(n * g) // world for g in range(world + 1)]
+    for r in ranks:
+        r.load_host(a, bounds[r.rank], bounds[r.rank + 1])
+        r.push_rows(bounds[r.rank], bounds[r.rank + 1])
+    errors = []
+
+    def work(r):
+        try:
+            r.invert()
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in ranks]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=200)
+    assert not errors, errors
+    assert ranks[0].stats()["distributed_gemms"] > 0
+    for r in ranks:
+        got = r.to_host()
+        np.testing.assert_array_equal(got, want)            # same kernels, same summation order -> same bits
+    np.testing.assert_allclose(want @ a, np.eye(n), atol=1e-9)
+    for r in ranks:
+        r.close()
+    for s in streams:
+        _ffi.call("vgp_stream_destroy", D, s)
+
+
+@pytest.mark.timeout(300)
+def test_two_processes_ipc():
+    cnt = _ffi.c_int(0)
+    _ffi.call("vgp_device_count", ctypes.byref(cnt))
+    if cnt.value < 2:
+        pytest.skip("needs two CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "dist_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=root)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "DIST_WORKER_OK" in res.stdout

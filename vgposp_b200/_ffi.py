@@ -98,6 +98,14 @@ SIGNATURES = {
     "vgp_greedy_segments": [c_vp, c_vp, c_i64, c_vp],
     "vgp_greedy_apply": [c_vp, c_vp, c_i64, c_int, P(c_i64), c_vp],
     "vgp_greedy_run": [c_vp, c_i64, c_vp],
+    "vgp_dist_create": [P(c_vp), c_int, c_int, c_int, c_i64, c_vp, P(c_vp)],
+    "vgp_dist_destroy": [c_vp],
+    "vgp_dist_matrix": [c_vp, P(c_vp), P(c_i64)],
+    "vgp_dist_connect": [c_vp, c_vp, c_int],
+    "vgp_dist_push_rows": [c_vp, c_i64, c_i64, c_vp],
+    "vgp_dist_barrier": [c_vp, c_vp],
+    "vgp_dist_spd_inverse": [c_vp, P(c_int), c_vp],
+    "vgp_dist_stats": [c_vp, P(c_i64), P(c_i64)],
     "vgp_greedy_comm_create": [c_vp, c_int, c_int, P(c_i64), c_vp, P(c_vp)],
     "vgp_greedy_comm_connect": [c_vp, c_vp, c_int],
     "vgp_greedy_run_peer": [c_vp, c_i64, c_vp],

@@ -41,7 +41,53 @@ struct GemmArgs {
     int lower;
     int64_t k_split;         // k range handled by one blockIdx.z slice (== k without split-K)
     int64_t c_split_stride;  // element offset between the partial outputs of consecutive slices
+    // distributed mode (dist_n > 0): this launch covers the linear tile range [tile0, tile0 + gridDim.x) of the
+    // whole product and stores every finished tile into all dist_n replicas (c + delta[q])
+    int dist_n;
+    int64_t tile0, tiles_n;
+    int64_t delta[DIST_MAX];
 };
+
+thread_local DistContext *g_dist = nullptr;
+void dense_set_dist(DistContext *ctx) { g_dist = ctx; }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct DistFlags {
+    unsigned long long *f[DIST_MAX];
+};
+// Cross-rank barrier in stream order: everything enqueued before it on every rank (including peer stores) is
+// complete and visible before anything enqueued after it on any rank starts.
+__global__ void dist_barrier_kernel(DistFlags fl, int rank, int nranks, unsigned long long seq) {
+    const int q = threadIdx.x;
+    if (q >= nranks) return;
+    __threadfence_system();
+    st_release_sys_u64(fl.f[q] + rank, seq);
+    const unsigned long long *mine = fl.f[rank] + q;
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u64(mine) < seq) {
+        if (clock64() - t0 > 40000000000LL) {               // ~20 s: a peer died
+            atomicExch(reinterpret_cast<int *>(fl.f[rank] + DIST_MAX), 1 + q);
+            break;
+        }
+    }
+}
+
+int dense_dist_barrier(DistContext &ctx, cudaStream_t s) {
+    DistFlags fl;
+    for (int q = 0; q < DIST_MAX; ++q) fl.f[q] = q < ctx.nranks ? ctx.flags[q] : nullptr;
+    dist_barrier_kernel<<<1, 32, 0, s>>>(fl, ctx.rank, ctx.nranks, ++ctx.seq);
+    VGP_LAUNCH_CHECK();
+    ++ctx.barriers;
+    return VGP_OK;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -64,12 +110,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double smem[];
     int tm, tn;
     if (p.lower) {
-        const int64_t b = blockIdx.x;
+        const int64_t b = p.tile0 + blockIdx.x;
         int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
         while ((int64_t)r * (r + 1) / 2 > b) --r;
         while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
         tm = r;
         tn = (int)(b - (int64_t)r * (r + 1) / 2);
+    } else if (p.dist_n > 0) {
+        const int64_t b = p.tile0 + blockIdx.x;
+        tm = (int)(b / p.tiles_n);
+        tn = (int)(b % p.tiles_n);
     } else {
         tn = blockIdx.x;
         tm = blockIdx.y;
@@ -157,9 +207,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs p) {
                 o.x = p.alpha * acc[i][j][0];
                 o.y = p.alpha * acc[i][j][1];
             }
-            *dst = o;
+            if (p.dist_n > 0) {
+                for (int q = 0; q < p.dist_n; ++q) *(dst + (p.delta[q] >> 1)) = o;     // every replica, peers over NVLink
+            } else {
+                *dst = o;
+            }
         }
     }
+    if (p.dist_n > 0) __threadfence_system();
 }
 
 template <bool AKC, bool BKC>
@@ -173,6 +228,17 @@ static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
     }
     const int64_t tm = p.m / BM, tn = p.n / BN;
     const unsigned splits = (unsigned)((p.k + p.k_split - 1) / p.k_split);
+    if (p.dist_n > 0) {
+        // p.tiles_n carries this rank's tile count on entry and the tile-column count in the kernel
+        GemmArgs q = p;
+        const int64_t mine = p.tiles_n;
+        q.tiles_n = tn;
+        if (mine > 0) {
+            gemm_kernel<AKC, BKC><<<dim3((unsigned)mine, 1, 1), GEMM_THREADS, GEMM_SMEM, s>>>(q);
+            VGP_LAUNCH_CHECK();
+        }
+        return VGP_OK;
+    }
     if (p.lower) {
         const int64_t blocks = tm * (tm + 1) / 2;
         gemm_kernel<AKC, BKC><<<dim3((unsigned)blocks, 1, splits), GEMM_THREADS, GEMM_SMEM, s>>>(p);
@@ -203,7 +269,25 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
                 "dense_gemm: operands must be 16-byte aligned");
     VGP_REQUIRE(tiles == GEMM_FULL || m == n, "dense_gemm: lower-tile mode needs a square C");
     VGP_REQUIRE(m / BM <= 65535, "dense_gemm: too many row tiles");
-    GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0, k, 0};
+    GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0, k, 0, 0, 0, 0, {0}};
+    DistContext *dc = g_dist;
+    if (dc && dc->nranks > 1) {
+        const int64_t tm = m / BM, tn = n / BN;
+        const int64_t total = tiles == GEMM_LOWER ? tm * (tm + 1) / 2 : tm * tn;
+        const char *c0 = (const char *)c, *c1 = (const char *)(c + (m - 1) * ldc + n);
+        const bool inside = c0 >= (const char *)dc->base && c1 <= (const char *)dc->base + dc->bytes;
+        if (inside && total >= dc->min_tiles && k >= dc->min_k) {
+            const int64_t each = total / dc->nranks, rem = total % dc->nranks;
+            p.dist_n = dc->nranks;
+            p.tile0 = dc->rank * each + (dc->rank < rem ? dc->rank : rem);
+            p.tiles_n = each + (dc->rank < rem ? 1 : 0);          // this rank's tile count (see gemm_launch)
+            for (int q = 0; q < dc->nranks; ++q) p.delta[q] = dc->delta[q];
+            ++dc->dist_gemms;
+            VGP_TRY(dense_dist_barrier(*dc, s));                  // every rank is done with all earlier work
+            VGP_TRY(gemm_dispatch(trans_a, trans_b, p, s));
+            return dense_dist_barrier(*dc, s);                    // every tile has landed in every replica
+        }
+    }
     return gemm_dispatch(trans_a, trans_b, p, s);
 }
 
@@ -232,7 +316,8 @@ int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
     VGP_REQUIRE(tiles == GEMM_FULL || (m == n && beta == 0.0), "dense_gemm_splitk: lower mode needs square C, beta 0");
     int64_t k_split = round_up((k + splits - 1) / splits, BK);
     const int real_splits = (int)((k + k_split - 1) / k_split);
-    GemmArgs p{a, b, partial, lda, ldb, n, m, n, k, alpha, 0.0, tiles == GEMM_LOWER ? 1 : 0, k_split, m * n};
+    GemmArgs p{a, b, partial, lda, ldb, n, m, n, k, alpha, 0.0, tiles == GEMM_LOWER ? 1 : 0, k_split, m * n,
+               0, 0, 0, {0}};
     VGP_TRY(gemm_dispatch(trans_a, trans_b, p, s));
     splitk_reduce_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, s>>>(partial, m * n, real_splits, beta, c, ldc, m, n,
                                                                         tiles == GEMM_LOWER ? 1 : 0);
@@ -710,6 +795,35 @@ int dense_lauum(double *x, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream
     VGP_REQUIRE(n > 0 && n % NB == 0, "dense_lauum: unpadded size");
     VGP_TRY(ws.ensure(0));
     return lauum_rec(x, n, ld, s);
+}
+
+// Load every kernel of this file now (CUDA loads modules lazily, and a lazy load can wait on kernels that are
+// spinning on a peer's flag) and set the opt-in shared-memory sizes.
+template <bool AKC, bool BKC>
+static int gemm_preload_one() {
+    cudaFuncAttributes fa;
+    VGP_CUDA(cudaFuncSetAttribute(gemm_kernel<AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_kernel<AKC, BKC>));
+    return VGP_OK;
+}
+int dense_preload() {
+    cudaFuncAttributes fa;
+    VGP_TRY((gemm_preload_one<true, true>()));
+    VGP_TRY((gemm_preload_one<true, false>()));
+    VGP_TRY((gemm_preload_one<false, false>()));
+    VGP_TRY((gemm_preload_one<false, true>()));
+    VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
+    VGP_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, potf2_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, trtri_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, lauum_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, block_copy_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, mirror_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, zero_upper_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, add_diag_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, dist_barrier_kernel));
+    return VGP_OK;
 }
 
 int dense_read_info(DenseWorkspace &ws, int *info_host, cudaStream_t s) {

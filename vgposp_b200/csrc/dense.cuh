@@ -16,6 +16,28 @@ struct DenseWorkspace {
     void release();
 };
 
+// Replicated-matrix distribution of the O(n^3) work over the GPUs of one box (setup row).
+// Every rank holds a full replica of the matrix being factorised.  A GEMM whose output lies inside the replica
+// and that is large enough is split by output tiles over the ranks, and the epilogue of the GEMM kernel stores
+// each finished tile into EVERY replica (peer stores over NVLink/NVSwitch): the all-gather is fused into the
+// GEMM, tile by tile.  Everything else (diagonal-block kernels, small GEMMs) runs redundantly on every rank.
+// Each output element is produced by exactly one rank with the same kernel and summation order as on one GPU,
+// so all replicas stay bitwise identical to the single-GPU result.
+constexpr int DIST_MAX = 8;
+struct DistContext {
+    int rank = 0, nranks = 1;
+    double *base = nullptr;                 // this rank's replica
+    size_t bytes = 0;
+    int64_t delta[DIST_MAX] = {0};          // replica base of rank q minus `base`, in doubles
+    unsigned long long *flags[DIST_MAX] = {nullptr};   // barrier flags of rank q (peer-mapped): u64[DIST_MAX] + error
+    unsigned long long seq = 0;
+    int64_t min_tiles = 296, min_k = 512;   // distribute a GEMM only above these (two waves of 148 SMs; NVLink-safe k)
+    int64_t dist_gemms = 0, barriers = 0;
+};
+void dense_set_dist(DistContext *ctx);      // thread-local; nullptr switches distribution off
+int dense_dist_barrier(DistContext &ctx, cudaStream_t s);
+int dense_preload();                        // load all dense kernels, set shared-memory opt-ins (current device)
+
 enum GemmTiles { GEMM_FULL = 0, GEMM_LOWER = 1 };   // LOWER: only tiles with tile_row >= tile_col
 
 // C[m,n] = alpha op(A) op(B) + beta C.  trans_a == 0: A stored [m][k]; 1: stored [k][m].

@@ -1,0 +1,238 @@
+// Distributed SPD inverse over the GPUs of one box ("Setup (Sigma -> P)").
+//
+// The reference inverts on one CPU (np.linalg.pinv inside every denominator, placement_algorithm2.py:399-413);
+// the single-GPU path here is dense_spd_inverse (potrf + trtri + lauum, dense.cu).  This file spreads that same
+// recursion over G ranks, one process (or thread) per GPU:
+//
+//   * every rank owns a full replica [n_pad][n_pad] of the matrix (20 GB at n = 50k, 80 GB at n = 100k -- sized
+//     for 180 GB of HBM3e next to the 10 + 10 GB greedy panels);
+//   * every large GEMM of the recursion is split by output tiles over the ranks and its epilogue stores each
+//     tile into all replicas through peer-mapped pointers (NVLink/NVSwitch) -- compute and all-gather in one
+//     kernel (dense.cu, DistContext); a flag barrier in stream order separates dependent operations;
+//   * diagonal-block kernels and small GEMMs run redundantly, so the replicas never diverge, and because every
+//     element is produced by the same kernel with the same summation order as on one GPU, the result is
+//     bitwise identical to dense_spd_inverse.
+//
+// Replicas and flag words are plain cudaMalloc allocations, exported with CUDA IPC for other processes.
+#include <string.h>
+
+#include <new>
+
+#include "dense.cuh"
+
+using namespace vgp;
+
+struct vgp_dist {
+    int device = 0;
+    int64_t n_pad = 0;
+    double *matrix = nullptr;
+    unsigned long long *flags = nullptr;        // u64[DIST_MAX] barrier words + int error
+    double *peer_matrix[DIST_MAX] = {nullptr};
+    int ipc = 0, connected = 0;
+    DistContext ctx;
+    DenseWorkspace ws;
+};
+
+namespace {
+constexpr size_t FLAG_BYTES = 8 * (DIST_MAX + 1);
+
+int check(vgp_dist *h) {
+    if (!h) {
+        set_error("dist handle is NULL");
+        return VGP_ERR_INVALID;
+    }
+    return VGP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t n, void *ipc_out,
+                    void **ptrs_out) {
+    VGP_REQUIRE(handle, "handle is NULL");
+    *handle = nullptr;
+    VGP_REQUIRE(nranks >= 1 && nranks <= DIST_MAX && rank >= 0 && rank < nranks, "bad rank %d of %d (max %d ranks)",
+                rank, nranks, DIST_MAX);
+    VGP_REQUIRE(n > 0, "bad size");
+    VGP_ENTER(device);
+    vgp_dist *h = new (std::nothrow) vgp_dist();
+    VGP_REQUIRE(h, "out of host memory");
+    h->device = device;
+    h->n_pad = round_up(n, TILE);
+    h->ctx.rank = rank;
+    h->ctx.nranks = nranks;
+    const size_t bytes = (size_t)h->n_pad * h->n_pad * 8;
+    cudaError_t e = cudaMalloc((void **)&h->matrix, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->flags, FLAG_BYTES);
+    if (e == cudaSuccess) e = cudaMemset(h->flags, 0, FLAG_BYTES);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(e, "replica allocation", __FILE__, __LINE__);
+        vgp_dist_destroy(h);
+        return rc;
+    }
+    h->ctx.base = h->matrix;
+    h->ctx.bytes = bytes;
+    // a GEMM tile of depth k costs 2*128*128*k flop and ships 128 KB to each of the other ranks: keep the
+    // stores of one SM below its share of the NVLink egress (900 GB/s) -> k >= 256 per rank
+    h->ctx.min_k = 256 * (nranks > 2 ? nranks : 2);
+    // everything that could allocate, free or load a module later happens now, before any rank can be spinning
+    int rc0 = dense_preload();
+    if (rc0 == VGP_OK) rc0 = h->ws.ensure(h->n_pad / TILE);
+    if (rc0 != VGP_OK) {
+        vgp_dist_destroy(h);
+        return rc0;
+    }
+    if (ipc_out) {
+        cudaIpcMemHandle_t a, b;
+        e = cudaIpcGetMemHandle(&a, h->matrix);
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(&b, h->flags);
+        if (e != cudaSuccess) {
+            int rc = cuda_fail(e, "cudaIpcGetMemHandle", __FILE__, __LINE__);
+            vgp_dist_destroy(h);
+            return rc;
+        }
+        memcpy(ipc_out, &a, sizeof a);
+        memcpy((char *)ipc_out + sizeof a, &b, sizeof b);
+    }
+    if (ptrs_out) {
+        ptrs_out[0] = h->matrix;
+        ptrs_out[1] = h->flags;
+    }
+    *handle = h;
+    return VGP_OK;
+}
+
+int vgp_dist_matrix(vgp_dist *h, double **matrix_dev, int64_t *ld) {
+    VGP_TRY(check(h));
+    if (matrix_dev) *matrix_dev = h->matrix;
+    if (ld) *ld = h->n_pad;
+    return VGP_OK;
+}
+
+int vgp_dist_connect(vgp_dist *h, const void *peers, int kind) {
+    VGP_TRY(check(h));
+    VGP_REQUIRE(peers && (kind == 0 || kind == 1), "bad arguments");
+    VGP_ENTER(h->device);
+    const int G = h->ctx.nranks, me = h->ctx.rank;
+    for (int q = 0; q < G; ++q) {
+        double *pm;
+        unsigned long long *pf;
+        if (q == me) {
+            pm = h->matrix;
+            pf = h->flags;
+        } else if (kind == 0) {
+            void *const *pp = (void *const *)peers;
+            pm = (double *)pp[2 * q];
+            pf = (unsigned long long *)pp[2 * q + 1];
+            VGP_REQUIRE(pm && pf, "peer %d pointers are NULL", q);
+            int peer_dev = -1;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, pm) == cudaSuccess) peer_dev = at.device;
+            if (peer_dev >= 0 && peer_dev != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(peer_dev, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+                cudaGetLastError();
+            }
+        } else {
+            cudaIpcMemHandle_t a, b;
+            const char *src = (const char *)peers + (size_t)q * 2 * sizeof a;
+            memcpy(&a, src, sizeof a);
+            memcpy(&b, src + sizeof a, sizeof b);
+            void *va = nullptr, *vb = nullptr;
+            VGP_CUDA(cudaIpcOpenMemHandle(&va, a, cudaIpcMemLazyEnablePeerAccess));
+            VGP_CUDA(cudaIpcOpenMemHandle(&vb, b, cudaIpcMemLazyEnablePeerAccess));
+            pm = (double *)va;
+            pf = (unsigned long long *)vb;
+        }
+        h->peer_matrix[q] = pm;
+        h->ctx.delta[q] = pm - h->matrix;
+        h->ctx.flags[q] = pf;
+        VGP_REQUIRE(h->ctx.delta[q] % 2 == 0, "peer replica is not 16-byte congruent");
+    }
+    h->ipc = kind;
+    h->connected = 1;
+    return VGP_OK;
+}
+
+// Push rows [r0, r1) of this rank's replica into every other replica (peer copies), e.g. after a host upload
+// that only this rank performed.  Follow with vgp_dist_barrier on all ranks.
+int vgp_dist_push_rows(vgp_dist *h, int64_t r0, int64_t r1, void *stream) {
+    VGP_TRY(check(h));
+    VGP_REQUIRE(h->connected, "vgp_dist_connect first");
+    VGP_REQUIRE(r0 >= 0 && r1 >= r0 && r1 <= h->n_pad, "bad row range");
+    if (r1 == r0) return VGP_OK;
+    VGP_ENTER(h->device);
+    const size_t off = (size_t)r0 * h->n_pad, count = (size_t)(r1 - r0) * h->n_pad * 8;
+    for (int q = 0; q < h->ctx.nranks; ++q) {
+        if (q == h->ctx.rank) continue;
+        VGP_CUDA(cudaMemcpyAsync(h->peer_matrix[q] + off, h->matrix + off, count, cudaMemcpyDefault,
+                                 (cudaStream_t)stream));
+    }
+    return VGP_OK;
+}
+
+int vgp_dist_barrier(vgp_dist *h, void *stream) {
+    VGP_TRY(check(h));
+    VGP_REQUIRE(h->connected, "vgp_dist_connect first");
+    VGP_ENTER(h->device);
+    if (h->ctx.nranks == 1) return VGP_OK;
+    return dense_dist_barrier(h->ctx, (cudaStream_t)stream);
+}
+
+int vgp_dist_spd_inverse(vgp_dist *h, int *info_host, void *stream) {
+    VGP_TRY(check(h));
+    VGP_REQUIRE(h->connected || h->ctx.nranks == 1, "vgp_dist_connect first");
+    if (info_host) *info_host = 0;
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const char *env = getenv("VGP_DIST_MIN_TILES");
+    if (env && *env) h->ctx.min_tiles = atoll(env);
+    env = getenv("VGP_DIST_MIN_K");
+    if (env && *env) h->ctx.min_k = atoll(env);
+    if (h->ctx.min_k < 2 * TILE) h->ctx.min_k = 2 * TILE;      // the k = 128 leaf GEMMs update their operand in place
+    dense_set_dist(h->ctx.nranks > 1 ? &h->ctx : nullptr);
+    int rc = VGP_OK;
+    if (h->ctx.nranks > 1) rc = dense_dist_barrier(h->ctx, s);      // every replica is filled
+    if (rc == VGP_OK) rc = dense_spd_inverse(h->matrix, h->n_pad, h->n_pad, h->ws, info_host, s);
+    if (rc == VGP_OK && h->ctx.nranks > 1) rc = dense_dist_barrier(h->ctx, s);
+    dense_set_dist(nullptr);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (rc == VGP_OK && e != cudaSuccess) rc = cuda_fail(e, "distributed inverse", __FILE__, __LINE__);
+    if (rc == VGP_OK && h->ctx.nranks > 1) {
+        int err = 0;
+        VGP_CUDA(cudaMemcpy(&err, h->flags + DIST_MAX, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err != 0) {
+            set_error("distributed inverse: barrier timed out waiting for rank %d", err - 1);
+            rc = VGP_ERR_STATE;
+        }
+    }
+    return rc;
+}
+
+int vgp_dist_stats(vgp_dist *h, int64_t *dist_gemms, int64_t *barriers) {
+    VGP_TRY(check(h));
+    if (dist_gemms) *dist_gemms = h->ctx.dist_gemms;
+    if (barriers) *barriers = h->ctx.barriers;
+    return VGP_OK;
+}
+
+int vgp_dist_destroy(vgp_dist *h) {
+    if (!h) return VGP_OK;
+    VGP_ENTER(h->device);
+    if (h->ipc && h->connected) {
+        for (int q = 0; q < h->ctx.nranks; ++q) {
+            if (q == h->ctx.rank) continue;
+            if (h->peer_matrix[q]) cudaIpcCloseMemHandle(h->peer_matrix[q]);
+            if (h->ctx.flags[q]) cudaIpcCloseMemHandle(h->ctx.flags[q]);
+        }
+    }
+    if (h->matrix) cudaFree(h->matrix);
+    if (h->flags) cudaFree(h->flags);
+    h->ws.release();
+    delete h;
+    return VGP_OK;
+}
+
+}  // extern "C"
