@@ -353,6 +353,14 @@ def run_ours(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_greedy(n, int(os.environ.get("VGP_BENCH_CPU_N", 8192)), 20, 2)
+    if world == 1 and not args.no_lazy:
+        try:
+            line["lazy_column"] = measure_lazy(args, dev, hbm_peak)
+            line["lazy_column"]["selections_equal_dense"] = all(
+                v["selection_head"] == line["selection_head"] for v in line["lazy_column"].values()
+                if isinstance(v, dict) and "selection_head" in v)
+        except Exception as e:      # noqa: BLE001
+            line["lazy_column"] = {"error": repr(e)}
     if world == 1 and not args.no_elbo:
         try:
             line["elbo"] = measure_elbo(dev, not args.no_cpu)
@@ -460,17 +468,88 @@ def measure_e2e(args, shard, dev, expect_sel):
         sc = np.zeros(k)
         secs = np.zeros(4)
         t0 = time.perf_counter()
-        call("vgp_placement_host", dev, host, n, n, k, 1e-8, 0.0, sel.ctypes.data, sc.ctypes.data, None,
-             secs.ctypes.data)
+        from vgposp_b200.greedy import FORMULATIONS
+        call("vgp_placement_host_ex", dev, host, n, n, k, 1e-8, 0.0, FORMULATIONS[args.e2e_formulation],
+             sel.ctypes.data, sc.ctypes.data, None, secs.ctypes.data)
         wall = time.perf_counter() - t0
     finally:
         call("vgp_host_free", host)
     same = bool(np.array_equal(sel[:len(expect_sel)], expect_sel[:k]))
     return {"value": k / secs[3], "unit": "selections/s", "h2d_bytes_per_step": nbytes / k, "d2h_bytes_per_step": 16,
-            "seconds": {"h2d": secs[0], "inverse": secs[1], "selections_and_d2h": secs[2], "total_events": secs[3],
-                        "total_wall": wall},
+            "seconds": {"h2d": secs[0], "factorisation": secs[1], "selections_and_d2h": secs[2],
+                        "total_events": secs[3], "total_wall": wall},
+            "formulation": args.e2e_formulation if args.e2e_formulation != "auto" else
+            ("auto -> lazy_factor (potrf + trtri, trigemv per selection)" if 35 * k < n else
+             "auto -> lazy_precision (potrf + trtri + lauum)"),
             "k": k, "selection_equals_resident_run": same,
-            "api": "vgp_placement_host == vgposp_b200.placement_algorithm2.placement_algorithm_1(cov_vv, k)"}
+            "api": "vgp_placement_host_ex == vgposp_b200.placement_algorithm2.placement_algorithm_1(cov_vv, k)"}
+
+
+def measure_lazy(args, dev, hbm_peak):
+    """Resident-state selections/s of the lazy-column formulation (csrc/lazy.cu), both modes, same workload.
+    Not the headline `value` (that is the north-star dense downdate); this is what `e2e` runs on."""
+    import torch
+    from vgposp_b200 import _ffi, greedy
+    from vgposp_b200._ffi import call
+    n = args.n
+    x, amp, ls, nugget = workload(n)
+    xd = _ffi.DeviceArray.from_host(x, dev)
+    steps, warm = args.steps, args.warmup
+    out = {}
+    for mode, name in ((1, "lazy_factor"), (0, "lazy_precision")):
+        h = greedy.LazyGreedy(n, steps + warm, dev, mode=mode)
+        h.build_cov_expquad(xd.ptr, 3, amp, ls, nugget)
+        h.sync()
+        t0 = time.perf_counter()
+        h.factor()
+        h.sync()
+        factor_s = time.perf_counter() - t0
+        h.run(warm)
+        h.sync()
+        h.reset()
+        h.sync()
+        l0 = h.launch_count()
+        e0, e1, ms = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_float()
+        call("vgp_event_record", dev, None, ctypes.byref(e0))
+        h.run(steps)
+        call("vgp_event_record", dev, None, ctypes.byref(e1))
+        h.sync()
+        call("vgp_event_elapsed_ms", dev, e0, e1, ctypes.byref(ms))
+        sel, scores = h.results()
+        launches = h.launch_count() - l0
+        n_pad = h.n_pad
+        rec = {"value": steps / (ms.value * 1e-3), "unit": "selections/s", "ms_per_step": ms.value / steps,
+               "gpu_launches": int(launches), "setup_s": factor_s,
+               "setup_flop": (2.0 if mode == 1 else 3.0) / 3.0 * float(n) ** 3,
+               "setup_tflops": (2.0 if mode == 1 else 3.0) / 3.0 * float(n) ** 3 / factor_s / 1e12,
+               "selection_head": [int(v) for v in sel[:8]]}
+        if mode == 1:
+            # trigemv_kernel: rows i >= y of the lower triangle of M, once: 8 * sum_{i >= y} (i + 1) bytes
+            h.reset()
+            h.profile(True)
+            h.run(steps)
+            h.sync()
+            tms, cnt = h.profile(False)
+            ys = np.asarray(sel[:steps - 1], dtype=np.float64)       # launch t streams the column of winner t - 1
+            algo = float(np.sum(4.0 * (float(n_pad) * (n_pad + 1) - ys * (ys + 1))))
+            rec["roofline"] = {"bound": "hbm", "kernel": "trigemv_kernel", "achieved": algo / (tms * 1e-3) / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s", "frac": algo / (tms * 1e-3) / 1e9 / hbm_peak,
+                               "algorithmic_bytes_per_launch": algo / max(cnt, 1), "kernel_ms_avg": tms / max(cnt, 1),
+                               "kernel_launches_timed": int(cnt),
+                               "kernel_share_of_step": tms / ms.value if ms.value > 0 else None, "traffic": None}
+        else:
+            t = np.arange(steps, dtype=np.float64)
+            algo = float(np.sum(8.0 * n * (2.0 * np.maximum(t - 1, 0) + 6.0)))
+            rec["roofline"] = {"bound": "hbm (latency-limited at these sizes)", "kernel": "lazy_step_kernel",
+                               "achieved": algo / (ms.value * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": algo / (ms.value * 1e-3) / 1e9 / hbm_peak,
+                               "algorithmic_bytes_per_launch": algo / steps, "kernel_ms_avg": ms.value / steps,
+                               "kernel_launches_timed": steps, "traffic": None}
+        h.close()
+        out[name] = rec
+    xd.free()
+    torch.cuda.synchronize()
+    return out
 
 
 def measure_e2e_sharded(args, shard, rank, world, dev, dist, expect_sel):
@@ -527,6 +606,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-elbo", action="store_true")
+    ap.add_argument("--no-lazy", action="store_true")
+    ap.add_argument("--e2e-formulation", default="auto", choices=["auto", "dense", "lazy_precision", "lazy_factor"])
     args = ap.parse_args()
     if args.k is None:
         args.k = args.steps

@@ -263,9 +263,41 @@ int vgp_greedy_launch_count(vgp_greedy *handle, int64_t *launches);
 int vgp_greedy_profile(vgp_greedy *handle, int enable);
 int vgp_greedy_profile_read(vgp_greedy *handle, double *total_ms, int64_t *launches);
 
+/* ---------------------------------------------------------------- greedy placement, lazy-column formulation -- */
+/* Same selections and scores as the vgp_greedy_* path (placement_algorithm2.py:105-145, :151-219, :371-413), but
+ * the precision of the unselected set is never rewritten: each step replays the rank-1 history on the winner's
+ * column only (SURVEY.md 8d "lazy-column formulation").  Single device, all candidates.
+ *   mode 0  P_0 = Sigma^-1 resident (potrf + trtri + lauum); scores bitwise equal to the dense downdate;
+ *   mode 1  only M = L^-1 resident (potrf + trtri = 2/3 of the flops); P_0[:, y] = M^T M e_y per selection by a
+ *           triangular matrix-vector kernel that streams rows >= y of M once (HBM-bound).
+ * matrices: cov_dev [n_pad][ld] is filled by the caller (rows/columns >= n zero) before vgp_lazy_factor;
+ * adopt_factor: the caller filled factor_dev itself (P_0 or M for the handle's mode). */
+typedef struct vgp_lazy vgp_lazy;
+int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, double small, double jitter, int mode);
+int vgp_lazy_destroy(vgp_lazy *handle);
+int vgp_lazy_matrices(vgp_lazy *handle, double **cov_dev, double **factor_dev, int64_t *ld);
+int vgp_lazy_factor(vgp_lazy *handle, int *info_host, void *stream);
+int vgp_lazy_adopt_factor(vgp_lazy *handle, void *stream);
+int vgp_lazy_reset(vgp_lazy *handle, void *stream);
+int vgp_lazy_run(vgp_lazy *handle, int64_t k, void *stream);
+int vgp_lazy_results(vgp_lazy *handle, int64_t *count, int64_t *selection_host, double *scores_host,
+                     int64_t capacity, void *stream);
+int vgp_lazy_record_scores(vgp_lazy *handle, int enable);
+int vgp_lazy_step_scores(vgp_lazy *handle, double *scores_host, int64_t capacity_rows, void *stream);
+int vgp_lazy_launch_count(vgp_lazy *handle, int64_t *launches);
+/* Returns the summed duration / count of the trigemv launches since profiling was last enabled, then sets it. */
+int vgp_lazy_profile(vgp_lazy *handle, int enable, double *total_ms, int64_t *launches);
+
 /* One-call form of placement_algorithm_1/2(cov_vv, k) (placement_algorithm2.py:128,151) for a HOST matrix:
  * H2D, factor, k selections, D2H.  cov_host [n, ld_host] row-major float64 (pageable or pinned).
- * seconds_host (optional, may be NULL): [h2d, factor, select, total] wall seconds measured with CUDA events. */
+ * seconds_host (optional, may be NULL): [h2d, factor, select, total] wall seconds measured with CUDA events.
+ * formulation: DENSE = precision downdate (vgp_greedy_*), LAZY_PRECISION / LAZY_FACTOR = vgp_lazy_* mode 0 / 1,
+ * AUTO = LAZY_FACTOR when 35 k < n (its cheaper setup wins), else LAZY_PRECISION.  vgp_placement_host == AUTO. */
+enum { VGP_FORMULATION_AUTO = -1, VGP_FORMULATION_DENSE = 0, VGP_FORMULATION_LAZY_PRECISION = 1,
+       VGP_FORMULATION_LAZY_FACTOR = 2 };
+int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
+                          double jitter, int formulation, int64_t *selection_host, double *scores_host,
+                          double *step_scores_host, double *seconds_host);
 int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
                        double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
                        double *seconds_host);

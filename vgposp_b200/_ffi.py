@@ -117,6 +117,19 @@ SIGNATURES = {
     "vgp_greedy_profile": [c_vp, c_int],
     "vgp_greedy_profile_read": [c_vp, P(c_dbl), P(c_i64)],
     "vgp_placement_host": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp],
+    "vgp_placement_host_ex": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgp_lazy_create": [P(c_vp), c_int, c_i64, c_i64, c_dbl, c_dbl, c_int],
+    "vgp_lazy_destroy": [c_vp],
+    "vgp_lazy_matrices": [c_vp, P(c_vp), P(c_vp), P(c_i64)],
+    "vgp_lazy_factor": [c_vp, P(c_int), c_vp],
+    "vgp_lazy_adopt_factor": [c_vp, c_vp],
+    "vgp_lazy_reset": [c_vp, c_vp],
+    "vgp_lazy_run": [c_vp, c_i64, c_vp],
+    "vgp_lazy_results": [c_vp, P(c_i64), c_vp, c_vp, c_i64, c_vp],
+    "vgp_lazy_record_scores": [c_vp, c_int],
+    "vgp_lazy_step_scores": [c_vp, c_vp, c_i64, c_vp],
+    "vgp_lazy_launch_count": [c_vp, P(c_i64)],
+    "vgp_lazy_profile": [c_vp, c_int, P(c_dbl), P(c_i64)],
 }
 _RESTYPES = {"vgp_last_error": ctypes.c_char_p}
 _NO_STATUS = {"vgp_abi_version", "vgp_last_error"}

@@ -956,9 +956,10 @@ int vgp_greedy_launch_count(vgp_greedy *h, int64_t *launches) {
     return VGP_OK;
 }
 
-int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
-                       double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
-                       double *seconds_host) {
+// formulation 0 of vgp_placement_host_ex (lazy.cu): the dense precision downdate
+int vgp_placement_host_dense(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
+                             double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
+                             double *seconds_host) {
     VGP_REQUIRE(cov_host && selection_host, "NULL argument");
     VGP_REQUIRE(n > 0 && ld_host >= n && k > 0 && k <= n, "bad sizes n=%lld ld=%lld k=%lld", (long long)n,
                 (long long)ld_host, (long long)k);

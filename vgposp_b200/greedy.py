@@ -183,6 +183,91 @@ class GreedyShard:
             pass
 
 
+class LazyGreedy:
+    """Lazy-column greedy on one device (csrc/lazy.cu): mode 0 keeps P_0 = Sigma^-1 resident, mode 1 only the
+    inverse Cholesky factor.  Same results as GreedyShard.run; the precision is never rewritten."""
+
+    def __init__(self, n, kmax, device=0, small=GUARD_NUMPY, jitter=0.0, mode=0, stream=None):
+        _ffi.require_device(device)
+        self.n, self.kmax, self.device, self.stream, self.mode = int(n), int(kmax), device, stream, int(mode)
+        h = c_vp()
+        call("vgp_lazy_create", ctypes.byref(h), device, self.n, self.kmax, float(small), float(jitter), self.mode)
+        self.handle = h.value
+        cov, fac, ld = c_vp(), c_vp(), c_i64()
+        call("vgp_lazy_matrices", self.handle, ctypes.byref(cov), ctypes.byref(fac), ctypes.byref(ld))
+        self.cov_ptr, self.fac_ptr, self.ld = cov.value, fac.value, ld.value
+        self.n_pad = self.ld
+
+    def load_cov_host(self, cov_vv):
+        a = np.asarray(cov_vv)
+        if a.dtype != np.float64 or a.strides[1] != 8:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == (self.n, self.n), "cov_vv must be [n, n]"
+        call("vgp_memcpy2d_h2d", self.device, self.cov_ptr, self.ld * 8, a.ctypes.data, a.strides[0], self.n * 8,
+             self.n, self.stream)
+        call("vgp_stream_sync", self.device, self.stream)
+
+    def build_cov_expquad(self, x_dev_ptr, d, amplitude, length_scale, nugget):
+        call("vgp_expquad_matrix", self.device, x_dev_ptr, self.n, x_dev_ptr, self.n, d, float(amplitude),
+             float(length_scale), float(nugget), 0, self.cov_ptr, self.ld, self.stream)
+
+    def factor(self):
+        info = c_int(0)
+        call("vgp_lazy_factor", self.handle, ctypes.byref(info), self.stream)
+
+    def adopt_factor(self):
+        call("vgp_lazy_adopt_factor", self.handle, self.stream)
+
+    def reset(self):
+        call("vgp_lazy_reset", self.handle, self.stream)
+
+    def record_scores(self, enable=True):
+        call("vgp_lazy_record_scores", self.handle, 1 if enable else 0)
+
+    def run(self, k):
+        call("vgp_lazy_run", self.handle, int(k), self.stream)
+
+    def results(self):
+        count = c_i64(0)
+        sel = np.full(self.kmax, -1, dtype=np.int64)
+        sc = np.zeros(self.kmax, dtype=np.float64)
+        call("vgp_lazy_results", self.handle, ctypes.byref(count), sel.ctypes.data, sc.ctypes.data, self.kmax,
+             self.stream)
+        return sel[:count.value], sc[:count.value]
+
+    def step_scores(self):
+        sel, _ = self.results()
+        out = np.empty((len(sel), self.n), dtype=np.float64)
+        if len(sel):
+            call("vgp_lazy_step_scores", self.handle, out.ctypes.data, len(sel), self.stream)
+        return out
+
+    def launch_count(self):
+        c = c_i64(0)
+        call("vgp_lazy_launch_count", self.handle, ctypes.byref(c))
+        return c.value
+
+    def profile(self, enable):
+        """Returns (summed trigemv ms, launches) since profiling was last enabled, then switches it."""
+        ms, cnt = ctypes.c_double(0), c_i64(0)
+        call("vgp_lazy_profile", self.handle, 1 if enable else 0, ctypes.byref(ms), ctypes.byref(cnt))
+        return ms.value, cnt.value
+
+    def sync(self):
+        call("vgp_stream_sync", self.device, self.stream)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            call("vgp_lazy_destroy", self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def check_selection(sel):
     """The reference crashes with `ValueError: list.remove(x): x not in list` when no candidate scores above
     -1 (placement_algorithm2.py:144 after argmax_ returned -1); keep that failure mode."""
@@ -190,9 +275,14 @@ def check_selection(sel):
         raise ValueError("list.remove(x): x not in list")
 
 
-def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_scores=False):
+FORMULATIONS = {"auto": -1, "dense": 0, "lazy_precision": 1, "lazy_factor": 2}     # VGP_FORMULATION_*
+
+
+def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_scores=False, formulation="auto"):
     """placement_algorithm_1/2(cov_vv, k) for a host matrix on one device: one C-ABI call
-    (H2D, potrf+potri, k selections, D2H).  Returns (selection, scores, step_scores or None, seconds)."""
+    (H2D, factorisation, k selections, D2H).  Returns (selection, scores, step_scores or None, seconds).
+    formulation: "dense" (precision downdate, north-star formulation), "lazy_precision", "lazy_factor"
+    (csrc/lazy.cu) or "auto" (lazy_factor when 35 k < n, else lazy_precision)."""
     _ffi.require_device(device)
     a = np.asarray(cov_vv)
     if a.ndim != 2 or a.shape[0] != a.shape[1]:
@@ -209,8 +299,9 @@ def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_s
     sc = np.zeros(k)
     steps = np.empty((k, n)) if want_step_scores else None
     secs = np.zeros(4)
-    call("vgp_placement_host", device, a.ctypes.data, n, a.strides[0] // 8, k, float(small), float(jitter),
-         sel.ctypes.data, sc.ctypes.data, steps.ctypes.data if want_step_scores else None, secs.ctypes.data)
+    call("vgp_placement_host_ex", device, a.ctypes.data, n, a.strides[0] // 8, k, float(small), float(jitter),
+         FORMULATIONS[formulation], sel.ctypes.data, sc.ctypes.data,
+         steps.ctypes.data if want_step_scores else None, secs.ctypes.data)
     check_selection(sel)
     return sel, sc, steps, secs
 
