@@ -566,14 +566,17 @@ def measure_e2e_sharded(args, shard, rank, world, dev, dist, expect_sel):
     call("vgp_host_alloc", rows * n * 8, ctypes.byref(host))
     try:
         # Sigma is symmetric: this rank's row slab is the transpose of its column panel (outside the timed region)
-        panel = np.empty((n, rows))
-        call("vgp_memcpy2d_d2h", dev, panel.ctypes.data, rows * 8, shard.cov_ptr, shard.ld * 8, rows * 8, n,
-             shard.stream)
-        shard.sync()
-        shard.close()
+        # (chunks of 4096 panel rows: the temporary stays small next to the 8 n^2 / G byte slab)
         slab = np.ctypeslib.as_array(ctypes.cast(host, ctypes.POINTER(ctypes.c_double)), shape=(rows, n))
-        np.copyto(slab, panel.T)
-        del panel
+        chunk = np.empty((4096, rows))
+        for i in range(0, n, 4096):
+            h = min(4096, n - i)
+            call("vgp_memcpy2d_d2h", dev, chunk.ctypes.data, rows * 8, shard.cov_ptr + i * shard.ld * 8,
+                 shard.ld * 8, rows * 8, h, shard.stream)
+            shard.sync()
+            slab[:, i:i + h] = chunk[:h].T
+        del chunk
+        shard.close()
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
