@@ -602,7 +602,9 @@ def main():
     ap.add_argument("--steps", type=int, default=K_FULL)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL, help="candidate count (default: the BASELINE workload)")
+    ap.add_argument("--n", type=int, default=int(os.environ.get("VGP_BENCH_N", N_FULL)),
+                    help="candidate count (default: the BASELINE workload; VGP_BENCH_N overrides it under torchrun, "
+                         "whose own parser claims a bare --n)")
     ap.add_argument("--k", type=int, default=None, help="selections of the e2e call (default: --steps)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: per-selection exchange through peer-memory mailboxes (default) or two NCCL all-gathers")
