@@ -290,7 +290,10 @@ int vgp_lazy_profile(vgp_lazy *handle, int enable, double *total_ms, int64_t *la
 
 /* One-call form of placement_algorithm_1/2(cov_vv, k) (placement_algorithm2.py:128,151) for a HOST matrix:
  * H2D, factor, k selections, D2H.  cov_host [n, ld_host] row-major float64 (pageable or pinned).
- * seconds_host (optional, may be NULL): [h2d, factor, select, total] wall seconds measured with CUDA events.
+ * seconds_host (optional, may be NULL): [h2d, factor, select, total] seconds measured with CUDA events.  In the lazy
+ * formulations cov_vv must be symmetric and only its lower triangle is read: it is copied in row chunks on a copy
+ * stream while the Cholesky of the leading blocks already runs (h2d and factor then both start at the first byte and
+ * overlap; total is not their sum).
  * formulation: DENSE = precision downdate (vgp_greedy_*), LAZY_PRECISION / LAZY_FACTOR = vgp_lazy_* mode 0 / 1,
  * AUTO = LAZY_FACTOR when 35 k < n (its cheaper setup wins), else LAZY_PRECISION.  vgp_placement_host == AUTO. */
 enum { VGP_FORMULATION_AUTO = -1, VGP_FORMULATION_DENSE = 0, VGP_FORMULATION_LAZY_PRECISION = 1,

@@ -51,6 +51,23 @@ struct GemmArgs {
 thread_local DistContext *g_dist = nullptr;
 void dense_set_dist(DistContext *ctx) { g_dist = ctx; }
 
+thread_local RowGate *g_gate = nullptr;
+void dense_set_gate(RowGate *gate) { g_gate = gate; }
+
+// `rows` storage rows starting at p are about to be touched by a launch on `s`
+static int gate_wait(const double *p, int64_t rows, cudaStream_t s) {
+    RowGate *g = g_gate;
+    if (!g || g->waited >= g->nchunks || p < g->base || p >= g->base + g->rows * g->ld) return VGP_OK;
+    const int64_t last = (p - g->base) / g->ld + rows - 1;
+    int chunk = (int)(last / g->chunk_rows);
+    if (chunk >= g->nchunks) chunk = g->nchunks - 1;
+    if (chunk >= g->waited) {
+        VGP_CUDA(cudaStreamWaitEvent(s, g->events[chunk], 0));
+        g->waited = chunk + 1;
+    }
+    return VGP_OK;
+}
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -270,6 +287,11 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
     VGP_REQUIRE(tiles == GEMM_FULL || m == n, "dense_gemm: lower-tile mode needs a square C");
     VGP_REQUIRE(m / BM <= 65535, "dense_gemm: too many row tiles");
     GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0, k, 0, 0, 0, 0, {0}};
+    if (g_gate) {
+        VGP_TRY(gate_wait(a, trans_a ? k : m, s));
+        VGP_TRY(gate_wait(b, trans_b ? n : k, s));
+        VGP_TRY(gate_wait(c, m, s));
+    }
     DistContext *dc = g_dist;
     if (dc && dc->nranks > 1) {
         const int64_t tm = m / BM, tn = n / BN;
@@ -720,6 +742,7 @@ int dense_trsm(int side, int trans, int64_t n, int64_t nrhs, double alpha, const
 static int potrf_rec(double *a, int64_t n, int64_t ld, int64_t row_offset, double *dinv, DenseWorkspace &ws,
                      cudaStream_t s) {
     if (n == NB) {
+        VGP_TRY(gate_wait(a, NB, s));
         potf2_kernel<<<1, 256, 0, s>>>(a, ld, ws.info, (int)row_offset);
         VGP_LAUNCH_CHECK();
         return block_trtri(a, ld, dinv, NB, 0, s);          // cache inv(L_ii) for every later solve

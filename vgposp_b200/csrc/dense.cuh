@@ -38,6 +38,19 @@ void dense_set_dist(DistContext *ctx);      // thread-local; nullptr switches di
 int dense_dist_barrier(DistContext &ctx, cudaStream_t s);
 int dense_preload();                        // load all dense kernels, set shared-memory opt-ins (current device)
 
+// Row gate: the matrix at `base` ([rows][ld]) is still arriving -- row chunk c (rows [c * chunk_rows, (c + 1) *
+// chunk_rows), columns up to the end of the chunk: the lower triangle by chunks) is complete once events[c], recorded
+// in chunk order on the stream that copies it, has fired.  While a gate is set, every dense_* launch that touches rows
+// of that matrix first makes its stream wait for the last chunk it needs, so a factorisation started right away runs
+// behind the copy front instead of behind the whole copy (the recursive Cholesky works top-left to bottom-right).
+struct RowGate {
+    const double *base = nullptr;
+    int64_t ld = 0, rows = 0, chunk_rows = 0;
+    cudaEvent_t *events = nullptr;
+    int nchunks = 0, waited = 0;            // chunks [0, waited) are already ordered before the compute stream
+};
+void dense_set_gate(RowGate *gate);         // thread-local; nullptr switches it off
+
 enum GemmTiles { GEMM_FULL = 0, GEMM_LOWER = 1 };   // LOWER: only tiles with tile_row >= tile_col
 
 // C[m,n] = alpha op(A) op(B) + beta C.  trans_a == 0: A stored [m][k]; 1: stored [k][m].

@@ -19,7 +19,9 @@
 // Algorithmic bytes of lazy_step_kernel at step t: 8 n (2 (t-1) + 6).
 #include <math.h>
 
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 #include "dense.cuh"
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(256) lazy_step_kernel(StepArgs a) {
                     const int64_t b0 = (y > j ? y : j) / RB;
                     for (int64_t b = b0; b < a.row_blocks; ++b) p += a.partial[b * a.n_pad + j];
                 }
-                acc = a.cov[y * a.ld + j];
+                acc = j <= y ? a.cov[y * a.ld + j] : a.cov[j * a.ld + y];      // Sigma is symmetric: lower triangle only
                 if (j == y) acc += a.jitter;
             }
             for (int64_t s0 = 0; s0 < hist; s0 += CHUNK) {
@@ -466,21 +468,37 @@ int vgp_lazy_adopt_factor(vgp_lazy *h, void *stream) {
     return vgp_lazy_reset(h, stream);
 }
 
-int vgp_lazy_factor(vgp_lazy *h, int *info_host, void *stream) {
-    VGP_TRY(check(h));
-    VGP_ENTER(h->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t mat = (size_t)h->n_pad * h->n_pad * 8;
-    VGP_CUDA(cudaMemcpyAsync(h->fac, h->cov, mat, cudaMemcpyDeviceToDevice, s));
-    if (h->jitter != 0.0) {
-        VGP_TRY(dense_add_diag(h->fac, h->n_pad, h->n, h->jitter, s));
+// fac <- the matrix to factorise, rows [r0, r1) (columns [0, r1): the lower triangle by row chunks):
+// Sigma + jitter on the diagonal, identity on the padding diagonal
+static int lazy_stage_rows(vgp_lazy *h, int64_t r0, int64_t r1, cudaStream_t s) {
+    VGP_CUDA(cudaMemcpy2DAsync(h->fac + r0 * h->n_pad, (size_t)h->n_pad * 8, h->cov + r0 * h->n_pad,
+                               (size_t)h->n_pad * 8, (size_t)r1 * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToDevice, s));
+    const int64_t live = (r1 < h->n ? r1 : h->n) - r0;
+    if (h->jitter != 0.0 && live > 0) {
+        VGP_TRY(dense_add_diag(h->fac + r0 * h->n_pad + r0, h->n_pad, live, h->jitter, s));
         ++h->launches;
     }
-    if (h->n_pad > h->n) {
+    if (r1 > h->n) {
         const int64_t extra = h->n_pad - h->n;
         lazy_pad_identity_kernel<<<(unsigned)((extra + 127) / 128), 128, 0, s>>>(h->fac, h->n_pad, h->n, h->n_pad);
         L_LAUNCH_CHECK(h);
     }
+    return VGP_OK;
+}
+
+static int lazy_factor_staged(vgp_lazy *h, int *info_host, cudaStream_t s);
+
+int vgp_lazy_factor(vgp_lazy *h, int *info_host, void *stream) {
+    VGP_TRY(check(h));
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    VGP_TRY(lazy_stage_rows(h, 0, h->n_pad, s));
+    return lazy_factor_staged(h, info_host, s);
+}
+
+// potrf + trtri (+ lauum + mirror in mode 0) of the staged matrix, then the initial denominators
+static int lazy_factor_staged(vgp_lazy *h, int *info_host, cudaStream_t s) {
+    void *stream = (void *)s;
     const int64_t before = g_launches;
     int rc = dense_potrf(h->fac, h->n_pad, h->n_pad, h->ws, s);
     if (rc == VGP_OK) rc = dense_read_info(h->ws, info_host, s);
@@ -644,14 +662,54 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
         vgp_lazy_destroy(h);
         return code;
     };
+    // H2D of the lower triangle in row chunks on a copy stream; the factorisation starts at once on `s` and every
+    // launch waits only for the last chunk it touches (RowGate, dense.cuh): the copy hides behind the Cholesky of
+    // the leading blocks.  Sigma is symmetric -- the strict upper triangle is never read (lazy_step_kernel).
+    constexpr int64_t CHUNK_ROWS = 2048;
+    const int nchunks = (int)((h->n_pad + CHUNK_ROWS - 1) / CHUNK_ROWS);
+    cudaStream_t cs = nullptr;
+    std::vector<cudaEvent_t> chunk_ev((size_t)nchunks, nullptr);
+    cudaError_t ce = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) return fail(cuda_fail(ce, "copy stream", __FILE__, __LINE__));
+    auto fail2 = [&](int code) {
+        dense_set_gate(nullptr);
+        cudaStreamSynchronize(cs);
+        for (auto &e : chunk_ev)
+            if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(cs);
+        return fail(code);
+    };
+    for (auto &e : chunk_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+            return fail2(cuda_fail(cudaGetLastError(), "chunk events", __FILE__, __LINE__));
     cudaEventRecord(ev[0], s);
-    cudaError_t ce = cudaMemcpy2DAsync(h->cov, (size_t)h->n_pad * 8, cov_host, (size_t)ld_host * 8, (size_t)n * 8,
-                                       (size_t)n, cudaMemcpyHostToDevice, s);
-    if (ce != cudaSuccess) return fail(cuda_fail(ce, "H2D of cov_vv", __FILE__, __LINE__));
-    cudaEventRecord(ev[1], s);
+    cudaStreamWaitEvent(cs, ev[0], 0);
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t r0 = (int64_t)c * CHUNK_ROWS, r1 = std::min(r0 + CHUNK_ROWS, h->n_pad);
+        const int64_t rows = std::min(r1, n) - r0, cols = std::min(r1, n);
+        if (rows > 0) {
+            ce = cudaMemcpy2DAsync(h->cov + r0 * h->n_pad, (size_t)h->n_pad * 8, cov_host + r0 * ld_host,
+                                   (size_t)ld_host * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice, cs);
+            if (ce != cudaSuccess) return fail2(cuda_fail(ce, "H2D of cov_vv", __FILE__, __LINE__));
+        }
+        rc = lazy_stage_rows(h, r0, r1, cs);
+        if (rc != VGP_OK) return fail2(rc);
+        cudaEventRecord(chunk_ev[(size_t)c], cs);
+    }
+    cudaEventRecord(ev[1], cs);                     // the last byte has arrived (overlaps the factorisation)
+    RowGate gate;
+    gate.base = h->fac;
+    gate.ld = h->n_pad;
+    gate.rows = h->n_pad;
+    gate.chunk_rows = CHUNK_ROWS;
+    gate.events = chunk_ev.data();
+    gate.nchunks = nchunks;
+    dense_set_gate(&gate);
     int info = 0;
-    rc = vgp_lazy_factor(h, &info, s);
-    if (rc != VGP_OK) return fail(rc);
+    rc = lazy_factor_staged(h, &info, s);
+    dense_set_gate(nullptr);
+    if (rc != VGP_OK) return fail2(rc);
+    cudaStreamWaitEvent(s, chunk_ev[(size_t)nchunks - 1], 0);     // (already implied; keeps `cov` ordered before the steps)
     cudaEventRecord(ev[2], s);
     if (step_scores_host) {
         rc = vgp_lazy_record_scores(h, 1);
@@ -673,14 +731,14 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
         float ms;
         cudaEventElapsedTime(&ms, ev[0], ev[1]);
         seconds_host[0] = ms * 1e-3;
-        cudaEventElapsedTime(&ms, ev[1], ev[2]);
+        cudaEventElapsedTime(&ms, ev[0], ev[2]);      // from the first byte: the copy runs underneath
         seconds_host[1] = ms * 1e-3;
         cudaEventElapsedTime(&ms, ev[2], ev[3]);
         seconds_host[2] = ms * 1e-3;
         cudaEventElapsedTime(&ms, ev[0], ev[3]);
         seconds_host[3] = ms * 1e-3;
     }
-    return fail(VGP_OK);
+    return fail2(VGP_OK);
 }
 
 int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
