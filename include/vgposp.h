@@ -94,6 +94,15 @@ int vgp_dlpack_view(const void *dl_managed_tensor, vgp_tensor_view *out);
 int vgp_expquad_matrix(int device, const double *x1_dev, int64_t n1, const double *x2_dev, int64_t n2, int d,
                        double amplitude, double length_scale, double diag_add, int64_t diag_col0,
                        double *out_dev, int64_t ld_out, void *stream);
+/* The same builder for the other stationary kernels the reference instantiates (r = |x1_i - x2_j|):
+ *   MATERN12  a^2 exp(-r / l)                                   tfkern.MaternOneHalf, gp_functions.py:160-163
+ *   MATERN32  a^2 (1 + z) exp(-z),           z = sqrt(3) r / l  tfkern.MaternThreeHalves
+ *   MATERN52  a^2 (1 + z + z^2/3) exp(-z),   z = sqrt(5) r / l  tfkern.MaternFiveHalves, main_architecture_2.py:184
+ * EXPQUAD is vgp_expquad_matrix.  Values agree with libm-based float64 evaluation to 2 ulp. */
+enum { VGP_KERNEL_EXPQUAD = 0, VGP_KERNEL_MATERN12 = 1, VGP_KERNEL_MATERN32 = 2, VGP_KERNEL_MATERN52 = 3 };
+int vgp_kernel_matrix(int device, int kind, const double *x1_dev, int64_t n1, const double *x2_dev, int64_t n2,
+                      int d, double amplitude, double length_scale, double diag_add, int64_t diag_col0,
+                      double *out_dev, int64_t ld_out, void *stream);
 
 /* ---------------------------------------------------------------- (2) dense float64 factorisations ---------- */
 /* C[m,n] = alpha * op(A) * op(B) + beta * C.  trans_a/trans_b: 0 = as stored, 1 = transposed.  Hand-written

@@ -52,6 +52,34 @@ def expquad_matrix(x1, x2, amplitude, length_scale, diag_add=0.0):
     return k
 
 
+KERNEL_KINDS = {"expquad": 0, "matern12": 1, "matern32": 2, "matern52": 3}
+
+
+def kernel_matrix(kind, x1, x2, amplitude, length_scale, diag_add=0.0):
+    """The stationary kernels the reference instantiates, in TFP's published form (r = |x - y|):
+    ExponentiatedQuadratic (variational_Gaussian_process_example.py:55-57); MaternOneHalf a^2 exp(-r/l)
+    (gp_functions.py:160-163); MaternThreeHalves a^2 (1 + z) exp(-z), z = sqrt(3) r / l; MaternFiveHalves
+    a^2 (1 + z + z^2/3) exp(-z), z = sqrt(5) r / l (main_architecture_2.py:184)."""
+    if kind == "expquad":
+        return expquad_matrix(x1, x2, amplitude, length_scale, diag_add)
+    r = np.sqrt(sqdist(x1, x2))
+    if kind == "matern12":
+        k = np.exp(-r / length_scale)
+    elif kind == "matern32":
+        z = np.sqrt(3.0) * r / length_scale
+        k = (1.0 + z) * np.exp(-z)
+    elif kind == "matern52":
+        z = np.sqrt(5.0) * r / length_scale
+        k = (1.0 + z + z * z / 3.0) * np.exp(-z)
+    else:
+        raise ValueError(kind)
+    k *= amplitude ** 2
+    if diag_add:
+        m = min(k.shape)
+        k[np.arange(m), np.arange(m)] += diag_add
+    return k
+
+
 def _chol(a):
     return cholesky(a, lower=True, check_finite=False)
 

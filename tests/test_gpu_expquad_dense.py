@@ -52,6 +52,44 @@ def test_expquad_odd_ld_and_panel_diagonal():
     np.testing.assert_allclose(got, want, rtol=1e-13)
 
 
+@pytest.mark.parametrize("kind", ["expquad", "matern12", "matern32", "matern52"])
+@pytest.mark.parametrize("n1,n2,d,same", [(33, 1030, 3, False), (513, 77, 5, False), (700, 700, 5, True), (130, 130, 3, True)])
+def test_kernel_matrix_kinds(kind, n1, n2, d, same):
+    """vgp_kernel_matrix, rectangular and symmetric paths, against the float64 NumPy statement of TFP's formulas.
+    Tolerance: 2 ulp of the fast exp + a few ulp of the Matern prefactor and sqrt -> 1e-13 relative."""
+    rng = np.random.default_rng(n1 + 31 * n2 + d)
+    x1 = rng.uniform(-2, 2, (n1, d))
+    x2 = x1 if same else rng.uniform(-2, 2, (n2, d))
+    d1 = dev(x1)
+    d2 = d1 if same else dev(x2)
+    out = _ffi.DeviceArray((n1, n2), np.float64, D).zero_()
+    _ffi.call("vgp_kernel_matrix", D, gpo.KERNEL_KINDS[kind], d1.ptr, n1, d2.ptr, n2, d, 0.8, 0.9, 0.03 if same else 0.0, 0,
+              out.ptr, n2, None)
+    got = out.to_host()
+    want = gpo.kernel_matrix(kind, x1, x2, 0.8, 0.9, diag_add=0.03 if same else 0.0)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-300)
+    if same:
+        assert np.array_equal(got, got.T)
+
+
+def test_expquad_fast_exp_edges():
+    """Arguments of the fast exp that leave its fast path: exact zero distance (value a^2 exactly), results below
+    2^-937 (libm branch, may be subnormal or 0), huge amplitude (libm kernels), and a wide sweep of exponents."""
+    x1 = np.zeros((3, 1))
+    x1[:, 0] = [0.0, 1.0, 40.0]
+    x2 = np.array([[0.0], [1.0 + 1e-9], [3.0], [12.0], [26.0], [27.5], [39.0]])
+    for amp in (1.0, 0.37, 1e25):
+        got = expquad(x1, x2, amp, 0.7)
+        want = gpo.expquad_matrix(x1, x2, amp, 0.7)
+        np.testing.assert_allclose(got, want, rtol=2e-13, atol=1e-310)
+        assert got[0, 0] == amp * amp
+    t = -np.linspace(0.0, 700.0, 4001)[:, None]               # exp(t) via l = 1/sqrt(2), x = sqrt(-t)
+    xs = np.sqrt(-t)
+    got = expquad(xs, np.zeros((1, 1)), 1.0, np.sqrt(0.5))
+    want = gpo.expquad_matrix(xs, np.zeros((1, 1)), 1.0, np.sqrt(0.5))
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-300)
+
+
 def test_expquad_empty_and_bad_arguments():
     out = _ffi.DeviceArray((4,), np.float64, D)
     _ffi.call("vgp_expquad_matrix", D, out.ptr, 0, out.ptr, 4, 3, 1.0, 1.0, 0.0, 0, out.ptr, 4, None)   # n1 == 0: no-op
@@ -137,3 +175,24 @@ def test_trsm(side, trans, n, nrhs):
     want = sla.solve_triangular(op, b, lower=not trans) if side == 0 else \
         sla.solve_triangular(op.T, b.T, lower=bool(trans)).T
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("trans", [0, 1])
+def test_trsm_right_in_place_many_rows_is_deterministic(trans):
+    """The right-side solves multiply B by inverted diagonal blocks IN PLACE (C aliases A).  With tiles narrower than
+    the 128-column block two CTAs would read what the other overwrites; the product must run on the 128x128
+    configuration (dense.cu, `in_place`).  Many row tiles and repeated runs make the race visible if it comes back."""
+    n, rows = 512, 16384
+    l = np.linalg.cholesky(spd(n, 3))
+    b = np.random.default_rng(9).standard_normal((rows, n))
+    dl = dev(l)
+    want = sla.solve_triangular(l if trans else l.T, b.T, lower=bool(trans)).T
+    first = None
+    for _ in range(4):
+        db = dev(b)
+        _ffi.call("vgp_trsm", D, 1, trans, n, rows, dl.ptr, n, db.ptr, n, None)
+        got = db.to_host()
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11 * np.abs(want).max())
+        if first is None:
+            first = got
+        assert np.array_equal(got, first)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vgp_event_elapsed_ms": [c_int, c_vp, c_vp, P(ctypes.c_float)],
     "vgp_dlpack_view": [c_vp, P(TensorView)],
     "vgp_expquad_matrix": [c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_i64, c_vp, c_i64, c_vp],
+    "vgp_kernel_matrix": [c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_i64, c_vp, c_i64, c_vp],
     "vgp_dgemm": [c_int, c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_i64, c_vp],
     "vgp_potrf": [c_int, c_vp, c_i64, c_i64, P(c_int), c_vp],
     "vgp_spd_inverse": [c_int, c_vp, c_i64, c_i64, P(c_int), c_vp],

@@ -17,6 +17,8 @@
 //     128x128 diagonal blocks are handled by single-CTA shared-memory kernels.  Diagonal-block solves
 //     multiply by an explicitly inverted 128x128 block (one more GEMM call, in place).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "dense.cuh"
 
@@ -25,11 +27,32 @@ namespace vgp {
 // =====================================================================================================
 // GEMM
 // =====================================================================================================
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, GEMM_THREADS = 256;
-constexpr int LDK = 20;    // k-contiguous operand tile  [128][LDK]   (stride = 32 B mod 128 B)
-constexpr int LDM = 132;   // k-strided   operand tile   [16][LDM]    (stride = 32 B mod 128 B)
-constexpr int TILE_DOUBLES = BM * LDK;                       // 2560 >= 16 * 132
-constexpr int GEMM_SMEM = STAGES * 2 * TILE_DOUBLES * 8;    // 122 880 B
+// Alignment every operand dimension must have (tile shapes below divide it).
+constexpr int BM = 128, BN = 128, BK = 16;
+
+// Tile configuration of gemm_kernel.  Warp tile is always 64 x 32 (8 x 4 DMMA 8x8x4 accumulators, 128 registers);
+// operands sit in shared memory with padded rows so that the 64-bit fragment loads of a warp (8 rows x 4 k) and the
+// 128-bit cp.async stores are bank-conflict free:
+//   k-contiguous operand tile  [rows][BK + 4]    row stride = 32 B mod 128 B
+//   k-strided   operand tile   [BK][rows + 4]    row stride = 32 B mod 128 B
+template <int BM_, int BN_, int BK_, int STAGES_, int MINB_>
+struct GemmCfg {
+    static constexpr int TM = BM_, TN = BN_, TK = BK_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int WARPS_M = TM / 64, WARPS_N = TN / 32, THREADS = 32 * WARPS_M * WARPS_N;
+    static constexpr int LDK = TK + 4, LDA = TM + 4, LDB = TN + 4;
+    static constexpr int A_DOUBLES = TM * LDK > TK * LDA ? TM * LDK : TK * LDA;
+    static constexpr int B_DOUBLES = TN * LDK > TK * LDB ? TN * LDK : TK * LDB;
+    static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+    static constexpr int SMEM = STAGES * STAGE_DOUBLES * 8;
+    static_assert(TM % 64 == 0 && TN % 32 == 0 && TK % 4 == 0 && BM % TM == 0 && BN % TN == 0 && TM % TN == 0, "tile");
+    static_assert((TM * TK / 2) % THREADS == 0 && (TN * TK / 2) % THREADS == 0, "load split");
+};
+// Measured on B200 (profiles/r01_gemm_sweep.json): the single-CTA 128x128 tile leaves the DMMA pipe idle 12.5 % of the
+// time (ncu: barrier + scoreboard stalls hit all 8 warps at once), 32.5 TFLOP/s at 8192^3; two 128x64 CTAs per SM
+// drift out of phase and cover each other's barrier / fill stalls: 35.0-35.6 TFLOP/s (cuBLAS DGEMM: 35.5-36.2), and
+// twice the tiles for the small products of the recursions.
+using CfgPair = GemmCfg<128, 64, 16, 3, 2>;     // default: 4 warps, 90 KB, two CTAs per SM
+using CfgBase = GemmCfg<128, 128, 16, 3, 1>;    // 8 warps, 120 KB, one CTA per SM: in-place products (see in_place)
 
 struct GemmArgs {
     const double *a;
@@ -39,6 +62,7 @@ struct GemmArgs {
     int64_t m, n, k;
     double alpha, beta;
     int lower;
+    int in_place;            // C aliases an operand: one CTA must own the whole aliased tile (128x128 configuration)
     int64_t k_split;         // k range handled by one blockIdx.z slice (== k without split-K)
     int64_t c_split_stride;  // element offset between the partial outputs of consecutive slices
     // distributed mode (dist_n > 0): this launch covers the linear tile range [tile0, tile0 + gridDim.x) of the
@@ -122,17 +146,21 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-template <bool AKC, bool BKC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs p) {
+template <class C, bool AKC, bool BKC>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) gemm_kernel(GemmArgs p) {
     extern __shared__ __align__(16) double smem[];
+    constexpr int TM = C::TM, TN = C::TN, TK = C::TK, STAGES = C::STAGES, THREADS = C::THREADS;
+    constexpr int LDK = C::LDK, LDA = C::LDA, LDB = C::LDB;
+    constexpr int RATIO = TM / TN;                              // tile columns per tile row on the diagonal
     int tm, tn;
     if (p.lower) {
+        // lower mode: row tm holds the RATIO * (tm + 1) tiles that touch the lower triangle (128-block granularity)
         const int64_t b = p.tile0 + blockIdx.x;
-        int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
-        while ((int64_t)r * (r + 1) / 2 > b) --r;
-        while ((int64_t)(r + 1) * (r + 2) / 2 <= b) ++r;
+        int r = (int)((sqrt(8.0 * (double)b / RATIO + 1.0) - 1.0) * 0.5);
+        while ((int64_t)RATIO * r * (r + 1) / 2 > b) --r;
+        while ((int64_t)RATIO * (r + 1) * (r + 2) / 2 <= b) ++r;
         tm = r;
-        tn = (int)(b - (int64_t)r * (r + 1) / 2);
+        tn = (int)(b - (int64_t)RATIO * r * (r + 1) / 2);
     } else if (p.dist_n > 0) {
         const int64_t b = p.tile0 + blockIdx.x;
         tm = (int)(b / p.tiles_n);
@@ -141,35 +169,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs p) {
         tn = blockIdx.x;
         tm = blockIdx.y;
     }
-    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+    const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+    const int wm0 = (warp / C::WARPS_N) * 64, wn0 = (warp % C::WARPS_N) * 32;
     const int64_t kbase = (int64_t)blockIdx.z * p.k_split;
     const int64_t klen = p.k - kbase < p.k_split ? p.k - kbase : p.k_split;
-    const int KT = (int)(klen / BK);
+    const int KT = (int)(klen / TK);
     double *cout = p.c + (int64_t)blockIdx.z * p.c_split_stride;
 
     auto load_stage = [&](int stage, int kt) {
-        double *sa = smem + (size_t)stage * 2 * TILE_DOUBLES;
-        double *sb = sa + TILE_DOUBLES;
-        const int64_t k0 = kbase + (int64_t)kt * BK;
+        double *sa = smem + (size_t)stage * C::STAGE_DOUBLES;
+        double *sb = sa + C::A_DOUBLES;
+        const int64_t k0 = kbase + (int64_t)kt * TK;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int c = tid + it * GEMM_THREADS;
+        for (int it = 0; it < TM * TK / 2 / THREADS; ++it) {
+            const int c = tid + it * THREADS;
             if (AKC) {
-                const int row = c >> 3, kc = c & 7;
+                const int row = c / (TK / 2), kc = c % (TK / 2);
                 cp_async16(sa + row * LDK + 2 * kc, p.a + (m0 + row) * p.lda + k0 + 2 * kc);
             } else {
-                const int kr = c >> 6, mc = c & 63;
-                cp_async16(sa + kr * LDM + 2 * mc, p.a + (k0 + kr) * p.lda + m0 + 2 * mc);
+                const int kr = c / (TM / 2), mc = c % (TM / 2);
+                cp_async16(sa + kr * LDA + 2 * mc, p.a + (k0 + kr) * p.lda + m0 + 2 * mc);
             }
+        }
+#pragma unroll
+        for (int it = 0; it < TN * TK / 2 / THREADS; ++it) {
+            const int c = tid + it * THREADS;
             if (BKC) {
-                const int row = c >> 3, kc = c & 7;
+                const int row = c / (TK / 2), kc = c % (TK / 2);
                 cp_async16(sb + row * LDK + 2 * kc, p.b + (n0 + row) * p.ldb + k0 + 2 * kc);
             } else {
-                const int kr = c >> 6, nc = c & 63;
-                cp_async16(sb + kr * LDM + 2 * nc, p.b + (k0 + kr) * p.ldb + n0 + 2 * nc);
+                const int kr = c / (TN / 2), nc = c % (TN / 2);
+                cp_async16(sb + kr * LDB + 2 * nc, p.b + (k0 + kr) * p.ldb + n0 + 2 * nc);
             }
         }
     };
@@ -180,27 +212,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    load_stage(0, 0);
-    cp_async_commit();
-    if (KT > 1) load_stage(1, 1);
-    cp_async_commit();
+#pragma unroll
+    for (int st = 0; st < STAGES - 1; ++st) {
+        if (st < KT) load_stage(st, st);
+        cp_async_commit();
+    }
 
     for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<1>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (kt + 2 < KT) load_stage((kt + 2) % STAGES, kt + 2);
+        if (kt + STAGES - 1 < KT) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
         cp_async_commit();
-        const double *sa = smem + (size_t)(kt % STAGES) * 2 * TILE_DOUBLES;
-        const double *sb = sa + TILE_DOUBLES;
+        const double *sa = smem + (size_t)(kt % STAGES) * C::STAGE_DOUBLES;
+        const double *sb = sa + C::A_DOUBLES;
 #pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
+        for (int kk = 0; kk < TK; kk += 4) {
             double af[8], bf[4];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                af[i] = AKC ? sa[(wm0 + 8 * i + g) * LDK + kk + t] : sa[(kk + t) * LDM + wm0 + 8 * i + g];
+                af[i] = AKC ? sa[(wm0 + 8 * i + g) * LDK + kk + t] : sa[(kk + t) * LDA + wm0 + 8 * i + g];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                bf[j] = BKC ? sb[(wn0 + 8 * j + g) * LDK + kk + t] : sb[(kk + t) * LDM + wn0 + 8 * j + g];
+                bf[j] = BKC ? sb[(wn0 + 8 * j + g) * LDK + kk + t] : sb[(kk + t) * LDB + wn0 + 8 * j + g];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -234,37 +267,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(GemmArgs p) {
     if (p.dist_n > 0) __threadfence_system();
 }
 
-template <bool AKC, bool BKC>
-static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
+// Tile configuration for one product.  The triangular solves multiply in place (C aliases A with n = 128, or B with
+// m = 128): then one CTA must own the whole aliased operand tile, which only the 128x128 tile guarantees.
+// VGP_GEMM_CFG = base | pair forces one for every product that may legally use it (measurement knob).
+enum GemmChoice { CHOICE_BASE = 0, CHOICE_PAIR = 1 };
+static int gemm_forced_choice() {
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("VGP_GEMM_CFG");
+        forced = -1;
+        if (e) {
+            if (!strcmp(e, "base")) forced = CHOICE_BASE;
+            if (!strcmp(e, "pair")) forced = CHOICE_PAIR;
+        }
+    }
+    return forced;
+}
+static GemmChoice gemm_choose(const GemmArgs &p) {
+    if (p.in_place) return CHOICE_BASE;
+    const int f = gemm_forced_choice();
+    if (f >= 0) return (GemmChoice)f;
+    return CHOICE_PAIR;
+}
+
+template <class C, bool AKC, bool BKC>
+static int gemm_launch_cfg(const GemmArgs &p, cudaStream_t s) {
     static bool configured[64] = {};
     int dev = 0;
     VGP_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        VGP_CUDA(cudaFuncSetAttribute(gemm_kernel<AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        VGP_CUDA(cudaFuncSetAttribute(gemm_kernel<C, AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured[dev] = true;
     }
-    const int64_t tm = p.m / BM, tn = p.n / BN;
+    const int64_t tm = p.m / C::TM, tn = p.n / C::TN;
     const unsigned splits = (unsigned)((p.k + p.k_split - 1) / p.k_split);
     if (p.dist_n > 0) {
-        // p.tiles_n carries this rank's tile count on entry and the tile-column count in the kernel
+        // p.tiles_n carries this rank's share (rank, nranks packed by dense_gemm) on entry, the tile-column count in
+        // the kernel: the linear tile range is cut here because the tile count depends on the configuration
         GemmArgs q = p;
-        const int64_t mine = p.tiles_n;
+        const int64_t total = p.lower ? (int64_t)(C::TM / C::TN) * tm * (tm + 1) / 2 : tm * tn;
+        const int64_t rank = p.tile0, nranks = p.tiles_n;
+        const int64_t each = total / nranks, rem = total % nranks;
+        q.tile0 = rank * each + (rank < rem ? rank : rem);
+        const int64_t mine = each + (rank < rem ? 1 : 0);
         q.tiles_n = tn;
         if (mine > 0) {
-            gemm_kernel<AKC, BKC><<<dim3((unsigned)mine, 1, 1), GEMM_THREADS, GEMM_SMEM, s>>>(q);
+            gemm_kernel<C, AKC, BKC><<<dim3((unsigned)mine, 1, 1), C::THREADS, C::SMEM, s>>>(q);
             VGP_LAUNCH_CHECK();
         }
         return VGP_OK;
     }
     if (p.lower) {
-        const int64_t blocks = tm * (tm + 1) / 2;
-        gemm_kernel<AKC, BKC><<<dim3((unsigned)blocks, 1, splits), GEMM_THREADS, GEMM_SMEM, s>>>(p);
+        const int64_t blocks = (int64_t)(C::TM / C::TN) * tm * (tm + 1) / 2;
+        gemm_kernel<C, AKC, BKC><<<dim3((unsigned)blocks, 1, splits), C::THREADS, C::SMEM, s>>>(p);
     } else {
         dim3 grid((unsigned)tn, (unsigned)tm, splits);
-        gemm_kernel<AKC, BKC><<<grid, GEMM_THREADS, GEMM_SMEM, s>>>(p);
+        gemm_kernel<C, AKC, BKC><<<grid, C::THREADS, C::SMEM, s>>>(p);
     }
     VGP_LAUNCH_CHECK();
     return VGP_OK;
+}
+
+template <bool AKC, bool BKC>
+static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
+    if (gemm_choose(p) == CHOICE_PAIR) return gemm_launch_cfg<CfgPair, AKC, BKC>(p, s);
+    return gemm_launch_cfg<CfgBase, AKC, BKC>(p, s);
 }
 
 static int gemm_dispatch(int trans_a, int trans_b, const GemmArgs &p, cudaStream_t s) {
@@ -286,7 +353,12 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
                 "dense_gemm: operands must be 16-byte aligned");
     VGP_REQUIRE(tiles == GEMM_FULL || m == n, "dense_gemm: lower-tile mode needs a square C");
     VGP_REQUIRE(m / BM <= 65535, "dense_gemm: too many row tiles");
-    GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0, k, 0, 0, 0, 0, {0}};
+    // in-place products of the triangular solves: C == A needs one tile column (n = 128, 128-wide tiles), C == B one
+    // tile row (m = 128, true for both configurations) -- then every CTA reads exactly the region it overwrites
+    VGP_REQUIRE(c != a || (!trans_a && n == BN), "dense_gemm: C aliases A with n = %lld", (long long)n);
+    VGP_REQUIRE(c != b || (!trans_b && m == BM), "dense_gemm: C aliases B with m = %lld", (long long)m);
+    GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0, c == a ? 1 : 0, k, 0, 0, 0,
+               0, {0}};
     if (g_gate) {
         VGP_TRY(gate_wait(a, trans_a ? k : m, s));
         VGP_TRY(gate_wait(b, trans_b ? n : k, s));
@@ -299,10 +371,9 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
         const char *c0 = (const char *)c, *c1 = (const char *)(c + (m - 1) * ldc + n);
         const bool inside = c0 >= (const char *)dc->base && c1 <= (const char *)dc->base + dc->bytes;
         if (inside && total >= dc->min_tiles && k >= dc->min_k) {
-            const int64_t each = total / dc->nranks, rem = total % dc->nranks;
             p.dist_n = dc->nranks;
-            p.tile0 = dc->rank * each + (dc->rank < rem ? dc->rank : rem);
-            p.tiles_n = each + (dc->rank < rem ? 1 : 0);          // this rank's tile count (see gemm_launch)
+            p.tile0 = dc->rank;                                   // (rank, nranks): gemm_launch_cfg cuts the tile range
+            p.tiles_n = dc->nranks;
             for (int q = 0; q < dc->nranks; ++q) p.delta[q] = dc->delta[q];
             ++dc->dist_gemms;
             VGP_TRY(dense_dist_barrier(*dc, s));                  // every rank is done with all earlier work
@@ -338,7 +409,7 @@ int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k,
     VGP_REQUIRE(tiles == GEMM_FULL || (m == n && beta == 0.0), "dense_gemm_splitk: lower mode needs square C, beta 0");
     int64_t k_split = round_up((k + splits - 1) / splits, BK);
     const int real_splits = (int)((k + k_split - 1) / k_split);
-    GemmArgs p{a, b, partial, lda, ldb, n, m, n, k, alpha, 0.0, tiles == GEMM_LOWER ? 1 : 0, k_split, m * n,
+    GemmArgs p{a, b, partial, lda, ldb, n, m, n, k, alpha, 0.0, tiles == GEMM_LOWER ? 1 : 0, 0, k_split, m * n,
                0, 0, 0, {0}};
     VGP_TRY(gemm_dispatch(trans_a, trans_b, p, s));
     splitk_reduce_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, s>>>(partial, m * n, real_splits, beta, c, ldc, m, n,
@@ -822,12 +893,17 @@ int dense_lauum(double *x, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream
 
 // Load every kernel of this file now (CUDA loads modules lazily, and a lazy load can wait on kernels that are
 // spinning on a peer's flag) and set the opt-in shared-memory sizes.
+template <class C, bool AKC, bool BKC>
+static int gemm_preload_cfg() {
+    cudaFuncAttributes fa;
+    VGP_CUDA(cudaFuncSetAttribute(gemm_kernel<C, AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_kernel<C, AKC, BKC>));
+    return VGP_OK;
+}
 template <bool AKC, bool BKC>
 static int gemm_preload_one() {
-    cudaFuncAttributes fa;
-    VGP_CUDA(cudaFuncSetAttribute(gemm_kernel<AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_kernel<AKC, BKC>));
-    return VGP_OK;
+    VGP_TRY((gemm_preload_cfg<CfgBase, AKC, BKC>()));
+    return gemm_preload_cfg<CfgPair, AKC, BKC>();
 }
 int dense_preload() {
     cudaFuncAttributes fa;

@@ -1,57 +1,117 @@
-// (1) ExponentiatedQuadratic kernel-matrix builder.
+// (1) Stationary kernel-matrix builder: ExponentiatedQuadratic and the Matern family.
 //
-// out[i][j] = a^2 exp(-|x1_i - x2_j|^2 / (2 l^2)) (+ diag_add on the shifted diagonal).
-// Stands in for tfkern.ExponentiatedQuadratic(...).matrix(x1, x2) (reference call sites:
-// variational_Gaussian_process_example.py:55-57, 3D_sin_wave.py:158-159, main_tests.py:617-619).
+//   ExpQuad      out[i][j] = a^2 exp(-|x1_i - x2_j|^2 / (2 l^2))          tfkern.ExponentiatedQuadratic(...).matrix
+//   Matern 1/2   a^2 exp(-r / l)                                           gp_functions.py:160-163 (create_cov_kernel)
+//   Matern 3/2   a^2 (1 + z) exp(-z),            z = sqrt(3) r / l
+//   Matern 5/2   a^2 (1 + z + z^2 / 3) exp(-z),  z = sqrt(5) r / l         main_architecture_2.py:184
+// (+ diag_add on the shifted diagonal).  Reference call sites of the ExpQuad form:
+// variational_Gaussian_process_example.py:55-57, 3D_sin_wave.py:158-159, main_tests.py:617-619.
 //
-// The op is HBM-write-bound (8 n1 n2 bytes out, 8 d (n1 + n2) bytes in): no tensor cores, each thread
-// produces two adjacent float64 and issues one 128-bit store; a warp writes 512 contiguous bytes per row.
-// The squared distance is the direct sum of squared coordinate differences (not |x|^2+|y|^2-2xy), which
-// keeps full float64 accuracy for near-by points.  The float64 exp() costs ~40 issue slots per element,
-// enough to make the full build FP64-issue-bound rather than write-bound; the symmetric path therefore
-// evaluates each off-diagonal 64x64 tile once and writes it twice (once transposed through shared memory).
+// The op is HBM-write-bound (8 n1 n2 bytes out, 8 d (n1 + n2) bytes in): no tensor cores, each thread produces two
+// adjacent float64 and issues one 128-bit store; a warp writes 512 contiguous bytes per row.  The squared distance
+// is the direct sum of squared coordinate differences (not |x|^2 + |y|^2 - 2 x.y), which keeps full float64 accuracy
+// for near-by points.
+//
+// FP64 issue budget.  B200 retires 64 FP64 lanes / clk / SM, i.e. ~22 FP64 instructions per 8-byte element at the
+// measured HBM write rate.  libm's exp() plus the distance is 26, which made the first version FP64-issue-bound.
+// `exp_nonpos` below is 12: arguments are never positive here, so the reduction is t = k ln2/32 + r with a
+// Cody-Waite pair (two FMAs, exact), a degree-6 polynomial on |r| <= ln2/64, one multiply by the table entry
+// a^2 2^(j/32) (32 entries in shared memory, amplitude folded in) and an integer add on the exponent field.
+// Measured against long-double exp over [-700, 0]: <= 1.94 ulp.  Underflow-range arguments, NaN and infinities take
+// the libm branch.  The symmetric path additionally evaluates each off-diagonal 64x64 tile once and writes it twice
+// (once transposed through shared memory); its CTAs walk 16x16 super-tiles so that both the direct and the mirrored
+// stores of concurrently running CTAs fall into the same 1024 x 1024 block of the output (8 KB row pieces in L2
+// instead of scattered 512-byte pieces).
 #include <math.h>
 
 #include "common.cuh"
 
 namespace vgp {
 
+enum { KIND_EXPQUAD = VGP_KERNEL_EXPQUAD, KIND_MATERN12 = VGP_KERNEL_MATERN12, KIND_MATERN32 = VGP_KERNEL_MATERN32,
+       KIND_MATERN52 = VGP_KERNEL_MATERN52 };
+
 struct ExpQuadArgs {
     const double *x1;
     const double *x2;
     int64_t n1, n2;
     double amp2;
-    double neg_half_inv_l2;
+    double c;                // ExpQuad: -1 / (2 l^2) (multiplies r^2);  Matern nu: -sqrt(2 nu) / l (multiplies r)
     double diag_add;
     int64_t diag_col0;
     double *out;
     int64_t ld;
 };
 
-template <int D>
-__device__ __forceinline__ double eq_value(const double (&a)[D], const double (&b)[D], double amp2, double c) {
+constexpr int EXP_TAB = 32;
+constexpr double EXP_INV_L = 46.16624130844683;            // 32 / ln 2
+constexpr double EXP_L_HI = 0.02166084939249829;           // ln 2 / 32, float64 head
+constexpr double EXP_L_LO = 7.247021293269686e-19;         //            and tail
+constexpr double EXP_MAGIC = 6755399441055744.0;           // 1.5 * 2^52: adding it rounds to the nearest integer
+
+// tab[j] = amp2 * 2^(j / 32)
+__device__ __forceinline__ void exp_table_fill(double *tab, double amp2) {
+    if (threadIdx.x < EXP_TAB) tab[threadIdx.x] = amp2 * exp2((double)threadIdx.x * (1.0 / EXP_TAB));
+}
+
+__device__ __noinline__ double exp_slow(double t, double amp2) { return amp2 * exp(t); }
+
+// amp2 * exp(t) for t <= 0 (amp2 within [2^-60, 2^60], checked by the launcher).  `kd` = MAGIC + (an integer within
+// 1 of 32 t / ln 2), formed by the caller with one FMA from whatever t was computed from.
+__device__ __forceinline__ double exp_nonpos(double t, double kd, const double *tab, double amp2) {
+    // t < -650 (result below 2^-937), NaN, -inf: libm.  Integer compare on the high word (t <= 0: the more negative,
+    // the larger the unsigned word) keeps the test off the FP64 pipe.
+    if ((unsigned)__double2hiint(t) > 0xC0845000u) return exp_slow(t, amp2);
+    const int k = __double2loint(kd);                       // k <= 0
+    kd -= EXP_MAGIC;
+    double r = fma(kd, -EXP_L_HI, t);
+    r = fma(kd, -EXP_L_LO, r);
+    double p = 1.0 / 720.0;
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = tab[k & (EXP_TAB - 1)] * p;
+    return __hiloint2double(__double2hiint(v) + ((k >> 5) << 20), __double2loint(v));     // v * 2^floor(k / 32)
+}
+
+template <int KIND, int D, bool FAST>
+__device__ __forceinline__ double kernel_value(const double (&a)[D], const double (&b)[D], double amp2, double c,
+                                               double cz, const double *tab) {
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         const double t = a[k] - b[k];
         s = fma(t, t, s);
     }
-    return amp2 * exp(s * c);
+    if (KIND == KIND_EXPQUAD) {
+        const double t = s * c;
+        return FAST ? exp_nonpos(t, fma(s, cz, EXP_MAGIC), tab, amp2) : amp2 * exp(t);
+    }
+    const double t = sqrt(s) * c;                           // -z
+    const double e = FAST ? exp_nonpos(t, fma(t, EXP_INV_L, EXP_MAGIC), tab, amp2) : amp2 * exp(t);
+    if (KIND == KIND_MATERN12) return e;
+    if (KIND == KIND_MATERN32) return (1.0 - t) * e;
+    return fma(t, fma(t, 1.0 / 3.0, -1.0), 1.0) * e;        // 1 + z + z^2 / 3
 }
 
 // ---- general rectangular path: CTA tile 32 rows x 512 columns, 256 threads, 2 columns per thread ------
 constexpr int EQ_ROWS = 32;
 constexpr int EQ_COLS = 512;
 
-template <int D, bool VEC>
-__global__ void __launch_bounds__(256) expquad_rect_kernel(ExpQuadArgs p) {
+template <int KIND, int D, bool VEC, bool FAST>
+__global__ void __launch_bounds__(256) kernel_rect_kernel(ExpQuadArgs p) {
     __shared__ double xs[EQ_ROWS][D];
+    __shared__ double tab[EXP_TAB];
     const int64_t row0 = (int64_t)blockIdx.y * EQ_ROWS;
     const int64_t col = (int64_t)blockIdx.x * EQ_COLS + 2 * threadIdx.x;
     for (int t = threadIdx.x; t < EQ_ROWS * D; t += 256) {
         const int64_t r = row0 + t / D;
         xs[t / D][t % D] = r < p.n1 ? p.x1[r * D + t % D] : 0.0;
     }
+    if (FAST) exp_table_fill(tab, p.amp2);
     double b0[D], b1[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -61,17 +121,15 @@ __global__ void __launch_bounds__(256) expquad_rect_kernel(ExpQuadArgs p) {
     __syncthreads();
     if (col >= p.n2) return;
     const int rows = (int)min((int64_t)EQ_ROWS, p.n1 - row0);
+    const double cz = p.c * EXP_INV_L;
 #pragma unroll 4
     for (int r = 0; r < rows; ++r) {
         double a[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) a[k] = xs[r][k];
-        double v0 = eq_value<D>(a, b0, p.amp2, p.neg_half_inv_l2);
-        double v1 = eq_value<D>(a, b1, p.amp2, p.neg_half_inv_l2);
-        const int64_t i = row0 + r;
-        if (i == p.diag_col0 + col) v0 += p.diag_add;
-        if (i == p.diag_col0 + col + 1) v1 += p.diag_add;
-        double *dst = p.out + i * p.ld + col;
+        const double v0 = kernel_value<KIND, D, FAST>(a, b0, p.amp2, p.c, cz, tab);
+        const double v1 = kernel_value<KIND, D, FAST>(a, b1, p.amp2, p.c, cz, tab);
+        double *dst = p.out + (row0 + r) * p.ld + col;
         if (VEC && col + 1 < p.n2) {
             *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
         } else {
@@ -79,23 +137,36 @@ __global__ void __launch_bounds__(256) expquad_rect_kernel(ExpQuadArgs p) {
             if (col + 1 < p.n2) dst[1] = v1;
         }
     }
+    // diagonal shift, outside the hot loop: the thread that owns column j also wrote out[diag_col0 + j][j]
+    if (p.diag_add != 0.0) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int64_t i = p.diag_col0 + col + e;
+            if (col + e < p.n2 && i >= row0 && i < row0 + rows) p.out[i * p.ld + col + e] += p.diag_add;
+        }
+    }
 }
 
-// ---- symmetric path: one CTA per 64x64 tile pair (I <= J) -------------------------------------------
+// ---- symmetric path: one CTA per 64x64 tile pair (I <= J), CTAs ordered by 16x16 super-tiles -----------
 constexpr int SQ = 64;
+constexpr int SUPER = 16;
 
-template <int D, bool VEC>
-__global__ void __launch_bounds__(256) expquad_sym_kernel(ExpQuadArgs p, int ntiles) {
+template <int KIND, int D, bool VEC, bool FAST>
+__global__ void __launch_bounds__(256) kernel_sym_kernel(ExpQuadArgs p, int ntiles, int nsuper) {
     __shared__ double xi[SQ][D];
     __shared__ double xj[SQ][D];
     __shared__ double tile[SQ][SQ + 1];
-    // linear block id -> (I, J) with I <= J, row-major over the upper triangle
-    int64_t b = blockIdx.x;
-    int I = (int)floor((2.0 * ntiles + 1.0 - sqrt((2.0 * ntiles + 1.0) * (2.0 * ntiles + 1.0) - 8.0 * (double)b)) * 0.5);
+    __shared__ double tab[EXP_TAB];
+    // linear super-block id -> (SI, SJ) with SI <= SJ, row-major over the upper triangle of super-tiles
+    const int64_t sb = blockIdx.x / (SUPER * SUPER);
+    const int local = (int)(blockIdx.x % (SUPER * SUPER));
+    int SI = (int)floor((2.0 * nsuper + 1.0 - sqrt((2.0 * nsuper + 1.0) * (2.0 * nsuper + 1.0) - 8.0 * (double)sb)) * 0.5);
     // guard against floating-point rounding of the closed form
-    while ((int64_t)I * ntiles - (int64_t)I * (I - 1) / 2 > b) --I;
-    while ((int64_t)(I + 1) * ntiles - (int64_t)(I + 1) * I / 2 <= b) ++I;
-    const int J = I + (int)(b - ((int64_t)I * ntiles - (int64_t)I * (I - 1) / 2));
+    while ((int64_t)SI * nsuper - (int64_t)SI * (SI - 1) / 2 > sb) --SI;
+    while ((int64_t)(SI + 1) * nsuper - (int64_t)(SI + 1) * SI / 2 <= sb) ++SI;
+    const int SJ = SI + (int)(sb - ((int64_t)SI * nsuper - (int64_t)SI * (SI - 1) / 2));
+    const int I = SI * SUPER + local / SUPER, J = SJ * SUPER + local % SUPER;
+    if (I >= ntiles || J >= ntiles || I > J) return;
     const int64_t r0 = (int64_t)I * SQ, c0 = (int64_t)J * SQ;
     const int64_t n = p.n1;
     for (int t = threadIdx.x; t < SQ * D; t += 256) {
@@ -103,9 +174,14 @@ __global__ void __launch_bounds__(256) expquad_sym_kernel(ExpQuadArgs p, int nti
         xi[t / D][t % D] = r < n ? p.x1[r * D + t % D] : 0.0;
         xj[t / D][t % D] = c < n ? p.x1[c * D + t % D] : 0.0;
     }
+    if (FAST) exp_table_fill(tab, p.amp2);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int jc = 2 * tx;
+    // lanes 8-15 and 24-31 store their two values in the opposite order: the 64-bit shared-memory stores of a
+    // half-warp then cover 16 distinct bank pairs (row stride 65 doubles keeps the transposed reads conflict-free)
+    const int odd = (tx >> 3) & 1;
+    const double cz = p.c * EXP_INV_L;
     double b0[D], b1[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -118,13 +194,13 @@ __global__ void __launch_bounds__(256) expquad_sym_kernel(ExpQuadArgs p, int nti
         double a[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) a[k] = xi[r][k];
-        double v0 = eq_value<D>(a, b0, p.amp2, p.neg_half_inv_l2);
-        double v1 = eq_value<D>(a, b1, p.amp2, p.neg_half_inv_l2);
+        double v0 = kernel_value<KIND, D, FAST>(a, b0, p.amp2, p.c, cz, tab);
+        double v1 = kernel_value<KIND, D, FAST>(a, b1, p.amp2, p.c, cz, tab);
         const int64_t i = r0 + r, j = c0 + jc;
         if (i == j) v0 += p.diag_add;
         if (i == j + 1) v1 += p.diag_add;
-        tile[r][jc] = v0;
-        tile[r][jc + 1] = v1;
+        tile[r][jc + odd] = odd ? v1 : v0;
+        tile[r][jc + 1 - odd] = odd ? v0 : v1;
         if (i < n && j < n) {
             double *dst = p.out + i * p.ld + j;
             if (VEC && j + 1 < n) {
@@ -137,9 +213,8 @@ __global__ void __launch_bounds__(256) expquad_sym_kernel(ExpQuadArgs p, int nti
     }
     if (I == J) return;
     __syncthreads();
-    // mirrored tile: out[c0 + j][r0 + i] = tile[i][j].  A warp writes 2 x 256 contiguous bytes of one
-    // output row with 64-bit stores; lane <-> i keeps the column reads of `tile` bank-conflict free
-    // (row stride 65 doubles), which a 128-bit (i, i+1) pairing would not.
+    // mirrored tile: out[c0 + j][r0 + i] = tile[i][j].  A warp writes 2 x 256 contiguous bytes of one output row
+    // with 64-bit stores; lane <-> i keeps the column reads of `tile` bank-conflict free.
 #pragma unroll
     for (int rr = 0; rr < SQ / 8; ++rr) {
         const int j = ty + 8 * rr;
@@ -153,20 +228,21 @@ __global__ void __launch_bounds__(256) expquad_sym_kernel(ExpQuadArgs p, int nti
     }
 }
 
-template <int D>
-static int launch_expquad(const ExpQuadArgs &p, bool symmetric, cudaStream_t s) {
+template <int KIND, int D, bool FAST>
+static int launch_kernel_matrix(const ExpQuadArgs &p, bool symmetric, cudaStream_t s) {
     const bool vec = (p.ld % 2 == 0) && (((uintptr_t)p.out) % 16 == 0);
     if (symmetric) {
         const int nt = (int)((p.n1 + SQ - 1) / SQ);
-        const int64_t blocks = (int64_t)nt * (nt + 1) / 2;
+        const int ns = (nt + SUPER - 1) / SUPER;
+        const int64_t blocks = (int64_t)ns * (ns + 1) / 2 * SUPER * SUPER;
         if (blocks > 0x7fffffffLL) {
-            set_error("expquad: matrix too large for one launch");
+            set_error("kernel matrix: too large for one launch");
             return VGP_ERR_INVALID;
         }
         if (vec)
-            expquad_sym_kernel<D, true><<<(unsigned)blocks, 256, 0, s>>>(p, nt);
+            kernel_sym_kernel<KIND, D, true, FAST><<<(unsigned)blocks, 256, 0, s>>>(p, nt, ns);
         else
-            expquad_sym_kernel<D, false><<<(unsigned)blocks, 256, 0, s>>>(p, nt);
+            kernel_sym_kernel<KIND, D, false, FAST><<<(unsigned)blocks, 256, 0, s>>>(p, nt, ns);
     } else {
         dim3 grid((unsigned)((p.n2 + EQ_COLS - 1) / EQ_COLS), (unsigned)((p.n1 + EQ_ROWS - 1) / EQ_ROWS));
         if (grid.y > 65535u) {
@@ -178,37 +254,46 @@ static int launch_expquad(const ExpQuadArgs &p, bool symmetric, cudaStream_t s) 
                 q.n1 = min(slab, p.n1 - r);
                 q.out = p.out + r * p.ld;
                 q.diag_col0 = p.diag_col0 - r;
-                VGP_TRY(launch_expquad<D>(q, false, s));
+                VGP_TRY((launch_kernel_matrix<KIND, D, FAST>(q, false, s)));
             }
             return VGP_OK;
         }
         if (vec)
-            expquad_rect_kernel<D, true><<<grid, 256, 0, s>>>(p);
+            kernel_rect_kernel<KIND, D, true, FAST><<<grid, 256, 0, s>>>(p);
         else
-            expquad_rect_kernel<D, false><<<grid, 256, 0, s>>>(p);
+            kernel_rect_kernel<KIND, D, false, FAST><<<grid, 256, 0, s>>>(p);
     }
     VGP_LAUNCH_CHECK();
     return VGP_OK;
 }
 
-int expquad_dispatch(const ExpQuadArgs &p, int d, bool symmetric, cudaStream_t s) {
+template <int KIND, int D>
+static int launch_kind_dim(const ExpQuadArgs &p, bool symmetric, cudaStream_t s) {
+    // the exponent-field scaling of exp_nonpos needs a^2 2^(j/32) p(r) to stay a normal number after * 2^-937
+    const bool fast = p.amp2 >= 0x1p-60 && p.amp2 <= 0x1p60;
+    return fast ? launch_kernel_matrix<KIND, D, true>(p, symmetric, s)
+                : launch_kernel_matrix<KIND, D, false>(p, symmetric, s);
+}
+
+template <int KIND>
+static int launch_kind(const ExpQuadArgs &p, int d, bool symmetric, cudaStream_t s) {
     switch (d) {
-        case 1: return launch_expquad<1>(p, symmetric, s);
-        case 2: return launch_expquad<2>(p, symmetric, s);
-        case 3: return launch_expquad<3>(p, symmetric, s);
-        case 4: return launch_expquad<4>(p, symmetric, s);
-        case 5: return launch_expquad<5>(p, symmetric, s);
-        case 6: return launch_expquad<6>(p, symmetric, s);
-        case 7: return launch_expquad<7>(p, symmetric, s);
-        case 8: return launch_expquad<8>(p, symmetric, s);
+        case 1: return launch_kind_dim<KIND, 1>(p, symmetric, s);
+        case 2: return launch_kind_dim<KIND, 2>(p, symmetric, s);
+        case 3: return launch_kind_dim<KIND, 3>(p, symmetric, s);
+        case 4: return launch_kind_dim<KIND, 4>(p, symmetric, s);
+        case 5: return launch_kind_dim<KIND, 5>(p, symmetric, s);
+        case 6: return launch_kind_dim<KIND, 6>(p, symmetric, s);
+        case 7: return launch_kind_dim<KIND, 7>(p, symmetric, s);
+        case 8: return launch_kind_dim<KIND, 8>(p, symmetric, s);
     }
-    set_error("expquad: feature dimension %d outside [1, 8]", d);
+    set_error("kernel matrix: feature dimension %d outside [1, 8]", d);
     return VGP_ERR_INVALID;
 }
 
-int expquad_dispatch_public(const double *x1, int64_t n1, const double *x2, int64_t n2, int d, double amplitude,
-                            double length_scale, double diag_add, int64_t diag_col0, double *out, int64_t ld,
-                            cudaStream_t s) {
+int kernel_matrix_dispatch(int kind, const double *x1, int64_t n1, const double *x2, int64_t n2, int d,
+                           double amplitude, double length_scale, double diag_add, int64_t diag_col0, double *out,
+                           int64_t ld, cudaStream_t s) {
     if (n1 == 0 || n2 == 0) return VGP_OK;
     ExpQuadArgs p;
     p.x1 = x1;
@@ -216,27 +301,56 @@ int expquad_dispatch_public(const double *x1, int64_t n1, const double *x2, int6
     p.n1 = n1;
     p.n2 = n2;
     p.amp2 = amplitude * amplitude;
-    p.neg_half_inv_l2 = -0.5 / (length_scale * length_scale);
     p.diag_add = diag_add;
     p.diag_col0 = diag_col0;
     p.out = out;
     p.ld = ld;
     const bool symmetric = (x1 == x2) && (n1 == n2) && diag_col0 == 0 && n1 >= 2 * SQ;
-    return expquad_dispatch(p, d, symmetric, s);
+    switch (kind) {
+        case KIND_EXPQUAD:
+            p.c = -0.5 / (length_scale * length_scale);
+            return launch_kind<KIND_EXPQUAD>(p, d, symmetric, s);
+        case KIND_MATERN12:
+            p.c = -1.0 / length_scale;
+            return launch_kind<KIND_MATERN12>(p, d, symmetric, s);
+        case KIND_MATERN32:
+            p.c = -sqrt(3.0) / length_scale;
+            return launch_kind<KIND_MATERN32>(p, d, symmetric, s);
+        case KIND_MATERN52:
+            p.c = -sqrt(5.0) / length_scale;
+            return launch_kind<KIND_MATERN52>(p, d, symmetric, s);
+    }
+    set_error("kernel matrix: unknown kernel kind %d", kind);
+    return VGP_ERR_INVALID;
+}
+
+int expquad_dispatch_public(const double *x1, int64_t n1, const double *x2, int64_t n2, int d, double amplitude,
+                            double length_scale, double diag_add, int64_t diag_col0, double *out, int64_t ld,
+                            cudaStream_t s) {
+    return kernel_matrix_dispatch(KIND_EXPQUAD, x1, n1, x2, n2, d, amplitude, length_scale, diag_add, diag_col0, out,
+                                  ld, s);
 }
 
 }  // namespace vgp
 
-extern "C" int vgp_expquad_matrix(int device, const double *x1_dev, int64_t n1, const double *x2_dev, int64_t n2,
-                                  int d, double amplitude, double length_scale, double diag_add,
-                                  int64_t diag_col0, double *out_dev, int64_t ld_out, void *stream) {
+extern "C" int vgp_kernel_matrix(int device, int kind, const double *x1_dev, int64_t n1, const double *x2_dev,
+                                 int64_t n2, int d, double amplitude, double length_scale, double diag_add,
+                                 int64_t diag_col0, double *out_dev, int64_t ld_out, void *stream) {
     VGP_REQUIRE(n1 >= 0 && n2 >= 0, "negative size");
     VGP_REQUIRE(ld_out >= n2, "ld_out %lld < n2 %lld", (long long)ld_out, (long long)n2);
     VGP_REQUIRE(length_scale > 0.0, "length_scale must be positive");
     VGP_REQUIRE(d >= 1 && d <= 8, "feature dimension %d outside [1, 8]", d);
+    VGP_REQUIRE(kind >= VGP_KERNEL_EXPQUAD && kind <= VGP_KERNEL_MATERN52, "unknown kernel kind %d", kind);
     if (n1 == 0 || n2 == 0) return VGP_OK;
     VGP_REQUIRE(x1_dev && x2_dev && out_dev, "NULL pointer");
     VGP_ENTER(device);
-    return vgp::expquad_dispatch_public(x1_dev, n1, x2_dev, n2, d, amplitude, length_scale, diag_add, diag_col0,
-                                        out_dev, ld_out, (cudaStream_t)stream);
+    return vgp::kernel_matrix_dispatch(kind, x1_dev, n1, x2_dev, n2, d, amplitude, length_scale, diag_add, diag_col0,
+                                       out_dev, ld_out, (cudaStream_t)stream);
+}
+
+extern "C" int vgp_expquad_matrix(int device, const double *x1_dev, int64_t n1, const double *x2_dev, int64_t n2,
+                                  int d, double amplitude, double length_scale, double diag_add,
+                                  int64_t diag_col0, double *out_dev, int64_t ld_out, void *stream) {
+    return vgp_kernel_matrix(device, VGP_KERNEL_EXPQUAD, x1_dev, n1, x2_dev, n2, d, amplitude, length_scale, diag_add,
+                             diag_col0, out_dev, ld_out, stream);
 }

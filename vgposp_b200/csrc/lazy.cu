@@ -18,6 +18,7 @@
 // U[t-1], W[t-1], diagonal and numerator updates) and scores every candidate for the next arg-max in one launch.
 // Algorithmic bytes of lazy_step_kernel at step t: 8 n (2 (t-1) + 6).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <new>
@@ -704,6 +705,8 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
     gate.chunk_rows = CHUNK_ROWS;
     gate.events = chunk_ev.data();
     gate.nchunks = nchunks;
+    const char *ov = getenv("VGP_H2D_OVERLAP");          // measurement knob: "0" = finish the copy before factorising
+    if (ov && ov[0] == '0') gate.waited = nchunks, cudaStreamWaitEvent(s, chunk_ev[(size_t)nchunks - 1], 0);
     dense_set_gate(&gate);
     int info = 0;
     rc = lazy_factor_staged(h, &info, s);
