@@ -73,21 +73,23 @@ def test_kernel_matrix_kinds(kind, n1, n2, d, same):
 
 
 def test_expquad_fast_exp_edges():
-    """Arguments of the fast exp that leave its fast path: exact zero distance (value a^2 exactly), results below
-    2^-937 (libm branch, may be subnormal or 0), huge amplitude (libm kernels), and a wide sweep of exponents."""
+    """Arguments at the edges of the fast exp: exact zero distance (value a^2 exactly), arguments below -650 (the fast
+    path returns exactly 0 where libm still has 1e-283 a^2 -- hence atol), huge amplitude (libm kernels, no flush),
+    and a dense sweep of exponents over the whole fast range."""
     x1 = np.zeros((3, 1))
     x1[:, 0] = [0.0, 1.0, 40.0]
     x2 = np.array([[0.0], [1.0 + 1e-9], [3.0], [12.0], [26.0], [27.5], [39.0]])
-    for amp in (1.0, 0.37, 1e25):
+    for amp, atol in ((1.0, 1e-282), (0.37, 1e-282), (1e25, 1e-310)):
         got = expquad(x1, x2, amp, 0.7)
         want = gpo.expquad_matrix(x1, x2, amp, 0.7)
-        np.testing.assert_allclose(got, want, rtol=2e-13, atol=1e-310)
+        np.testing.assert_allclose(got, want, rtol=2e-13, atol=atol)
         assert got[0, 0] == amp * amp
     t = -np.linspace(0.0, 700.0, 4001)[:, None]               # exp(t) via l = 1/sqrt(2), x = sqrt(-t)
     xs = np.sqrt(-t)
     got = expquad(xs, np.zeros((1, 1)), 1.0, np.sqrt(0.5))
     want = gpo.expquad_matrix(xs, np.zeros((1, 1)), 1.0, np.sqrt(0.5))
-    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-300)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-282)
+    assert np.all(got[t[:, 0] > -649.0] > 0.0)
 
 
 def test_expquad_empty_and_bad_arguments():

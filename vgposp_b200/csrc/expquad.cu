@@ -17,8 +17,7 @@
 // `exp_nonpos` below is 12: arguments are never positive here, so the reduction is t = k ln2/32 + r with a
 // Cody-Waite pair (two FMAs, exact), a degree-6 polynomial on |r| <= ln2/64, one multiply by the table entry
 // a^2 2^(j/32) (32 entries in shared memory, amplitude folded in) and an integer add on the exponent field.
-// Measured against long-double exp over [-700, 0]: <= 1.94 ulp.  Underflow-range arguments, NaN and infinities take
-// the libm branch.  The symmetric path additionally evaluates each off-diagonal 64x64 tile once and writes it twice
+// Measured against long-double exp over [-650, 0]: <= 1.94 ulp; below -650 the result is 0.  The symmetric path additionally evaluates each off-diagonal 64x64 tile once and writes it twice
 // (once transposed through shared memory); its CTAs walk 16x16 super-tiles so that both the direct and the mirrored
 // stores of concurrently running CTAs fall into the same 1024 x 1024 block of the output (8 KB row pieces in L2
 // instead of scattered 512-byte pieces).
@@ -45,36 +44,44 @@ struct ExpQuadArgs {
 
 constexpr int EXP_TAB = 32;
 constexpr double EXP_INV_L = 46.16624130844683;            // 32 / ln 2
-constexpr double EXP_L_HI = 0.02166084939249829;           // ln 2 / 32, float64 head
-constexpr double EXP_L_LO = 7.247021293269686e-19;         //            and tail
-constexpr double EXP_MAGIC = 6755399441055744.0;           // 1.5 * 2^52: adding it rounds to the nearest integer
+// Constants of exp_nonpos live in constant memory so that every FP64 instruction takes them as a c[bank][offset]
+// operand; as literals the compiler rebuilt each 64-bit immediate with two UMOVs per use, one issue slot per DFMA
+// in a kernel that ncu showed to be issue-bound (82 % issue-active).
+__constant__ double EXP_K[10] = {
+    6755399441055744.0,          // [0] MAGIC = 1.5 * 2^52: adding it rounds to the nearest integer
+    -0.02166084939249829,        // [1] -ln 2 / 32, float64 head
+    -7.247021293269686e-19,      // [2]             and tail
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,      // [3..8] Taylor coefficients, degree 6 .. 1
+    1.0 / 3.0};                  // [9] Matern 5/2
 
 // tab[j] = amp2 * 2^(j / 32)
 __device__ __forceinline__ void exp_table_fill(double *tab, double amp2) {
     if (threadIdx.x < EXP_TAB) tab[threadIdx.x] = amp2 * exp2((double)threadIdx.x * (1.0 / EXP_TAB));
 }
 
-__device__ __noinline__ double exp_slow(double t, double amp2) { return amp2 * exp(t); }
-
 // amp2 * exp(t) for t <= 0 (amp2 within [2^-60, 2^60], checked by the launcher).  `kd` = MAGIC + (an integer within
-// 1 of 32 t / ln 2), formed by the caller with one FMA from whatever t was computed from.
-__device__ __forceinline__ double exp_nonpos(double t, double kd, const double *tab, double amp2) {
-    // t < -650 (result below 2^-937), NaN, -inf: libm.  Integer compare on the high word (t <= 0: the more negative,
-    // the larger the unsigned word) keeps the test off the FP64 pipe.
-    if ((unsigned)__double2hiint(t) > 0xC0845000u) return exp_slow(t, amp2);
+// 1 of 32 t / ln 2), formed by the caller with one FMA from whatever t was computed from.  Branch-free: arguments
+// below -650 (results under 2^-937 a^2, far below anything a covariance carries) and -inf give exactly 0; NaN
+// propagates through the polynomial.  <= 1.94 ulp against long-double exp on [-650, 0].
+__device__ __forceinline__ double exp_nonpos(double t, double kd, const double *tab) {
     const int k = __double2loint(kd);                       // k <= 0
-    kd -= EXP_MAGIC;
-    double r = fma(kd, -EXP_L_HI, t);
-    r = fma(kd, -EXP_L_LO, r);
-    double p = 1.0 / 720.0;
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    kd -= EXP_K[0];
+    double r = fma(kd, EXP_K[1], t);
+    r = fma(kd, EXP_K[2], r);
+    double p = EXP_K[3];
+    p = fma(p, r, EXP_K[4]);
+    p = fma(p, r, EXP_K[5]);
+    p = fma(p, r, EXP_K[6]);
+    p = fma(p, r, EXP_K[7]);
+    p = fma(p, r, EXP_K[8]);
+    p = fma(p, r, EXP_K[8]);
     const double v = tab[k & (EXP_TAB - 1)] * p;
-    return __hiloint2double(__double2hiint(v) + ((k >> 5) << 20), __double2loint(v));     // v * 2^floor(k / 32)
+    // v * 2^floor(k / 32) through the exponent field; integer tests on the high word of t (t <= 0: the more
+    // negative, the larger the unsigned word) keep the range check off the FP64 pipe
+    const unsigned th = (unsigned)__double2hiint(t);
+    const bool tiny = th > 0xC0845000u && (th < 0xFFF00000u || (th == 0xFFF00000u && __double2loint(t) == 0));
+    const int hi = __double2hiint(v) + ((k & ~(EXP_TAB - 1)) << 15);
+    return __hiloint2double(tiny ? 0 : hi, tiny ? 0 : __double2loint(v));
 }
 
 template <int KIND, int D, bool FAST>
@@ -88,21 +95,49 @@ __device__ __forceinline__ double kernel_value(const double (&a)[D], const doubl
     }
     if (KIND == KIND_EXPQUAD) {
         const double t = s * c;
-        return FAST ? exp_nonpos(t, fma(s, cz, EXP_MAGIC), tab, amp2) : amp2 * exp(t);
+        return FAST ? exp_nonpos(t, fma(s, cz, EXP_K[0]), tab) : amp2 * exp(t);
     }
     const double t = sqrt(s) * c;                           // -z
-    const double e = FAST ? exp_nonpos(t, fma(t, EXP_INV_L, EXP_MAGIC), tab, amp2) : amp2 * exp(t);
+    const double e = FAST ? exp_nonpos(t, fma(t, EXP_INV_L, EXP_K[0]), tab) : amp2 * exp(t);
     if (KIND == KIND_MATERN12) return e;
-    if (KIND == KIND_MATERN32) return (1.0 - t) * e;
-    return fma(t, fma(t, 1.0 / 3.0, -1.0), 1.0) * e;        // 1 + z + z^2 / 3
+    if (KIND == KIND_MATERN32) return (EXP_K[8] - t) * e;
+    return fma(t, fma(t, EXP_K[9], -EXP_K[8]), EXP_K[8]) * e;      // 1 + z + z^2 / 3
 }
 
 // ---- general rectangular path: CTA tile 32 rows x 512 columns, 256 threads, 2 columns per thread ------
 constexpr int EQ_ROWS = 32;
 constexpr int EQ_COLS = 512;
 
-template <int KIND, int D, bool VEC, bool FAST>
-__global__ void __launch_bounds__(256) kernel_rect_kernel(ExpQuadArgs p) {
+// FULL: the tile lies inside the matrix and 128-bit stores are legal -- no bounds tests in the loop
+template <int KIND, int D, bool FAST, bool FULL>
+__device__ __forceinline__ void rect_tile(const ExpQuadArgs &p, const double (*xs)[D], const double *tab,
+                                          int64_t row0, int64_t col, int rows, bool vec) {
+    double b0[D], b1[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        b0[k] = (FULL || col < p.n2) ? p.x2[col * D + k] : 0.0;
+        b1[k] = (FULL || col + 1 < p.n2) ? p.x2[(col + 1) * D + k] : 0.0;
+    }
+    const double cz = p.c * EXP_INV_L;
+    double *dst = p.out + row0 * p.ld + col;
+#pragma unroll 4
+    for (int r = 0; r < (FULL ? EQ_ROWS : rows); ++r, dst += p.ld) {
+        double a[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) a[k] = xs[r][k];
+        const double v0 = kernel_value<KIND, D, FAST>(a, b0, p.amp2, p.c, cz, tab);
+        const double v1 = kernel_value<KIND, D, FAST>(a, b1, p.amp2, p.c, cz, tab);
+        if (FULL || (vec && col + 1 < p.n2)) {
+            *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+        } else {
+            dst[0] = v0;
+            if (col + 1 < p.n2) dst[1] = v1;
+        }
+    }
+}
+
+template <int KIND, int D, bool FAST>
+__global__ void __launch_bounds__(256) kernel_rect_kernel(ExpQuadArgs p, int vec) {
     __shared__ double xs[EQ_ROWS][D];
     __shared__ double tab[EXP_TAB];
     const int64_t row0 = (int64_t)blockIdx.y * EQ_ROWS;
@@ -112,31 +147,14 @@ __global__ void __launch_bounds__(256) kernel_rect_kernel(ExpQuadArgs p) {
         xs[t / D][t % D] = r < p.n1 ? p.x1[r * D + t % D] : 0.0;
     }
     if (FAST) exp_table_fill(tab, p.amp2);
-    double b0[D], b1[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        b0[k] = col < p.n2 ? p.x2[col * D + k] : 0.0;
-        b1[k] = col + 1 < p.n2 ? p.x2[(col + 1) * D + k] : 0.0;
-    }
     __syncthreads();
     if (col >= p.n2) return;
     const int rows = (int)min((int64_t)EQ_ROWS, p.n1 - row0);
-    const double cz = p.c * EXP_INV_L;
-#pragma unroll 4
-    for (int r = 0; r < rows; ++r) {
-        double a[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) a[k] = xs[r][k];
-        const double v0 = kernel_value<KIND, D, FAST>(a, b0, p.amp2, p.c, cz, tab);
-        const double v1 = kernel_value<KIND, D, FAST>(a, b1, p.amp2, p.c, cz, tab);
-        double *dst = p.out + (row0 + r) * p.ld + col;
-        if (VEC && col + 1 < p.n2) {
-            *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
-        } else {
-            dst[0] = v0;
-            if (col + 1 < p.n2) dst[1] = v1;
-        }
-    }
+    const bool full = vec && rows == EQ_ROWS && ((int64_t)blockIdx.x + 1) * EQ_COLS <= p.n2;      // CTA-uniform
+    if (full)
+        rect_tile<KIND, D, FAST, true>(p, xs, tab, row0, col, rows, true);
+    else
+        rect_tile<KIND, D, FAST, false>(p, xs, tab, row0, col, rows, vec != 0);
     // diagonal shift, outside the hot loop: the thread that owns column j also wrote out[diag_col0 + j][j]
     if (p.diag_add != 0.0) {
 #pragma unroll
@@ -149,13 +167,77 @@ __global__ void __launch_bounds__(256) kernel_rect_kernel(ExpQuadArgs p) {
 
 // ---- symmetric path: one CTA per 64x64 tile pair (I <= J), CTAs ordered by 16x16 super-tiles -----------
 constexpr int SQ = 64;
+constexpr int SQ_LD = SQ + 2;       // 16-byte aligned rows for 128-bit stores; (SQ_LD / 2) odd: a quarter-warp reading one
+                                    // column pair of 8 consecutive rows with 128-bit loads covers all 32 banks
 constexpr int SUPER = 16;
 
-template <int KIND, int D, bool VEC, bool FAST>
-__global__ void __launch_bounds__(256) kernel_sym_kernel(ExpQuadArgs p, int ntiles, int nsuper) {
+template <int KIND, int D, bool FAST, bool FULL>
+__device__ __forceinline__ void sym_tile(const ExpQuadArgs &p, const double (*xi)[D], const double (*xj)[D],
+                                         double (*tile)[SQ_LD], const double *tab, int64_t r0, int64_t c0, bool diag,
+                                         bool vec) {
+    const int64_t n = p.n1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int jc = 2 * tx;
+    const double cz = p.c * EXP_INV_L;
+    double b0[D], b1[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        b0[k] = xj[jc][k];
+        b1[k] = xj[jc + 1][k];
+    }
+    double *dst = p.out + (r0 + ty) * p.ld + c0 + jc;
+#pragma unroll
+    for (int rr = 0; rr < SQ / 8; ++rr, dst += 8 * p.ld) {
+        const int r = ty + 8 * rr;
+        double a[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) a[k] = xi[r][k];
+        double v0 = kernel_value<KIND, D, FAST>(a, b0, p.amp2, p.c, cz, tab);
+        double v1 = kernel_value<KIND, D, FAST>(a, b1, p.amp2, p.c, cz, tab);
+        if (diag) {                                         // I == J: r0 == c0
+            if (r == jc) v0 += p.diag_add;
+            if (r == jc + 1) v1 += p.diag_add;
+        }
+        *reinterpret_cast<double2 *>(&tile[r][jc]) = make_double2(v0, v1);
+        if (FULL) {
+            *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+        } else if (r0 + r < n && c0 + jc < n) {
+            if (vec && c0 + jc + 1 < n) {
+                *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+            } else {
+                dst[0] = v0;
+                if (c0 + jc + 1 < n) dst[1] = v1;
+            }
+        }
+    }
+    if (diag) return;
+    __syncthreads();
+    // mirrored tile: out[c0 + j][r0 + i] = tile[i][j].  Lane <-> i: one 128-bit shared load brings two output rows
+    // (j, j + 1) of column i, each row of the output receives 256 contiguous bytes per warp store.
+#pragma unroll
+    for (int q = 0; q < SQ / 16; ++q) {
+        const int j = 2 * (ty + 8 * q);
+        double *m0 = p.out + (c0 + j) * p.ld + r0 + tx;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = tx + 32 * h;
+            const double2 v = *reinterpret_cast<const double2 *>(&tile[i][j]);
+            if (FULL) {
+                m0[32 * h] = v.x;
+                m0[p.ld + 32 * h] = v.y;
+            } else if (r0 + i < n) {
+                if (c0 + j < n) m0[32 * h] = v.x;
+                if (c0 + j + 1 < n) m0[p.ld + 32 * h] = v.y;
+            }
+        }
+    }
+}
+
+template <int KIND, int D, bool FAST>
+__global__ void __launch_bounds__(256) kernel_sym_kernel(ExpQuadArgs p, int ntiles, int nsuper, int vec) {
     __shared__ double xi[SQ][D];
     __shared__ double xj[SQ][D];
-    __shared__ double tile[SQ][SQ + 1];
+    __shared__ __align__(16) double tile[SQ][SQ_LD];
     __shared__ double tab[EXP_TAB];
     // linear super-block id -> (SI, SJ) with SI <= SJ, row-major over the upper triangle of super-tiles
     const int64_t sb = blockIdx.x / (SUPER * SUPER);
@@ -176,61 +258,16 @@ __global__ void __launch_bounds__(256) kernel_sym_kernel(ExpQuadArgs p, int ntil
     }
     if (FAST) exp_table_fill(tab, p.amp2);
     __syncthreads();
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int jc = 2 * tx;
-    // lanes 8-15 and 24-31 store their two values in the opposite order: the 64-bit shared-memory stores of a
-    // half-warp then cover 16 distinct bank pairs (row stride 65 doubles keeps the transposed reads conflict-free)
-    const int odd = (tx >> 3) & 1;
-    const double cz = p.c * EXP_INV_L;
-    double b0[D], b1[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        b0[k] = xj[jc][k];
-        b1[k] = xj[jc + 1][k];
-    }
-#pragma unroll
-    for (int rr = 0; rr < SQ / 8; ++rr) {
-        const int r = ty + 8 * rr;
-        double a[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) a[k] = xi[r][k];
-        double v0 = kernel_value<KIND, D, FAST>(a, b0, p.amp2, p.c, cz, tab);
-        double v1 = kernel_value<KIND, D, FAST>(a, b1, p.amp2, p.c, cz, tab);
-        const int64_t i = r0 + r, j = c0 + jc;
-        if (i == j) v0 += p.diag_add;
-        if (i == j + 1) v1 += p.diag_add;
-        tile[r][jc + odd] = odd ? v1 : v0;
-        tile[r][jc + 1 - odd] = odd ? v0 : v1;
-        if (i < n && j < n) {
-            double *dst = p.out + i * p.ld + j;
-            if (VEC && j + 1 < n) {
-                *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
-            } else {
-                dst[0] = v0;
-                if (j + 1 < n) dst[1] = v1;
-            }
-        }
-    }
-    if (I == J) return;
-    __syncthreads();
-    // mirrored tile: out[c0 + j][r0 + i] = tile[i][j].  A warp writes 2 x 256 contiguous bytes of one output row
-    // with 64-bit stores; lane <-> i keeps the column reads of `tile` bank-conflict free.
-#pragma unroll
-    for (int rr = 0; rr < SQ / 8; ++rr) {
-        const int j = ty + 8 * rr;
-        const int64_t row = c0 + j;
-        if (row >= n) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int i = tx + 32 * h;
-            if (r0 + i < n) p.out[row * p.ld + r0 + i] = tile[i][j];
-        }
-    }
+    const bool full = vec && c0 + SQ <= n;                  // (r0 <= c0) CTA-uniform
+    if (full)
+        sym_tile<KIND, D, FAST, true>(p, xi, xj, tile, tab, r0, c0, I == J, true);
+    else
+        sym_tile<KIND, D, FAST, false>(p, xi, xj, tile, tab, r0, c0, I == J, vec != 0);
 }
 
 template <int KIND, int D, bool FAST>
 static int launch_kernel_matrix(const ExpQuadArgs &p, bool symmetric, cudaStream_t s) {
-    const bool vec = (p.ld % 2 == 0) && (((uintptr_t)p.out) % 16 == 0);
+    const int vec = ((p.ld % 2 == 0) && (((uintptr_t)p.out) % 16 == 0)) ? 1 : 0;
     if (symmetric) {
         const int nt = (int)((p.n1 + SQ - 1) / SQ);
         const int ns = (nt + SUPER - 1) / SUPER;
@@ -239,10 +276,7 @@ static int launch_kernel_matrix(const ExpQuadArgs &p, bool symmetric, cudaStream
             set_error("kernel matrix: too large for one launch");
             return VGP_ERR_INVALID;
         }
-        if (vec)
-            kernel_sym_kernel<KIND, D, true, FAST><<<(unsigned)blocks, 256, 0, s>>>(p, nt, ns);
-        else
-            kernel_sym_kernel<KIND, D, false, FAST><<<(unsigned)blocks, 256, 0, s>>>(p, nt, ns);
+        kernel_sym_kernel<KIND, D, FAST><<<(unsigned)blocks, 256, 0, s>>>(p, nt, ns, vec);
     } else {
         dim3 grid((unsigned)((p.n2 + EQ_COLS - 1) / EQ_COLS), (unsigned)((p.n1 + EQ_ROWS - 1) / EQ_ROWS));
         if (grid.y > 65535u) {
@@ -258,10 +292,7 @@ static int launch_kernel_matrix(const ExpQuadArgs &p, bool symmetric, cudaStream
             }
             return VGP_OK;
         }
-        if (vec)
-            kernel_rect_kernel<KIND, D, true, FAST><<<grid, 256, 0, s>>>(p);
-        else
-            kernel_rect_kernel<KIND, D, false, FAST><<<grid, 256, 0, s>>>(p);
+        kernel_rect_kernel<KIND, D, FAST><<<grid, 256, 0, s>>>(p, vec);
     }
     VGP_LAUNCH_CHECK();
     return VGP_OK;
