@@ -491,7 +491,45 @@ constexpr int BLOCK_SMEM = NB * SLD * 8;    // 132 096 B
 // memory (broadcast / conflict-free) and issues 64 FMAs.
 
 // Lower Cholesky of one diagonal block, in place; strict upper triangle zeroed.  Right-looking, the pivot
-// column travels through a double-buffered 128-entry shared array: one barrier per column.
+// column travels through a double-buffered 128-entry shared array: one barrier per column.  The column loop is
+// split into 8 panels of 16 columns with the panel index a template parameter: which register holds column j,
+// which rows / columns lie behind the pivot (and need no update) are then compile-time facts, and the trailing
+// update shrinks with the panel -- the first version carried them as run-time selects (374 FSEL per column, 200 us
+// per block, issue-bound; ncu launch list of the ELBO step).
+template <int SJ>
+__device__ __forceinline__ void potf2_panel(double (&v)[8][8], double (*colbuf)[NB], int ti, int tc, int *info,
+                                            int row_offset) {
+#pragma unroll 1
+    for (int jj = 0; jj < 16; ++jj) {
+        const int j = 16 * SJ + jj, jb = j & 1;
+        if (tc == jj) {
+#pragma unroll
+            for (int r = SJ; r < 8; ++r) colbuf[jb][ti + 16 * r] = v[r][SJ];
+        }
+        __syncthreads();
+        const double d = colbuf[jb][j];
+        if (!(d > 0.0) && threadIdx.x == 0) atomicCAS(info, 0, row_offset + j + 1);
+        const double piv = sqrt(d);
+        const double inv = 1.0 / piv;
+        double lr[8], lc[8];
+#pragma unroll
+        for (int r = SJ; r < 8; ++r) lr[r] = (r > SJ || ti > jj) ? colbuf[jb][ti + 16 * r] * inv : 0.0;     // i > j
+#pragma unroll
+        for (int s = SJ; s < 8; ++s) lc[s] = (s > SJ || tc > jj) ? colbuf[jb][tc + 16 * s] * inv : 0.0;     // c > j
+#pragma unroll
+        for (int r = SJ; r < 8; ++r)
+#pragma unroll
+            for (int s = SJ; s <= r; ++s) v[r][s] = fma(-lr[r], lc[s], v[r][s]);      // lower blocks only
+        if (tc == jj) {        // column j is final: store L[i][j]
+#pragma unroll
+            for (int r = SJ; r < 8; ++r) {
+                if (r > SJ || ti > jj) v[r][SJ] = lr[r];
+                else if (ti == jj) v[r][SJ] = piv;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, int *info, int row_offset) {
     __shared__ double colbuf[2][NB];
     const int ti = threadIdx.x >> 4, tc = threadIdx.x & 15;
@@ -503,51 +541,14 @@ __global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, in
             const int i = ti + 16 * r, c = tc + 16 * s;
             v[r][s] = c <= i ? a[(int64_t)i * ld + c] : 0.0;
         }
-#pragma unroll 1
-    for (int j = 0; j < NB; ++j) {
-        const int jb = j & 1, sj = j >> 4, tcj = j & 15;
-        if (tc == tcj) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = ti + 16 * r;
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    if (s == sj && i >= j) colbuf[jb][i] = v[r][s];
-            }
-        }
-        __syncthreads();
-        const double d = colbuf[jb][j];
-        if (!(d > 0.0) && threadIdx.x == 0) atomicCAS(info, 0, row_offset + j + 1);
-        const double piv = sqrt(d);
-        const double inv = 1.0 / piv;
-        double lr[8], lc[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int i = ti + 16 * r;
-            lr[r] = i > j ? colbuf[jb][i] * inv : 0.0;
-        }
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const int c = tc + 16 * s;
-            lc[s] = c > j ? colbuf[jb][c] * inv : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int s = 0; s < 8; ++s) v[r][s] = fma(-lr[r], lc[s], v[r][s]);
-        if (tc == tcj) {        // column j is final: store L[i][j]
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = ti + 16 * r;
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    if (s == sj) {
-                        if (i > j) v[r][s] = lr[r];
-                        else if (i == j) v[r][s] = piv;
-                    }
-            }
-        }
-    }
+    potf2_panel<0>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<1>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<2>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<3>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<4>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<5>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<6>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<7>(v, colbuf, ti, tc, info, row_offset);
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -560,6 +561,35 @@ __global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, in
 // out = inv(L) for one lower 128-block (strict upper of `out` zeroed); `transpose` writes inv(L)^T.
 // Forward substitution on the identity, all 128 right-hand sides at once: after row k of X is final, every
 // later row gets the rank-1 correction  B[i][:] -= L[i][k] X[k][:].  L sits in shared memory, B/X in registers.
+// Same panel split as potf2: X is lower triangular, so row k only has columns <= k, and only rows > k change.
+template <int RK>
+__device__ __forceinline__ void trtri_panel(double (&x)[8][8], const double *sm, double (*rowbuf)[NB], int ti,
+                                            int tc) {
+#pragma unroll 1
+    for (int kk = 0; kk < 16; ++kk) {
+        const int k = 16 * RK + kk, kb = k & 1;
+        if (ti == kk) {
+#pragma unroll
+            for (int s = 0; s <= RK; ++s) rowbuf[kb][tc + 16 * s] = x[RK][s];
+        }
+        __syncthreads();
+        const double dinv = 1.0 / sm[k * SLD + k];
+        double xr[8], lk[8];
+#pragma unroll
+        for (int s = 0; s <= RK; ++s) xr[s] = rowbuf[kb][tc + 16 * s] * dinv;
+#pragma unroll
+        for (int r = RK; r < 8; ++r) lk[r] = (r > RK || ti > kk) ? sm[(ti + 16 * r) * SLD + k] : 0.0;    // i > k
+#pragma unroll
+        for (int r = RK; r < 8; ++r)
+#pragma unroll
+            for (int s = 0; s <= RK; ++s) x[r][s] = fma(-lk[r], xr[s], x[r][s]);
+        if (ti == kk) {
+#pragma unroll
+            for (int s = 0; s <= RK; ++s) x[RK][s] = xr[s];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256, 1) trtri_kernel(const double *l, int64_t ldl, double *out, int64_t ldo,
                                                        int transpose) {
     extern __shared__ __align__(16) double sm[];          // L, [128][129]
@@ -575,38 +605,14 @@ __global__ void __launch_bounds__(256, 1) trtri_kernel(const double *l, int64_t 
 #pragma unroll
         for (int s = 0; s < 8; ++s) x[r][s] = (ti + 16 * r == tc + 16 * s) ? 1.0 : 0.0;
     __syncthreads();
-#pragma unroll 1
-    for (int k = 0; k < NB; ++k) {
-        const int kb = k & 1, rk = k >> 4, tik = k & 15;
-        if (ti == tik) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    if (r == rk) rowbuf[kb][tc + 16 * s] = x[r][s];
-        }
-        __syncthreads();
-        const double dinv = 1.0 / sm[k * SLD + k];
-        double xr[8], lk[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) xr[s] = rowbuf[kb][tc + 16 * s] * dinv;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int i = ti + 16 * r;
-            lk[r] = i > k ? sm[i * SLD + k] : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int s = 0; s < 8; ++s) x[r][s] = fma(-lk[r], xr[s], x[r][s]);
-        if (ti == tik) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int s = 0; s < 8; ++s)
-                    if (r == rk) x[r][s] = xr[s];
-        }
-    }
+    trtri_panel<0>(x, sm, rowbuf, ti, tc);
+    trtri_panel<1>(x, sm, rowbuf, ti, tc);
+    trtri_panel<2>(x, sm, rowbuf, ti, tc);
+    trtri_panel<3>(x, sm, rowbuf, ti, tc);
+    trtri_panel<4>(x, sm, rowbuf, ti, tc);
+    trtri_panel<5>(x, sm, rowbuf, ti, tc);
+    trtri_panel<6>(x, sm, rowbuf, ti, tc);
+    trtri_panel<7>(x, sm, rowbuf, ti, tc);
     // `out` may alias `l`: every thread finished reading L from global memory before the first barrier
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -836,12 +842,13 @@ int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream
 
 // copy a cached [128][128] inverse into the matrix (it already has a zero strict upper triangle)
 __global__ void __launch_bounds__(256) block_copy_kernel(const double *src, double *dst, int64_t ldd) {
-    for (int e = threadIdx.x; e < NB * NB; e += 256) dst[(int64_t)(e >> 7) * ldd + (e & 127)] = src[e];
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < NB * NB; e += gridDim.x * 256)
+        dst[(int64_t)(e >> 7) * ldd + (e & 127)] = src[e];
 }
 
 static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, DenseWorkspace &ws, cudaStream_t s) {
     if (n == NB) {
-        block_copy_kernel<<<1, 256, 0, s>>>(dinv, l, ld);
+        block_copy_kernel<<<16, 256, 0, s>>>(dinv, l, ld);
         VGP_LAUNCH_CHECK();
         return VGP_OK;
     }

@@ -190,6 +190,8 @@ struct vgp_elbo {
     double *partial = nullptr, *rowacc = nullptr, *gradz = nullptr;
     int splits_n = 1, splits_b = 1;
     DenseWorkspace ws[3];
+    cudaStream_t side[2] = {nullptr, nullptr};      // the two inverses that only need K_zz run beside the N-sized work
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int64_t launches = 0;
     double last_terms[5] = {0, 0, 0, 0, 0};
     double *mat(int id) const { return mats + (size_t)id * mp * mp; }
@@ -251,6 +253,20 @@ int lincomb(const Terms &t, double *out, int64_t mp, cudaStream_t s) {
     return VGP_OK;
 }
 
+// *out = sum_{i < m} log L[i][i]: one block, fixed tree (runs on whichever stream factorised L)
+__global__ void __launch_bounds__(256) logdiag_kernel(const double *l, int64_t ld, int64_t m, double *out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < m; i += 256) acc += log(l[i * ld + i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
 // dst = (src + shift I on the valid block, identity on the padding)^-1, log-determinant of the valid block -> slot
 int invert(vgp_elbo *h, const double *src, double shift, double *dst, DenseWorkspace &ws, Reducer &red, int slot,
            cudaStream_t s) {
@@ -259,7 +275,8 @@ int invert(vgp_elbo *h, const double *src, double shift, double *dst, DenseWorks
     VGP_LAUNCH_CHECK();
     VGP_TRY(pad_identity(dst, mp, h->m, mp, s));
     VGP_TRY(dense_potrf(dst, mp, mp, ws, s));
-    VGP_TRY(red.run(SumLogDiag{dst, mp}, h->m, slot));
+    logdiag_kernel<<<1, 256, 0, s>>>(dst, mp, h->m, red.scal + slot);
+    VGP_LAUNCH_CHECK();
     VGP_TRY(dense_trtri(dst, mp, mp, ws, s));
     VGP_TRY(dense_lauum(dst, mp, mp, ws, s));
     return dense_mirror_lower(dst, mp, mp, s);
@@ -292,6 +309,15 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
 
     // ---- kernel blocks and sufficient statistics ---------------------------------------------------
     VGP_TRY(expquad_dispatch_public(h->z, m, h->z, m, h->d, a, l, 0.0, 0, M(K_), mp, s));
+    // fork: (K + eps I)^-1 and K^-1 depend on K_zz only; their latency-bound chains of small kernels run on two side
+    // streams underneath the K_zx build and the m x m x N SYRK
+    VGP_CUDA(cudaEventRecord(h->ev_fork, s));
+    VGP_CUDA(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
+    VGP_CUDA(cudaStreamWaitEvent(h->side[1], h->ev_fork, 0));
+    VGP_TRY(invert(h, M(K_), eps, M(Q_), h->ws[0], red, S_LDKT, h->side[0]));
+    VGP_CUDA(cudaEventRecord(h->ev_join[0], h->side[0]));
+    VGP_TRY(invert(h, M(K_), 0.0, M(KINV_), h->ws[2], red, S_LDK, h->side[1]));
+    VGP_CUDA(cudaEventRecord(h->ev_join[1], h->side[1]));
     VGP_TRY(expquad_dispatch_public(h->z, m, h->x, n, h->d, a, l, 0.0, -1 - n, h->kzx, h->np_, s));
     VGP_TRY(expquad_dispatch_public(h->z, m, xb, b, h->d, a, l, 0.0, -1 - b, h->kzb, h->bp, s));
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->np_, 1.0, h->kzx, h->np_, h->kzx, h->np_, 0.0, M(G_), mp, h->splits_n,
@@ -303,14 +329,14 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(red.run(DotVec{yb, yb}, b, S_YY));
 
     // ---- inverses -----------------------------------------------------------------------------------
-    VGP_TRY(invert(h, M(K_), eps, M(Q_), h->ws[0], red, S_LDKT, s));
     {   // M = K + beta G + eps I
         const int64_t count = mp * mp;
         axpby_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(M(K_), 1.0, M(G_), beta, 0.0, m, M(TMP_), mp, count);
         VGP_LAUNCH_CHECK();
     }
     VGP_TRY(invert(h, M(TMP_), eps, M(SG_), h->ws[1], red, S_LDM, s));
-    VGP_TRY(invert(h, M(K_), 0.0, M(KINV_), h->ws[2], red, S_LDK, s));
+    VGP_CUDA(cudaStreamWaitEvent(s, h->ev_join[0], 0));        // join
+    VGP_CUDA(cudaStreamWaitEvent(s, h->ev_join[1], 0));
 
     // ---- forward vectors ----------------------------------------------------------------------------
     VGP_TRY(matvec(M(SG_), mp, m, m, V(V_), 1.0, V(U_), s));           // u = Sigma v
@@ -488,8 +514,13 @@ int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const do
         }
     }
     cudaError_t e = cudaMemcpy(h->z, z_init_host, (size_t)m * d * 8, cudaMemcpyHostToDevice);
+    for (auto &st : h->side)
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    for (auto &ev : h->ev_join)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
-        int rc = cuda_fail(e, "Z upload", __FILE__, __LINE__);
+        int rc = cuda_fail(e, "Z upload / side streams", __FILE__, __LINE__);
         vgp_elbo_destroy(h);
         return rc;
     }
@@ -504,6 +535,11 @@ int vgp_elbo_destroy(vgp_elbo *h) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &w : h->ws) w.release();
+    for (auto &st : h->side)
+        if (st) cudaStreamDestroy(st);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (auto &e : h->ev_join)
+        if (e) cudaEventDestroy(e);
     delete h;
     return VGP_OK;
 }
