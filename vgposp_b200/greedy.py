@@ -320,52 +320,85 @@ def connect_peers_torch(shard, rank, world, dist, device):
     dist.barrier()                       # nobody stores into a mailbox that is not mapped and zeroed yet
 
 
+class ShardedPlacer:
+    """placement_algorithm_1/2(cov_vv, k) over the GPUs of one box, one process per GPU: the persistent part.
+
+    Construction is the one-time connection of the ranks (what ncclCommInitRank is to a collective): the replica of
+    the distributed inverse and the greedy panels are allocated, every peer's replica and mailbox are mapped through
+    CUDA IPC (which also enables peer access between the device pairs) and the padding is initialised.  `place` can
+    then be called any number of times; each call is H2D of this rank's row slab, NVLink push into every replica,
+    distributed inverse (csrc/dist.cu), the column panels cut from the replica, k selections with the peer-memory
+    exchange and D2H of the result.  `dist` is torch.distributed (used only for the IPC handle exchange)."""
+
+    def __init__(self, n, kmax, rank, world, dist, device, stream=None, small=GUARD_NUMPY, jitter=0.0):
+        import time
+        from .dist_inverse import DistInverse
+        t0 = time.perf_counter()
+        self.n, self.kmax, self.rank, self.world = int(n), int(kmax), int(rank), int(world)
+        self.device, self.stream = device, stream
+        self.bounds = shard_bounds(self.n, self.world)
+        self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        dev_name = "cuda:%d" % device
+        self.inv = DistInverse(self.n, self.rank, self.world, device, stream=stream)
+        self.shard = GreedyShard(self.n, self.r0, self.r1, self.kmax, device, small=small, jitter=jitter, stream=stream)
+        self.inv.connect_torch(dist, dev_name)
+        connect_peers_torch(self.shard, self.rank, self.world, dist, dev_name)
+        self.inv.fill_padding()
+        self.shard.sync()
+        self.connect_seconds = time.perf_counter() - t0
+
+    def place(self, cov_rows, k=None):
+        """`cov_rows`: this rank's HOST row slab cov_vv[bounds[rank]:bounds[rank + 1], :] (a full [n, n] matrix is
+        accepted too).  Returns (selection, scores, seconds dict)."""
+        import time
+        k = self.kmax if k is None else int(k)
+        assert 0 < k <= self.kmax
+        n, r0, r1, inv, shard = self.n, self.r0, self.r1, self.inv, self.shard
+        a = np.asarray(cov_rows)
+        if a.shape[0] == n and self.world > 1:
+            a = a[r0:r1]
+        assert a.shape == (r1 - r0, n) and a.dtype == np.float64 and a.strides[1] == 8, \
+            "cov_rows must be this rank's row slab"
+        secs = {}
+        t1 = time.perf_counter()
+        call("vgp_memcpy2d_h2d", self.device, inv.ptr + r0 * inv.ld * 8, inv.ld * 8, a.ctypes.data, a.strides[0], n * 8,
+             r1 - r0, self.stream)
+        inv.push_rows(r0, r1)
+        inv.barrier()                                     # every slab has landed in every replica
+        call("vgp_memcpy2d_d2d", self.device, shard.cov_ptr, shard.ld * 8, inv.ptr + r0 * 8, inv.ld * 8, (r1 - r0) * 8,
+             n, self.stream)
+        shard.sync()
+        secs["h2d_push"] = time.perf_counter() - t1
+        t2 = time.perf_counter()
+        inv.invert()
+        secs["inverse"] = time.perf_counter() - t2
+        t3 = time.perf_counter()
+        shard.load_prec_device(inv.ptr, inv.ld)
+        shard.reset()
+        shard.run_peer(k)
+        shard.comm_status()
+        sel, scores = shard.results()
+        secs["selections_and_d2h"] = time.perf_counter() - t3
+        secs["total"] = time.perf_counter() - t1
+        check_selection(sel)
+        return sel, scores, secs
+
+    def close(self):
+        self.shard.close()
+        self.inv.close()
+
+
 def place_sharded(cov_rows, n, k, rank, world, dist, device, stream=None, small=GUARD_NUMPY, jitter=0.0):
-    """placement_algorithm_1/2(cov_vv, k) over the GPUs of one box, one process per GPU.  `cov_rows` is this
-    rank's HOST row slab cov_vv[bounds[rank]:bounds[rank + 1], :] (a full [n, n] matrix is accepted too).  All of it
-    happens here: H2D of the slab, NVLink push into every replica, distributed inverse (csrc/dist.cu), the
-    column panels cut from the replica, k selections with the peer-memory exchange, D2H of the result.
-    Returns (selection, scores, seconds dict).  `dist` is torch.distributed (used for the IPC handle exchange)."""
+    """One-shot form: connect, place, disconnect.  Returns (selection, scores, seconds dict); `alloc_connect` is
+    the one-time part a long-lived process pays once (ShardedPlacer)."""
     import time
-    from .dist_inverse import DistInverse
-    a = np.asarray(cov_rows)
-    bounds = shard_bounds(n, world)
-    r0, r1 = bounds[rank], bounds[rank + 1]
-    if a.shape[0] == n and world > 1:
-        a = a[r0:r1]
-    assert a.shape == (r1 - r0, n) and a.dtype == np.float64 and a.strides[1] == 8, "cov_rows must be this rank's row slab"
-    dev_name = "cuda:%d" % device
-    secs = {}
     t0 = time.perf_counter()
-    inv = DistInverse(n, rank, world, device, stream=stream)
-    shard = GreedyShard(n, r0, r1, k, device, small=small, jitter=jitter, stream=stream)
-    inv.connect_torch(dist, dev_name)
-    connect_peers_torch(shard, rank, world, dist, dev_name)
-    inv.fill_padding()
-    secs["alloc_connect"] = time.perf_counter() - t0
-    t1 = time.perf_counter()
-    call("vgp_memcpy2d_h2d", device, inv.ptr + r0 * inv.ld * 8, inv.ld * 8, a.ctypes.data, a.strides[0], n * 8,
-         r1 - r0, stream)
-    inv.push_rows(r0, r1)
-    inv.barrier()                                     # every slab has landed in every replica
-    call("vgp_memcpy2d_d2d", device, shard.cov_ptr, shard.ld * 8, inv.ptr + r0 * 8, inv.ld * 8, (r1 - r0) * 8, n,
-         stream)
-    shard.sync()
-    secs["h2d_push"] = time.perf_counter() - t1
-    t2 = time.perf_counter()
-    inv.invert()
-    secs["inverse"] = time.perf_counter() - t2
-    t3 = time.perf_counter()
-    shard.load_prec_device(inv.ptr, inv.ld)
-    shard.reset()
-    shard.run_peer(k)
-    shard.comm_status()
-    sel, scores = shard.results()
-    secs["selections_and_d2h"] = time.perf_counter() - t3
-    shard.close()
-    inv.close()
-    secs["total"] = time.perf_counter() - t0
-    check_selection(sel)
+    placer = ShardedPlacer(n, k, rank, world, dist, device, stream=stream, small=small, jitter=jitter)
+    try:
+        sel, scores, secs = placer.place(cov_rows, k)
+    finally:
+        placer.close()
+    secs = dict(secs, alloc_connect=placer.connect_seconds, total=time.perf_counter() - t0)
     return sel, scores, secs
 
 
