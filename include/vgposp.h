@@ -166,6 +166,29 @@ int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const dou
                     double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
                     double *var_dev, void *stream);
 
+/* The same five calls for any kernel of vgp_kernel_matrix (`kind` = VGP_KERNEL_*): the reference's exact GP is
+ * built on tfkern.MaternOneHalf (main.py:94, gp_functions.py:160-163), its 5-D VGP on tfkern.MaternFiveHalves
+ * (main_architecture_2.py:184).  The un-suffixed names above are the ExponentiatedQuadratic forms. */
+int vgp_gp_logprob_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev,
+                     double amplitude, double length_scale, double noise_variance, double jitter,
+                     double *logprob_host, void *stream);
+int vgp_gp_regression_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev,
+                        const double *xt_dev, int64_t t, double amplitude, double length_scale,
+                        double noise_variance, double predictive_noise_variance, double divisor_jitter,
+                        double *mean_dev, double *var_dev, void *stream);
+int vgp_vgp_optimal_posterior_k(int device, int kind, const double *z_dev, int64_t m, const double *x_dev,
+                                int64_t n_obs, int d, const double *y_dev, double amplitude, double length_scale,
+                                double noise_variance, double jitter, int legacy_scale_orientation,
+                                double *loc_dev, double *scale_dev, void *stream);
+int vgp_vgp_loss_k(int device, int kind, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                   const double *scale_dev, const double *xb_dev, const double *yb_dev, int64_t b,
+                   double amplitude, double length_scale, double noise_variance, double kl_weight, double jitter,
+                   vgp_vgp_terms *terms_host, void *stream);
+int vgp_vgp_predict_k(int device, int kind, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                      const double *scale_dev, const double *xt_dev, int64_t t, double amplitude,
+                      double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
+                      double *var_dev, void *stream);
+
 /* ---------------------------------------------------------------- VGP training step (a4-a7) ---------------- */
 /* Reference-faithful ELBO training (variational_Gaussian_process_example.py:47-102): amplitude = softplus(v[0]),
  * length_scale = offset + softplus(v[1]), noise = softplus(v[2]); (loc, scale) are the Titsias optimum over ALL

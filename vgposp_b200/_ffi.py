@@ -79,6 +79,15 @@ SIGNATURES = {
                      P(VgpTerms), c_vp],
     "vgp_vgp_predict": [c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp,
                         c_vp],
+    "vgp_gp_logprob_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, P(c_dbl), c_vp],
+    "vgp_gp_regression_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl,
+                            c_vp, c_vp, c_vp],
+    "vgp_vgp_optimal_posterior_k": [c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_dbl,
+                                    c_int, c_vp, c_vp, c_vp],
+    "vgp_vgp_loss_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl,
+                       c_dbl, P(VgpTerms), c_vp],
+    "vgp_vgp_predict_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_vp,
+                          c_vp, c_vp],
     "vgp_elbo_create": [P(c_vp), c_int, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl,
                         c_dbl],
     "vgp_elbo_destroy": [c_vp],

@@ -16,7 +16,7 @@ using namespace vgp;
 
 extern "C" {
 
-int vgp_gp_logprob(int device, const double *x_dev, int64_t n, int d, const double *y_dev, double amplitude,
+int vgp_gp_logprob_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev, double amplitude,
                    double length_scale, double noise_variance, double jitter, double *logprob_host,
                    void *stream) {
     VGP_REQUIRE(x_dev && y_dev && logprob_host && n > 0, "bad argument");
@@ -28,7 +28,7 @@ int vgp_gp_logprob(int device, const double *x_dev, int64_t n, int d, const doub
         Buf k, yb;
         Reducer red;
         rc = red.init(s);
-        if (rc == VGP_OK) rc = kernel_cholesky(x_dev, n, d, amplitude, length_scale, noise_variance + jitter, k, ws, s);
+        if (rc == VGP_OK) rc = kernel_cholesky(kind, x_dev, n, d, amplitude, length_scale, noise_variance + jitter, k, ws, s);
         if (rc == VGP_OK) rc = yb.alloc(n, 1, s);
         if (rc == VGP_OK) rc = copy_vec_to_col0(y_dev, n, yb);
         if (rc == VGP_OK) rc = dense_trsm(0, 0, k.rows, yb.cols, 1.0, k.p, k.cols, yb.p, yb.cols, ws, true, s);
@@ -43,7 +43,7 @@ int vgp_gp_logprob(int device, const double *x_dev, int64_t n, int d, const doub
     return rc;
 }
 
-int vgp_gp_regression(int device, const double *x_dev, int64_t n, int d, const double *y_dev,
+int vgp_gp_regression_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev,
                       const double *xt_dev, int64_t t, double amplitude, double length_scale,
                       double noise_variance, double predictive_noise_variance, double divisor_jitter,
                       double *mean_dev, double *var_dev, void *stream) {
@@ -54,10 +54,10 @@ int vgp_gp_regression(int device, const double *x_dev, int64_t n, int d, const d
     int rc;
     {
         Buf k, yb, c;
-        rc = kernel_cholesky(x_dev, n, d, amplitude, length_scale, noise_variance + divisor_jitter, k, ws, s);
+        rc = kernel_cholesky(kind, x_dev, n, d, amplitude, length_scale, noise_variance + divisor_jitter, k, ws, s);
         if (rc == VGP_OK) rc = c.alloc(n, t, s);
         if (rc == VGP_OK)
-            rc = expquad_dispatch_public(x_dev, n, xt_dev, t, d, amplitude, length_scale, 0.0, 0, c.p, c.cols, s);
+            rc = kernel_matrix_dispatch(kind, x_dev, n, xt_dev, t, d, amplitude, length_scale, 0.0, 0, c.p, c.cols, s);
         if (rc == VGP_OK) rc = dense_trsm(0, 0, k.rows, c.cols, 1.0, k.p, k.cols, c.p, c.cols, ws, true, s);
         if (rc == VGP_OK) rc = yb.alloc(n, 1, s);
         if (rc == VGP_OK) rc = copy_vec_to_col0(y_dev, n, yb);
@@ -82,7 +82,7 @@ int vgp_gp_regression(int device, const double *x_dev, int64_t n, int d, const d
     return rc;
 }
 
-int vgp_vgp_optimal_posterior(int device, const double *z_dev, int64_t m, const double *x_dev, int64_t n_obs,
+int vgp_vgp_optimal_posterior_k(int device, int kind, const double *z_dev, int64_t m, const double *x_dev, int64_t n_obs,
                               int d, const double *y_dev, double amplitude, double length_scale,
                               double noise_variance, double jitter, int legacy_scale_orientation,
                               double *loc_dev, double *scale_dev, void *stream) {
@@ -109,14 +109,14 @@ int vgp_vgp_optimal_posterior(int device, const double *z_dev, int64_t m, const 
         if (rc == VGP_OK) rc = v.alloc(m, 1, s);
         if (rc == VGP_OK) rc = sig.alloc(m, m, s);
         if (rc == VGP_OK)
-            rc = expquad_dispatch_public(z_dev, m, z_dev, m, d, amplitude, length_scale, 0.0, 0, kzz.p, kzz.cols, s);
+            rc = kernel_matrix_dispatch(kind, z_dev, m, z_dev, m, d, amplitude, length_scale, 0.0, 0, kzz.p, kzz.cols, s);
         for (int64_t c0 = 0; c0 < n_obs && rc == VGP_OK; c0 += chunk) {
             const int64_t cn = n_obs - c0 < chunk ? n_obs - c0 : chunk;
             if (cn < chunk) rc = cudaMemsetAsync(kzx.p, 0, (size_t)kzx.rows * kzx.cols * 8, s) == cudaSuccess
                                      ? VGP_OK
                                      : VGP_ERR_CUDA;
             if (rc == VGP_OK)
-                rc = expquad_dispatch_public(z_dev, m, x_dev + c0 * d, cn, d, amplitude, length_scale, 0.0, -1 - n_obs,
+                rc = kernel_matrix_dispatch(kind, z_dev, m, x_dev + c0 * d, cn, d, amplitude, length_scale, 0.0, -1 - n_obs,
                                              kzx.p, kzx.cols, s);
             // gram += K_zx K_zx^T ;  v += K_zx y
             if (rc == VGP_OK)
@@ -179,7 +179,7 @@ int vgp_vgp_optimal_posterior(int device, const double *z_dev, int64_t m, const 
     return rc;
 }
 
-int vgp_vgp_loss(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+int vgp_vgp_loss_k(int device, int kind, const double *z_dev, int64_t m, int d, const double *loc_dev,
                  const double *scale_dev, const double *xb_dev, const double *yb_dev, int64_t b,
                  double amplitude, double length_scale, double noise_variance, double kl_weight, double jitter,
                  vgp_vgp_terms *terms_host, void *stream) {
@@ -194,7 +194,7 @@ int vgp_vgp_loss(int device, const double *z_dev, int64_t m, int d, const double
         Reducer red;
         rc = red.init(s);
         // L = chol(K_zz + jitter I)
-        if (rc == VGP_OK) rc = kernel_cholesky(z_dev, m, d, amplitude, length_scale, jitter, l, ws, s);
+        if (rc == VGP_OK) rc = kernel_cholesky(kind, z_dev, m, d, amplitude, length_scale, jitter, l, ws, s);
         // q = L^-1 q_loc (kept for the KL), then alpha = L^-T q
         if (rc == VGP_OK) rc = q.alloc(m, 1, s);
         if (rc == VGP_OK) rc = copy_vec_to_col0(loc_dev, m, q);
@@ -204,7 +204,7 @@ int vgp_vgp_loss(int device, const double *z_dev, int64_t m, int d, const double
         // K_zb, mu_b = K_zb^T alpha, ll
         if (rc == VGP_OK) rc = kzb.alloc(m, b, s);
         if (rc == VGP_OK)
-            rc = expquad_dispatch_public(z_dev, m, xb_dev, b, d, amplitude, length_scale, 0.0, -1 - b, kzb.p, kzb.cols, s);
+            rc = kernel_matrix_dispatch(kind, z_dev, m, xb_dev, b, d, amplitude, length_scale, 0.0, -1 - b, kzb.p, kzb.cols, s);
         if (rc == VGP_OK) rc = mu.alloc(b, 1, s, false);
         if (rc == VGP_OK) {
             gemv_t_kernel<<<(unsigned)((b + 255) / 256), 256, 0, s>>>(kzb.p, kzb.cols, m, b, q.p, q.cols, mu.p);
@@ -255,7 +255,7 @@ int vgp_vgp_loss(int device, const double *z_dev, int64_t m, int d, const double
     return rc;
 }
 
-int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+int vgp_vgp_predict_k(int device, int kind, const double *z_dev, int64_t m, int d, const double *loc_dev,
                     const double *scale_dev, const double *xt_dev, int64_t t, double amplitude,
                     double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
                     double *var_dev, void *stream) {
@@ -267,14 +267,14 @@ int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const dou
     int rc;
     {
         Buf l, kzt, c, q, a, e;
-        rc = kernel_cholesky(z_dev, m, d, amplitude, length_scale, jitter, l, ws, s);
+        rc = kernel_cholesky(kind, z_dev, m, d, amplitude, length_scale, jitter, l, ws, s);
         if (rc == VGP_OK) rc = q.alloc(m, 1, s);
         if (rc == VGP_OK) rc = copy_vec_to_col0(loc_dev, m, q);
         if (rc == VGP_OK) rc = dense_trsm(0, 0, l.rows, q.cols, 1.0, l.p, l.cols, q.p, q.cols, ws, true, s);
         if (rc == VGP_OK) rc = dense_trsm(0, 1, l.rows, q.cols, 1.0, l.p, l.cols, q.p, q.cols, ws, true, s);
         if (rc == VGP_OK) rc = kzt.alloc(m, t, s);
         if (rc == VGP_OK)
-            rc = expquad_dispatch_public(z_dev, m, xt_dev, t, d, amplitude, length_scale, 0.0, -1 - t, kzt.p, kzt.cols, s);
+            rc = kernel_matrix_dispatch(kind, z_dev, m, xt_dev, t, d, amplitude, length_scale, 0.0, -1 - t, kzt.p, kzt.cols, s);
         if (rc == VGP_OK && mean_dev) {
             gemv_t_kernel<<<(unsigned)((t + 255) / 256), 256, 0, s>>>(kzt.p, kzt.cols, m, t, q.p, q.cols, mean_dev);
             ++g_launches;
@@ -307,6 +307,43 @@ int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const dou
     }
     ws.release();
     return rc;
+}
+
+/* ExponentiatedQuadratic forms (the kernel of variational_Gaussian_process_example.py:55-57). */
+int vgp_gp_logprob(int device, const double *x_dev, int64_t n, int d, const double *y_dev, double amplitude,
+                   double length_scale, double noise_variance, double jitter, double *logprob_host,
+                   void *stream) {
+    return vgp_gp_logprob_k(device, VGP_KERNEL_EXPQUAD, x_dev, n, d, y_dev, amplitude, length_scale, noise_variance,
+                            jitter, logprob_host, stream);
+}
+int vgp_gp_regression(int device, const double *x_dev, int64_t n, int d, const double *y_dev,
+                      const double *xt_dev, int64_t t, double amplitude, double length_scale,
+                      double noise_variance, double predictive_noise_variance, double divisor_jitter,
+                      double *mean_dev, double *var_dev, void *stream) {
+    return vgp_gp_regression_k(device, VGP_KERNEL_EXPQUAD, x_dev, n, d, y_dev, xt_dev, t, amplitude, length_scale,
+                               noise_variance, predictive_noise_variance, divisor_jitter, mean_dev, var_dev, stream);
+}
+int vgp_vgp_optimal_posterior(int device, const double *z_dev, int64_t m, const double *x_dev, int64_t n_obs,
+                              int d, const double *y_dev, double amplitude, double length_scale,
+                              double noise_variance, double jitter, int legacy_scale_orientation,
+                              double *loc_dev, double *scale_dev, void *stream) {
+    return vgp_vgp_optimal_posterior_k(device, VGP_KERNEL_EXPQUAD, z_dev, m, x_dev, n_obs, d, y_dev, amplitude,
+                                       length_scale, noise_variance, jitter, legacy_scale_orientation, loc_dev,
+                                       scale_dev, stream);
+}
+int vgp_vgp_loss(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                 const double *scale_dev, const double *xb_dev, const double *yb_dev, int64_t b,
+                 double amplitude, double length_scale, double noise_variance, double kl_weight, double jitter,
+                 vgp_vgp_terms *terms_host, void *stream) {
+    return vgp_vgp_loss_k(device, VGP_KERNEL_EXPQUAD, z_dev, m, d, loc_dev, scale_dev, xb_dev, yb_dev, b, amplitude,
+                          length_scale, noise_variance, kl_weight, jitter, terms_host, stream);
+}
+int vgp_vgp_predict(int device, const double *z_dev, int64_t m, int d, const double *loc_dev,
+                    const double *scale_dev, const double *xt_dev, int64_t t, double amplitude,
+                    double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
+                    double *var_dev, void *stream) {
+    return vgp_vgp_predict_k(device, VGP_KERNEL_EXPQUAD, z_dev, m, d, loc_dev, scale_dev, xt_dev, t, amplitude,
+                             length_scale, predictive_noise_variance, jitter, mean_dev, var_dev, stream);
 }
 
 }  // extern "C"

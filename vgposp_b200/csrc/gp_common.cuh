@@ -11,6 +11,9 @@ namespace vgp {
 int expquad_dispatch_public(const double *x1, int64_t n1, const double *x2, int64_t n2, int d, double amplitude,
                             double length_scale, double diag_add, int64_t diag_col0, double *out, int64_t ld,
                             cudaStream_t s);
+int kernel_matrix_dispatch(int kind, const double *x1, int64_t n1, const double *x2, int64_t n2, int d,
+                           double amplitude, double length_scale, double diag_add, int64_t diag_col0, double *out,
+                           int64_t ld, cudaStream_t s);
 
 namespace {
 
@@ -204,10 +207,10 @@ int copy_matrix(const double *src, int64_t lds, int64_t r, int64_t c, Buf &dst) 
 }
 
 // K(x, x) + shift I, padded with identity, factorised in place.
-int kernel_cholesky(const double *x, int64_t n, int d, double amplitude, double length_scale, double shift, Buf &k,
-                    DenseWorkspace &ws, cudaStream_t s) {
+int kernel_cholesky(int kind, const double *x, int64_t n, int d, double amplitude, double length_scale, double shift,
+                    Buf &k, DenseWorkspace &ws, cudaStream_t s) {
     VGP_TRY(k.alloc(n, n, s));
-    VGP_TRY(expquad_dispatch_public(x, n, x, n, d, amplitude, length_scale, shift, 0, k.p, k.cols, s));
+    VGP_TRY(kernel_matrix_dispatch(kind, x, n, x, n, d, amplitude, length_scale, shift, 0, k.p, k.cols, s));
     VGP_TRY(pad_identity(k.p, k.cols, n, k.rows, s));
     VGP_TRY(dense_potrf(k.p, k.rows, k.cols, ws, s));
     return dense_read_info(ws, nullptr, s);
