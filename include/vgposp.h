@@ -127,6 +127,18 @@ int vgp_spd_inverse(int device, double *a_dev, int64_t n, int64_t lda, int *info
 int vgp_trsm(int device, int side, int trans, int64_t n, int64_t nrhs, const double *l_dev, int64_t ldl,
              double *b_dev, int64_t ldb, void *stream);
 
+/* Empirical covariance of n locations from S samples each: cov[i][j] = biased sample
+ * covariance of rows i and j of m_dev [n, ldm] -- np.cov(tracers_i, tracers_j, bias=True)[0, 1] for every pair
+ * (gp_functions.py:1019-1057 create_cov_matrix; tfp.stats.covariance at main_architecture_2.py:431), as one centring
+ * pass plus one lower-tile SYRK on the DMMA GEMM; the result is exactly symmetric. */
+int vgp_empirical_cov(int device, const double *m_dev, int64_t n, int64_t s_samples, int64_t ldm, double *cov_dev,
+                      int64_t ldc, void *stream);
+/* The reference's decay filter on such a covariance, in place: cov[i][j] *= exp(-(beta delta_ij)^2 / (2 pi)), delta
+ * the Euclidean distance between the integer grid indices idx_dev [n, 3] (int32) of the two locations; factors below
+ * `cutoff` (0.01 there) become exact zeros (main_architecture_2_sampledistribution.py:376-394). */
+int vgp_cov_taper(int device, double *cov_dev, int64_t n, int64_t ldc, const int *idx_dev, double beta,
+                  double cutoff, void *stream);
+
 /* ---------------------------------------------------------------- exact GP (a2, a3) ------------------------- */
 /* log N(y | 0, K + (noise + jitter) I), K ExpQuad on x_dev [n, d].  Replaces
  * gpf.fit_gp(kernel, x, noise).log_prob(y) (gp_functions.py:166-172; 3D_sin_wave.py:161-172).
@@ -188,6 +200,13 @@ int vgp_vgp_predict_k(int device, int kind, const double *z_dev, int64_t m, int 
                       const double *scale_dev, const double *xt_dev, int64_t t, double amplitude,
                       double length_scale, double predictive_noise_variance, double jitter, double *mean_dev,
                       double *var_dev, void *stream);
+
+/* Exact-GP log marginal likelihood and its gradient with respect to (amplitude, length_scale, noise_variance)
+ * [grads_host, 3 doubles]: what TF's autodiff hands to tf.train.AdamOptimizer(lr).minimize(-log_likelihood) in
+ * gpf.tf_train_gp_adam (gp_functions.py:179-182; main.py:110, lr 0.1).  Blocking. */
+int vgp_gp_logprob_grad_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev,
+                          double amplitude, double length_scale, double noise_variance, double jitter,
+                          double *logprob_host, double *grads_host, void *stream);
 
 /* ---------------------------------------------------------------- VGP training step (a4-a7) ---------------- */
 /* Reference-faithful ELBO training (variational_Gaussian_process_example.py:47-102): amplitude = softplus(v[0]),

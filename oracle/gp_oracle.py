@@ -92,8 +92,13 @@ def _bwd(l, b):
     return solve_triangular(l, b, lower=True, trans="T", check_finite=False)
 
 
-def gp_log_prob(x, y, amplitude, length_scale, noise_variance, jitter=DEFAULT_JITTER, mean=0.0):
+def _kern(kind):
+    return lambda x1, x2, a, l, diag_add=0.0: kernel_matrix(kind, x1, x2, a, l, diag_add)
+
+
+def gp_log_prob(x, y, amplitude, length_scale, noise_variance, jitter=DEFAULT_JITTER, mean=0.0, kind="expquad"):
     """Exact-GP marginal log-likelihood: L = chol(K + (s2 + jitter) I)."""
+    expquad_matrix = _kern(kind)
     n = x.shape[0]
     l = _chol(expquad_matrix(x, x, amplitude, length_scale, noise_variance + jitter))
     z = _fwd(l, y - mean)
@@ -101,8 +106,9 @@ def gp_log_prob(x, y, amplitude, length_scale, noise_variance, jitter=DEFAULT_JI
 
 
 def gp_regression(x_obs, y_obs, x_pred, amplitude, length_scale, noise_variance,
-                  predictive_noise_variance=0.0, divisor_jitter=0.0, mean=0.0, full_cov=False):
+                  predictive_noise_variance=0.0, divisor_jitter=0.0, mean=0.0, full_cov=False, kind="expquad"):
     """Posterior mean / (co)variance of GaussianProcessRegressionModel."""
+    expquad_matrix = _kern(kind)
     l = _chol(expquad_matrix(x_obs, x_obs, amplitude, length_scale, noise_variance + divisor_jitter))
     k_xt = expquad_matrix(x_obs, x_pred, amplitude, length_scale)
     c = _fwd(l, k_xt)
@@ -115,9 +121,10 @@ def gp_regression(x_obs, y_obs, x_pred, amplitude, length_scale, noise_variance,
 
 
 def optimal_variational_posterior(z, x, y, amplitude, length_scale, noise_variance,
-                                  jitter=DEFAULT_JITTER, legacy_scale_orientation=False):
+                                  jitter=DEFAULT_JITTER, legacy_scale_orientation=False, kind="expquad"):
     """Titsias optimum.  Returns (loc [m], scale [m,m]) with S = scale @ scale.T =
     K_zz Sigma K_zz; `legacy_scale_orientation` returns L_Sigma^-1 K_zz (S = scale.T @ scale)."""
+    expquad_matrix = _kern(kind)
     k_zz = expquad_matrix(z, z, amplitude, length_scale)
     k_zx = expquad_matrix(z, x, amplitude, length_scale)
     sigma_inv = k_zz + (k_zx @ k_zx.T) / noise_variance
@@ -129,8 +136,9 @@ def optimal_variational_posterior(z, x, y, amplitude, length_scale, noise_varian
 
 
 def vgp_terms(z, q_loc, q_scale, x_b, y_b, amplitude, length_scale, noise_variance, kl_weight,
-              jitter=DEFAULT_JITTER):
+              jitter=DEFAULT_JITTER, kind="expquad"):
     """All pieces of the negative ELBO of SURVEY.md A.2 (dict), S = q_scale @ q_scale.T."""
+    expquad_matrix = _kern(kind)
     m, b = z.shape[0], x_b.shape[0]
     l = _chol(expquad_matrix(z, z, amplitude, length_scale, jitter))
     k_zb = expquad_matrix(z, x_b, amplitude, length_scale)
@@ -157,8 +165,9 @@ def vgp_loss(*args, **kwargs):
 
 
 def vgp_predict(z, q_loc, q_scale, x_t, amplitude, length_scale, predictive_noise_variance=0.0,
-                jitter=DEFAULT_JITTER):
+                jitter=DEFAULT_JITTER, kind="expquad"):
     """Predictive mean and marginal variance of the VGP at x_t (last paragraph)."""
+    expquad_matrix = _kern(kind)
     l = _chol(expquad_matrix(z, z, amplitude, length_scale, jitter))
     k_zt = expquad_matrix(z, x_t, amplitude, length_scale)
     c = _fwd(l, k_zt)
@@ -167,6 +176,46 @@ def vgp_predict(z, q_loc, q_scale, x_t, amplitude, length_scale, predictive_nois
     e = q_scale.T @ d
     var = amplitude ** 2 - np.sum(c * c, axis=0) + np.sum(e * e, axis=0) + predictive_noise_variance
     return mean, var
+
+
+def gp_log_prob_grad(x, y, amplitude, length_scale, noise_variance, jitter=DEFAULT_JITTER, kind="expquad"):
+    """(log_prob, d log_prob / d (amplitude, length_scale, noise_variance)): dL/dtheta = tr(W dC/dtheta) with
+    W = (alpha alpha^T - C^-1) / 2 -- what TF autodiff gives tf_train_gp_adam (gp_functions.py:179-182)."""
+    c = kernel_matrix(kind, x, x, amplitude, length_scale, noise_variance + jitter)
+    cinv = np.linalg.inv(c)
+    alpha = cinv @ y
+    w = 0.5 * (np.outer(alpha, alpha) - cinv)
+    k = kernel_matrix(kind, x, x, amplitude, length_scale)
+    r2 = sqdist(x, x)
+    r = np.sqrt(r2)
+    if kind == "expquad":
+        dk = k * r2 / length_scale ** 3
+    elif kind == "matern12":
+        dk = k * r / length_scale ** 2
+    elif kind == "matern32":
+        z = np.sqrt(3.0) * r / length_scale
+        dk = amplitude ** 2 * z * z * np.exp(-z) / length_scale
+    else:
+        z = np.sqrt(5.0) * r / length_scale
+        dk = amplitude ** 2 * (z * z / 3.0) * (1.0 + z) * np.exp(-z) / length_scale
+    grads = np.array([2.0 * np.sum(w * k) / amplitude, np.sum(w * dk), np.trace(w)])
+    return gp_log_prob(x, y, amplitude, length_scale, noise_variance, jitter, kind=kind), grads
+
+
+def gp_train_adam(x, y, v_init, lr, iters, jitter=DEFAULT_JITTER, kind="matern12", tiny=np.finfo(np.float64).tiny):
+    """The exact-GP training loop of gpf.tf_optimize_model_params (gp_functions.py:228-259) on the unconstrained
+    variables v = (v_amplitude, v_length_scale, v_noise), theta = tiny + softplus(v) (:124-135), Adam on -log_prob
+    (:179-182).  One initial run, then iters + 1 recorded steps; returns (lls [iters + 1], final v)."""
+    v = np.array(v_init, dtype=np.float64)
+    opt = TfAdam(3, lr)
+    lls = np.zeros(iters + 1)
+    for it in range(iters + 2):
+        theta = tiny + softplus(v)
+        ll, g = gp_log_prob_grad(x, y, theta[0], theta[1], theta[2], jitter, kind)
+        if it > 0:
+            lls[it - 1] = ll
+        v = opt.step(v, -g / (1.0 + np.exp(-v)))
+    return lls, v
 
 
 class TfAdam:

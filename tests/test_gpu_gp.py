@@ -28,16 +28,18 @@ def test_gp_log_prob(n, d):
     x, y = data(n, n, max(d, 2)) if d > 1 else (np.linspace(-1, 1, n)[:, None], np.sin(np.linspace(-1, 1, n)))
     x = x[:, :d]
     amp, ls, noise = 1.3, 0.7, 0.05
-    gp = gpf.fit_gp(gpf.create_cov_kernel(amp, ls), x, noise)
+    gp = gpf.fit_gp(gpf.ExponentiatedQuadratic(amp, ls), x, noise)
     want = gpo.gp_log_prob(x, y, amp, ls, noise)
     assert gp.log_prob(y) == pytest.approx(want, rel=RTOL)
+    gp = gpf.fit_gp(gpf.create_cov_kernel(amp, ls), x, noise)              # the reference's choice: MaternOneHalf
+    assert gp.log_prob(y) == pytest.approx(gpo.gp_log_prob(x, y, amp, ls, noise, kind="matern12"), rel=RTOL)
 
 
 def test_gp_regression_model():
     x, y = data(400, 3)
     xt = np.random.default_rng(9).uniform(-2, 2, (333, 3))
     amp, ls, noise, pnoise = 0.9, 0.8, 0.02, 0.01
-    gprm = gpf.tf_gp_regression_model(gpf.create_cov_kernel(amp, ls), xt, x, y, noise, pnoise)
+    gprm = gpf.tf_gp_regression_model(gpf.ExponentiatedQuadratic(amp, ls), xt, x, y, noise, pnoise)
     mean, var = gpo.gp_regression(x, y, xt, amp, ls, noise, pnoise)
     np.testing.assert_allclose(gprm.mean(), mean, rtol=RTOL, atol=1e-12)
     np.testing.assert_allclose(gprm.variance(), var, rtol=1e-7, atol=1e-12)    # a^2 - |c|^2 cancels to ~1e-2
@@ -55,7 +57,7 @@ def test_positive_parameters_and_calc_H():
     H = gpf.calc_H(3, 2, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, gp.log_prob, None, None, y)
     for i in range(3):
         for j in range(2):
-            want = gpo.gp_log_prob(x, y, 40 * (1 + j) / 2, 40 * (1 + i) / 3, float(noise))
+            want = gpo.gp_log_prob(x, y, 40 * (1 + j) / 2, 40 * (1 + i) / 3, float(noise), kind="matern12")
             assert H[i, j] == pytest.approx(want, rel=RTOL)
 
 
@@ -115,8 +117,103 @@ def test_dlpack_zero_copy_device_inputs():
     arr = _ffi.as_device_f64(xt, 0)
     assert arr.ptr == xt.data_ptr()                          # consumed in place, no copy
     gp = gpf.fit_gp(gpf.create_cov_kernel(1.0, 0.5), xt, 0.1)
-    assert gp.log_prob(yt) == pytest.approx(gpo.gp_log_prob(x, y, 1.0, 0.5, 0.1), rel=RTOL)
+    assert gp.log_prob(yt) == pytest.approx(gpo.gp_log_prob(x, y, 1.0, 0.5, 0.1, kind="matern12"), rel=RTOL)
     k = gpf.ExponentiatedQuadratic(1.0, 0.5).matrix(xt, xt)
     np.testing.assert_allclose(k, gpo.expquad_matrix(x, x, 1.0, 0.5), rtol=1e-13)
     with pytest.raises(TypeError):
         _ffi.as_device_f64(xt.float(), 0)
+
+
+KINDS = {"expquad": gpf.ExponentiatedQuadratic, "matern12": gpf.MaternOneHalf, "matern32": gpf.MaternThreeHalves,
+         "matern52": gpf.MaternFiveHalves}
+
+
+@pytest.mark.parametrize("kind", ["matern12", "matern32", "matern52"])
+def test_matern_kernels_through_gp_and_vgp(kind):
+    """The kernels the reference actually instantiates (MaternOneHalf main.py:94, MaternFiveHalves over 5-D xyztp
+    inputs main_architecture_2.py:184) through every GP / VGP entry point."""
+    x, y = data(500, 11, d=5)
+    xt = np.random.default_rng(12).uniform(-2, 2, (200, 5))
+    amp, ls, noise = 1.1, 1.4, 0.04
+    k = KINDS[kind](amp, ls)
+    assert gpf.fit_gp(k, x, noise).log_prob(y) == pytest.approx(gpo.gp_log_prob(x, y, amp, ls, noise, kind=kind), rel=RTOL)
+    gprm = gpf.tf_gp_regression_model(k, xt, x, y, noise, 0.0)
+    mean, var = gpo.gp_regression(x, y, xt, amp, ls, noise, 0.0, kind=kind)
+    np.testing.assert_allclose(gprm.mean(), mean, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(gprm.variance(), var, rtol=1e-7, atol=1e-12)
+    z = np.random.default_rng(13).uniform(-2, 2, (64, 5))
+    loc, scale = gpf.VariationalGaussianProcess.optimal_variational_posterior(k, z, x, y, noise)
+    want_loc, want_scale = gpo.optimal_variational_posterior(z, x, y, amp, ls, noise, kind=kind)
+    np.testing.assert_allclose(loc, want_loc, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(scale @ scale.T, want_scale @ want_scale.T, rtol=1e-7, atol=1e-10)
+    vgp = gpf.VariationalGaussianProcess(k, xt, z, want_loc, want_scale, noise)
+    idx = np.random.default_rng(14).integers(500, size=128)
+    got = vgp.variational_loss(y[idx], x[idx], kl_weight=128 / 500, return_terms=True)
+    want = gpo.vgp_terms(z, want_loc, want_scale, x[idx], y[idx], amp, ls, noise, 128 / 500, kind=kind)
+    for key in ("loss", "ll", "kl"):
+        assert got[key] == pytest.approx(want[key], rel=1e-8)
+    wm, wv = gpo.vgp_predict(z, want_loc, want_scale, xt, amp, ls, kind=kind)
+    np.testing.assert_allclose(vgp.mean(), wm, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(vgp.variance(), wv, rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.parametrize("kind", ["expquad", "matern12", "matern32", "matern52"])
+@pytest.mark.parametrize("n,d", [(25, 2), (300, 3), (700, 5)])
+def test_gp_log_prob_gradient(kind, n, d):
+    """vgp_gp_logprob_grad_k against the closed form of the oracle (itself checked by finite differences)."""
+    x, y = data(n, 3 * n, d=max(d, 2))
+    x = x[:, :d]
+    amp, ls, noise = 0.9, 0.7, 0.05
+    gp = gpf.fit_gp(KINDS[kind](amp, ls), x, noise)
+    ll, grads = gp.log_prob_and_grad(y)
+    want_ll, want_g = gpo.gp_log_prob_grad(x, y, amp, ls, noise, kind=kind)
+    assert ll[0] == pytest.approx(want_ll, rel=RTOL)
+    np.testing.assert_allclose(grads[0], want_g, rtol=1e-8, atol=1e-9 * np.abs(want_g).max())
+
+
+def test_tf_train_gp_adam_training_loop():
+    """main.py:80-110 + gpf.tf_optimize_model_params: softplus-constrained (amplitude, length_scale, noise), Adam(0.1)
+    on -log_likelihood, MaternOneHalf kernel.  The whole trajectory must follow the CPU restatement."""
+    x, y = data(25, 21, d=2)                                            # main.py:418-419 uses 25 points
+    amp, amp_assign, amp_p, lensc, lensc_assign, lensc_p, emb, emb_assign, emb_p, noise = \
+        gpf.tf_Placeholder_assign_test(np.array([0.54]), np.array([0.54]), np.array([0.54]))
+    sess = gpf.reset_session()
+    obs = gpf.placeholder(np.float64, (1, 25), "obs")
+    gp = gpf.fit_gp(gpf.create_cov_kernel(amp, lensc), x, noise)
+    log_likelihood = gp.log_prob(obs)
+    train_op = gpf.tf_train_gp_adam(log_likelihood, 0.1)
+    lls = gpf.tf_optimize_model_params(sess, 30, train_op, log_likelihood, None, None, None, None, None, y, obs)
+    want_lls, want_v = gpo.gp_train_adam(x, y, [0.54, 0.54, 0.54], 0.1, 30, kind="matern12")
+    assert lls.shape == (31, 1)
+    np.testing.assert_allclose(lls[:, 0], want_lls, rtol=1e-8)
+    got_v = [amp.variable.value[0], lensc.variable.value[0], noise.variable.value[0]]
+    np.testing.assert_allclose(got_v, want_v, rtol=1e-7)
+    assert lls[-1, 0] > lls[0, 0]
+    # sess.run([train_op, log_likelihood]) returns the value the update was computed from
+    before = log_likelihood(y)
+    _, ll_run = sess.run([train_op, log_likelihood], feed_dict={obs: y.reshape(1, 25)})
+    assert ll_run[0] == pytest.approx(before[0], rel=1e-12)
+    assert gpf.do_assign(sess, amp, amp_assign, amp_p, [1.7])[0] == pytest.approx(1.7, rel=1e-14)
+
+
+def test_batch_of_two_gps():
+    """INIT arrays of length 2 (main.py:80-88): two independent GPs over the same index points, observations [2, n],
+    log_likelihood[0] / [1] (main.py:105-107), both trained by one train op."""
+    x, y0 = data(40, 31, d=2)
+    y = np.stack([y0, np.cos(x[:, 0]) + 0.05 * np.random.default_rng(1).standard_normal(40)])
+    amp, _, _, lensc, _, _, _, _, _, noise = gpf.tf_Placeholder_assign_test(np.array([0.54, 0.9]), np.array([0.54, 0.3]),
+                                                                            np.array([0.54, 0.2]))
+    obs = gpf.placeholder(np.float64, (2, 40))
+    gp = gpf.fit_gp(gpf.create_cov_kernel(amp, lensc), x, noise)
+    ll = gp.log_prob(y)
+    a, l, s = amp.numpy(), lensc.numpy(), noise.numpy()
+    for i in range(2):
+        assert ll[i] == pytest.approx(gpo.gp_log_prob(x, y[i], a[i], l[i], s[i], kind="matern12"), rel=RTOL)
+    node = gp.log_prob(obs)
+    assert node[1](y) == pytest.approx(ll[1], rel=1e-14)
+    train_op = gpf.tf_train_gp_adam(node, 0.1)
+    lls = gpf.tf_optimize_model_params(None, 5, train_op, node, None, None, None, None, None, y, obs)
+    assert lls.shape == (6, 2)
+    for i, v0 in enumerate([[0.54, 0.54, 0.54], [0.9, 0.3, 0.2]]):
+        want, _ = gpo.gp_train_adam(x, y[i], v0, 0.1, 5, kind="matern12")
+        np.testing.assert_allclose(lls[:, i], want, rtol=1e-8)

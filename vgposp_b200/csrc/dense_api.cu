@@ -2,6 +2,8 @@
 // are copied into 128-padded scratch (identity on the padding diagonal where a factorisation needs it),
 // the padded kernels run, and the result is copied back.  The greedy and GP paths call dense.cuh directly
 // on padded storage they own and never pay for these copies.
+#include <math.h>
+
 #include "dense.cuh"
 
 using namespace vgp;
@@ -65,9 +67,84 @@ int copy_lower(const double *src, int64_t lds, double *dst, int64_t ldd, int64_t
     return VGP_OK;
 }
 
+// row i of m [n][ld] (first s columns) minus its mean, in place; one CTA per row, fixed reduction tree
+__global__ void __launch_bounds__(256) centre_rows_kernel(double *m, int64_t ld, int64_t s) {
+    __shared__ double sh[256];
+    double *row = m + (int64_t)blockIdx.x * ld;
+    double acc = 0.0;
+    for (int64_t j = threadIdx.x; j < s; j += 256) acc += row[j];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    const double mean = sh[0] / (double)s;
+    for (int64_t j = threadIdx.x; j < s; j += 256) row[j] -= mean;
+}
+
+// c[i][j] *= exp(-(beta delta_ij)^2 / (2 pi)) with delta the Euclidean distance of the integer grid indices of
+// locations i and j; factors below `cutoff` become exact zeros (main_architecture_2_sampledistribution.py:376-394)
+__global__ void __launch_bounds__(256) taper_kernel(double *c, int64_t ld, int64_t n, const int *__restrict__ idx,
+                                                    double beta, double cutoff) {
+    const int64_t i = blockIdx.y;
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    const double d0 = (double)(idx[i * 3] - idx[j * 3]), d1 = (double)(idx[i * 3 + 1] - idx[j * 3 + 1]),
+                 d2 = (double)(idx[i * 3 + 2] - idx[j * 3 + 2]);
+    const double delta = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    const double bd = beta * delta;
+    double decay = exp(-(bd * bd) / (2.0 * M_PI));
+    if (decay < cutoff) decay = 0.0;
+    c[i * ld + j] *= decay;
+}
+
 }  // namespace vgp
 
 extern "C" {
+
+/* cov[i][j] = mean_s((m[i][s] - mean_i)(m[j][s] - mean_j)): the biased sample covariance of every pair of rows --
+ * np.cov(tracers_loc_i, tracers_loc_j, bias=True)[0, 1] for all (i, j) at once (gp_functions.py:1019-1057;
+ * tfp.stats.covariance in main_architecture_2.py:431).  One centring pass, one lower-tile split-K SYRK on the DMMA
+ * GEMM, mirrored: exactly symmetric. */
+int vgp_empirical_cov(int device, const double *m_dev, int64_t n, int64_t s_samples, int64_t ldm, double *cov_dev,
+                      int64_t ldc, void *stream) {
+    VGP_REQUIRE(n >= 0 && s_samples > 0 && ldm >= s_samples && ldc >= n, "bad sizes");
+    if (n == 0) return VGP_OK;
+    VGP_REQUIRE(m_dev && cov_dev, "NULL pointer");
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    Padded pm, pc, part;
+    VGP_TRY(pm.alloc(n, s_samples, s));
+    VGP_TRY(pc.alloc(n, n, s));
+    VGP_TRY(pm.load(m_dev, ldm, n, s_samples));
+    centre_rows_kernel<<<(unsigned)n, 256, 0, s>>>(pm.p, pm.cols, s_samples);
+    VGP_LAUNCH_CHECK();
+    const int64_t tiles = (pc.rows / TILE) * (pc.rows / TILE + 1) / 2;
+    int splits = (int)(592 / (2 * tiles));                      // about two waves of 128x64 CTAs
+    const int64_t max_splits = pm.cols / 256 > 0 ? pm.cols / 256 : 1;
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    VGP_TRY(part.alloc(pc.rows * splits, pc.cols, s));
+    VGP_TRY(dense_gemm_splitk(0, 1, pc.rows, pc.rows, pm.cols, 1.0 / (double)s_samples, pm.p, pm.cols, pm.p, pm.cols,
+                              0.0, pc.p, pc.cols, splits, part.p, s, GEMM_LOWER));
+    return pc.store(cov_dev, ldc, n, n);
+}
+
+/* In-place taper of a covariance by the reference's decay filter over integer grid indices idx_dev [n, 3] (int32):
+ * factor exp(-(beta delta)^2 / (2 pi)), zero below `cutoff` (0.01 in the reference). */
+int vgp_cov_taper(int device, double *cov_dev, int64_t n, int64_t ldc, const int *idx_dev, double beta,
+                  double cutoff, void *stream) {
+    VGP_REQUIRE(n >= 0 && ldc >= n, "bad sizes");
+    if (n == 0) return VGP_OK;
+    VGP_REQUIRE(cov_dev && idx_dev, "NULL pointer");
+    VGP_REQUIRE(n <= 65535, "vgp_cov_taper: n too large for one launch");
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    taper_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, s>>>(cov_dev, ldc, n, idx_dev, beta, cutoff);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
 
 int vgp_dgemm(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
               const double *a_dev, int64_t lda, const double *b_dev, int64_t ldb, double beta, double *c_dev,

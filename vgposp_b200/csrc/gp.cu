@@ -12,9 +12,161 @@
 // Scalar reductions are two-stage with a fixed tree: results are run-to-run deterministic.
 #include "gp_common.cuh"
 
+namespace vgp {
+namespace gp_detail {
+
+// Row i of the fused gradient reduction of the exact-GP log marginal likelihood:
+//   W_ij = (alpha_i alpha_j - Cinv_ij) / 2,  rowacc[i] = ( sum_j W_ij K_ij,  sum_j W_ij dK_ij/dl,  W_ii )
+// K and dK/dl are re-evaluated from the coordinates (nothing but Cinv is read from HBM).  One CTA per row, fixed
+// reduction tree: deterministic.
+template <int KIND, int D>
+__global__ void __launch_bounds__(256) gp_grad_kernel(const double *__restrict__ x, int64_t n,
+                                                      const double *__restrict__ cinv, int64_t ld,
+                                                      const double *__restrict__ alpha, int64_t astride, double amp2,
+                                                      double ls, double *rowacc) {
+    __shared__ double sh[3][256];
+    const int64_t i = blockIdx.x;
+    double xi[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) xi[k] = x[i * D + k];
+    const double ai = alpha[i * astride];
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += 256) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const double t = xi[k] - x[j * D + k];
+            s2 = fma(t, t, s2);
+        }
+        double kv, dk;
+        if (KIND == VGP_KERNEL_EXPQUAD) {
+            kv = amp2 * exp(-0.5 * s2 / (ls * ls));
+            dk = kv * s2 / (ls * ls * ls);
+        } else {
+            const double r = sqrt(s2);
+            if (KIND == VGP_KERNEL_MATERN12) {
+                kv = amp2 * exp(-r / ls);
+                dk = kv * r / (ls * ls);
+            } else if (KIND == VGP_KERNEL_MATERN32) {
+                const double z = sqrt(3.0) * r / ls, e = amp2 * exp(-z);
+                kv = (1.0 + z) * e;
+                dk = z * z * e / ls;
+            } else {
+                const double z = sqrt(5.0) * r / ls, e = amp2 * exp(-z);
+                kv = (1.0 + z + z * z / 3.0) * e;
+                dk = (z * z / 3.0) * (1.0 + z) * e / ls;
+            }
+        }
+        const double w = 0.5 * (ai * alpha[j * astride] - cinv[i * ld + j]);
+        acc0 = fma(w, kv, acc0);
+        acc1 = fma(w, dk, acc1);
+        if (j == i) acc2 = w;
+    }
+    sh[0][threadIdx.x] = acc0;
+    sh[1][threadIdx.x] = acc1;
+    sh[2][threadIdx.x] = acc2;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) rowacc[i * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+struct ColSum3 {
+    const double *a;
+    int c;
+    __device__ double operator()(int64_t e) const { return a[e * 3 + c]; }
+};
+
+template <int KIND>
+int launch_gp_grad(int d, const double *x, int64_t n, const double *cinv, int64_t ld, const double *alpha,
+                   int64_t astride, double amp2, double ls, double *rowacc, cudaStream_t s) {
+    const unsigned g = (unsigned)n;
+    switch (d) {
+#define VGP_CASE(DD)                                                                                      \
+    case DD:                                                                                              \
+        gp_grad_kernel<KIND, DD><<<g, 256, 0, s>>>(x, n, cinv, ld, alpha, astride, amp2, ls, rowacc);     \
+        break;
+        VGP_CASE(1) VGP_CASE(2) VGP_CASE(3) VGP_CASE(4) VGP_CASE(5) VGP_CASE(6) VGP_CASE(7) VGP_CASE(8)
+#undef VGP_CASE
+        default:
+            set_error("feature dimension %d outside [1, 8]", d);
+            return VGP_ERR_INVALID;
+    }
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+}  // namespace gp_detail
+}  // namespace vgp
+
 using namespace vgp;
+using namespace vgp::gp_detail;
 
 extern "C" {
+
+/* log N(y | 0, C), C = K + (noise + jitter) I, and its gradient with respect to (amplitude, length_scale,
+ * noise_variance): dL/dtheta = tr(W dC/dtheta), W = (alpha alpha^T - C^-1) / 2, alpha = C^-1 y.  What TF's autodiff
+ * hands to tf.train.AdamOptimizer(...).minimize(-log_likelihood) in gpf.tf_train_gp_adam (gp_functions.py:179-182,
+ * main.py:110). */
+int vgp_gp_logprob_grad_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev,
+                          double amplitude, double length_scale, double noise_variance, double jitter,
+                          double *logprob_host, double *grads_host, void *stream) {
+    VGP_REQUIRE(x_dev && y_dev && logprob_host && grads_host && n > 0, "bad argument");
+    VGP_REQUIRE(kind >= VGP_KERNEL_EXPQUAD && kind <= VGP_KERNEL_MATERN52, "unknown kernel kind %d", kind);
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    DenseWorkspace ws;
+    int rc;
+    {
+        Buf k, yb, acc;
+        Reducer red;
+        rc = red.init(s);
+        if (rc == VGP_OK) rc = kernel_cholesky(kind, x_dev, n, d, amplitude, length_scale, noise_variance + jitter, k, ws, s);
+        if (rc == VGP_OK) rc = yb.alloc(n, 1, s);
+        if (rc == VGP_OK) rc = acc.alloc(n, 3, s, false);
+        if (rc == VGP_OK) rc = copy_vec_to_col0(y_dev, n, yb);
+        if (rc == VGP_OK) rc = dense_trsm(0, 0, k.rows, yb.cols, 1.0, k.p, k.cols, yb.p, yb.cols, ws, true, s);
+        if (rc == VGP_OK) rc = red.run(SumSqStrided{yb.p, yb.cols}, n, 0);
+        if (rc == VGP_OK) rc = red.run(SumLogDiag{k.p, k.cols}, n, 1);
+        if (rc == VGP_OK) rc = dense_trsm(0, 1, k.rows, yb.cols, 1.0, k.p, k.cols, yb.p, yb.cols, ws, true, s);   // alpha
+        if (rc == VGP_OK) rc = dense_trtri(k.p, k.rows, k.cols, ws, s);
+        if (rc == VGP_OK) rc = dense_lauum(k.p, k.rows, k.cols, ws, s);
+        if (rc == VGP_OK) rc = dense_mirror_lower(k.p, k.rows, k.cols, s);                                       // C^-1
+        if (rc == VGP_OK) {
+            const double a2 = amplitude * amplitude;
+            switch (kind) {
+                case VGP_KERNEL_EXPQUAD:
+                    rc = launch_gp_grad<VGP_KERNEL_EXPQUAD>(d, x_dev, n, k.p, k.cols, yb.p, yb.cols, a2, length_scale, acc.p, s);
+                    break;
+                case VGP_KERNEL_MATERN12:
+                    rc = launch_gp_grad<VGP_KERNEL_MATERN12>(d, x_dev, n, k.p, k.cols, yb.p, yb.cols, a2, length_scale, acc.p, s);
+                    break;
+                case VGP_KERNEL_MATERN32:
+                    rc = launch_gp_grad<VGP_KERNEL_MATERN32>(d, x_dev, n, k.p, k.cols, yb.p, yb.cols, a2, length_scale, acc.p, s);
+                    break;
+                default:
+                    rc = launch_gp_grad<VGP_KERNEL_MATERN52>(d, x_dev, n, k.p, k.cols, yb.p, yb.cols, a2, length_scale, acc.p, s);
+            }
+        }
+        for (int c = 0; c < 3 && rc == VGP_OK; ++c) rc = red.run(ColSum3{acc.p, c}, n, 2 + c);
+        double h[5] = {0, 0, 0, 0, 0};
+        if (rc == VGP_OK) rc = red.fetch(h, 5);
+        if (rc == VGP_OK) {
+            *logprob_host = -0.5 * h[0] - h[1] - 0.5 * (double)n * log(2.0 * M_PI);
+            grads_host[0] = 2.0 * h[2] / amplitude;
+            grads_host[1] = h[3];
+            grads_host[2] = h[4];
+        }
+    }
+    cudaStreamSynchronize(s);
+    ws.release();
+    return rc;
+}
 
 int vgp_gp_logprob_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev, double amplitude,
                    double length_scale, double noise_variance, double jitter, double *logprob_host,

@@ -5,8 +5,13 @@ the same names return small eager objects whose numeric methods call the CUDA li
 
     reference (gp_functions.py)                          here
     ---------------------------------------------------  -------------------------------------------------
-    create_cov_kernel(amp, lensc)            :160-163    ExponentiatedQuadratic(amp, lensc)   [see note]
-    fit_gp(kernel, idx_pts, noise_var)       :166-172    GaussianProcess(...).log_prob(y)
+    create_cov_kernel(amp, lensc)            :160-163    MaternOneHalf(amp, lensc) (also ExponentiatedQuadratic,
+                                                         MaternThreeHalves, MaternFiveHalves)
+    fit_gp(kernel, idx_pts, noise_var)       :166-172    GaussianProcess(...).log_prob(y | placeholder)
+    tf_train_gp_adam(log_likelihood, lr)     :179-182    AdamTrainOp: device log-prob gradient + TF-Adam in softplus space
+    tf_optimize_model_params(...)            :228-259    the training loop, returns lls
+    reset_session / do_assign                :112-121,222-225   Session stand-in
+    create_meshgrid, slice_grid_xyz, py_get_coord_idxs, denormalize_coord, create_cov_matrix  :262,1215-1247,1019
     tf_gp_regression_model(...)              :283-297    GaussianProcessRegressionModel(...).mean()/.variance()
     tf_Variable / invert_softplus / tf_Placeholder_assign_test :48-65,106-109,124-149   Positive parameters
     calc_H(...)                              :864-876    likelihood surface by re-evaluating log_prob
@@ -16,8 +21,8 @@ and, for the variational path (variational_Gaussian_process_example.py:68-99),
 `VariationalGaussianProcess.optimal_variational_posterior / .variational_loss / .mean / .variance`.
 
 Notes
-  * `create_cov_kernel` in the reference currently returns MaternOneHalf with ExponentiatedQuadratic left in a
-    comment (gp_functions.py:162); this path implements the ExpQuad kernel named by the north star.
+  * `create_cov_kernel` returns MaternOneHalf like the reference (gp_functions.py:162); the ExpQuad kernel named by
+    the north star is `ExponentiatedQuadratic`.  The hand-derived ELBO training step (VgpTrainer) is ExpQuad-only.
   * gp_functions.py carries an older copy of the greedy whose `nominator` appends y to A (:653-661) and therefore
     degenerates to [0, 1, 2, ...]; the names here forward to the corrected semantics of placement_algorithm2.py.
   * TF1 graph tensors cannot be exported through DLPack; eager tensors (TF >= 2.2: tf.experimental.dlpack.to_dlpack)
@@ -87,8 +92,13 @@ def invert_softplus(place_holder, variable, name="assign_op"):
 
 
 class Placeholder:
-    def __init__(self, shape, name=None):
-        self.shape, self.name = tuple(shape), name
+    def __init__(self, shape, name=None, dtype=np.float64):
+        self.shape, self.name, self.value = tuple(shape), name, None
+
+
+def placeholder(dtype=np.float64, shape=(), name=None):
+    """tf.placeholder's role for observation feeds (main.py: obs_value_placeholder)."""
+    return Placeholder(shape, name)
 
 
 class AssignOp:
@@ -125,10 +135,18 @@ def tf_Placeholder_assign_test(AMPLITUDE_INIT, LENGTHSCALE_INIT, INIT_OBSNOISEVA
     return amp, amp_assign, amp_plh, lensc, lensc_assign, lensc_plh, emb, emb_assign, emb_plh, obs_noise_var
 
 
-def _scalar(v):
-    if isinstance(v, Positive):
-        return float(v)
-    return float(np.asarray(v.numpy() if hasattr(v, "numpy") else v, dtype=np.float64).reshape(-1)[0])
+def _values(v):
+    return np.asarray(v.numpy() if hasattr(v, "numpy") else v, dtype=np.float64).reshape(-1)
+
+
+def _size(v):
+    return int(_values(v).size)
+
+
+def _scalar(v, index=0):
+    """Element `index` of a parameter (length-1 parameters broadcast over a batch of GPs, Appendix A.4)."""
+    a = _values(v)
+    return float(a[index if a.size > 1 else 0])
 
 
 def _points(x):
@@ -157,16 +175,19 @@ def _vector(y):
 # --------------------------------------------------------------------------------------------------
 # kernel (a1)
 # --------------------------------------------------------------------------------------------------
-class ExponentiatedQuadratic:
-    """k(x, y) = amplitude^2 exp(-|x - y|^2 / (2 length_scale^2)) -- tfkern.ExponentiatedQuadratic's role at
-    variational_Gaussian_process_example.py:55-57, 3D_sin_wave.py:158-159."""
+class _StationaryKernel:
+    """Common part of the stationary kernels; `KIND` is the VGP_KERNEL_* code of include/vgposp.h."""
+    KIND = 0
 
     def __init__(self, amplitude, length_scale, feature_ndims=1):
         assert feature_ndims == 1
         self.amplitude, self.length_scale = amplitude, length_scale
 
-    def params(self):
-        return _scalar(self.amplitude), _scalar(self.length_scale)
+    def params(self, index=0):
+        return _scalar(self.amplitude, index), _scalar(self.length_scale, index)
+
+    def batch_size(self):
+        return max(_size(self.amplitude), _size(self.length_scale))
 
     def matrix_device(self, x1, x2, diag_add=0.0):
         a, l = self.params()
@@ -176,7 +197,8 @@ class ExponentiatedQuadratic:
         assert d2.shape[1] == d, "feature dimensions differ"
         ld = n2 + (n2 % 2)
         out = _ffi.DeviceArray((n1, ld), np.float64, DEVICE)
-        call("vgp_expquad_matrix", DEVICE, d1.ptr, n1, d2.ptr, n2, d, a, l, float(diag_add), 0, out.ptr, ld, None)
+        call("vgp_kernel_matrix", DEVICE, self.KIND, d1.ptr, n1, d2.ptr, n2, d, a, l, float(diag_add), 0, out.ptr, ld,
+             None)
         return out, n2
 
     def matrix(self, x1, x2):
@@ -191,16 +213,41 @@ class ExponentiatedQuadratic:
     _apply = apply
 
 
+class ExponentiatedQuadratic(_StationaryKernel):
+    """k(x, y) = amplitude^2 exp(-|x - y|^2 / (2 length_scale^2)) -- tfkern.ExponentiatedQuadratic's role at
+    variational_Gaussian_process_example.py:55-57, 3D_sin_wave.py:158-159."""
+    KIND = 0
+
+
+class MaternOneHalf(_StationaryKernel):
+    """amplitude^2 exp(-|x - y| / length_scale) -- tfkern.MaternOneHalf (main.py:94, gp_functions.py:162)."""
+    KIND = 1
+
+
+class MaternThreeHalves(_StationaryKernel):
+    """amplitude^2 (1 + z) exp(-z), z = sqrt(3) |x - y| / length_scale -- tfkern.MaternThreeHalves."""
+    KIND = 2
+
+
+class MaternFiveHalves(_StationaryKernel):
+    """amplitude^2 (1 + z + z^2/3) exp(-z), z = sqrt(5) |x - y| / length_scale -- tfkern.MaternFiveHalves
+    (main_architecture_2.py:184)."""
+    KIND = 3
+
+
 def create_cov_kernel(amp, lensc):
-    """gp_functions.py:160-163 (ExpQuad, see the module note)."""
-    return ExponentiatedQuadratic(amp, lensc)
+    """gp_functions.py:160-163: the reference returns MaternOneHalf (ExponentiatedQuadratic is left in its comment)."""
+    return MaternOneHalf(amp, lensc)
 
 
 # --------------------------------------------------------------------------------------------------
 # exact GP (a2, a3)
 # --------------------------------------------------------------------------------------------------
 class GaussianProcess:
-    """tfd.GaussianProcess's role in fit_gp (gp_functions.py:166-172): zero mean, ExpQuad kernel."""
+    """tfd.GaussianProcess's role in fit_gp (gp_functions.py:166-172): zero mean, stationary kernel.
+
+    Parameters of length 2 (the reference's INIT arrays of shape [2], main.py:80-88) make a batch of two independent
+    GPs over the same index points; `log_prob` of observations [2, n] then returns both values (main.py:105-107)."""
 
     def __init__(self, kernel, index_points, observation_noise_variance=0.0, jitter=DEFAULT_JITTER,
                  validate_args=False):
@@ -208,20 +255,198 @@ class GaussianProcess:
         self.observation_noise_variance = observation_noise_variance
         self._x = _points(index_points)
 
+    def batch_size(self):
+        return max(self.kernel.batch_size(), _size(self.observation_noise_variance))
+
+    def _rows(self, observations):
+        n = self._x.shape[0]
+        y = np.asarray(observations.to_host() if isinstance(observations, _ffi.DeviceArray) else observations,
+                       dtype=np.float64)
+        assert y.size % n == 0, "observations must have one value per index point"
+        return y.reshape(-1, n)
+
     def log_prob(self, observations):
-        a, l = self.kernel.params()
-        y = _vector(observations)
+        """float for one GP, ndarray [b] for a batch; a `Placeholder` gives a lazy `LogProb` node to run with a feed
+        (the reference's graph tensor)."""
+        if isinstance(observations, Placeholder):
+            return LogProb(self, observations)
+        on_device = isinstance(observations, _ffi.DeviceArray) or \
+            (hasattr(observations, "__dlpack__") and not isinstance(observations, np.ndarray))
+        if on_device and self.batch_size() == 1:
+            rows = [observations]                            # consumed where it lies (DLPack / DeviceArray)
+        else:
+            rows = self._rows(observations)
+        b = max(self.batch_size(), len(rows))
         n, d = self._x.shape
-        assert y.size == n, "observations must have one value per index point"
-        out = ctypes.c_double()
-        call("vgp_gp_logprob", DEVICE, self._x.ptr, n, d, y.ptr, a, l, _scalar(self.observation_noise_variance),
-             float(self.jitter), ctypes.byref(out), None)
-        return out.value
+        out = np.zeros(b)
+        for i in range(b):
+            a, l = self.kernel.params(i)
+            y = _vector(rows[i if len(rows) > 1 else 0])
+            assert y.size == n, "observations must have one value per index point"
+            v = ctypes.c_double()
+            call("vgp_gp_logprob_k", DEVICE, self.kernel.KIND, self._x.ptr, n, d, y.ptr, a, l,
+                 _scalar(self.observation_noise_variance, i), float(self.jitter), ctypes.byref(v), None)
+            out[i] = v.value
+        return float(out[0]) if b == 1 else out
+
+    def log_prob_and_grad(self, observations):
+        """(log_prob [b], gradient [b, 3] with respect to the constrained (amplitude, length_scale, noise variance))."""
+        rows = self._rows(observations)
+        b = max(self.batch_size(), len(rows))
+        n, d = self._x.shape
+        out, grads = np.zeros(b), np.zeros((b, 3))
+        for i in range(b):
+            a, l = self.kernel.params(i)
+            y = _vector(rows[i if len(rows) > 1 else 0])
+            v = ctypes.c_double()
+            call("vgp_gp_logprob_grad_k", DEVICE, self.kernel.KIND, self._x.ptr, n, d, y.ptr, a, l,
+                 _scalar(self.observation_noise_variance, i), float(self.jitter), ctypes.byref(v),
+                 grads[i].ctypes.data, None)
+            out[i] = v.value
+        return out, grads
+
+
+class LogProb:
+    """`gp.log_prob(placeholder)`: the reference's `log_likelihood` graph tensor.  Call it with the observations
+    (or `.run({placeholder: value})`); index it (`log_likelihood[0]`) for one element of a batch."""
+
+    def __init__(self, gp, placeholder, index=None):
+        self.gp, self.placeholder, self.index = gp, placeholder, index
+
+    def __call__(self, observations=None):
+        if observations is None:
+            observations = self.placeholder.value
+        v = np.atleast_1d(self.gp.log_prob(observations))
+        return v if self.index is None else v[self.index]
+
+    def run(self, feed_dict=None):
+        return self(None if not feed_dict else feed_dict.get(self.placeholder))
+
+    def __getitem__(self, index):
+        return LogProb(self.gp, self.placeholder, index)
+
+
+class AdamTrainOp:
+    """`tf.train.AdamOptimizer(lr).minimize(-log_likelihood)` (gp_functions.py:179-182) on the softplus-unconstrained
+    variables behind the GP's amplitude, length scale and noise variance (TF defaults beta1 .9, beta2 .999, eps 1e-8;
+    TF's update lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), v -= lr_t m / (sqrt(v) + eps)).  `run(observations)` evaluates
+    log-likelihood and gradient on the device at the current parameters, applies one update, and returns the
+    log-likelihood(s) of before the update -- what `sess.run([train_op, log_likelihood], feed)` yields."""
+
+    def __init__(self, node, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        assert isinstance(node, LogProb), "tf_train_gp_adam expects gp.log_prob(placeholder)"
+        self.node, self.lr, self.b1, self.b2, self.eps = node, float(learning_rate), beta1, beta2, epsilon
+        gp = node.gp
+        self.params = [gp.kernel.amplitude, gp.kernel.length_scale, gp.observation_noise_variance]
+        self.m = [np.zeros_like(_unconstrained(p)) if isinstance(p, Positive) else None for p in self.params]
+        self.v = [np.zeros_like(_unconstrained(p)) if isinstance(p, Positive) else None for p in self.params]
+        self.t = 0
+
+    def run(self, observations=None):
+        if observations is None:
+            observations = self.node.placeholder.value
+        ll, grads = self.node.gp.log_prob_and_grad(observations)
+        self.t += 1
+        lr_t = self.lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        for q, p in enumerate(self.params):
+            if not isinstance(p, Positive):
+                continue                                     # a constant: not trainable
+            u = _unconstrained(p)
+            g = grads[:, q] if u.size > 1 else np.array([grads[:, q].sum()])
+            g = -g.reshape(u.shape) * _sigmoid(u)            # d(-ll)/du = -(dll/dtheta) softplus'(u)
+            self.m[q] = self.b1 * self.m[q] + (1.0 - self.b1) * g
+            self.v[q] = self.b2 * self.v[q] + (1.0 - self.b2) * g * g
+            p.variable.assign(u - lr_t * self.m[q] / (np.sqrt(self.v[q]) + self.eps))
+        return ll
+
+
+def _unconstrained(p):
+    return np.atleast_1d(np.asarray(p.variable.value, dtype=np.float64))
+
+
+def _sigmoid(u):
+    return 1.0 / (1.0 + np.exp(-u))
 
 
 def fit_gp(kernel, obs_idx_pts, obs_noise_var):
     return GaussianProcess(kernel=kernel, index_points=obs_idx_pts, observation_noise_variance=obs_noise_var,
                            validate_args=True)
+
+
+def tf_train_gp_adam(feature, LEARNING_RATE):
+    """gp_functions.py:179-182: Adam on -feature, feature = gp.log_prob(placeholder)."""
+    return AdamTrainOp(feature, LEARNING_RATE)
+
+
+def do_assign(sess, feature, feature_assign, feature_plh, feature_arr):
+    """gp_functions.py:222-225: run the assign op with the placeholder's value, return the constrained feature."""
+    feature_assign(feature_arr)
+    return np.asarray(feature.numpy())
+
+
+class Session:
+    """Stand-in for the reference's module-global tf.InteractiveSession (gp_functions.py:112-121): `run` evaluates
+    the eager nodes of this module (LogProb, AdamTrainOp, AssignOp, Positive) with a feed dict."""
+
+    def run(self, fetches, feed_dict=None):
+        feed_dict = feed_dict or {}
+        for plh, value in feed_dict.items():
+            plh.value = value
+        single = not isinstance(fetches, (list, tuple))
+        out = []
+        for f in ([fetches] if single else fetches):
+            if isinstance(f, AdamTrainOp):
+                f.last = f.run()
+                out.append(None)
+            elif isinstance(f, LogProb):
+                out.append(f())
+            elif isinstance(f, AssignOp):
+                out.append(f(f.placeholder.value))
+            elif hasattr(f, "numpy"):
+                out.append(np.asarray(f.numpy()))
+            else:
+                out.append(f)
+        # a train op fetched together with its log-likelihood: both come from the same evaluation (pre-update)
+        ops = [f for f in ([fetches] if single else fetches) if isinstance(f, AdamTrainOp)]
+        if ops and not single:
+            for i, f in enumerate(fetches):
+                if isinstance(f, LogProb) and f.gp is ops[0].node.gp:
+                    v = np.atleast_1d(ops[0].last)
+                    out[i] = v if f.index is None else v[f.index]
+        return out[0] if single else out
+
+    def close(self):
+        pass
+
+
+sess = None
+
+
+def reset_session():
+    """gp_functions.py:112-121: a fresh global session."""
+    global sess
+    sess = Session()
+    return sess
+
+
+def tf_optimize_model_params(sess, num_iters, train_op, log_likelihood, summ=None, writer=None, saver=None,
+                             LOGDIR=None, LOGCHECKPT=None, obs_train_dataset=None, obs_value_placeholder=None):
+    """gp_functions.py:228-259: one initial run, then num_iters + 1 training steps; returns the log-likelihoods
+    `lls` [num_iters + 1, 1 or 2] (of before each update).  Summaries / checkpoints (`summ`, `writer`, `saver`) are
+    TensorBoard plumbing outside the hot path: when given they are called the way the reference calls them."""
+    data = np.asarray(obs_train_dataset, dtype=np.float64)
+    cols = 2 if data.ndim == 2 else 1
+    lls = np.zeros([num_iters + 1, cols], np.float64)
+    feed = data.reshape(obs_value_placeholder.shape) if obs_value_placeholder is not None else data
+    train_op.run(feed)                                               # :245-247, the initial run
+    for i in range(num_iters + 1):
+        lls[i] = np.atleast_1d(train_op.run(feed))[:cols]
+        if writer is not None and summ is not None:
+            writer.add_summary(summ, i)
+        if saver is not None and i % 200 == 0:
+            import os
+            saver.save(sess, os.path.join(LOGDIR, LOGCHECKPT), i)
+    return lls
 
 
 class GaussianProcessRegressionModel:
@@ -243,7 +468,7 @@ class GaussianProcessRegressionModel:
         t = self._xt.shape[0]
         mean = _ffi.DeviceArray((t,), np.float64, DEVICE)
         var = _ffi.DeviceArray((t,), np.float64, DEVICE)
-        call("vgp_gp_regression", DEVICE, self._x.ptr, n, d, self._y.ptr, self._xt.ptr, t, a, l,
+        call("vgp_gp_regression_k", DEVICE, self.kernel.KIND, self._x.ptr, n, d, self._y.ptr, self._xt.ptr, t, a, l,
              _scalar(self.observation_noise_variance), _scalar(self.predictive_noise_variance),
              float(self.divisor_jitter), mean.ptr, var.ptr, None)
         self._cache = (mean.to_host(), var.to_host())
@@ -267,6 +492,39 @@ def tf_gp_regression_model(kernel, pred_idx_pts, obs_idx_pts, obs, obs_noise_var
                                           predictive_noise_variance=pred_noise_var)
 
 
+def create_meshgrid(pred_x, pred_y):
+    """gp_functions.py:262-280: predictive index points [len(pred_x) * len(pred_y), 2]."""
+    h = np.array(np.meshgrid(pred_x, pred_y, sparse=False))
+    return h.swapaxes(0, -1).reshape(-1, 2)
+
+
+def slice_grid_xyz(i0, i1, i2, linsp_x, linsp_y, linsp_z):
+    """gp_functions.py:1215-1223: the coordinate triple at grid indices (i0, i1, i2)."""
+    return np.array([np.asarray(linsp_x)[int(i0)], np.asarray(linsp_y)[int(i1)], np.asarray(linsp_z)[int(i2)]])
+
+
+def py_get_coord_idxs(sel_idx, xyz_idxs):
+    """gp_functions.py:1226-1237: grid-index rows of the first 7 selected locations, in selection order."""
+    xyz_idxs = np.asarray(xyz_idxs)
+    return np.vstack([xyz_idxs[sel_idx[i], :].reshape(1, 3) for i in range(7)])
+
+
+def denormalize_coord(sel_norm_coord):
+    """gp_functions.py:1239-1247 (in place, like the reference)."""
+    stdev_var = 0.0007434639347162126 * 3000000
+    mean_var = 0.0018159087825037148
+    sel_norm_coord[:, :3] = sel_norm_coord[:, :3] * stdev_var + mean_var
+    return sel_norm_coord
+
+
+def create_cov_matrix(minmax_x, minmax_y, minmax_z, minmax_pressure, minmax_temperature, SPATIAL_COVER,
+                      SPATIAL_COV_PR_TEMP, encoder, sess=None):
+    """gp_functions.py:1019-1057 (see vgposp_b200.cov_producer.create_cov_matrix)."""
+    from .cov_producer import create_cov_matrix as impl
+    return impl(minmax_x, minmax_y, minmax_z, minmax_pressure, minmax_temperature, SPATIAL_COVER,
+                SPATIAL_COV_PR_TEMP, encoder, sess)
+
+
 def calc_H(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, log_likelihood, sess=None,
            obs_values_placeholder=None, obs_train_dataset=None):
     """Likelihood surface over (length_scale, amplitude) = 40 (1+i)/X, 40 (1+j)/Y (gp_functions.py:864-876).
@@ -277,7 +535,7 @@ def calc_H(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p,
         for j in range(YEDGES):
             lensc_assign([40 * np.double((1 + i) / XEDGES)])
             amp_assign([40 * np.double((1 + j) / YEDGES)])
-            H[i, j] = log_likelihood(y) if y is not None else log_likelihood()
+            H[i, j] = np.atleast_1d(log_likelihood(y) if y is not None else log_likelihood())[0]      # :875, L[0]
     return H
 
 
@@ -311,7 +569,7 @@ class VariationalGaussianProcess:
         m, d = z.shape
         loc = _ffi.DeviceArray((m,), np.float64, DEVICE)
         scale = _ffi.DeviceArray((m, m), np.float64, DEVICE)
-        call("vgp_vgp_optimal_posterior", DEVICE, z.ptr, m, x.ptr, x.shape[0], d, y.ptr, a, l,
+        call("vgp_vgp_optimal_posterior_k", DEVICE, kernel.KIND, z.ptr, m, x.ptr, x.shape[0], d, y.ptr, a, l,
              _scalar(observation_noise_variance), float(jitter), 1 if legacy_scale_orientation else 0, loc.ptr,
              scale.ptr, None)
         return (loc, scale) if as_device else (loc.to_host(), scale.to_host())
@@ -322,7 +580,8 @@ class VariationalGaussianProcess:
         yb = _vector(observations)
         m, d = self._z.shape
         terms = _ffi.VgpTerms()
-        call("vgp_vgp_loss", DEVICE, self._z.ptr, m, d, self._loc.ptr, self._scale.ptr, xb.ptr, yb.ptr, xb.shape[0],
+        call("vgp_vgp_loss_k", DEVICE, self.kernel.KIND, self._z.ptr, m, d, self._loc.ptr, self._scale.ptr, xb.ptr,
+             yb.ptr, xb.shape[0],
              a, l, _scalar(self.observation_noise_variance), float(kl_weight), float(self.jitter),
              ctypes.byref(terms), None)
         if return_terms:
@@ -335,7 +594,8 @@ class VariationalGaussianProcess:
         t = self._xt.shape[0]
         mean = _ffi.DeviceArray((t,), np.float64, DEVICE)
         var = _ffi.DeviceArray((t,), np.float64, DEVICE) if want_var else None
-        call("vgp_vgp_predict", DEVICE, self._z.ptr, m, d, self._loc.ptr, self._scale.ptr, self._xt.ptr, t, a, l,
+        call("vgp_vgp_predict_k", DEVICE, self.kernel.KIND, self._z.ptr, m, d, self._loc.ptr, self._scale.ptr,
+             self._xt.ptr, t, a, l,
              _scalar(self.predictive_noise_variance), float(self.jitter), mean.ptr, var.ptr if want_var else None,
              None)
         return mean.to_host(), (var.to_host() if want_var else None)
