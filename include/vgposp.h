@@ -333,6 +333,11 @@ int vgp_lazy_reset(vgp_lazy *handle, void *stream);
 int vgp_lazy_run(vgp_lazy *handle, int64_t k, void *stream);
 int vgp_lazy_results(vgp_lazy *handle, int64_t *count, int64_t *selection_host, double *scores_host,
                      int64_t capacity, void *stream);
+/* Algorithm 3, the local-kernel greedy of snippets_a3.sparse_placement_algorithm_3 (snippets_a3.py:43-364): the
+ * candidates are the points of an i0 x i1 x i2 grid (index = i2 i1 a + i2 b + c); after each selection only the
+ * deltas inside the index box [i - cutoff, i + cutoff) per axis around the winner are re-evaluated, the rest of the
+ * cache stays stale; recorded step scores are then the columns of delta_cached_iters.  cutoff = 0: exact greedy. */
+int vgp_lazy_set_local(vgp_lazy *handle, int64_t i0, int64_t i1, int64_t i2, int64_t cutoff);
 int vgp_lazy_record_scores(vgp_lazy *handle, int enable);
 int vgp_lazy_step_scores(vgp_lazy *handle, double *scores_host, int64_t capacity_rows, void *stream);
 int vgp_lazy_launch_count(vgp_lazy *handle, int64_t *launches);

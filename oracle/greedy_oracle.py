@@ -119,6 +119,83 @@ def literal_placement_algorithm_2(cov_vv, k, small=GUARD_NUMPY, jitter=0.0):
     return A, evaluations
 
 
+def _sparse_argmax(cache, A):
+    """sparse_argmax_cache_linear, placement_algorithm2.py:24-50: max of the cache over V \\ A, first index achieving
+    it (tf.where(...)[0, 0] over the index-ordered set difference)."""
+    taken = np.zeros(len(cache), dtype=bool)
+    taken[list(A)] = True
+    s = np.where(taken, -np.inf, cache)
+    return int(np.argmax(s))
+
+
+def literal_sparse_placement_algorithm_2(cov_vv, k, small=GUARD_TF_GRAPH, jitter=JITTER_TF_GRAPH, inf=1e8):
+    """The TF-graph lazy greedy, snippets_a2.py:679-822: cache starts at INF = 1e8 (:690), every entry stale at the
+    start of a selection (:726), the arg-max entry is re-evaluated until an up-to-date one wins (while_true_outside),
+    delta with the graph's jitter 1e-6 (:161-163) and guard 1e-7 (:480); the cache is stored in column len(A) - 1 of
+    delta_cached_iters BEFORE the winner's entry is zeroed (:771-797).
+    Returns (sorted A -- the graph's unordered sparse set --, len(A), delta_cached_iters [N, k],
+    A_selection_and_delta [k, 2] = (index, delta) in selection order)."""
+    n = cov_vv.shape[0]
+    A, A_bar = [], list(range(n))
+    cache = np.full(n, inf)
+    dci = np.zeros((n, k))
+    sel = np.zeros((k, 2))
+    while len(A) < k:
+        fresh = np.zeros(n, dtype=bool)
+        while True:
+            y = _sparse_argmax(cache, A)
+            if fresh[y]:
+                break
+            cache[y] = literal_delta(y, A, A_bar, cov_vv, small, jitter)
+            fresh[y] = True
+        A.append(y)
+        A_bar.remove(y)
+        sel[len(A) - 1] = (y, cache[y])
+        dci[:, len(A) - 1] = cache
+        cache[y] = 0.0
+    return sorted(A), len(A), dci, sel
+
+
+def literal_sparse_placement_algorithm_3(cov_vv, k, cover_spatial, cutoff, small=GUARD_TF_GRAPH,
+                                         jitter=JITTER_TF_GRAPH):
+    """Local-kernel greedy, snippets_a3.py:43-364.  All deltas are evaluated once with A empty (whD, :71-120); then
+    k - 1 times: arg-max of the cache over V \\ A, the winner joins A and its entry is zeroed, and ONLY the
+    candidates inside the index box [i - cutoff, min(i + cutoff, I)) per axis around the winner (:231-262; index =
+    I2 I1 i0 + I2 i1 + i2, :189-194) are re-evaluated against the new A (entries of selected points stay 0,
+    :223-226); everything else keeps its stale value.  Column i + 1 of delta_cached_iters receives the cache after
+    round i (:300-304); the k-th winner is taken from the last cache (:356-358).
+    Returns (A in selection order, final cache [N], delta_cached_iters [N, k])."""
+    i0n, i1n, i2n = (int(v) for v in cover_spatial)
+    n = cov_vv.shape[0]
+    assert n == i0n * i1n * i2n
+    A, A_bar = [], list(range(n))
+    cache = np.array([literal_delta(y, A, A_bar, cov_vv, small, jitter) for y in range(n)])
+    dci = np.zeros((n, k))
+    dci[:, 0] = cache
+    for i in range(k - 1):
+        y = _sparse_argmax(cache, A)
+        A.append(y)
+        A_bar.remove(y)
+        cache[y] = 0.0
+        c0 = y // (i1n * i2n)
+        c1 = (y - c0 * i1n * i2n) // i2n
+        c2 = y - c0 * i1n * i2n - c1 * i2n
+        for j0 in range(max(c0 - cutoff, 0), min(c0 + cutoff, i0n)):
+            for j1 in range(max(c1 - cutoff, 0), min(c1 + cutoff, i1n)):
+                for j2 in range(max(c2 - cutoff, 0), min(c2 + cutoff, i2n)):
+                    yj = i1n * i2n * j0 + i2n * j1 + j2
+                    if yj in A:
+                        cache[yj] = 0.0
+                    else:
+                        cache[yj] = literal_delta(yj, A, A_bar, cov_vv, small, jitter)
+        snap = cache.copy()
+        snap[y] = 0.0
+        dci[:, i + 1] = snap
+    y = _sparse_argmax(cache, A)
+    A.append(y)
+    return A, cache, dci
+
+
 # --------------------------------------------------------------------------------------------------
 # incremental form (what the CUDA kernels compute)
 # --------------------------------------------------------------------------------------------------

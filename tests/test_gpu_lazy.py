@@ -132,3 +132,40 @@ def test_properties_at_size():
         else:
             np.testing.assert_allclose(scores, dscores, rtol=1e-10)
         assert np.all(np.diff(scores) <= 1e-12 * scores[:-1])
+
+
+def _jittered_grid_cov(cover, ls, seed):
+    idx = np.indices(cover).reshape(3, -1).T.astype(np.float64)
+    pts = idx + np.random.default_rng(seed).uniform(-0.3, 0.3, idx.shape)       # breaks the lattice's exact ties
+    d = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    return np.exp(-d / (2 * ls * ls)) + 1e-2 * np.eye(len(pts))
+
+
+@pytest.mark.parametrize("cover,cutoff,k", [((4, 4, 2), 2, 6), ((5, 3, 3), 1, 5), ((6, 6, 1), 3, 7)])
+def test_algorithm_3_local_kernel_greedy(cover, cutoff, k):
+    """snippets_a3.sparse_placement_algorithm_3 against its literal CPU restatement: selection order, the final cache
+    and every column of delta_cached_iters (stale entries included)."""
+    from vgposp_b200 import snippets_a3
+    cov = _jittered_grid_cov(cover, 1.2, sum(cover))
+    want_A, want_cache, want_dci = go.literal_sparse_placement_algorithm_3(cov, k, cover, cutoff)
+    A, cache, dci = snippets_a3.sparse_placement_algorithm_3(cov, k, cover, cutoff)
+    assert [int(v) for v in A] == want_A
+    np.testing.assert_allclose(dci, want_dci, rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(cache, want_cache, rtol=1e-7, atol=1e-12)
+    # a box that covers the whole grid makes every entry fresh: algorithm 3 == exact greedy (graph numerics)
+    A_full, _, _ = snippets_a3.sparse_placement_algorithm_3(cov, k, cover, max(cover))
+    assert [int(v) for v in A_full] == go.literal_placement_algorithm_1(cov, k, small=1e-7, jitter=1e-6)
+
+
+def test_tf_graph_algorithm_2_outputs():
+    """snippets_a2.sparse_placement_algorithm_2: the four outputs of the graph (:822) against the literal restatement."""
+    from vgposp_b200 import snippets_a2
+    cover = (4, 3, 3)
+    cov = _jittered_grid_cov(cover, 1.0, 7)
+    k = 6
+    want_A, want_len, want_dci, want_sel = go.literal_sparse_placement_algorithm_2(cov, k)
+    A, len_A, dci, sel = snippets_a2.sparse_placement_algorithm_2(cov, k, cover)
+    assert [int(v) for v in A] == want_A and len_A == want_len == k
+    assert [int(v) for v in sel[:, 0]] == [int(v) for v in want_sel[:, 0]]
+    np.testing.assert_allclose(sel[:, 1], want_sel[:, 1], rtol=1e-7)
+    np.testing.assert_allclose(dci, want_dci, rtol=1e-7, atol=1e-12)

@@ -140,6 +140,7 @@ SIGNATURES = {
     "vgp_lazy_run": [c_vp, c_i64, c_vp],
     "vgp_lazy_results": [c_vp, P(c_i64), c_vp, c_vp, c_i64, c_vp],
     "vgp_lazy_record_scores": [c_vp, c_int],
+    "vgp_lazy_set_local": [c_vp, c_i64, c_i64, c_i64, c_i64],
     "vgp_lazy_step_scores": [c_vp, c_vp, c_i64, c_vp],
     "vgp_lazy_launch_count": [c_vp, P(c_i64)],
     "vgp_lazy_profile": [c_vp, c_int, P(c_dbl), P(c_i64)],

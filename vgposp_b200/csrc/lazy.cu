@@ -45,6 +45,8 @@ struct vgp_lazy {
     int64_t *sel = nullptr;
     double *sel_score = nullptr, *step_scores = nullptr;
     int record = 0, factored = 0;
+    int64_t loc_i1 = 0, loc_i2 = 0, loc_cutoff = 0;   // algorithm 3: grid strides I1, I2 and the index-box half-width
+    double *cache = nullptr;                          // algorithm 3: the (partly stale) delta cache [n_pad]
     int64_t t = 0, launches = 0;
     int blocks = 0;
     DenseWorkspace ws;
@@ -191,6 +193,8 @@ struct StepArgs {
     unsigned *counter;
     int64_t *sel;
     double *sel_score, *step_row;
+    double *cache;                  // algorithm 3 (local re-evaluation) when non-NULL
+    int64_t loc_i1, loc_i2, loc_cutoff;
 };
 
 // Apply the winner of step t-1 (if any) to column j, then score j for step t; last block picks the winner.
@@ -260,7 +264,7 @@ __global__ void __launch_bounds__(256) lazy_step_kernel(StepArgs a) {
     // ---- score for step t (placement_algorithm2.py:105-125) -------------------------------------------------
     double s = NEG_INF;
     int64_t idx = INT64_MAX;
-    if (live) {
+    if (live && !a.cache) {
         if (!tk) {
             const double den = 1.0 / dj - a.jitter;
             const double nom = nj - a.jitter;
@@ -274,6 +278,35 @@ __global__ void __launch_bounds__(256) lazy_step_kernel(StepArgs a) {
         } else if (a.step_row) {
             a.step_row[j] = nan("");
         }
+    } else if (live) {
+        // Algorithm 3 (snippets_a3.py:43-364): the arg-max runs over a cache of deltas of which only the entries
+        // inside the index box around the previous winner are refreshed; entries of selected points are 0.
+        double c = 0.0;
+        if (!tk) {
+            bool refresh = a.t == 0;                                        // first pass: every delta (whD, :71-120)
+            if (!refresh) {
+                const int64_t y = a.cur[(a.t - 1) & 1].index, s0 = a.loc_i1 * a.loc_i2;
+                const int64_t y0 = y / s0, y1 = (y - y0 * s0) / a.loc_i2, y2 = y - y0 * s0 - y1 * a.loc_i2;
+                const int64_t j0 = j / s0, j1 = (j - j0 * s0) / a.loc_i2, j2 = j - j0 * s0 - j1 * a.loc_i2;
+                const int64_t c_ = a.loc_cutoff;                            // [i - cutoff, i + cutoff) per axis, :231-262
+                refresh = j0 >= y0 - c_ && j0 < y0 + c_ && j1 >= y1 - c_ && j1 < y1 + c_ && j2 >= y2 - c_ &&
+                          j2 < y2 + c_;
+            }
+            if (refresh) {
+                const double den = 1.0 / dj - a.jitter;
+                const double nom = nj - a.jitter;
+                c = nom / den;
+                if (fabs(den) < a.small_ || fabs(nom) < a.small_) c = 0.0;
+            } else {
+                c = a.cache[j];
+            }
+            if (c > -1.0) {
+                s = c;
+                idx = j;
+            }
+        }
+        a.cache[j] = c;
+        if (a.step_row) a.step_row[j] = c;                                  // delta_cached_iters[:, t]
     }
     __shared__ int64_t win_idx;
     __shared__ double win_score;
@@ -415,7 +448,7 @@ int vgp_lazy_destroy(vgp_lazy *h) {
     if (!h) return VGP_OK;
     VGP_ENTER(h->device);
     void *ptrs[] = {h->cov, h->fac, h->d, h->d0, h->num, h->taken, h->U, h->W, h->inv, h->partial, h->partials,
-                    h->cur, h->counter, h->sel, h->sel_score, h->step_scores};
+                    h->cur, h->counter, h->sel, h->sel_score, h->step_scores, h->cache};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &e : h->pe)
@@ -566,6 +599,10 @@ int vgp_lazy_run(vgp_lazy *h, int64_t k, void *stream) {
         a.sel = h->sel;
         a.sel_score = h->sel_score;
         a.step_row = (h->record && h->step_scores) ? h->step_scores + h->t * h->n : nullptr;
+        a.cache = h->loc_cutoff > 0 ? h->cache : nullptr;
+        a.loc_i1 = h->loc_i1;
+        a.loc_i2 = h->loc_i2;
+        a.loc_cutoff = h->loc_cutoff;
         lazy_step_kernel<<<h->blocks, 256, 0, s>>>(a);
         L_LAUNCH_CHECK(h);
         ++h->t;
@@ -585,6 +622,28 @@ int vgp_lazy_results(vgp_lazy *h, int64_t *count, int64_t *selection_host, doubl
     if (scores_host && c > 0)
         VGP_CUDA(cudaMemcpyAsync(scores_host, h->sel_score, (size_t)c * 8, cudaMemcpyDeviceToHost, s));
     VGP_CUDA(cudaStreamSynchronize(s));
+    return VGP_OK;
+}
+
+/* Algorithm 3 (snippets_a3.sparse_placement_algorithm_3): candidates are the points of an I0 x I1 x I2 grid
+ * (index = I2 I1 i0 + I2 i1 + i2); after each selection only the deltas inside the index box
+ * [i - cutoff, i + cutoff) per axis around the winner are re-evaluated, every other entry of the cache keeps its stale
+ * value.  cutoff = 0 switches back to the exact greedy.  Call before vgp_lazy_run (and after any reset). */
+int vgp_lazy_set_local(vgp_lazy *h, int64_t i0, int64_t i1, int64_t i2, int64_t cutoff) {
+    VGP_TRY(check(h));
+    VGP_REQUIRE(cutoff >= 0, "negative cutoff");
+    if (cutoff == 0) {
+        h->loc_cutoff = 0;
+        return VGP_OK;
+    }
+    VGP_REQUIRE(i0 > 0 && i1 > 0 && i2 > 0 && i0 * i1 * i2 == h->n, "grid %lld x %lld x %lld does not have n = %lld points",
+                (long long)i0, (long long)i1, (long long)i2, (long long)h->n);
+    VGP_REQUIRE(h->t == 0, "set the local mode before the first selection");
+    VGP_ENTER(h->device);
+    if (!h->cache) VGP_CUDA(cudaMalloc((void **)&h->cache, (size_t)h->n_pad * 8));
+    h->loc_i1 = i1;
+    h->loc_i2 = i2;
+    h->loc_cutoff = cutoff;
     return VGP_OK;
 }
 

@@ -224,6 +224,12 @@ class LazyGreedy:
     def record_scores(self, enable=True):
         call("vgp_lazy_record_scores", self.handle, 1 if enable else 0)
 
+    def set_local(self, cover_spatial, cutoff):
+        """Algorithm 3 (snippets_a3.py:43-364): re-evaluate only the index box of half-width `cutoff` around each
+        winner on the I0 x I1 x I2 grid; cutoff 0 = exact greedy."""
+        i0, i1, i2 = (int(v) for v in cover_spatial)
+        call("vgp_lazy_set_local", self.handle, i0, i1, i2, int(cutoff))
+
     def run(self, k):
         call("vgp_lazy_run", self.handle, int(k), self.stream)
 
