@@ -208,6 +208,15 @@ int vgp_gp_logprob_grad_k(int device, int kind, const double *x_dev, int64_t n, 
                           double amplitude, double length_scale, double noise_variance, double jitter,
                           double *logprob_host, double *grads_host, void *stream);
 
+/* log_prob of the same observations under `batch` hyper-parameter triples params_host [batch][3] = (amplitude,
+ * length_scale, noise_variance) -> logprob_host [batch]: the likelihood-surface sweep of gpf.calc_H
+ * (gp_functions.py:864-876; 160 x 160 evaluations at main.py:400-401, 60 x 60 at main_GP_fit.py:122-123) as one launch
+ * when n <= 127 (one CTA per triple, kernel build + Cholesky + solve in registers), otherwise one vgp_gp_logprob_k
+ * per triple.  Triples whose matrix is not positive definite give NaN.  Blocking. */
+int vgp_gp_logprob_batch_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev,
+                           const double *params_host, int64_t batch, double jitter, double *logprob_host,
+                           void *stream);
+
 /* ---------------------------------------------------------------- VGP training step (a4-a7) ---------------- */
 /* Reference-faithful ELBO training (variational_Gaussian_process_example.py:47-102): amplitude = softplus(v[0]),
  * length_scale = offset + softplus(v[1]), noise = softplus(v[2]); (loc, scale) are the Titsias optimum over ALL

@@ -217,3 +217,40 @@ def test_batch_of_two_gps():
     for i, v0 in enumerate([[0.54, 0.54, 0.54], [0.9, 0.3, 0.2]]):
         want, _ = gpo.gp_train_adam(x, y[i], v0, 0.1, 5, kind="matern12")
         np.testing.assert_allclose(lls[:, i], want, rtol=1e-8)
+
+
+@pytest.mark.parametrize("kind", ["expquad", "matern12", "matern52"])
+@pytest.mark.parametrize("n,d", [(1, 1), (25, 2), (100, 5), (127, 3), (140, 3)])
+def test_batched_log_prob_sweep(kind, n, d):
+    """vgp_gp_logprob_batch_k (one CTA per hyper-parameter triple for n <= 127, per-triple calls above) against the
+    single-evaluation oracle."""
+    import ctypes
+    x, y = data(n, 5 * n + d, d=max(d, 2))
+    x = x[:, :d]
+    rng = np.random.default_rng(n)
+    params = np.column_stack([rng.uniform(0.3, 3.0, 40), rng.uniform(0.2, 4.0, 40), rng.uniform(0.01, 0.5, 40)])
+    out = np.empty(40)
+    xd, yd = gpf._points(x), gpf._vector(y)
+    gpf.call("vgp_gp_logprob_batch_k", 0, gpo.KERNEL_KINDS[kind], xd.ptr, n, d, yd.ptr, params.ctypes.data, 40, 1e-6,
+             out.ctypes.data, None)
+    want = [gpo.gp_log_prob(x, y, a, l, s, kind=kind) for a, l, s in params]
+    np.testing.assert_allclose(out, want, rtol=RTOL)
+
+
+def test_calc_H_is_one_launch_and_matches_the_loop():
+    """gpf.calc_H over a 12 x 9 grid on 25 points (main.py:400-419 uses 160 x 160 on 25): batched path == the
+    sequential statement of gp_functions.py:864-876, and the variables end where the loop leaves them."""
+    x, y = data(25, 77, d=2)
+    amp, amp_assign, amp_p, lensc, lensc_assign, lensc_p, _, _, _, noise = \
+        gpf.tf_Placeholder_assign_test(np.array([0.54]), np.array([0.54]), np.array([0.3]))
+    gp = gpf.fit_gp(gpf.create_cov_kernel(amp, lensc), x, noise)
+    H = gpf.calc_H(12, 9, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, gp.log_prob, None, None, y)
+    assert float(lensc) == pytest.approx(40.0) and float(amp) == pytest.approx(40.0)
+    s2 = float(noise)
+    for i in range(12):
+        for j in range(9):
+            want = gpo.gp_log_prob(x, y, 40 * (1 + j) / 9, 40 * (1 + i) / 12, s2, kind="matern12")
+            assert H[i, j] == pytest.approx(want, rel=RTOL)
+    obs = gpf.placeholder(np.float64, (1, 25))
+    H2 = gpf.calc_H(12, 9, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, gp.log_prob(obs), None, obs, y)
+    assert np.array_equal(H, H2)

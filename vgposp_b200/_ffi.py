@@ -82,6 +82,7 @@ SIGNATURES = {
     "vgp_gp_logprob_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, P(c_dbl), c_vp],
     "vgp_empirical_cov": [c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp],
     "vgp_cov_taper": [c_int, c_vp, c_i64, c_i64, c_vp, c_dbl, c_dbl, c_vp],
+    "vgp_gp_logprob_batch_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_dbl, c_vp, c_vp],
     "vgp_gp_logprob_grad_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_dbl, c_dbl, c_dbl, c_dbl, P(c_dbl), c_vp, c_vp],
     "vgp_gp_regression_k": [c_int, c_int, c_vp, c_i64, c_int, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl,
                             c_vp, c_vp, c_vp],

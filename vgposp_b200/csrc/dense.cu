@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include "dense.cuh"
+#include "block128.cuh"
 
 namespace vgp {
 
@@ -481,7 +482,6 @@ int dense_mirror_lower(double *a, int64_t n, int64_t ld, cudaStream_t s) {
 // =====================================================================================================
 // 128 x 128 diagonal-block kernels (one CTA, block resident in shared memory)
 // =====================================================================================================
-constexpr int NB = 128;
 constexpr int SLD = NB + 1;
 constexpr int BLOCK_SMEM = NB * SLD * 8;    // 132 096 B
 
@@ -496,40 +496,6 @@ constexpr int BLOCK_SMEM = NB * SLD * 8;    // 132 096 B
 // which rows / columns lie behind the pivot (and need no update) are then compile-time facts, and the trailing
 // update shrinks with the panel -- the first version carried them as run-time selects (374 FSEL per column, 200 us
 // per block, issue-bound; ncu launch list of the ELBO step).
-template <int SJ>
-__device__ __forceinline__ void potf2_panel(double (&v)[8][8], double (*colbuf)[NB], int ti, int tc, int *info,
-                                            int row_offset) {
-#pragma unroll 1
-    for (int jj = 0; jj < 16; ++jj) {
-        const int j = 16 * SJ + jj, jb = j & 1;
-        if (tc == jj) {
-#pragma unroll
-            for (int r = SJ; r < 8; ++r) colbuf[jb][ti + 16 * r] = v[r][SJ];
-        }
-        __syncthreads();
-        const double d = colbuf[jb][j];
-        if (!(d > 0.0) && threadIdx.x == 0) atomicCAS(info, 0, row_offset + j + 1);
-        const double piv = sqrt(d);
-        const double inv = 1.0 / piv;
-        double lr[8], lc[8];
-#pragma unroll
-        for (int r = SJ; r < 8; ++r) lr[r] = (r > SJ || ti > jj) ? colbuf[jb][ti + 16 * r] * inv : 0.0;     // i > j
-#pragma unroll
-        for (int s = SJ; s < 8; ++s) lc[s] = (s > SJ || tc > jj) ? colbuf[jb][tc + 16 * s] * inv : 0.0;     // c > j
-#pragma unroll
-        for (int r = SJ; r < 8; ++r)
-#pragma unroll
-            for (int s = SJ; s <= r; ++s) v[r][s] = fma(-lr[r], lc[s], v[r][s]);      // lower blocks only
-        if (tc == jj) {        // column j is final: store L[i][j]
-#pragma unroll
-            for (int r = SJ; r < 8; ++r) {
-                if (r > SJ || ti > jj) v[r][SJ] = lr[r];
-                else if (ti == jj) v[r][SJ] = piv;
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, int *info, int row_offset) {
     __shared__ double colbuf[2][NB];
     const int ti = threadIdx.x >> 4, tc = threadIdx.x & 15;

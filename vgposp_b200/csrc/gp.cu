@@ -10,6 +10,9 @@
 // Everything is float64.  Matrices live in 128-padded scratch (identity on the padding diagonal of every
 // factorised matrix, zeros elsewhere), so padded rows/columns contribute exact zeros to every norm.
 // Scalar reductions are two-stage with a fixed tree: results are run-to-run deterministic.
+#include <vector>
+
+#include "block128.cuh"
 #include "gp_common.cuh"
 
 namespace vgp {
@@ -74,6 +77,116 @@ __global__ void __launch_bounds__(256) gp_grad_kernel(const double *__restrict__
         __syncthreads();
     }
     if (threadIdx.x < 3) rowacc[i * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// ---- batched exact-GP likelihood (calc_H, gp_functions.py:864-876): one CTA per hyper-parameter triple ---------
+// The n <= 127 observations of the reference's likelihood-surface sweeps (25 points at main.py:418-419) fit one
+// 128-block: the CTA builds C = K + (noise + jitter) I straight into the register tile of the elimination kernel, with
+// y as row n of the block (the Cholesky of [[C, y], [y^T, big]] has L^-1 y as its row n), factorises the panels that
+// hold live rows, and reduces log-determinant and quadratic form -- no global-memory traffic but x, y and 8 bytes out.
+template <int KIND, int D>
+__global__ void __launch_bounds__(256, 1) gp_logprob_batch_kernel(const double *__restrict__ x, int n,
+                                                                  const double *__restrict__ y,
+                                                                  const double *__restrict__ params, double jitter,
+                                                                  double *out, int *info) {
+    __shared__ double colbuf[2][NB];
+    __shared__ double xs[NB][D];
+    __shared__ double ys[NB];
+    __shared__ double red[2][256];
+    const int b = blockIdx.x;
+    const double amp = params[3 * b], ls = params[3 * b + 1], shift = params[3 * b + 2] + jitter;
+    const double amp2 = amp * amp;
+    for (int t = threadIdx.x; t < NB * D; t += 256) xs[t / D][t % D] = t / D < n ? x[t] : 0.0;
+    for (int t = threadIdx.x; t < NB; t += 256) ys[t] = t < n ? y[t] : 0.0;
+    __syncthreads();
+    const int ti = threadIdx.x >> 4, tc = threadIdx.x & 15;
+    double v[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const int i = ti + 16 * r, c = tc + 16 * s;
+            double val = 0.0;
+            if (c <= i) {
+                if (i < n) {
+                    double s2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const double t = xs[i][k] - xs[c][k];
+                        s2 = fma(t, t, s2);
+                    }
+                    if (KIND == VGP_KERNEL_EXPQUAD) {
+                        val = amp2 * exp(-0.5 * s2 / (ls * ls));
+                    } else {
+                        const double rr = sqrt(s2);
+                        if (KIND == VGP_KERNEL_MATERN12) {
+                            val = amp2 * exp(-rr / ls);
+                        } else if (KIND == VGP_KERNEL_MATERN32) {
+                            const double z = sqrt(3.0) * rr / ls;
+                            val = amp2 * (1.0 + z) * exp(-z);
+                        } else {
+                            const double z = sqrt(5.0) * rr / ls;
+                            val = amp2 * (1.0 + z + z * z / 3.0) * exp(-z);
+                        }
+                    }
+                    if (i == c) val += shift;
+                } else if (i == n) {
+                    val = c < n ? ys[c] : 1e300;           // row n = y^T, its pivot kept huge and harmless
+                } else {
+                    val = i == c ? 1.0 : 0.0;              // identity padding
+                }
+            }
+            v[r][s] = val;
+        }
+    // only the panels that contain rows 0 .. n need eliminating
+    int *flag = info + b;
+    const int panels = n / 16 + 1;
+    potf2_panel<0>(v, colbuf, ti, tc, flag, 0);
+    if (panels > 1) potf2_panel<1>(v, colbuf, ti, tc, flag, 0);
+    if (panels > 2) potf2_panel<2>(v, colbuf, ti, tc, flag, 0);
+    if (panels > 3) potf2_panel<3>(v, colbuf, ti, tc, flag, 0);
+    if (panels > 4) potf2_panel<4>(v, colbuf, ti, tc, flag, 0);
+    if (panels > 5) potf2_panel<5>(v, colbuf, ti, tc, flag, 0);
+    if (panels > 6) potf2_panel<6>(v, colbuf, ti, tc, flag, 0);
+    if (panels > 7) potf2_panel<7>(v, colbuf, ti, tc, flag, 0);
+    double logdet = 0.0, quad = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s <= r; ++s) {
+            const int i = ti + 16 * r, c = tc + 16 * s;
+            if (i == c && i < n) logdet += log(v[r][s]);
+            if (i == n && c < n) quad = fma(v[r][s], v[r][s], quad);
+        }
+    red[0][threadIdx.x] = logdet;
+    red[1][threadIdx.x] = quad;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + off];
+            red[1][threadIdx.x] += red[1][threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[b] = -0.5 * red[1][0] - red[0][0] - 0.5 * (double)n * log(2.0 * M_PI);
+}
+
+template <int KIND>
+int launch_gp_batch(int d, const double *x, int n, const double *y, const double *params, int64_t batch,
+                    double jitter, double *out, int *info, cudaStream_t s) {
+    switch (d) {
+#define VGP_CASE(DD)                                                                                              \
+    case DD:                                                                                                      \
+        gp_logprob_batch_kernel<KIND, DD><<<(unsigned)batch, 256, 0, s>>>(x, n, y, params, jitter, out, info);    \
+        break;
+        VGP_CASE(1) VGP_CASE(2) VGP_CASE(3) VGP_CASE(4) VGP_CASE(5) VGP_CASE(6) VGP_CASE(7) VGP_CASE(8)
+#undef VGP_CASE
+        default:
+            set_error("feature dimension %d outside [1, 8]", d);
+            return VGP_ERR_INVALID;
+    }
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
 }
 
 struct ColSum3 {
@@ -458,6 +571,56 @@ int vgp_vgp_predict_k(int device, int kind, const double *z_dev, int64_t m, int 
         cudaStreamSynchronize(s);
     }
     ws.release();
+    return rc;
+}
+
+/* log_prob of the same observations under `batch` hyper-parameter triples params_host [batch][3] = (amplitude,
+ * length_scale, noise_variance): the likelihood-surface sweep of gpf.calc_H (gp_functions.py:864-876; 160 x 160
+ * evaluations at main.py:400-401) as ONE launch when n <= 127 (one CTA per triple, the whole factorisation in
+ * registers), otherwise one vgp_gp_logprob_k per triple.  Non-positive-definite triples return NaN. */
+int vgp_gp_logprob_batch_k(int device, int kind, const double *x_dev, int64_t n, int d, const double *y_dev,
+                           const double *params_host, int64_t batch, double jitter, double *logprob_host,
+                           void *stream) {
+    VGP_REQUIRE(x_dev && y_dev && params_host && logprob_host && n > 0 && batch >= 0, "bad argument");
+    VGP_REQUIRE(kind >= VGP_KERNEL_EXPQUAD && kind <= VGP_KERNEL_MATERN52, "unknown kernel kind %d", kind);
+    if (batch == 0) return VGP_OK;
+    if (n > NB - 1) {
+        for (int64_t b = 0; b < batch; ++b) {
+            int rc = vgp_gp_logprob_k(device, kind, x_dev, n, d, y_dev, params_host[3 * b], params_host[3 * b + 1],
+                                      params_host[3 * b + 2], jitter, logprob_host + b, stream);
+            if (rc == VGP_ERR_NOT_PD) logprob_host[b] = nan("");
+            else if (rc != VGP_OK) return rc;
+        }
+        return VGP_OK;
+    }
+    VGP_ENTER(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    double *params = nullptr, *out = nullptr;
+    int *info = nullptr;
+    VGP_CUDA(cudaMallocAsync((void **)&params, (size_t)batch * 24, s));
+    VGP_CUDA(cudaMallocAsync((void **)&out, (size_t)batch * 8, s));
+    VGP_CUDA(cudaMallocAsync((void **)&info, (size_t)batch * 4, s));
+    VGP_CUDA(cudaMemcpyAsync(params, params_host, (size_t)batch * 24, cudaMemcpyHostToDevice, s));
+    VGP_CUDA(cudaMemsetAsync(info, 0, (size_t)batch * 4, s));
+    int rc;
+    switch (kind) {
+        case VGP_KERNEL_EXPQUAD: rc = launch_gp_batch<VGP_KERNEL_EXPQUAD>(d, x_dev, (int)n, y_dev, params, batch, jitter, out, info, s); break;
+        case VGP_KERNEL_MATERN12: rc = launch_gp_batch<VGP_KERNEL_MATERN12>(d, x_dev, (int)n, y_dev, params, batch, jitter, out, info, s); break;
+        case VGP_KERNEL_MATERN32: rc = launch_gp_batch<VGP_KERNEL_MATERN32>(d, x_dev, (int)n, y_dev, params, batch, jitter, out, info, s); break;
+        default: rc = launch_gp_batch<VGP_KERNEL_MATERN52>(d, x_dev, (int)n, y_dev, params, batch, jitter, out, info, s);
+    }
+    if (rc == VGP_OK) {
+        std::vector<int> flags((size_t)batch);
+        cudaError_t e = cudaMemcpyAsync(logprob_host, out, (size_t)batch * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(flags.data(), info, (size_t)batch * 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "batched log_prob", __FILE__, __LINE__);
+        for (int64_t b = 0; rc == VGP_OK && b < batch; ++b)
+            if (flags[(size_t)b] != 0 && flags[(size_t)b] <= n) logprob_host[b] = nan("");
+    }
+    cudaFreeAsync(params, s);
+    cudaFreeAsync(out, s);
+    cudaFreeAsync(info, s);
     return rc;
 }
 

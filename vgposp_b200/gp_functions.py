@@ -527,10 +527,32 @@ def create_cov_matrix(minmax_x, minmax_y, minmax_z, minmax_pressure, minmax_temp
 
 def calc_H(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, log_likelihood, sess=None,
            obs_values_placeholder=None, obs_train_dataset=None):
-    """Likelihood surface over (length_scale, amplitude) = 40 (1+i)/X, 40 (1+j)/Y (gp_functions.py:864-876).
-    `log_likelihood` is a callable of the observations (e.g. `gp.log_prob`); `sess` is accepted and ignored."""
+    """Likelihood surface over (length_scale, amplitude) = 40 (1+i)/X, 40 (1+j)/Y (gp_functions.py:864-876):
+    H[i, j] = log_likelihood[0] with both parameters assigned.  `log_likelihood` is `gp.log_prob` (bound method) or
+    the `gp.log_prob(placeholder)` node; `sess` is accepted and ignored.
+
+    The reference issues X * Y session runs, each a kernel build + Cholesky (25 600 of them at main.py:400-401).  When
+    the GP is known and has at most 127 observations the whole sweep is ONE launch -- one CTA per grid point, kernel
+    matrix, Cholesky and solve in registers (vgp_gp_logprob_batch_k); otherwise the evaluations run one by one."""
     H = np.zeros([XEDGES, YEDGES])
-    y = None if obs_train_dataset is None else np.asarray(obs_train_dataset, dtype=np.float64).reshape(-1)
+    y = None if obs_train_dataset is None else np.asarray(obs_train_dataset, dtype=np.float64)
+    gp = log_likelihood.gp if isinstance(log_likelihood, LogProb) else getattr(log_likelihood, "__self__", None)
+    if isinstance(gp, GaussianProcess) and y is not None and gp._x.shape[0] <= 127 and \
+            gp.kernel.amplitude is amp and gp.kernel.length_scale is lensc:
+        n, d = gp._x.shape
+        y0 = _vector(gp._rows(y)[0])
+        ls_grid = 40.0 * (1.0 + np.arange(XEDGES)) / XEDGES
+        amp_grid = 40.0 * (1.0 + np.arange(YEDGES)) / YEDGES
+        params = np.empty((XEDGES, YEDGES, 3))
+        params[:, :, 0] = amp_grid[None, :]
+        params[:, :, 1] = ls_grid[:, None]
+        params[:, :, 2] = _scalar(gp.observation_noise_variance)
+        out = np.empty(XEDGES * YEDGES)
+        call("vgp_gp_logprob_batch_k", DEVICE, gp.kernel.KIND, gp._x.ptr, n, d, y0.ptr, params.ctypes.data,
+             XEDGES * YEDGES, float(gp.jitter), out.ctypes.data, None)
+        lensc_assign(np.full(np.shape(_values(lensc)), ls_grid[-1]))         # the state the reference's loop leaves
+        amp_assign(np.full(np.shape(_values(amp)), amp_grid[-1]))
+        return out.reshape(XEDGES, YEDGES)
     for i in range(XEDGES):
         for j in range(YEDGES):
             lensc_assign([40 * np.double((1 + i) / XEDGES)])
