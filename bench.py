@@ -46,7 +46,7 @@ def workload(n):
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Polls NVML (SM clock, throttle reasons) every 100 ms on a side thread while the timed region runs."""
+    """Polls NVML (SM clock, throttle reasons) every 20 ms on a side thread while the timed region runs."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
@@ -84,7 +84,7 @@ class ClockSampler:
             except Exception as e:    # noqa: BLE001
                 self.err = repr(e)
                 return
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv:
