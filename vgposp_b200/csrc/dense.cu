@@ -16,6 +16,7 @@
 //     one or two large GEMMs on rectangular off-diagonal blocks plus recursion on the diagonal blocks;
 //     128x128 diagonal blocks are handled by single-CTA shared-memory kernels.  Diagonal-block solves
 //     multiply by an explicitly inverted 128x128 block (one more GEMM call, in place).
+#include <cuda.h>          // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -268,10 +269,254 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) gemm_kernel(GemmArgs p) {
     if (p.dist_n > 0) __threadfence_system();
 }
 
+// -----------------------------------------------------------------------------------------------------
+// TMA-fed variant for two k-contiguous operands (A [m][k], B [n][k]: the Cholesky's TRSM / SYRK updates and the
+// ELBO's K_zx K_zx^T).  One elected thread arms an mbarrier with the byte count of a stage and issues two
+// cp.async.bulk.tensor.2d loads (A box 16 k x 128 rows, B box 16 k x 64 rows); the tiles land densely in shared memory
+// under the 128-byte hardware swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)); every thread waits on the
+// barrier's phase instead of cp.async.wait_group.  The 8 x 4 float64 DMMA fragment (lane g,t reads row g, k t) is
+// conflict-free under that swizzle only if the rows of a half-warp differ in bits 1-2 of (r & 7): fragment i therefore
+// takes the rows 16 (i / 2) + 2 g + (i % 2) of the warp tile (even / odd rows of a 16-row group) instead of 8
+// consecutive ones -- pure bookkeeping, the accumulators just belong to permuted rows / columns, and the epilogue
+// reassembles four consecutive columns per thread from the two fragments of a group (two 128-bit stores).
+// Same tile shape, warp tile and two-CTAs-per-SM residency as CfgPair; 4 stages of 24 KB.
+// -----------------------------------------------------------------------------------------------------
+namespace tma {
+constexpr int TM = 128, TN = 64, TK = 16, STAGES = 4, THREADS = 128;
+constexpr int A_BYTES = TM * TK * 8, B_BYTES = TN * TK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + STAGES * 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 8000000000LL) __trap();      // ~4 s: a lost transaction fails the launch instead of hanging
+    }
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+}  // namespace tma
+
+__global__ void __launch_bounds__(tma::THREADS, 2)
+    gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
+    using namespace tma;
+    extern __shared__ unsigned char raw[];
+    const unsigned raw_addr = smem_u32(raw);
+    unsigned char *sm = raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // SWIZZLE_128B wants 1024-byte alignment
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + STAGES * STAGE_BYTES);
+    constexpr int RATIO = TM / TN;
+    int tm, tn;
+    if (p.lower) {
+        const int64_t b = p.tile0 + blockIdx.x;
+        int r = (int)((sqrt(8.0 * (double)b / RATIO + 1.0) - 1.0) * 0.5);
+        while ((int64_t)RATIO * r * (r + 1) / 2 > b) --r;
+        while ((int64_t)RATIO * (r + 1) * (r + 2) / 2 <= b) ++r;
+        tm = r;
+        tn = (int)(b - (int64_t)RATIO * r * (r + 1) / 2);
+    } else if (p.dist_n > 0) {
+        const int64_t b = p.tile0 + blockIdx.x;
+        tm = (int)(b / p.tiles_n);
+        tn = (int)(b % p.tiles_n);
+    } else {
+        tn = blockIdx.x;
+        tm = blockIdx.y;
+    }
+    const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp >> 1) * 64, wn0 = (warp & 1) * 32;
+    const int64_t kbase = (int64_t)blockIdx.z * p.k_split;
+    const int64_t klen = p.k - kbase < p.k_split ? p.k - kbase : p.k_split;
+    const int KT = (int)(klen / TK);
+    double *cout = p.c + (int64_t)blockIdx.z * p.c_split_stride;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES; ++st) mbar_init(smem_u32(&bars[st]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int kt) {        // thread 0 only
+        const int stage = kt % STAGES;
+        const unsigned bar = smem_u32(&bars[stage]);
+        const unsigned dst = smem_u32(sm + stage * STAGE_BYTES);
+        const int k0 = (int)(kbase + (int64_t)kt * TK);
+        mbar_expect_tx(bar, STAGE_BYTES);
+        tma_load_2d(dst, &map_a, k0, (int)m0, bar);
+        tma_load_2d(dst + A_BYTES, &map_b, k0, (int)n0, bar);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < STAGES - 1; ++st)
+            if (st < KT) issue(st);
+    }
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // byte offsets inside a swizzled tile: row r (128 bytes), 16-byte chunk ((k >> 1) ^ (r & 7)), half (k & 1).
+    // For every fragment of this thread (r & 7) = 2 (g & 3) + (i & 1): the chunk is ((kk / 2) ^ gx) | ((t >> 1) ^ e).
+    const int gx = 2 * (g & 3);
+    const unsigned a_row = (unsigned)((wm0 + 2 * g) * 128 + (t & 1) * 8);
+    const unsigned b_row = (unsigned)(A_BYTES + (wn0 + 2 * g) * 128 + (t & 1) * 8);
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int stage = kt % STAGES;
+        __syncthreads();                                   // everyone is done with k-tile kt - 1: its stage is free
+        if (tid == 0 && kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
+        mbar_wait(smem_u32(&bars[stage]), (unsigned)((kt / STAGES) & 1));
+        const unsigned char *st = sm + stage * STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+            const int ck = (kk / 2) ^ gx;
+            const unsigned off0 = (unsigned)((ck | (t >> 1)) << 4), off1 = (unsigned)((ck | ((t >> 1) ^ 1)) << 4);
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                af[i] = *reinterpret_cast<const double *>(st + a_row + (i >> 1) * 2048 + (i & 1) * 128 +
+                                                          ((i & 1) ? off1 : off0));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + (j & 1) * 128 +
+                                                          ((j & 1) ? off1 : off0));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+
+    // epilogue: fragment i holds rows 16 (i / 2) + 2 g + (i % 2); the two column fragments of a 16-column group hold
+    // columns 4 t + {0, 2} and 4 t + {1, 3}: four consecutive columns per thread
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t r = m0 + wm0 + 16 * (i >> 1) + 2 * g + (i & 1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double2 *dst = reinterpret_cast<double2 *>(cout + r * p.ldc + n0 + wn0 + 16 * q + 4 * t);
+            double2 o0, o1;
+            if (p.beta != 0.0) {
+                const double2 old0 = dst[0], old1 = dst[1];
+                o0.x = fma(p.alpha, acc[i][2 * q][0], p.beta * old0.x);
+                o0.y = fma(p.alpha, acc[i][2 * q + 1][0], p.beta * old0.y);
+                o1.x = fma(p.alpha, acc[i][2 * q][1], p.beta * old1.x);
+                o1.y = fma(p.alpha, acc[i][2 * q + 1][1], p.beta * old1.y);
+            } else {
+                o0.x = p.alpha * acc[i][2 * q][0];
+                o0.y = p.alpha * acc[i][2 * q + 1][0];
+                o1.x = p.alpha * acc[i][2 * q][1];
+                o1.y = p.alpha * acc[i][2 * q + 1][1];
+            }
+            if (p.dist_n > 0) {
+                for (int d = 0; d < p.dist_n; ++d) {                 // every replica, peers over NVLink
+                    double2 *rep = dst + (p.delta[d] >> 1);
+                    rep[0] = o0;
+                    rep[1] = o1;
+                }
+            } else {
+                dst[0] = o0;
+                dst[1] = o1;
+            }
+        }
+    }
+    if (p.dist_n > 0) __threadfence_system();
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TensorMapEncodeFn)ptr;
+    }
+    return fn;
+}
+
+// k-contiguous operand [rows][ld] -> tensor map with boxes of 16 k x box_rows rows, 128-byte swizzle
+static int make_operand_map(CUtensorMap *map, const double *base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    VGP_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)tma::TK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VGP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VGP_OK;
+}
+
+static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
+    static bool configured[64] = {};
+    int dev = 0;
+    VGP_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
+        configured[dev] = true;
+    }
+    alignas(64) CUtensorMap ma, mb;
+    VGP_TRY(make_operand_map(&ma, p.a, p.m, p.k, p.lda, tma::TM));
+    VGP_TRY(make_operand_map(&mb, p.b, p.n, p.k, p.ldb, tma::TN));
+    const int64_t tm = p.m / tma::TM, tn = p.n / tma::TN;
+    const unsigned splits = (unsigned)((p.k + p.k_split - 1) / p.k_split);
+    constexpr int RATIO = tma::TM / tma::TN;
+    if (p.dist_n > 0) {
+        GemmArgs q = p;
+        const int64_t total = p.lower ? (int64_t)RATIO * tm * (tm + 1) / 2 : tm * tn;
+        const int64_t rank = p.tile0, nranks = p.tiles_n;
+        const int64_t each = total / nranks, rem = total % nranks;
+        q.tile0 = rank * each + (rank < rem ? rank : rem);
+        const int64_t mine = each + (rank < rem ? 1 : 0);
+        q.tiles_n = tn;
+        if (mine > 0) {
+            gemm_tma_kernel<<<dim3((unsigned)mine, 1, 1), tma::THREADS, tma::SMEM, s>>>(ma, mb, q);
+            VGP_LAUNCH_CHECK();
+        }
+        return VGP_OK;
+    }
+    if (p.lower) {
+        const int64_t blocks = (int64_t)RATIO * tm * (tm + 1) / 2;
+        gemm_tma_kernel<<<dim3((unsigned)blocks, 1, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
+    } else {
+        gemm_tma_kernel<<<dim3((unsigned)tn, (unsigned)tm, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
+    }
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
 // Tile configuration for one product.  The triangular solves multiply in place (C aliases A with n = 128, or B with
 // m = 128): then one CTA must own the whole aliased operand tile, which only the 128x128 tile guarantees.
-// VGP_GEMM_CFG = base | pair forces one for every product that may legally use it (measurement knob).
-enum GemmChoice { CHOICE_BASE = 0, CHOICE_PAIR = 1 };
+// VGP_GEMM_CFG = base | pair | tma forces one for every product that may legally use it (measurement knob).
+enum GemmChoice { CHOICE_BASE = 0, CHOICE_PAIR = 1, CHOICE_TMA = 2 };
 static int gemm_forced_choice() {
     static int forced = -2;
     if (forced == -2) {
@@ -280,6 +525,7 @@ static int gemm_forced_choice() {
         if (e) {
             if (!strcmp(e, "base")) forced = CHOICE_BASE;
             if (!strcmp(e, "pair")) forced = CHOICE_PAIR;
+            if (!strcmp(e, "tma")) forced = CHOICE_TMA;
         }
     }
     return forced;
@@ -288,7 +534,7 @@ static GemmChoice gemm_choose(const GemmArgs &p) {
     if (p.in_place) return CHOICE_BASE;
     const int f = gemm_forced_choice();
     if (f >= 0) return (GemmChoice)f;
-    return CHOICE_PAIR;
+    return CHOICE_TMA;              // TMA producer where both operands are k-contiguous, CfgPair (cp.async) otherwise
 }
 
 template <class C, bool AKC, bool BKC>
@@ -331,7 +577,9 @@ static int gemm_launch_cfg(const GemmArgs &p, cudaStream_t s) {
 
 template <bool AKC, bool BKC>
 static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
-    if (gemm_choose(p) == CHOICE_PAIR) return gemm_launch_cfg<CfgPair, AKC, BKC>(p, s);
+    const GemmChoice c = gemm_choose(p);
+    if (c == CHOICE_TMA && AKC && BKC) return gemm_launch_tma(p, s);       // the TMA producer serves k-contiguous pairs
+    if (c != CHOICE_BASE) return gemm_launch_cfg<CfgPair, AKC, BKC>(p, s);
     return gemm_launch_cfg<CfgBase, AKC, BKC>(p, s);
 }
 
@@ -886,6 +1134,8 @@ int dense_preload() {
     VGP_TRY((gemm_preload_one<false, true>()));
     VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
     VGP_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, potf2_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, trtri_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, lauum_kernel));
