@@ -314,6 +314,11 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map
 }
 }  // namespace tma
 
+// BKC: B stored [n][k] (one box of 16 k x 64 rows).  !BKC: B stored [k][n] -- four boxes of 16 k x 16 n (2 KB each, the
+// 128-byte rows now run along n); a B fragment then takes the columns {0,1,8,9,2,3,10,11} (+4 for the odd fragment) of
+// its box, which keeps the 16 lanes of a half-warp on 16 distinct 8-byte words, and pairs of accumulators still
+// belong to adjacent columns.
+template <bool BKC>
 __global__ void __launch_bounds__(tma::THREADS, 2)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
     using namespace tma;
@@ -361,7 +366,12 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
         const int k0 = (int)(kbase + (int64_t)kt * TK);
         mbar_expect_tx(bar, STAGE_BYTES);
         tma_load_2d(dst, &map_a, k0, (int)m0, bar);
-        tma_load_2d(dst + A_BYTES, &map_b, k0, (int)n0, bar);
+        if (BKC) {
+            tma_load_2d(dst + A_BYTES, &map_b, k0, (int)n0, bar);
+        } else {
+#pragma unroll
+            for (int bx = 0; bx < TN / 16; ++bx) tma_load_2d(dst + A_BYTES + bx * 2048, &map_b, (int)n0 + 16 * bx, k0, bar);
+        }
     };
     if (tid == 0) {
 #pragma unroll
@@ -379,7 +389,9 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
     // For every fragment of this thread (r & 7) = 2 (g & 3) + (i & 1): the chunk is ((kk / 2) ^ gx) | ((t >> 1) ^ e).
     const int gx = 2 * (g & 3);
     const unsigned a_row = (unsigned)((wm0 + 2 * g) * 128 + (t & 1) * 8);
-    const unsigned b_row = (unsigned)(A_BYTES + (wn0 + 2 * g) * 128 + (t & 1) * 8);
+    const unsigned b_row = BKC ? (unsigned)(A_BYTES + (wn0 + 2 * g) * 128 + (t & 1) * 8)
+                               : (unsigned)(A_BYTES + (wn0 / 16) * 2048 + t * 128 + (g & 1) * 8);
+    const int pg = ((g >> 1) & 1) * 4 + (g >> 2);          // (column >> 1) of this lane inside its 16-column box
 
     for (int kt = 0; kt < KT; ++kt) {
         const int stage = kt % STAGES;
@@ -396,15 +408,52 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
             for (int i = 0; i < 8; ++i)
                 af[i] = *reinterpret_cast<const double *>(st + a_row + (i >> 1) * 2048 + (i & 1) * 128 +
                                                           ((i & 1) ? off1 : off0));
+            if (BKC) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + (j & 1) * 128 +
-                                                          ((j & 1) ? off1 : off0));
+                for (int j = 0; j < 4; ++j)
+                    bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + (j & 1) * 128 +
+                                                              ((j & 1) ? off1 : off0));
+            } else {
+                // row kk + t of the box, chunk ((column >> 1) ^ (row & 7)); (kk + t) & 7 = (kk & 4) | t
+                const int kt7 = (kk & 4) | t;
+                const unsigned o0 = (unsigned)(kk * 128 + ((pg ^ kt7) << 4)), o1 = (unsigned)(kk * 128 + (((pg | 2) ^ kt7) << 4));
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + ((j & 1) ? o1 : o0));
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
+    }
+    if (!BKC) {
+        // B fragment j = 2 q + e of box q holds, for this thread, the adjacent columns {0, 8, 2, 10}[t] + 4 e (+ 0, 1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t r = m0 + wm0 + 16 * (i >> 1) + 2 * g + (i & 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = 16 * (j >> 1) + ((t & 1) * 8 + (t >> 1) * 2) + 4 * (j & 1);
+                double2 *dst = reinterpret_cast<double2 *>(cout + r * p.ldc + n0 + wn0 + col);
+                double2 o;
+                if (p.beta != 0.0) {
+                    const double2 old = *dst;
+                    o.x = fma(p.alpha, acc[i][j][0], p.beta * old.x);
+                    o.y = fma(p.alpha, acc[i][j][1], p.beta * old.y);
+                } else {
+                    o.x = p.alpha * acc[i][j][0];
+                    o.y = p.alpha * acc[i][j][1];
+                }
+                if (p.dist_n > 0) {
+                    for (int d = 0; d < p.dist_n; ++d) *(dst + (p.delta[d] >> 1)) = o;
+                } else {
+                    *dst = o;
+                }
+            }
+        }
+        if (p.dist_n > 0) __threadfence_system();
+        return;
     }
 
     // epilogue: fragment i holds rows 16 (i / 2) + 2 g + (i % 2); the two column fragments of a 16-column group hold
@@ -475,17 +524,21 @@ static int make_operand_map(CUtensorMap *map, const double *base, int64_t rows, 
     return VGP_OK;
 }
 
+template <bool BKC>
 static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
     static bool configured[64] = {};
     int dev = 0;
     VGP_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
+        VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
         configured[dev] = true;
     }
     alignas(64) CUtensorMap ma, mb;
     VGP_TRY(make_operand_map(&ma, p.a, p.m, p.k, p.lda, tma::TM));
-    VGP_TRY(make_operand_map(&mb, p.b, p.n, p.k, p.ldb, tma::TN));
+    if (BKC)
+        VGP_TRY(make_operand_map(&mb, p.b, p.n, p.k, p.ldb, tma::TN));
+    else
+        VGP_TRY(make_operand_map(&mb, p.b, p.k, p.n, p.ldb, 16));        // [k][n]: boxes of 16 n x 16 k
     const int64_t tm = p.m / tma::TM, tn = p.n / tma::TN;
     const unsigned splits = (unsigned)((p.k + p.k_split - 1) / p.k_split);
     constexpr int RATIO = tma::TM / tma::TN;
@@ -498,16 +551,16 @@ static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
         const int64_t mine = each + (rank < rem ? 1 : 0);
         q.tiles_n = tn;
         if (mine > 0) {
-            gemm_tma_kernel<<<dim3((unsigned)mine, 1, 1), tma::THREADS, tma::SMEM, s>>>(ma, mb, q);
+            gemm_tma_kernel<BKC><<<dim3((unsigned)mine, 1, 1), tma::THREADS, tma::SMEM, s>>>(ma, mb, q);
             VGP_LAUNCH_CHECK();
         }
         return VGP_OK;
     }
     if (p.lower) {
         const int64_t blocks = (int64_t)RATIO * tm * (tm + 1) / 2;
-        gemm_tma_kernel<<<dim3((unsigned)blocks, 1, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
+        gemm_tma_kernel<BKC><<<dim3((unsigned)blocks, 1, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
     } else {
-        gemm_tma_kernel<<<dim3((unsigned)tn, (unsigned)tm, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
+        gemm_tma_kernel<BKC><<<dim3((unsigned)tn, (unsigned)tm, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
     }
     VGP_LAUNCH_CHECK();
     return VGP_OK;
@@ -578,7 +631,7 @@ static int gemm_launch_cfg(const GemmArgs &p, cudaStream_t s) {
 template <bool AKC, bool BKC>
 static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
     const GemmChoice c = gemm_choose(p);
-    if (c == CHOICE_TMA && AKC && BKC) return gemm_launch_tma(p, s);       // the TMA producer serves k-contiguous pairs
+    if (c == CHOICE_TMA && AKC) return gemm_launch_tma<BKC>(p, s);         // TMA producer: A k-contiguous, B either way
     if (c != CHOICE_BASE) return gemm_launch_cfg<CfgPair, AKC, BKC>(p, s);
     return gemm_launch_cfg<CfgBase, AKC, BKC>(p, s);
 }
@@ -1134,8 +1187,10 @@ int dense_preload() {
     VGP_TRY((gemm_preload_one<false, true>()));
     VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
     VGP_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
-    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel));
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<true>));
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<false>));
     VGP_CUDA(cudaFuncGetAttributes(&fa, potf2_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, trtri_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, lauum_kernel));
