@@ -236,6 +236,14 @@ int vgp_elbo_loss_grad(vgp_elbo *handle, const double *xb_dev, const double *yb_
 /* One training step: loss + gradient + Adam update; *loss_host is the loss before the update (what
  * sess.run([train_op, loss]) returns, :123-125). */
 int vgp_elbo_step(vgp_elbo *handle, const double *xb_dev, const double *yb_dev, double *loss_host, void *stream);
+/* N-axis sharding of the training step over the GPUs of a box: every rank creates its handle
+ * on its slice of the observations and registers a sum-all-reduce; the step then calls it at the two places where a
+ * sum over ALL observations is needed -- G = K_zx K_zx^T [m_pad^2] with v = K_zx y [m_pad], and the kernel push-through
+ * sums [m (2 + d)] -- on device buffers, in stream order (3 calls, ~2 MB per step at m = 512).  Everything of size m
+ * runs replicated, so all ranks hold bitwise identical parameters after every step.  n_total = observations over all
+ * ranks (sets kl_weight = B / n_total).  The callback returns 0 on success; every rank must pass the same minibatch. */
+typedef int (*vgp_allreduce_fn)(void *ctx, double *buf_dev, int64_t count, void *stream);
+int vgp_elbo_set_exchange(vgp_elbo *handle, int64_t n_total, vgp_allreduce_fn fn, void *ctx);
 int vgp_elbo_get_params(vgp_elbo *handle, double *v3_host, double *z_host, void *stream);
 int vgp_elbo_set_params(vgp_elbo *handle, const double *v3_host, const double *z_host, void *stream);
 int vgp_elbo_launch_count(vgp_elbo *handle, int64_t *launches);

@@ -105,3 +105,64 @@ def test_config3_shape_runs_and_is_finite():
     lm = tr.loss_and_grad(x[idx], y[idx])[0]
     assert g[1] == pytest.approx((lp - lm) / (2 * h), rel=1e-5)
     tr.close()
+
+
+def test_n_axis_sharding_two_ranks_as_threads():
+    """the training step sharded over the observations.  Two trainers, each on half of the data,
+    exchange the three all-reduced buffers through a callback (here: two threads on one device, summed with torch);
+    losses and parameters must follow the single-trainer run on all the data, and the two replicas must stay bitwise
+    identical."""
+    import threading
+    torch = pytest.importorskip("torch")
+    n, m, b, d = 6000, 64, 256, 3
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-2, 2, (n, d))
+    y = np.sum(np.sin(2 * np.pi * x), axis=1) + 0.1 * rng.standard_normal(n)
+    z = rng.uniform(-2, 2, (m, d))
+    single = gpf.VgpTrainer(x, y, z, b)
+    barrier = threading.Barrier(2)
+    pending = [None, None]
+
+    def make_allreduce(rank):
+        def allreduce(t):
+            torch.cuda.synchronize()
+            pending[rank] = t
+            barrier.wait()
+            total = pending[0] + pending[1]
+            torch.cuda.synchronize()
+            barrier.wait()
+            t.copy_(total)
+            torch.cuda.synchronize()
+            barrier.wait()
+        return allreduce
+
+    halves = [gpf.VgpTrainer(x[r::2], y[r::2], z, b, allreduce=make_allreduce(r), n_total=n) for r in range(2)]
+    batches = [rng.integers(n, size=b) for _ in range(6)]
+    want = [single.step(x[i], y[i]) for i in batches]
+    got = [[], []]
+    errors = []
+
+    def work(rank):
+        try:
+            for i in batches:
+                got[rank].append(halves[rank].step(x[i], y[i]))
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    np.testing.assert_allclose(got[0], want, rtol=1e-9)
+    assert got[0] == got[1]                                   # replicas: identical sums in, identical arithmetic
+    v0, z0 = halves[0].variables()
+    v1, z1 = halves[1].variables()
+    vs, zs = single.variables()
+    assert np.array_equal(v0, v1) and np.array_equal(z0, z1)
+    np.testing.assert_allclose(v0, vs, rtol=1e-8)
+    np.testing.assert_allclose(z0, zs, rtol=1e-7, atol=1e-9)
+    for t in halves + [single]:
+        t.close()

@@ -97,6 +97,7 @@ SIGNATURES = {
     "vgp_elbo_destroy": [c_vp],
     "vgp_elbo_loss_grad": [c_vp, c_vp, c_vp, P(c_dbl), c_vp, c_vp, P(VgpTerms), c_vp],
     "vgp_elbo_step": [c_vp, c_vp, c_vp, P(c_dbl), c_vp],
+    "vgp_elbo_set_exchange": [c_vp, c_i64, c_vp, c_vp],
     "vgp_elbo_get_params": [c_vp, c_vp, c_vp, c_vp],
     "vgp_elbo_set_params": [c_vp, c_vp, c_vp, c_vp],
     "vgp_elbo_launch_count": [c_vp, P(c_i64)],
@@ -231,6 +232,24 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+
+
+class _CudaArrayView:
+    """Minimal __cuda_array_interface__ holder: lets torch alias a device buffer this library owns."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def torch_view_f64(ptr, count, device=0):
+    """A torch float64 tensor aliasing `count` doubles at device address `ptr` (zero-copy; plumbing for
+    torch.distributed collectives on the library's buffers)."""
+    import torch
+    return torch.as_tensor(_CudaArrayView(ptr, count), device="cuda:%d" % device)
 
 
 class DeviceArray:

@@ -190,6 +190,11 @@ struct vgp_elbo {
     double *partial = nullptr, *rowacc = nullptr, *gradz = nullptr;
     int splits_n = 1, splits_b = 1;
     DenseWorkspace ws[3];
+    // N-axis sharding: this handle holds n of n_total observations; the two sums over the
+    // observations (G = K_zx K_zx^T with v = K_zx y, and the kernel push-through sums) are all-reduced by the caller
+    int64_t n_total = 0;
+    vgp_allreduce_fn allreduce = nullptr;
+    void *allreduce_ctx = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};      // the two inverses that only need K_zz run beside the N-sized work
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     int64_t launches = 0;
@@ -295,7 +300,15 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
                   double *z_gscale, cudaStream_t s) {
     const int64_t m = h->m, mp = h->mp, n = h->n, b = h->b;
     const double a = softplus_h(h->v[0]), l = h->ls_offset + softplus_h(h->v[1]), noise = softplus_h(h->v[2]);
-    const double beta = 1.0 / noise, w = (double)b / (double)n, eps = h->jitter;
+    const double beta = 1.0 / noise, w = (double)b / (double)(h->n_total > 0 ? h->n_total : n), eps = h->jitter;
+    auto exchange = [&](double *buf, int64_t count) -> int {
+        if (!h->allreduce) return VGP_OK;
+        if (h->allreduce(h->allreduce_ctx, buf, count, (void *)s) != 0) {
+            set_error("ELBO step: the all-reduce callback failed");
+            return VGP_ERR_STATE;
+        }
+        return VGP_OK;
+    };
     const int64_t before = g_launches;
     Reducer red;
     VGP_TRY(red.init(s));
@@ -325,6 +338,8 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->bp, 1.0, h->kzb, h->bp, h->kzb, h->bp, 0.0, M(GB_), mp, h->splits_b,
                               h->partial, s, GEMM_LOWER));
     VGP_TRY(matvec(h->kzx, h->np_, m, n, h->y, 1.0, V(V_), s));
+    VGP_TRY(exchange(M(G_), mp * mp));                  // sums over all observations, one 8 m^2 byte all-reduce
+    VGP_TRY(exchange(V(V_), mp));
     VGP_TRY(matvec(h->kzb, h->bp, m, b, yb, 1.0, V(VB_), s));
     VGP_TRY(red.run(DotVec{yb, yb}, b, S_YY));
 
@@ -405,6 +420,7 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     // ---- push through the kernel ---------------------------------------------------------------------
     VGP_TRY(dense_gemm(0, 0, mp, h->np_, mp, 1.0, M(GBAR2_), mp, h->kzx, h->np_, 0.0, h->wzx, h->np_, GEMM_FULL, s));
     VGP_TRY(kernback(h, h->wzx, h->kzx, h->np_, h->x, n, V(VBAR_), h->y, 1.0, s));
+    VGP_TRY(exchange(h->rowacc, m * (2 + h->d)));       // the observation-sized part of the push-through sums
     VGP_TRY(dense_gemm(0, 0, mp, h->bp, mp, 1.0, M(GBBAR2_), mp, h->kzb, h->bp, 0.0, h->wzb, h->bp, GEMM_FULL, s));
     VGP_TRY(kernback(h, h->wzb, h->kzb, h->bp, xb, b, V(VBBAR_), yb, 1.0, s));
     VGP_TRY(kernback(h, M(KBAR_), M(K_), mp, h->z, m, nullptr, nullptr, 2.0, s));
@@ -588,6 +604,16 @@ int vgp_elbo_step(vgp_elbo *h, const double *xb_dev, const double *yb_dev, doubl
                                                                h->b1, h->b2, h->eps);
     VGP_LAUNCH_CHECK();
     ++h->launches;
+    return VGP_OK;
+}
+
+int vgp_elbo_set_exchange(vgp_elbo *h, int64_t n_total, vgp_allreduce_fn fn, void *ctx) {
+    VGP_REQUIRE(h, "NULL handle");
+    VGP_REQUIRE(n_total >= h->n, "n_total %lld is smaller than this handle's %lld observations", (long long)n_total,
+                (long long)h->n);
+    h->n_total = n_total;
+    h->allreduce = fn;
+    h->allreduce_ctx = ctx;
     return VGP_OK;
 }
 

@@ -647,7 +647,11 @@ class VgpTrainer:
     """
 
     def __init__(self, x_train, y_train, inducing_index_points, batch_size, v_amplitude=0.54, v_length_scale=0.54,
-                 v_noise=0.54, length_scale_offset=1e-5, jitter=DEFAULT_JITTER, learning_rate=0.01):
+                 v_noise=0.54, length_scale_offset=1e-5, jitter=DEFAULT_JITTER, learning_rate=0.01, allreduce=None,
+                 n_total=None):
+        """`allreduce(device_view)`: sum-all-reduce over the ranks of a 1-D float64 device buffer, in place and in stream
+        order (e.g. `lambda t: torch.distributed.all_reduce(t)`); then (x_train, y_train) is THIS rank's slice of the
+        observations, `n_total` their number over all ranks, and every rank must feed the same minibatches."""
         self._x, self._y = _points(x_train), _vector(y_train)          # kept alive: the handle borrows them
         z = np.ascontiguousarray(np.asarray(inducing_index_points, dtype=np.float64))
         if z.ndim == 1:
@@ -661,6 +665,23 @@ class VgpTrainer:
              float(length_scale_offset), float(jitter), float(learning_rate))
         self.handle = h.value
         self.length_scale_offset, self.jitter = length_scale_offset, jitter
+        self._cb = None
+        if allreduce is not None:
+            views = {}
+
+            def _cb(ctx, ptr, count, stream):
+                try:
+                    key = (ptr, count)
+                    if key not in views:
+                        views[key] = _ffi.torch_view_f64(ptr, count, DEVICE)
+                    allreduce(views[key])
+                    return 0
+                except Exception as e:       # noqa: BLE001 -- must not unwind through the C frame
+                    self._cb_error = e
+                    return 1
+
+            self._cb = _ffi.ALLREDUCE_FN(_cb)                      # kept alive with the trainer
+            call("vgp_elbo_set_exchange", self.handle, int(n_total if n_total is not None else self.n), self._cb, None)
 
     def _batch(self, xb, yb):
         xb, yb = _points(xb), _vector(yb)
