@@ -282,9 +282,20 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) gemm_kernel(GemmArgs p) {
 // Same tile shape, warp tile and two-CTAs-per-SM residency as CfgPair; 4 stages of 24 KB.
 // -----------------------------------------------------------------------------------------------------
 namespace tma {
-constexpr int TM = 128, TN = 64, TK = 16, STAGES = 4, THREADS = 128;
-constexpr int A_BYTES = TM * TK * 8, B_BYTES = TN * TK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + STAGES * 8;
+constexpr int TK = 16, STAGES = 4, THREADS = 128;
+// CTA tile TM x TN, four warps (2 x 2) of WM x WN.  Big: the throughput shape.  Small: four times the CTAs for the
+// same product and half the DMMA chain per warp and k-tile -- for products too small to fill the SMs with Big tiles
+// (the m^3 products of the ELBO's reverse sweep, the leaves of the recursive factorisations), which are bound by the
+// latency of one CTA's k loop, not by the pipe.
+template <int TM_, int TN_, int MINB_>
+struct Shape {
+    static constexpr int TM = TM_, TN = TN_, MINB = MINB_, WM = TM_ / 2, WN = TN_ / 2, FI = WM / 8, FJ = WN / 8;
+    static constexpr int A_BYTES = TM * TK * 8, B_BYTES = TN * TK * 8, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + STAGES * 8;
+    static_assert(WM % 16 == 0 && WN % 16 == 0 && STAGE_BYTES % 1024 == 0, "fragment groups are 16 rows / columns");
+};
+using Big = Shape<128, 64, 2>;
+using Small = Shape<64, 64, 3>;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -318,10 +329,11 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map
 // 128-byte rows now run along n); a B fragment then takes the columns {0,1,8,9,2,3,10,11} (+4 for the odd fragment) of
 // its box, which keeps the 16 lanes of a half-warp on 16 distinct 8-byte words, and pairs of accumulators still
 // belong to adjacent columns.
-template <bool BKC>
-__global__ void __launch_bounds__(tma::THREADS, 2)
+template <class S, bool BKC>
+__global__ void __launch_bounds__(tma::THREADS, S::MINB)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
     using namespace tma;
+    constexpr int TM = S::TM, TN = S::TN, FI = S::FI, FJ = S::FJ, A_BYTES = S::A_BYTES, STAGE_BYTES = S::STAGE_BYTES;
     extern __shared__ unsigned char raw[];
     const unsigned raw_addr = smem_u32(raw);
     unsigned char *sm = raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);      // SWIZZLE_128B wants 1024-byte alignment
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
     const int64_t m0 = (int64_t)tm * TM, n0 = (int64_t)tn * TN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 1) * 64, wn0 = (warp & 1) * 32;
+    const int wm0 = (warp >> 1) * S::WM, wn0 = (warp & 1) * S::WN;
     const int64_t kbase = (int64_t)blockIdx.z * p.k_split;
     const int64_t klen = p.k - kbase < p.k_split ? p.k - kbase : p.k_split;
     const int KT = (int)(klen / TK);
@@ -379,11 +391,11 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
             if (st < KT) issue(st);
     }
 
-    double acc[8][4][2];
+    double acc[FI][FJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < FI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < FJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // byte offsets inside a swizzled tile: row r (128 bytes), 16-byte chunk ((k >> 1) ^ (r & 7)), half (k & 1).
     // For every fragment of this thread (r & 7) = 2 (g & 3) + (i & 1): the chunk is ((kk / 2) ^ gx) | ((t >> 1) ^ e).
@@ -403,14 +415,14 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
         for (int kk = 0; kk < TK; kk += 4) {
             const int ck = (kk / 2) ^ gx;
             const unsigned off0 = (unsigned)((ck | (t >> 1)) << 4), off1 = (unsigned)((ck | ((t >> 1) ^ 1)) << 4);
-            double af[8], bf[4];
+            double af[FI], bf[FJ];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < FI; ++i)
                 af[i] = *reinterpret_cast<const double *>(st + a_row + (i >> 1) * 2048 + (i & 1) * 128 +
                                                           ((i & 1) ? off1 : off0));
             if (BKC) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < FJ; ++j)
                     bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + (j & 1) * 128 +
                                                               ((j & 1) ? off1 : off0));
             } else {
@@ -418,22 +430,22 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
                 const int kt7 = (kk & 4) | t;
                 const unsigned o0 = (unsigned)(kk * 128 + ((pg ^ kt7) << 4)), o1 = (unsigned)(kk * 128 + (((pg | 2) ^ kt7) << 4));
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < FJ; ++j)
                     bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + ((j & 1) ? o1 : o0));
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < FI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < FJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     if (!BKC) {
         // B fragment j = 2 q + e of box q holds, for this thread, the adjacent columns {0, 8, 2, 10}[t] + 4 e (+ 0, 1)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < FI; ++i) {
             const int64_t r = m0 + wm0 + 16 * (i >> 1) + 2 * g + (i & 1);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < FJ; ++j) {
                 const int col = 16 * (j >> 1) + ((t & 1) * 8 + (t >> 1) * 2) + 4 * (j & 1);
                 double2 *dst = reinterpret_cast<double2 *>(cout + r * p.ldc + n0 + wn0 + col);
                 double2 o;
@@ -459,10 +471,10 @@ __global__ void __launch_bounds__(tma::THREADS, 2)
     // epilogue: fragment i holds rows 16 (i / 2) + 2 g + (i % 2); the two column fragments of a 16-column group hold
     // columns 4 t + {0, 2} and 4 t + {1, 3}: four consecutive columns per thread
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < FI; ++i) {
         const int64_t r = m0 + wm0 + 16 * (i >> 1) + 2 * g + (i & 1);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < FJ / 2; ++q) {
             double2 *dst = reinterpret_cast<double2 *>(cout + r * p.ldc + n0 + wn0 + 16 * q + 4 * t);
             double2 o0, o1;
             if (p.beta != 0.0) {
@@ -524,24 +536,24 @@ static int make_operand_map(CUtensorMap *map, const double *base, int64_t rows, 
     return VGP_OK;
 }
 
-template <bool BKC>
+template <class S, bool BKC>
 static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
     static bool configured[64] = {};
     int dev = 0;
     VGP_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
+        VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<S, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
         configured[dev] = true;
     }
     alignas(64) CUtensorMap ma, mb;
-    VGP_TRY(make_operand_map(&ma, p.a, p.m, p.k, p.lda, tma::TM));
+    VGP_TRY(make_operand_map(&ma, p.a, p.m, p.k, p.lda, S::TM));
     if (BKC)
-        VGP_TRY(make_operand_map(&mb, p.b, p.n, p.k, p.ldb, tma::TN));
+        VGP_TRY(make_operand_map(&mb, p.b, p.n, p.k, p.ldb, S::TN));
     else
         VGP_TRY(make_operand_map(&mb, p.b, p.k, p.n, p.ldb, 16));        // [k][n]: boxes of 16 n x 16 k
-    const int64_t tm = p.m / tma::TM, tn = p.n / tma::TN;
+    const int64_t tm = p.m / S::TM, tn = p.n / S::TN;
     const unsigned splits = (unsigned)((p.k + p.k_split - 1) / p.k_split);
-    constexpr int RATIO = tma::TM / tma::TN;
+    constexpr int RATIO = S::TM / S::TN;
     if (p.dist_n > 0) {
         GemmArgs q = p;
         const int64_t total = p.lower ? (int64_t)RATIO * tm * (tm + 1) / 2 : tm * tn;
@@ -551,16 +563,16 @@ static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
         const int64_t mine = each + (rank < rem ? 1 : 0);
         q.tiles_n = tn;
         if (mine > 0) {
-            gemm_tma_kernel<BKC><<<dim3((unsigned)mine, 1, 1), tma::THREADS, tma::SMEM, s>>>(ma, mb, q);
+            gemm_tma_kernel<S, BKC><<<dim3((unsigned)mine, 1, 1), tma::THREADS, S::SMEM, s>>>(ma, mb, q);
             VGP_LAUNCH_CHECK();
         }
         return VGP_OK;
     }
     if (p.lower) {
         const int64_t blocks = (int64_t)RATIO * tm * (tm + 1) / 2;
-        gemm_tma_kernel<BKC><<<dim3((unsigned)blocks, 1, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
+        gemm_tma_kernel<S, BKC><<<dim3((unsigned)blocks, 1, splits), tma::THREADS, S::SMEM, s>>>(ma, mb, p);
     } else {
-        gemm_tma_kernel<BKC><<<dim3((unsigned)tn, (unsigned)tm, splits), tma::THREADS, tma::SMEM, s>>>(ma, mb, p);
+        gemm_tma_kernel<S, BKC><<<dim3((unsigned)tn, (unsigned)tm, splits), tma::THREADS, S::SMEM, s>>>(ma, mb, p);
     }
     VGP_LAUNCH_CHECK();
     return VGP_OK;
@@ -631,7 +643,14 @@ static int gemm_launch_cfg(const GemmArgs &p, cudaStream_t s) {
 template <bool AKC, bool BKC>
 static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
     const GemmChoice c = gemm_choose(p);
-    if (c == CHOICE_TMA && AKC) return gemm_launch_tma<BKC>(p, s);         // TMA producer: A k-contiguous, B either way
+    if (c == CHOICE_TMA && AKC) {                                          // TMA producer: A k-contiguous, B either way
+        // fewer Big tiles than half the SMs: the product is bound by the latency of one CTA's k loop -> Small tiles
+        // (the lower-tile mode stays Big: its tile enumeration assumes TM = 128 row blocks)
+        const int64_t big_tiles = (p.m / tma::Big::TM) * (p.n / tma::Big::TN) * ((p.k + p.k_split - 1) / p.k_split);
+        static const int small_below = getenv("VGP_GEMM_SMALL_BELOW") ? atoi(getenv("VGP_GEMM_SMALL_BELOW")) : 74;
+        if (!p.lower && big_tiles < small_below) return gemm_launch_tma<tma::Small, BKC>(p, s);
+        return gemm_launch_tma<tma::Big, BKC>(p, s);
+    }
     if (c != CHOICE_BASE) return gemm_launch_cfg<CfgPair, AKC, BKC>(p, s);
     return gemm_launch_cfg<CfgBase, AKC, BKC>(p, s);
 }
@@ -1187,10 +1206,14 @@ int dense_preload() {
     VGP_TRY((gemm_preload_one<false, true>()));
     VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
     VGP_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
-    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<true>));
-    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<false>));
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Big, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Big::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Big, true>));
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Big, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Big::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Big, false>));
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Small, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Small::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Small, true>));
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Small, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Small::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Small, false>));
     VGP_CUDA(cudaFuncGetAttributes(&fa, potf2_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, trtri_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, lauum_kernel));
