@@ -128,3 +128,58 @@ def test_golden_still_matches_reference_code(golden):
         assert [int(s) for s in sel] == golden.selection(name)
         sel2, out = ref_extract.run_quiet(ref["placement_algorithm_2"], cov, k)
         assert out.splitlines() == golden.cases[name]["alg2_stdout"]
+
+
+def _grid_cov(cover, ls, seed):
+    idx = np.indices(cover).reshape(3, -1).T.astype(np.float64)
+    pts = idx + np.random.default_rng(seed).uniform(-0.3, 0.3, idx.shape)
+    d = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    return np.exp(-d / (2 * ls * ls)) + 1e-2 * np.eye(len(pts))
+
+
+def test_tf_graph_algorithm_2_restatement_is_consistent():
+    """snippets_a2.sparse_placement_algorithm_2 restated: same winners as the pinned literal lazy greedy run with the
+    graph's constants; delta_cached_iters column t holds the winner's delta at its row and zeros at earlier winners."""
+    cov = _grid_cov((3, 3, 2), 1.0, 3)
+    k = 5
+    A, len_A, dci, sel = go.literal_sparse_placement_algorithm_2(cov, k)
+    want, _ = go.literal_placement_algorithm_2(cov, k, small=go.GUARD_TF_GRAPH, jitter=go.JITTER_TF_GRAPH)
+    assert [int(v) for v in sel[:, 0]] == want and A == sorted(want) and len_A == k
+    for t in range(k):
+        assert dci[want[t], t] == sel[t, 1]
+        assert np.all(dci[want[:t], t] == 0.0)
+        assert dci[:, t].max() <= 1e8
+
+
+def test_algorithm_3_restatement_limits():
+    """snippets_a3 restated: a box covering the grid re-evaluates everything (== exact greedy with the graph's
+    constants); with a small box the first two winners still agree (the first cache is complete, the second arg-max
+    only sees refreshed neighbours and still-valid upper bounds), and column 0 of delta_cached_iters is the A = {}
+    delta of every point."""
+    cover = (4, 3, 2)
+    cov = _grid_cov(cover, 1.1, 5)
+    k = 5
+    exact = go.literal_placement_algorithm_1(cov, k, small=go.GUARD_TF_GRAPH, jitter=go.JITTER_TF_GRAPH)
+    A_full, cache, dci = go.literal_sparse_placement_algorithm_3(cov, k, cover, max(cover))
+    assert A_full == exact
+    A_loc, _, dci_loc = go.literal_sparse_placement_algorithm_3(cov, k, cover, 1)
+    assert A_loc[0] == exact[0] and len(set(A_loc)) == k
+    n = cov.shape[0]
+    first = [go.literal_delta(y, [], list(range(n)), cov, go.GUARD_TF_GRAPH, go.JITTER_TF_GRAPH) for y in range(n)]
+    np.testing.assert_allclose(dci_loc[:, 0], first, rtol=1e-14)
+    assert np.all(dci_loc[A_loc[:-1], -1] == 0.0)
+
+
+def test_lazy_cache_replay_host_logic():
+    """vgposp_b200.snippets_a2.lazy_cache_replay (host index scan over device step scores) against the literal graph
+    restatement, fed with the literal per-step deltas."""
+    from vgposp_b200 import snippets_a2
+    cov = _grid_cov((3, 2, 2), 0.9, 8)
+    k = 4
+    A, _, want_dci, want_sel = go.literal_sparse_placement_algorithm_2(cov, k)
+    order, per_step = go.literal_placement_algorithm_1(cov, k, small=go.GUARD_TF_GRAPH, jitter=go.JITTER_TF_GRAPH,
+                                                       return_scores=True)
+    got_order, dci, sel = snippets_a2.lazy_cache_replay(np.array(per_step), k)
+    assert got_order == order == [int(v) for v in want_sel[:, 0]]
+    np.testing.assert_allclose(dci, want_dci, rtol=1e-14)
+    np.testing.assert_allclose(sel, want_sel, rtol=1e-14)
