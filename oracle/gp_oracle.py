@@ -15,6 +15,10 @@ Appendix A.2-A.5 and are anchored on the reference's call sites:
     Adam                  gp_functions.py:179-182 (tf.train.AdamOptimizer defaults)
     softplus params       gp_functions.py:124-135, variational_Gaussian_process_example.py:47-61
 
+The exact-GP functions and all four kernel families are additionally pinned to an independent third-party
+implementation available in this image, scikit-learn's GaussianProcessRegressor (tests/test_oracle_gp_sklearn.py:
+kernel matrices 1e-12, log marginal likelihood 1e-10, posterior mean/std, LML gradient).
+
 The one first-party NumPy statement of kernel -> Cholesky -> solve -> posterior variance in the
 reference, `plot_confidence_interval.py:17-19,26,43-51`, is reproduced by `expquad_matrix`,
 `gp_regression` (see tests/test_oracle_gp.py).

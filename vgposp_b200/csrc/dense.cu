@@ -646,7 +646,8 @@ static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
     if (c == CHOICE_TMA && AKC) {                                          // TMA producer: A k-contiguous, B either way
         // fewer Big tiles than half the SMs: the product is bound by the latency of one CTA's k loop -> Small tiles
         // (the lower-tile mode stays Big: its tile enumeration assumes TM = 128 row blocks)
-        const int64_t big_tiles = (p.m / tma::Big::TM) * (p.n / tma::Big::TN) * ((p.k + p.k_split - 1) / p.k_split);
+        int64_t big_tiles = (p.m / tma::Big::TM) * (p.n / tma::Big::TN) * ((p.k + p.k_split - 1) / p.k_split);
+        if (p.dist_n > 0) big_tiles /= p.tiles_n;         // distributed product: this rank's share (tiles_n = ranks here)
         static const int small_below = getenv("VGP_GEMM_SMALL_BELOW") ? atoi(getenv("VGP_GEMM_SMALL_BELOW")) : 74;
         if (!p.lower && big_tiles < small_below) return gemm_launch_tma<tma::Small, BKC>(p, s);
         return gemm_launch_tma<tma::Big, BKC>(p, s);
