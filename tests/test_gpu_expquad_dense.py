@@ -198,3 +198,36 @@ def test_trsm_right_in_place_many_rows_is_deterministic(trans):
         if first is None:
             first = got
         assert np.array_equal(got, first)
+
+
+@pytest.mark.parametrize("trans", [0, 1])
+def test_trsm_left_in_place_is_deterministic(trans):
+    """The left-side solves multiply B by inverted diagonal blocks in place with C aliasing B (m = 128 rows, many
+    columns): one CTA must own all 128 rows of its column block, so the 64-row tile shape must not be chosen.
+    Few columns (small tile count -> the small-tile heuristic would apply) and repeated runs expose the race."""
+    n, cols = 512, 384
+    l = np.linalg.cholesky(spd(n, 5))
+    b = np.random.default_rng(11).standard_normal((n, cols))
+    dl = dev(l)
+    want = sla.solve_triangular(l.T if trans else l, b, lower=not trans)
+    first = None
+    for _ in range(20):
+        db = dev(b)
+        _ffi.call("vgp_trsm", D, 0, trans, n, cols, dl.ptr, n, db.ptr, cols, None)
+        got = db.to_host()
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11 * np.abs(want).max())
+        if first is None:
+            first = got
+        assert np.array_equal(got, first)
+
+
+def test_spd_inverse_is_run_to_run_deterministic():
+    a = spd(512, 9)
+    outs = []
+    for _ in range(10):
+        d = dev(a)
+        info = ctypes.c_int(0)
+        _ffi.call("vgp_spd_inverse", D, d.ptr, 512, 512, ctypes.byref(info), None)
+        outs.append(d.to_host())
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])

@@ -168,7 +168,7 @@ def load(build_if_missing=True):
                 raise
     if not os.path.exists(LIB_PATH):
         raise VgpError(VGP_ERR_STATE, "libvgposp.so not built (run python -m vgposp_b200.build)")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(os.environ.get("VGP_LIB", LIB_PATH))        # VGP_LIB: A/B comparisons of two builds
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

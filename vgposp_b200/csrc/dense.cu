@@ -64,7 +64,8 @@ struct GemmArgs {
     int64_t m, n, k;
     double alpha, beta;
     int lower;
-    int in_place;            // C aliases an operand: one CTA must own the whole aliased tile (128x128 configuration)
+    int in_place;            // bit 0: C aliases A (n = 128: needs 128-wide tiles, CfgBase); bit 1: C aliases B (m = 128:
+                             // needs 128-row tiles -- every configuration except tma::Small)
     int64_t k_split;         // k range handled by one blockIdx.z slice (== k without split-K)
     int64_t c_split_stride;  // element offset between the partial outputs of consecutive slices
     // distributed mode (dist_n > 0): this launch covers the linear tile range [tile0, tile0 + gridDim.x) of the
@@ -578,8 +579,11 @@ static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
     return VGP_OK;
 }
 
-// Tile configuration for one product.  The triangular solves multiply in place (C aliases A with n = 128, or B with
-// m = 128): then one CTA must own the whole aliased operand tile, which only the 128x128 tile guarantees.
+// Tile configuration for one product.  The triangular solves multiply in place: C aliases A with n = 128 (then one CTA
+// must own all 128 columns of its row block: only the 128x128 tile), or C aliases B with m = 128 (then one CTA must
+// own all 128 rows of its column block: every shape with 128-row tiles, i.e. not tma::Small -- a 64-row tile there let
+// two CTAs overwrite rows the other was still reading, an intermittent wrong K^-1 in the ELBO step until it was
+// excluded).
 // VGP_GEMM_CFG = base | pair | tma forces one for every product that may legally use it (measurement knob).
 enum GemmChoice { CHOICE_BASE = 0, CHOICE_PAIR = 1, CHOICE_TMA = 2 };
 static int gemm_forced_choice() {
@@ -596,7 +600,7 @@ static int gemm_forced_choice() {
     return forced;
 }
 static GemmChoice gemm_choose(const GemmArgs &p) {
-    if (p.in_place) return CHOICE_BASE;
+    if (p.in_place & 1) return CHOICE_BASE;
     const int f = gemm_forced_choice();
     if (f >= 0) return (GemmChoice)f;
     return CHOICE_TMA;              // TMA producer where both operands are k-contiguous, CfgPair (cp.async) otherwise
@@ -649,7 +653,7 @@ static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
         int64_t big_tiles = (p.m / tma::Big::TM) * (p.n / tma::Big::TN) * ((p.k + p.k_split - 1) / p.k_split);
         if (p.dist_n > 0) big_tiles /= p.tiles_n;         // distributed product: this rank's share (tiles_n = ranks here)
         static const int small_below = getenv("VGP_GEMM_SMALL_BELOW") ? atoi(getenv("VGP_GEMM_SMALL_BELOW")) : 74;
-        if (!p.lower && big_tiles < small_below) return gemm_launch_tma<tma::Small, BKC>(p, s);
+        if (!p.lower && !p.in_place && big_tiles < small_below) return gemm_launch_tma<tma::Small, BKC>(p, s);
         return gemm_launch_tma<tma::Big, BKC>(p, s);
     }
     if (c != CHOICE_BASE) return gemm_launch_cfg<CfgPair, AKC, BKC>(p, s);
@@ -679,8 +683,8 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
     // tile row (m = 128, true for both configurations) -- then every CTA reads exactly the region it overwrites
     VGP_REQUIRE(c != a || (!trans_a && n == BN), "dense_gemm: C aliases A with n = %lld", (long long)n);
     VGP_REQUIRE(c != b || (!trans_b && m == BM), "dense_gemm: C aliases B with m = %lld", (long long)m);
-    GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0, c == a ? 1 : 0, k, 0, 0, 0,
-               0, {0}};
+    GemmArgs p{a, b, c, lda, ldb, ldc, m, n, k, alpha, beta, tiles == GEMM_LOWER ? 1 : 0,
+               (c == a ? 1 : 0) | (c == b ? 2 : 0), k, 0, 0, 0, 0, {0}};
     if (g_gate) {
         VGP_TRY(gate_wait(a, trans_a ? k : m, s));
         VGP_TRY(gate_wait(b, trans_b ? n : k, s));

@@ -24,6 +24,8 @@
 // against this implementation.
 //
 // FLOP per step at m = 512, N = 200k: 2 m^2 N (SYRK as GEMM) + 2 m^2 N (W) = 2.1e11 -> FP64 tensor pipe bound.
+#include <stdlib.h>
+
 #include <new>
 
 #include "gp_common.cuh"
@@ -197,6 +199,8 @@ struct vgp_elbo {
     void *allreduce_ctx = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};      // the two inverses that only need K_zz run beside the N-sized work
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_gb = nullptr, ev_bar = nullptr, ev_mini = nullptr;
+    double *rowacc2 = nullptr;                      // push-through sums of the minibatch / K_zz parts (side stream)
     int64_t launches = 0;
     double last_terms[5] = {0, 0, 0, 0, 0};
     double *mat(int id) const { return mats + (size_t)id * mp * mp; }
@@ -208,23 +212,23 @@ namespace elbo_detail {
 
 template <int D>
 int launch_kernback(vgp_elbo *h, const double *w, const double *kmat, int64_t ld, const double *x2, int64_t n2,
-                    const double *vbar, const double *yvec, double zscale, cudaStream_t s) {
-    kernback_kernel<D><<<(unsigned)h->m, 256, 0, s>>>(w, kmat, ld, h->z, x2, n2, vbar, yvec, zscale, h->rowacc);
+                    const double *vbar, const double *yvec, double zscale, double *acc, cudaStream_t s) {
+    kernback_kernel<D><<<(unsigned)h->m, 256, 0, s>>>(w, kmat, ld, h->z, x2, n2, vbar, yvec, zscale, acc);
     VGP_LAUNCH_CHECK();
     return VGP_OK;
 }
 
 int kernback(vgp_elbo *h, const double *w, const double *kmat, int64_t ld, const double *x2, int64_t n2,
-             const double *vbar, const double *yvec, double zscale, cudaStream_t s) {
+             const double *vbar, const double *yvec, double zscale, double *acc, cudaStream_t s) {
     switch (h->d) {
-        case 1: return launch_kernback<1>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
-        case 2: return launch_kernback<2>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
-        case 3: return launch_kernback<3>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
-        case 4: return launch_kernback<4>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
-        case 5: return launch_kernback<5>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
-        case 6: return launch_kernback<6>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
-        case 7: return launch_kernback<7>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
-        case 8: return launch_kernback<8>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, s);
+        case 1: return launch_kernback<1>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
+        case 2: return launch_kernback<2>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
+        case 3: return launch_kernback<3>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
+        case 4: return launch_kernback<4>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
+        case 5: return launch_kernback<5>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
+        case 6: return launch_kernback<6>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
+        case 7: return launch_kernback<7>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
+        case 8: return launch_kernback<8>(h, w, kmat, ld, x2, n2, vbar, yvec, zscale, acc, s);
     }
     return VGP_ERR_INVALID;
 }
@@ -314,10 +318,16 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(red.init(s));
     auto M = [&](int id) { return h->mat(id); };
     auto V = [&](int id) { return h->vec(id); };
-    auto mm = [&](const double *A, const double *B, double *C) {
-        return dense_gemm(0, 0, mp, mp, mp, 1.0, A, mp, B, mp, 0.0, C, mp, GEMM_FULL, s);
+    auto mm_on = [&](cudaStream_t st, const double *A, const double *B, double *C) {
+        return dense_gemm(0, 0, mp, mp, mp, 1.0, A, mp, B, mp, 0.0, C, mp, GEMM_FULL, st);
     };
+    auto mm = [&](const double *A, const double *B, double *C) { return mm_on(s, A, B, C); };
+    // measurement knob: bit 0 = the K/Q/Gb products on a side stream, bit 1 = the minibatch push-through on a side stream
+    static const int overlap = getenv("VGP_ELBO_OVERLAP") ? atoi(getenv("VGP_ELBO_OVERLAP")) : 3;
+    cudaStream_t sb = (overlap & 1) ? h->side[0] : s;       // products that need only K, Q, Gb
+    cudaStream_t sd = (overlap & 2) ? h->side[1] : s;       // minibatch / K_zz push-through
     VGP_CUDA(cudaMemsetAsync(h->rowacc, 0, (size_t)m * (2 + h->d) * 8, s));
+    VGP_CUDA(cudaMemsetAsync(h->rowacc2, 0, (size_t)m * (2 + h->d) * 8, s));
     VGP_CUDA(cudaMemsetAsync(h->vecs, 0, (size_t)NVEC_ * mp * 8, s));
 
     // ---- kernel blocks and sufficient statistics ---------------------------------------------------
@@ -328,7 +338,6 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_CUDA(cudaStreamWaitEvent(h->side[0], h->ev_fork, 0));
     VGP_CUDA(cudaStreamWaitEvent(h->side[1], h->ev_fork, 0));
     VGP_TRY(invert(h, M(K_), eps, M(Q_), h->ws[0], red, S_LDKT, h->side[0]));
-    VGP_CUDA(cudaEventRecord(h->ev_join[0], h->side[0]));
     VGP_TRY(invert(h, M(K_), 0.0, M(KINV_), h->ws[2], red, S_LDK, h->side[1]));
     VGP_CUDA(cudaEventRecord(h->ev_join[1], h->side[1]));
     VGP_TRY(expquad_dispatch_public(h->z, m, h->x, n, h->d, a, l, 0.0, -1 - n, h->kzx, h->np_, s));
@@ -337,6 +346,25 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
                               h->partial, s, GEMM_LOWER));
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->bp, 1.0, h->kzb, h->bp, h->kzb, h->bp, 0.0, M(GB_), mp, h->splits_b,
                               h->partial, s, GEMM_LOWER));
+    // the six m^3 products that need only K, Q and Gb follow (K + eps I)^-1 on its side stream, underneath the
+    // inversion of M on the main stream
+    VGP_CUDA(cudaEventRecord(h->ev_gb, s));
+    if (sb != s) {
+        VGP_CUDA(cudaStreamWaitEvent(sb, h->ev_gb, 0));
+    } else {
+        VGP_CUDA(cudaEventRecord(h->ev_join[0], h->side[0]));      // Q alone; the products then follow on `s`
+        VGP_CUDA(cudaStreamWaitEvent(s, h->ev_join[0], 0));
+    }
+    auto six = [&](cudaStream_t st) -> int {
+        VGP_TRY(mm_on(st, M(Q_), M(GB_), M(T1_)));
+        VGP_TRY(mm_on(st, M(T1_), M(Q_), M(R_)));            // R = Q Gb Q
+        VGP_TRY(mm_on(st, M(K_), M(R_), M(KR_)));
+        VGP_TRY(mm_on(st, M(KR_), M(K_), M(KRK_)));
+        VGP_TRY(mm_on(st, M(K_), M(Q_), M(KQ_)));
+        return mm_on(st, M(KQ_), M(K_), M(KQK_));
+    };
+    VGP_TRY(six(sb));
+    if (sb != s) VGP_CUDA(cudaEventRecord(h->ev_join[0], h->side[0]));
     VGP_TRY(matvec(h->kzx, h->np_, m, n, h->y, 1.0, V(V_), s));
     VGP_TRY(exchange(M(G_), mp * mp));                  // sums over all observations, one 8 m^2 byte all-reduce
     VGP_TRY(exchange(V(V_), mp));
@@ -364,8 +392,6 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(red.run(DotVec{V(MU_), V(AL_)}, m, S_MUAL));
 
     // ---- forward matrices ---------------------------------------------------------------------------
-    VGP_TRY(mm(M(Q_), M(GB_), M(T1_)));
-    VGP_TRY(mm(M(T1_), M(Q_), M(R_)));            // R = Q Gb Q
     VGP_TRY(mm(M(SG_), M(K_), M(T2_)));           // T2 = Sigma K
     VGP_TRY(mm(M(K_), M(T2_), M(S_)));            // S = K Sigma K
     VGP_TRY(red.run(DotRegion{M(Q_), M(GB_), mp, m}, m * m, S_TRQGB));
@@ -376,13 +402,9 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(mm(M(T2_), M(R_), M(T2R_)));
     VGP_TRY(mm(M(R_), M(S_), M(RS_)));
     VGP_TRY(mm(M(RS_), M(Q_), M(RSQ_)));
-    VGP_TRY(mm(M(K_), M(R_), M(KR_)));
-    VGP_TRY(mm(M(KR_), M(K_), M(KRK_)));
     VGP_TRY(mm(M(Q_), M(S_), M(QS_)));
     VGP_TRY(mm(M(QS_), M(Q_), M(QSQ_)));
     VGP_TRY(mm(M(T2_), M(Q_), M(T2Q_)));
-    VGP_TRY(mm(M(K_), M(Q_), M(KQ_)));
-    VGP_TRY(mm(M(KQ_), M(K_), M(KQK_)));
     {   // alpha_bar = beta (Gb alpha - vb);  qa = Q alpha_bar;  mu_bar = w alpha + qa;  u_bar = beta K mu_bar
         const unsigned gb = (unsigned)((mp + 255) / 256);
         axpby_vec_kernel<<<gb, 256, 0, s>>>(V(GBAL_), beta, V(VB_), -beta, V(ALBAR_), m);
@@ -418,12 +440,22 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(lincomb(Terms().add(M(Q_), -beta).add(M(QSQ_), beta).rank1(V(AL_), V(AL_), beta), M(GBBAR2_), mp, s));
 
     // ---- push through the kernel ---------------------------------------------------------------------
+    // the minibatch and K_zz parts run on a side stream (own accumulator) underneath the N-sized product
+    VGP_CUDA(cudaEventRecord(h->ev_bar, s));
+    VGP_CUDA(cudaStreamWaitEvent(sd, h->ev_bar, 0));
+    VGP_TRY(dense_gemm(0, 0, mp, h->bp, mp, 1.0, M(GBBAR2_), mp, h->kzb, h->bp, 0.0, h->wzb, h->bp, GEMM_FULL, sd));
+    VGP_TRY(kernback(h, h->wzb, h->kzb, h->bp, xb, b, V(VBBAR_), yb, 1.0, h->rowacc2, sd));
+    VGP_TRY(kernback(h, M(KBAR_), M(K_), mp, h->z, m, nullptr, nullptr, 2.0, h->rowacc2, sd));
+    VGP_CUDA(cudaEventRecord(h->ev_mini, sd));
     VGP_TRY(dense_gemm(0, 0, mp, h->np_, mp, 1.0, M(GBAR2_), mp, h->kzx, h->np_, 0.0, h->wzx, h->np_, GEMM_FULL, s));
-    VGP_TRY(kernback(h, h->wzx, h->kzx, h->np_, h->x, n, V(VBAR_), h->y, 1.0, s));
+    VGP_TRY(kernback(h, h->wzx, h->kzx, h->np_, h->x, n, V(VBAR_), h->y, 1.0, h->rowacc, s));
     VGP_TRY(exchange(h->rowacc, m * (2 + h->d)));       // the observation-sized part of the push-through sums
-    VGP_TRY(dense_gemm(0, 0, mp, h->bp, mp, 1.0, M(GBBAR2_), mp, h->kzb, h->bp, 0.0, h->wzb, h->bp, GEMM_FULL, s));
-    VGP_TRY(kernback(h, h->wzb, h->kzb, h->bp, xb, b, V(VBBAR_), yb, 1.0, s));
-    VGP_TRY(kernback(h, M(KBAR_), M(K_), mp, h->z, m, nullptr, nullptr, 2.0, s));
+    VGP_CUDA(cudaStreamWaitEvent(s, h->ev_mini, 0));
+    {
+        const int64_t cnt = m * (2 + h->d);
+        axpby_vec_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(h->rowacc, 1.0, h->rowacc2, 1.0, h->rowacc, cnt);
+        VGP_LAUNCH_CHECK();
+    }
     VGP_TRY(red.run(ColSum{h->rowacc, 2 + h->d, 0}, m, S_ACC0));
     VGP_TRY(red.run(ColSum{h->rowacc, 2 + h->d, 1}, m, S_ACC1));
 
@@ -518,7 +550,7 @@ int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const do
         {(void **)&h->kzx, (size_t)h->mp * h->np_ * 8}, {(void **)&h->wzx, (size_t)h->mp * h->np_ * 8},
         {(void **)&h->kzb, (size_t)h->mp * h->bp * 8},  {(void **)&h->wzb, (size_t)h->mp * h->bp * 8},
         {(void **)&h->partial, (size_t)smax * mm}, {(void **)&h->rowacc, (size_t)m * (2 + d) * 8},
-        {(void **)&h->gradz, (size_t)m * d * 8},
+        {(void **)&h->gradz, (size_t)m * d * 8},         {(void **)&h->rowacc2, (size_t)m * (2 + d) * 8},
     };
     for (auto &al : allocs) {
         cudaError_t e = cudaMalloc(al.p, al.bytes);
@@ -535,6 +567,8 @@ int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const do
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     for (auto &ev : h->ev_join)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (cudaEvent_t *ev : {&h->ev_gb, &h->ev_bar, &h->ev_mini})
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "Z upload / side streams", __FILE__, __LINE__);
         vgp_elbo_destroy(h);
@@ -547,7 +581,8 @@ int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const do
 int vgp_elbo_destroy(vgp_elbo *h) {
     if (!h) return VGP_OK;
     VGP_ENTER(h->device);
-    void *ptrs[] = {h->z, h->mz, h->vz, h->mats, h->vecs, h->kzx, h->wzx, h->kzb, h->wzb, h->partial, h->rowacc, h->gradz};
+    void *ptrs[] = {h->z, h->mz, h->vz, h->mats, h->vecs, h->kzx, h->wzx, h->kzb, h->wzb, h->partial, h->rowacc, h->gradz,
+                    h->rowacc2};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &w : h->ws) w.release();
@@ -555,6 +590,8 @@ int vgp_elbo_destroy(vgp_elbo *h) {
         if (st) cudaStreamDestroy(st);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (auto &e : h->ev_join)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->ev_gb, h->ev_bar, h->ev_mini})
         if (e) cudaEventDestroy(e);
     delete h;
     return VGP_OK;
