@@ -31,7 +31,9 @@ struct DistContext {
     int64_t delta[DIST_MAX] = {0};          // replica base of rank q minus `base`, in doubles
     unsigned long long *flags[DIST_MAX] = {nullptr};   // barrier flags of rank q (peer-mapped): u64[DIST_MAX] + error
     unsigned long long seq = 0;
-    int64_t min_tiles = 296, min_k = 512;   // distribute a GEMM only above these (two waves of 148 SMs; NVLink-safe k)
+    // distribute a GEMM only above these.  Measured at n = 50k on 8 GPUs: 296 / 512 (98 distributed products) inverts in
+    // 1.26 s, 96 / 256 (1157 products, two flag barriers each) in 1.07 s (profiles/r01_bench_n50k_g8_thresholds.json)
+    int64_t min_tiles = 96, min_k = 256;
     int64_t dist_gemms = 0, barriers = 0;
 };
 void dense_set_dist(DistContext *ctx);      // thread-local; nullptr switches distribution off
