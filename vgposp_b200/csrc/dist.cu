@@ -73,9 +73,8 @@ int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t
     }
     h->ctx.base = h->matrix;
     h->ctx.bytes = bytes;
-    // a GEMM tile of depth k costs 2*128*128*k flop and ships 128 KB to each of the other ranks: keep the
-    // stores of one SM below its share of the NVLink egress (900 GB/s) -> k >= 256 per rank
-    h->ctx.min_k = 256 * (nranks > 2 ? nranks : 2);
+    // thresholds: DistContext defaults (dense.cuh) -- measured on 8 GPUs; the NVLink egress of the tile stores
+    // (64 KB per 128x64 tile and peer) stays below a rank's 900 GB/s share down to k = 256
     // everything that could allocate, free or load a module later happens now, before any rank can be spinning
     int rc0 = dense_preload();
     if (rc0 == VGP_OK) rc0 = h->ws.ensure(h->n_pad / TILE);
