@@ -647,7 +647,8 @@ static int gemm_launch_cfg(const GemmArgs &p, cudaStream_t s) {
 template <bool AKC, bool BKC>
 static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
     const GemmChoice c = gemm_choose(p);
-    if (c == CHOICE_TMA && AKC) {                                          // TMA producer: A k-contiguous, B either way
+    if (c == CHOICE_TMA && AKC && tensor_map_encoder()) {                  // TMA producer: A k-contiguous, B either way
+        // (a driver without cuTensorMapEncodeTiled falls through to the cp.async ring)
         // fewer Big tiles than half the SMs: the product is bound by the latency of one CTA's k loop -> Small tiles
         // (the lower-tile mode stays Big: its tile enumeration assumes TM = 128 row blocks)
         int64_t big_tiles = (p.m / tma::Big::TM) * (p.n / tma::Big::TN) * ((p.k + p.k_split - 1) / p.k_split);
