@@ -326,11 +326,11 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map
 }
 }  // namespace tma
 
-// BKC: B stored [n][k] (one box of 16 k x 64 rows).  !BKC: B stored [k][n] -- four boxes of 16 k x 16 n (2 KB each, the
-// 128-byte rows now run along n); a B fragment then takes the columns {0,1,8,9,2,3,10,11} (+4 for the odd fragment) of
-// its box, which keeps the 16 lanes of a half-warp on 16 distinct 8-byte words, and pairs of accumulators still
-// belong to adjacent columns.
-template <class S, bool BKC>
+// AKC / BKC: operand stored k-contiguous ([rows][k]: one box of 16 k x TM / TN rows).  Otherwise it is stored [k][rows]
+// and arrives as boxes of 16 k x 16 rows (2 KB each, the 128-byte rows now run along m / n); a fragment then takes the
+// rows {0,1,8,9,2,3,10,11} (+4 for the odd fragment) of its box, which keeps the 16 lanes of a half-warp on 16 distinct
+// 8-byte words -- and for B, pairs of accumulators still belong to adjacent columns.
+template <class S, bool AKC, bool BKC>
 __global__ void __launch_bounds__(tma::THREADS, S::MINB)
     gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
     using namespace tma;
@@ -378,7 +378,12 @@ __global__ void __launch_bounds__(tma::THREADS, S::MINB)
         const unsigned dst = smem_u32(sm + stage * STAGE_BYTES);
         const int k0 = (int)(kbase + (int64_t)kt * TK);
         mbar_expect_tx(bar, STAGE_BYTES);
-        tma_load_2d(dst, &map_a, k0, (int)m0, bar);
+        if (AKC) {
+            tma_load_2d(dst, &map_a, k0, (int)m0, bar);
+        } else {
+#pragma unroll
+            for (int bx = 0; bx < TM / 16; ++bx) tma_load_2d(dst + bx * 2048, &map_a, (int)m0 + 16 * bx, k0, bar);
+        }
         if (BKC) {
             tma_load_2d(dst + A_BYTES, &map_b, k0, (int)n0, bar);
         } else {
@@ -401,7 +406,11 @@ __global__ void __launch_bounds__(tma::THREADS, S::MINB)
     // byte offsets inside a swizzled tile: row r (128 bytes), 16-byte chunk ((k >> 1) ^ (r & 7)), half (k & 1).
     // For every fragment of this thread (r & 7) = 2 (g & 3) + (i & 1): the chunk is ((kk / 2) ^ gx) | ((t >> 1) ^ e).
     const int gx = 2 * (g & 3);
-    const unsigned a_row = (unsigned)((wm0 + 2 * g) * 128 + (t & 1) * 8);
+    const unsigned a_row = AKC ? (unsigned)((wm0 + 2 * g) * 128 + (t & 1) * 8)
+                               : (unsigned)((wm0 / 16) * 2048 + t * 128 + (g & 1) * 8);
+    // row of the warp tile that fragment i's accumulators belong to (see the two operand layouts above)
+    const int perm_g = ((g >> 1) & 1) * 8 + (g >> 2) * 2 + (g & 1);           // {0,1,8,9,2,3,10,11}[g]
+    auto frag_row = [&](int i) { return AKC ? 16 * (i >> 1) + 2 * g + (i & 1) : 16 * (i >> 1) + perm_g + 4 * (i & 1); };
     const unsigned b_row = BKC ? (unsigned)(A_BYTES + (wn0 + 2 * g) * 128 + (t & 1) * 8)
                                : (unsigned)(A_BYTES + (wn0 / 16) * 2048 + t * 128 + (g & 1) * 8);
     const int pg = ((g >> 1) & 1) * 4 + (g >> 2);          // (column >> 1) of this lane inside its 16-column box
@@ -417,19 +426,25 @@ __global__ void __launch_bounds__(tma::THREADS, S::MINB)
             const int ck = (kk / 2) ^ gx;
             const unsigned off0 = (unsigned)((ck | (t >> 1)) << 4), off1 = (unsigned)((ck | ((t >> 1) ^ 1)) << 4);
             double af[FI], bf[FJ];
+            // k-strided boxes: row kk + t of the box, chunk ((column >> 1) ^ (row & 7)); (kk + t) & 7 = (kk & 4) | t
+            const int kt7 = (kk & 4) | t;
+            const unsigned o0 = (unsigned)(kk * 128 + ((pg ^ kt7) << 4)), o1 = (unsigned)(kk * 128 + (((pg | 2) ^ kt7) << 4));
+            if (AKC) {
 #pragma unroll
-            for (int i = 0; i < FI; ++i)
-                af[i] = *reinterpret_cast<const double *>(st + a_row + (i >> 1) * 2048 + (i & 1) * 128 +
-                                                          ((i & 1) ? off1 : off0));
+                for (int i = 0; i < FI; ++i)
+                    af[i] = *reinterpret_cast<const double *>(st + a_row + (i >> 1) * 2048 + (i & 1) * 128 +
+                                                              ((i & 1) ? off1 : off0));
+            } else {
+#pragma unroll
+                for (int i = 0; i < FI; ++i)
+                    af[i] = *reinterpret_cast<const double *>(st + a_row + (i >> 1) * 2048 + ((i & 1) ? o1 : o0));
+            }
             if (BKC) {
 #pragma unroll
                 for (int j = 0; j < FJ; ++j)
                     bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + (j & 1) * 128 +
                                                               ((j & 1) ? off1 : off0));
             } else {
-                // row kk + t of the box, chunk ((column >> 1) ^ (row & 7)); (kk + t) & 7 = (kk & 4) | t
-                const int kt7 = (kk & 4) | t;
-                const unsigned o0 = (unsigned)(kk * 128 + ((pg ^ kt7) << 4)), o1 = (unsigned)(kk * 128 + (((pg | 2) ^ kt7) << 4));
 #pragma unroll
                 for (int j = 0; j < FJ; ++j)
                     bf[j] = *reinterpret_cast<const double *>(st + b_row + (j >> 1) * 2048 + ((j & 1) ? o1 : o0));
@@ -444,7 +459,7 @@ __global__ void __launch_bounds__(tma::THREADS, S::MINB)
         // B fragment j = 2 q + e of box q holds, for this thread, the adjacent columns {0, 8, 2, 10}[t] + 4 e (+ 0, 1)
 #pragma unroll
         for (int i = 0; i < FI; ++i) {
-            const int64_t r = m0 + wm0 + 16 * (i >> 1) + 2 * g + (i & 1);
+            const int64_t r = m0 + wm0 + frag_row(i);
 #pragma unroll
             for (int j = 0; j < FJ; ++j) {
                 const int col = 16 * (j >> 1) + ((t & 1) * 8 + (t >> 1) * 2) + 4 * (j & 1);
@@ -473,7 +488,7 @@ __global__ void __launch_bounds__(tma::THREADS, S::MINB)
     // columns 4 t + {0, 2} and 4 t + {1, 3}: four consecutive columns per thread
 #pragma unroll
     for (int i = 0; i < FI; ++i) {
-        const int64_t r = m0 + wm0 + 16 * (i >> 1) + 2 * g + (i & 1);
+        const int64_t r = m0 + wm0 + frag_row(i);
 #pragma unroll
         for (int q = 0; q < FJ / 2; ++q) {
             double2 *dst = reinterpret_cast<double2 *>(cout + r * p.ldc + n0 + wn0 + 16 * q + 4 * t);
@@ -537,17 +552,20 @@ static int make_operand_map(CUtensorMap *map, const double *base, int64_t rows, 
     return VGP_OK;
 }
 
-template <class S, bool BKC>
+template <class S, bool AKC, bool BKC>
 static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
     static bool configured[64] = {};
     int dev = 0;
     VGP_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<S, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+        VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<S, AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
         configured[dev] = true;
     }
     alignas(64) CUtensorMap ma, mb;
-    VGP_TRY(make_operand_map(&ma, p.a, p.m, p.k, p.lda, S::TM));
+    if (AKC)
+        VGP_TRY(make_operand_map(&ma, p.a, p.m, p.k, p.lda, S::TM));
+    else
+        VGP_TRY(make_operand_map(&ma, p.a, p.k, p.m, p.lda, 16));        // [k][m]: boxes of 16 m x 16 k
     if (BKC)
         VGP_TRY(make_operand_map(&mb, p.b, p.n, p.k, p.ldb, S::TN));
     else
@@ -564,16 +582,16 @@ static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
         const int64_t mine = each + (rank < rem ? 1 : 0);
         q.tiles_n = tn;
         if (mine > 0) {
-            gemm_tma_kernel<S, BKC><<<dim3((unsigned)mine, 1, 1), tma::THREADS, S::SMEM, s>>>(ma, mb, q);
+            gemm_tma_kernel<S, AKC, BKC><<<dim3((unsigned)mine, 1, 1), tma::THREADS, S::SMEM, s>>>(ma, mb, q);
             VGP_LAUNCH_CHECK();
         }
         return VGP_OK;
     }
     if (p.lower) {
         const int64_t blocks = (int64_t)RATIO * tm * (tm + 1) / 2;
-        gemm_tma_kernel<S, BKC><<<dim3((unsigned)blocks, 1, splits), tma::THREADS, S::SMEM, s>>>(ma, mb, p);
+        gemm_tma_kernel<S, AKC, BKC><<<dim3((unsigned)blocks, 1, splits), tma::THREADS, S::SMEM, s>>>(ma, mb, p);
     } else {
-        gemm_tma_kernel<S, BKC><<<dim3((unsigned)tn, (unsigned)tm, splits), tma::THREADS, S::SMEM, s>>>(ma, mb, p);
+        gemm_tma_kernel<S, AKC, BKC><<<dim3((unsigned)tn, (unsigned)tm, splits), tma::THREADS, S::SMEM, s>>>(ma, mb, p);
     }
     VGP_LAUNCH_CHECK();
     return VGP_OK;
@@ -647,15 +665,17 @@ static int gemm_launch_cfg(const GemmArgs &p, cudaStream_t s) {
 template <bool AKC, bool BKC>
 static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
     const GemmChoice c = gemm_choose(p);
-    if (c == CHOICE_TMA && AKC && tensor_map_encoder()) {                  // TMA producer: A k-contiguous, B either way
+    if (c == CHOICE_TMA && tensor_map_encoder()) {                         // TMA producer, all four operand layouts
         // (a driver without cuTensorMapEncodeTiled falls through to the cp.async ring)
         // fewer Big tiles than half the SMs: the product is bound by the latency of one CTA's k loop -> Small tiles
         // (the lower-tile mode stays Big: its tile enumeration assumes TM = 128 row blocks)
         int64_t big_tiles = (p.m / tma::Big::TM) * (p.n / tma::Big::TN) * ((p.k + p.k_split - 1) / p.k_split);
         if (p.dist_n > 0) big_tiles /= p.tiles_n;         // distributed product: this rank's share (tiles_n = ranks here)
         static const int small_below = getenv("VGP_GEMM_SMALL_BELOW") ? atoi(getenv("VGP_GEMM_SMALL_BELOW")) : 74;
-        if (!p.lower && !p.in_place && big_tiles < small_below) return gemm_launch_tma<tma::Small, BKC>(p, s);
-        return gemm_launch_tma<tma::Big, BKC>(p, s);
+        if (!p.lower && !p.in_place && big_tiles < small_below) return gemm_launch_tma<tma::Small, AKC, BKC>(p, s);
+        // a k-strided A arrives as eight 2 KB boxes per stage: measured equal to (B k-strided) or 1.5 % behind
+        // (B k-contiguous) the cp.async ring on large products, so those keep the ring; 34.1-34.6 vs 34.3-35.1 TFLOP/s
+        if (AKC) return gemm_launch_tma<tma::Big, AKC, BKC>(p, s);
     }
     if (c != CHOICE_BASE) return gemm_launch_cfg<CfgPair, AKC, BKC>(p, s);
     return gemm_launch_cfg<CfgBase, AKC, BKC>(p, s);
@@ -1204,6 +1224,13 @@ static int gemm_preload_one() {
     VGP_TRY((gemm_preload_cfg<CfgBase, AKC, BKC>()));
     return gemm_preload_cfg<CfgPair, AKC, BKC>();
 }
+template <class S, bool AKC, bool BKC>
+static int tma_preload() {
+    cudaFuncAttributes fa;
+    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<S, AKC, BKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<S, AKC, BKC>));
+    return VGP_OK;
+}
 int dense_preload() {
     cudaFuncAttributes fa;
     VGP_TRY((gemm_preload_one<true, true>()));
@@ -1212,14 +1239,14 @@ int dense_preload() {
     VGP_TRY((gemm_preload_one<false, true>()));
     VGP_CUDA(cudaFuncSetAttribute(trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
     VGP_CUDA(cudaFuncSetAttribute(lauum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_SMEM));
-    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Big, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Big::SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Big, true>));
-    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Big, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Big::SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Big, false>));
-    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Small, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Small::SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Small, true>));
-    VGP_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<tma::Small, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::Small::SMEM));
-    VGP_CUDA(cudaFuncGetAttributes(&fa, gemm_tma_kernel<tma::Small, false>));
+    VGP_TRY((tma_preload<tma::Big, true, true>()));
+    VGP_TRY((tma_preload<tma::Big, true, false>()));
+    VGP_TRY((tma_preload<tma::Big, false, true>()));
+    VGP_TRY((tma_preload<tma::Big, false, false>()));
+    VGP_TRY((tma_preload<tma::Small, true, true>()));
+    VGP_TRY((tma_preload<tma::Small, true, false>()));
+    VGP_TRY((tma_preload<tma::Small, false, true>()));
+    VGP_TRY((tma_preload<tma::Small, false, false>()));
     VGP_CUDA(cudaFuncGetAttributes(&fa, potf2_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, trtri_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, lauum_kernel));
