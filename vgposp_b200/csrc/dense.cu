@@ -8,10 +8,12 @@
 // Design
 //   * Every matrix is row-major with all dimensions multiples of 128 (callers pad with an identity block),
 //     so no kernel has edge cases.
-//   * All O(n^3) work funnels into ONE kernel, `gemm_kernel`: CTA tile 128x128x16, 8 warps of 64x32,
-//     float64 tensor-core MMA (mma.sync.m8n8k4.f64 -> DMMA), operands staged through a 3-deep
-//     cp.async ring in shared memory with bank-conflict-free padded layouts for both operand
-//     orientations.  tcgen05 has no f64 kind, so DMMA is the tensor path for this dtype.
+//   * All O(n^3) work funnels into one GEMM, float64 tensor-core MMA (mma.sync.m8n8k4.f64 -> DMMA; tcgen05 has no
+//     f64 kind, and the larger f64 mma shapes decompose into DMMA.8x8x4 on sm_100a), in two producers:
+//       - `gemm_tma_kernel`: operands staged by TMA (cp.async.bulk.tensor.2d + mbarrier, 128-byte swizzle, 4 stages),
+//         CTA tile 128x64 (two CTAs per SM) or 64x64 for latency-bound small products -- the default;
+//       - `gemm_kernel`: a 3-deep cp.async ring with padded conflict-free layouts, CTA tile 128x64 or 128x128 -- for
+//         large products with a k-strided A and for the in-place products of the triangular solves.
 //   * Cholesky, L^-1 and L^-T L^-1 are the classic recursive (2x2 block) formulations: each level is
 //     one or two large GEMMs on rectangular off-diagonal blocks plus recursion on the diagonal blocks;
 //     128x128 diagonal blocks are handled by single-CTA shared-memory kernels.  Diagonal-block solves
