@@ -71,6 +71,27 @@ def main():
     np.testing.assert_allclose(sc2, want2_scores, rtol=1e-9)
     dist.barrier()
     placer.close()
+    # the ELBO training step sharded over the observations: NCCL all-reduces on the library's own buffers
+    import vgposp_b200.gp_functions as gpf
+    gpf.DEVICE = local
+    nobs, m, b = 4000, 64, 256
+    rng = np.random.default_rng(3)
+    xo = rng.uniform(-2, 2, (nobs, 3))
+    yo = np.sum(np.sin(2 * np.pi * xo), axis=1) + 0.1 * rng.standard_normal(nobs)
+    zo = rng.uniform(-2, 2, (m, 3))
+    batches = [rng.integers(nobs, size=b) for _ in range(4)]
+    single = gpf.VgpTrainer(xo, yo, zo, b)
+    want_losses = [single.step(xo[i], yo[i]) for i in batches]
+    sharded = gpf.VgpTrainer(xo[rank::world], yo[rank::world], zo, b, allreduce=lambda t: dist.all_reduce(t), n_total=nobs)
+    got_losses = [sharded.step(xo[i], yo[i]) for i in batches]
+    np.testing.assert_allclose(got_losses, want_losses, rtol=1e-9)
+    v_mine, z_mine = sharded.variables()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (v_mine.tolist(), z_mine.tolist()))
+    assert all(g == gathered[0] for g in gathered), "replicas diverged"
+    single.close()
+    sharded.close()
+    dist.barrier()
     if rank == 0:
         print("DIST_WORKER_OK", [int(s) for s in sel], flush=True)
     dist.destroy_process_group()
