@@ -140,8 +140,19 @@ def cpu_greedy(n_full, n_sample, steps, warmup):
                   "(inverse %.1f s, kernel build %.1f s at the sample size) excluded like `value`"
                   % (n_sample, steps, warmup, n_sample, n_full, tm["setup_s"], build_s),
         "ms_per_step_sample": per_step * 1e3, "ms_per_step_scaled": per_step * 1e3 / scale,
-        "host": {"cpu_count": cores, "omp_threads": threads},
+        "host": {"cpu_count": cores, "omp_threads": threads, "blas": _blas_vendor(),
+                 "env": {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}},
     }
+
+
+def _blas_vendor():
+    """Which BLAS / LAPACK numpy links (the inverse of the CPU arm runs there)."""
+    try:
+        cfg = np.show_config(mode="dicts")
+        b = cfg.get("Build Dependencies", {}).get("blas", {})
+        return "%s %s" % (b.get("name"), b.get("version"))
+    except Exception:      # noqa: BLE001
+        return None
 
 
 def run_reference(args, rank, world):
