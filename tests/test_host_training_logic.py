@@ -1,0 +1,77 @@
+"""CPU tests of the host-side training logic of the drop-in gp_functions module (no GPU: the GP is a stub with an
+analytic log-likelihood): softplus parameterisation, TF-Adam update, Session.run fetch semantics, lls shapes."""
+import numpy as np
+
+from oracle import gp_oracle as gpo
+import vgposp_b200.gp_functions as gpf
+
+
+class _Kernel:
+    KIND = 0
+
+    def __init__(self, amp, ls):
+        self.amplitude, self.length_scale = amp, ls
+
+
+class _StubGP:
+    """log-likelihood -sum_b |theta_b - target|^2 / 2 of the constrained parameters theta = (amp, ls, noise)."""
+
+    def __init__(self, amp, ls, noise, target):
+        self.kernel, self.observation_noise_variance, self.target = _Kernel(amp, ls), noise, np.asarray(target)
+
+    def theta(self):
+        return np.stack([np.atleast_1d(p.numpy()) for p in
+                         (self.kernel.amplitude, self.kernel.length_scale, self.observation_noise_variance)], axis=1)
+
+    def log_prob(self, observations):
+        return -0.5 * np.sum((self.theta() - self.target) ** 2, axis=1)
+
+    def log_prob_and_grad(self, observations):
+        th = self.theta()
+        return -0.5 * np.sum((th - self.target) ** 2, axis=1), -(th - self.target)
+
+
+def test_adam_train_op_follows_tf_adam_in_softplus_space():
+    amp, _, _, lensc, _, _, _, _, _, noise = gpf.tf_Placeholder_assign_test(np.array([0.54]), np.array([0.3]), np.array([1.2]))
+    target = np.array([2.0, 0.7, 0.05])
+    gp = _StubGP(amp, lensc, noise, target)
+    obs = gpf.placeholder(np.float64, (1, 4))
+    node = gpf.LogProb(gp, obs)
+    op = gpf.tf_train_gp_adam(node, 0.1)
+    lls = gpf.tf_optimize_model_params(gpf.reset_session(), 25, op, node, None, None, None, None, None,
+                                       np.zeros(4), obs)
+    # the same loop with the oracle's Adam on the unconstrained variables
+    v = np.array([0.54, 0.3, 1.2])
+    adam = gpo.TfAdam(3, 0.1)
+    want = []
+    tiny = np.finfo(np.float64).tiny
+    for it in range(27):
+        th = tiny + gpo.softplus(v)
+        if it > 0:
+            want.append(-0.5 * np.sum((th - target) ** 2))
+        v = adam.step(v, (th - target) / (1.0 + np.exp(-v)))
+    assert lls.shape == (26, 1)
+    np.testing.assert_allclose(lls[:, 0], want, rtol=1e-12)
+    got_v = [amp.variable.value[0], lensc.variable.value[0], noise.variable.value[0]]
+    np.testing.assert_allclose(got_v, v, rtol=1e-12)
+    assert lls[-1, 0] > lls[0, 0]
+
+
+def test_session_run_fetches_and_batch_of_two():
+    amp, amp_assign, amp_p, lensc, _, _, _, _, _, noise = gpf.tf_Placeholder_assign_test(
+        np.array([0.54, 0.9]), np.array([0.3, 0.4]), np.array([1.2, 0.8]))
+    gp = _StubGP(amp, lensc, noise, np.array([1.0, 1.0, 1.0]))
+    obs = gpf.placeholder(np.float64, (2, 3))
+    node = gpf.LogProb(gp, obs)
+    op = gpf.tf_train_gp_adam(node, 0.05)
+    sess = gpf.reset_session()
+    before = node(np.zeros((2, 3)))
+    _, ll, ll1 = sess.run([op, node, node[1]], feed_dict={obs: np.zeros((2, 3))})
+    np.testing.assert_allclose(ll, before)                      # fetched with the train op: the pre-update value
+    assert ll1 == before[1]
+    assert not np.allclose(node(), before)                      # parameters moved
+    lls = gpf.tf_optimize_model_params(sess, 3, op, node, None, None, None, None, None, np.zeros((2, 3)), obs)
+    assert lls.shape == (4, 2)
+    amp_assign([2.0, 3.0])
+    np.testing.assert_allclose(amp.numpy(), [2.0, 3.0], rtol=1e-14)
+    assert np.allclose(gpf.do_assign(sess, amp, amp_assign, amp_p, [0.5, 0.6]), [0.5, 0.6])
