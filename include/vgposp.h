@@ -342,6 +342,15 @@ int vgp_greedy_profile_read(vgp_greedy *handle, double *total_ms, int64_t *launc
  * adopt_factor: the caller filled factor_dev itself (P_0 or M for the handle's mode). */
 typedef struct vgp_lazy vgp_lazy;
 int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, double small, double jitter, int mode);
+/* Sharded lazy-column greedy over the ranks of a connected vgp_dist (one box, one process or thread per GPU): mode 1
+ * with M = L^-1 in the replicas; per selection the triangular matrix-vector product is split by 512-row blocks over
+ * the ranks, every rank stores its blocks' partial sums into all ranks' buffers over NVLink (the tail behind the
+ * replicas) and one flag barrier follows; the O(n t) step kernel runs replicated, summing the blocks in the
+ * single-device order -- every rank selects the same winners, scores bitwise those of one device.  Every rank: fill
+ * cov_dev (vgp_lazy_matrices) and the replica with Sigma, vgp_dist_factor_inverse, vgp_lazy_adopt_factor, vgp_lazy_run. */
+struct vgp_dist;
+int vgp_lazy_create_dist(vgp_lazy **handle, struct vgp_dist *dist, int64_t n, int64_t kmax, double small,
+                         double jitter);
 int vgp_lazy_destroy(vgp_lazy *handle);
 int vgp_lazy_matrices(vgp_lazy *handle, double **cov_dev, double **factor_dev, int64_t *ld);
 int vgp_lazy_factor(vgp_lazy *handle, int *info_host, void *stream);
@@ -397,6 +406,10 @@ int vgp_dist_connect(vgp_dist *handle, const void *peers, int kind);
 int vgp_dist_push_rows(vgp_dist *handle, int64_t row0, int64_t row1, void *stream);
 int vgp_dist_barrier(vgp_dist *handle, void *stream);
 int vgp_dist_spd_inverse(vgp_dist *handle, int *info_host, void *stream);
+/* potrf + trtri only: the replicas end up holding M = L^-1 (lower triangle; 2/3 of the flops of the inverse) -- the
+ * state of the sharded lazy-column greedy (vgp_lazy_create_dist).  vgp_dist_add_diag: replica[i][i] += value, i < n. */
+int vgp_dist_factor_inverse(vgp_dist *handle, int *info_host, void *stream);
+int vgp_dist_add_diag(vgp_dist *handle, int64_t n, double value, void *stream);
 int vgp_dist_stats(vgp_dist *handle, int64_t *distributed_gemms, int64_t *barriers);
 
 #if defined(__GNUC__)

@@ -60,17 +60,19 @@ def main():
     shard.close()
     inv.close()
     # the persistent one-call form: connect once, place twice (a second covariance through the same mappings)
-    placer = greedy.ShardedPlacer(n, k, rank, world, dist, local, stream=stream)
-    sel1, sc1, _ = placer.place(cov[bounds[rank]:bounds[rank + 1]], k)
-    assert [int(s) for s in sel1] == want_sel, (rank, sel1, want_sel)
-    np.testing.assert_allclose(sc1, want_scores, rtol=1e-9)
     cov2 = cov + 0.05 * np.eye(n)
     want2, want2_scores = go.incremental_greedy_c(cov2, k - 3)
-    sel2, sc2, _ = placer.place(cov2, k - 3)                       # full matrix accepted too
-    assert [int(s) for s in sel2] == want2, (rank, sel2, want2)
-    np.testing.assert_allclose(sc2, want2_scores, rtol=1e-9)
-    dist.barrier()
-    placer.close()
+    for form in ("dense", "lazy", "auto"):
+        placer = greedy.ShardedPlacer(n, k, rank, world, dist, local, stream=stream, formulation=form)
+        sel1, sc1, secs = placer.place(cov[bounds[rank]:bounds[rank + 1]], k)
+        assert secs["formulation"] == ("dense" if form == "dense" else "lazy")
+        assert [int(s) for s in sel1] == want_sel, (form, rank, sel1, want_sel)
+        np.testing.assert_allclose(sc1, want_scores, rtol=1e-9)
+        sel2, sc2, _ = placer.place(cov2, k - 3)                       # full matrix accepted too
+        assert [int(s) for s in sel2] == want2, (form, rank, sel2, want2)
+        np.testing.assert_allclose(sc2, want2_scores, rtol=1e-9)
+        dist.barrier()
+        placer.close()
     # the ELBO training step sharded over the observations: NCCL all-reduces on the library's own buffers
     import vgposp_b200.gp_functions as gpf
     gpf.DEVICE = local

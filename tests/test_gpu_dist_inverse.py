@@ -94,3 +94,67 @@ def test_two_processes_ipc():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=root)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DIST_WORKER_OK" in res.stdout
+
+
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("n,world,k", [(1000, 2, 12), (1664, 3, 20), (2050, 4, 9), (700, 2, 600)])
+def test_sharded_lazy_factor_greedy_threads(n, world, k, monkeypatch):
+    """The one-call path on G ranks: replicas factorised to L^-1 by the distributed potrf + trtri, the triangular
+    matrix-vector product of every selection split over the ranks (csrc/lazy.cu, vgp_lazy_create_dist).  Every rank
+    must return the single-device lazy-factor result bit for bit, and the CPU oracle's selection."""
+    from oracle import greedy_oracle as go
+    from vgposp_b200 import greedy
+    monkeypatch.setenv("VGP_DIST_MIN_TILES", "2")
+    monkeypatch.setenv("VGP_DIST_MIN_K", "256")
+    a = spd(n, n + 1)
+    want = greedy.place_single(a, k, D, want_step_scores=True, formulation="lazy_factor")
+    streams = []
+    for _ in range(world):
+        s = ctypes.c_void_p()
+        _ffi.call("vgp_stream_create", D, ctypes.byref(s))
+        streams.append(s)
+    ranks = [DistInverse(n, r, world, D, stream=streams[r]) for r in range(world)]
+    for r in ranks:
+        r.connect_pointers([q.pointers for q in ranks])
+        r.fill_padding()
+    lazies = [greedy.LazyGreedy.from_dist(r, k) for r in ranks]
+    bounds = [(n * g) // world for g in range(world + 1)]
+    for r in ranks:
+        r.load_host(a, bounds[r.rank], bounds[r.rank + 1])
+        r.push_rows(bounds[r.rank], bounds[r.rank + 1])
+    errors, out = [], [None] * world
+
+    def work(i):
+        try:
+            r, lz = ranks[i], lazies[i]
+            r.barrier()
+            lz.load_cov_device(r.ptr, r.ld)
+            lz.record_scores(True)
+            r.factor_inverse()
+            lz.adopt_factor()
+            lz.run(k)
+            sel, sc = lz.results()
+            out[i] = (sel[:k], sc[:k], lz.step_scores()[:k])
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=200)
+    assert not errors, errors
+    for sel, sc, steps in out:
+        np.testing.assert_array_equal(sel, want[0])
+        np.testing.assert_array_equal(sc, want[1])
+        np.testing.assert_array_equal(steps, want[2])
+    if k <= 50:
+        oracle_sel, oracle_scores = go.incremental_greedy(a, k)[:2]
+        assert [int(s) for s in out[0][0]] == oracle_sel
+        np.testing.assert_allclose(out[0][1], oracle_scores, rtol=1e-9)
+    for lz in lazies:
+        lz.close()
+    for r in ranks:
+        r.close()
+    for s in streams:
+        _ffi.call("vgp_stream_destroy", D, s)

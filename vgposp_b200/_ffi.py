@@ -120,6 +120,9 @@ SIGNATURES = {
     "vgp_dist_push_rows": [c_vp, c_i64, c_i64, c_vp],
     "vgp_dist_barrier": [c_vp, c_vp],
     "vgp_dist_spd_inverse": [c_vp, P(c_int), c_vp],
+    "vgp_dist_factor_inverse": [c_vp, P(c_int), c_vp],
+    "vgp_dist_add_diag": [c_vp, c_i64, c_dbl, c_vp],
+    "vgp_lazy_create_dist": [P(c_vp), c_vp, c_i64, c_i64, c_dbl, c_dbl],
     "vgp_dist_stats": [c_vp, P(c_i64), P(c_i64)],
     "vgp_greedy_comm_create": [c_vp, c_int, c_int, P(c_i64), c_vp, P(c_vp)],
     "vgp_greedy_comm_connect": [c_vp, c_vp, c_int],

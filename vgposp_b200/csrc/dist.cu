@@ -22,16 +22,7 @@
 
 using namespace vgp;
 
-struct vgp_dist {
-    int device = 0;
-    int64_t n_pad = 0;
-    double *matrix = nullptr;
-    unsigned long long *flags = nullptr;        // u64[DIST_MAX] barrier words + int error
-    double *peer_matrix[DIST_MAX] = {nullptr};
-    int ipc = 0, connected = 0;
-    DistContext ctx;
-    DenseWorkspace ws;
-};
+#include "dist.cuh"
 
 namespace {
 constexpr size_t FLAG_BYTES = 8 * (DIST_MAX + 1);
@@ -62,7 +53,11 @@ int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t
     h->ctx.rank = rank;
     h->ctx.nranks = nranks;
     const size_t bytes = (size_t)h->n_pad * h->n_pad * 8;
-    cudaError_t e = cudaMalloc((void **)&h->matrix, bytes);
+    // the tail behind the replica (peer-mapped with it): two parity buffers of [row blocks][n_pad] partial sums for the
+    // sharded lazy-column greedy (lazy.cu)
+    h->tail_rows = 2 * ((h->n_pad + DIST_TAIL_RB - 1) / DIST_TAIL_RB);
+    cudaError_t e = cudaMalloc((void **)&h->matrix, bytes + (size_t)h->tail_rows * h->n_pad * 8);
+    if (e == cudaSuccess) e = cudaMemset(h->matrix + (size_t)h->n_pad * h->n_pad, 0, (size_t)h->tail_rows * h->n_pad * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->flags, FLAG_BYTES);
     if (e == cudaSuccess) e = cudaMemset(h->flags, 0, FLAG_BYTES);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -172,6 +167,14 @@ int vgp_dist_push_rows(vgp_dist *h, int64_t r0, int64_t r1, void *stream) {
     return VGP_OK;
 }
 
+// replica[i][i] += value for i < n (every rank on its own replica: e.g. the TF-graph variant's jitter before factorising)
+int vgp_dist_add_diag(vgp_dist *h, int64_t n, double value, void *stream) {
+    VGP_TRY(check(h));
+    VGP_REQUIRE(n >= 0 && n <= h->n_pad, "bad size");
+    VGP_ENTER(h->device);
+    return dense_add_diag(h->matrix, h->n_pad, n, value, (cudaStream_t)stream);
+}
+
 int vgp_dist_barrier(vgp_dist *h, void *stream) {
     VGP_TRY(check(h));
     VGP_REQUIRE(h->connected, "vgp_dist_connect first");
@@ -180,7 +183,15 @@ int vgp_dist_barrier(vgp_dist *h, void *stream) {
     return dense_dist_barrier(h->ctx, (cudaStream_t)stream);
 }
 
-int vgp_dist_spd_inverse(vgp_dist *h, int *info_host, void *stream) {
+static int dist_run(vgp_dist *h, int *info_host, void *stream, bool factor_only);
+
+int vgp_dist_spd_inverse(vgp_dist *h, int *info_host, void *stream) { return dist_run(h, info_host, stream, false); }
+
+/* potrf + trtri only: the replicas end up holding M = L^-1 (lower triangle), what the lazy-column greedy with the
+ * inverse factor resident needs -- 2/3 of the flops of the inverse. */
+int vgp_dist_factor_inverse(vgp_dist *h, int *info_host, void *stream) { return dist_run(h, info_host, stream, true); }
+
+static int dist_run(vgp_dist *h, int *info_host, void *stream, bool factor_only) {
     VGP_TRY(check(h));
     VGP_REQUIRE(h->connected || h->ctx.nranks == 1, "vgp_dist_connect first");
     if (info_host) *info_host = 0;
@@ -194,7 +205,12 @@ int vgp_dist_spd_inverse(vgp_dist *h, int *info_host, void *stream) {
     dense_set_dist(h->ctx.nranks > 1 ? &h->ctx : nullptr);
     int rc = VGP_OK;
     if (h->ctx.nranks > 1) rc = dense_dist_barrier(h->ctx, s);      // every replica is filled
-    if (rc == VGP_OK) rc = dense_spd_inverse(h->matrix, h->n_pad, h->n_pad, h->ws, info_host, s);
+    if (rc == VGP_OK && !factor_only) rc = dense_spd_inverse(h->matrix, h->n_pad, h->n_pad, h->ws, info_host, s);
+    if (rc == VGP_OK && factor_only) {
+        rc = dense_potrf(h->matrix, h->n_pad, h->n_pad, h->ws, s);
+        if (rc == VGP_OK) rc = dense_read_info(h->ws, info_host, s);
+        if (rc == VGP_OK) rc = dense_trtri(h->matrix, h->n_pad, h->n_pad, h->ws, s);
+    }
     if (rc == VGP_OK && h->ctx.nranks > 1) rc = dense_dist_barrier(h->ctx, s);
     dense_set_dist(nullptr);
     cudaError_t e = cudaStreamSynchronize(s);

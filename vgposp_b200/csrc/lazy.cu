@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "dense.cuh"
+#include "dist.cuh"
 
 using namespace vgp;
 
@@ -45,6 +46,11 @@ struct vgp_lazy {
     int64_t *sel = nullptr;
     double *sel_score = nullptr, *step_scores = nullptr;
     int record = 0, factored = 0;
+    // sharded form (vgp_lazy_create_dist): `fac` is the replica of a vgp_dist, `partial` its peer-visible tail (two
+    // parity buffers); the row blocks of the triangular matrix-vector product are dealt round-robin to the ranks
+    vgp_dist *dist = nullptr;
+    int own_fac = 1, own_partial = 1;
+    int64_t partial_parity_stride = 0;                // doubles between the two parity buffers (0: single buffer)
     int64_t loc_i1 = 0, loc_i2 = 0, loc_cutoff = 0;   // algorithm 3: grid strides I1, I2 and the index-box half-width
     double *cache = nullptr;                          // algorithm 3: the (partly stale) delta cache [n_pad]
     int64_t t = 0, launches = 0;
@@ -102,11 +108,18 @@ __device__ __forceinline__ void block_argmax(double &s, int64_t &i, int &slot) {
 }
 
 // partial[rb][c] = sum over the rows i of row block rb, i >= y, c <= i, of  M[i][c] * (SQUARE ? M[i][c] : M[i][y])
+struct TrigemvPeers {          // sharded form: this rank computes the row blocks rb % nranks == rank and stores them
+    int rank = 0, nranks = 1;  // into the partial buffer of every rank (delta[q] = that buffer minus the local one)
+    int64_t delta[DIST_MAX] = {0};
+};
+
 template <bool SQUARE>
 __global__ void __launch_bounds__(256) trigemv_kernel(const double *__restrict__ m, int64_t ld, int64_t n_pad,
-                                                      const vgp_candidate *cur, double *__restrict__ partial) {
+                                                      const vgp_candidate *cur, double *__restrict__ partial,
+                                                      TrigemvPeers peers) {
     const int rb = blockIdx.y, cb = blockIdx.x;
     if (cb > rb) return;                                       // above the diagonal
+    if (peers.nranks > 1 && rb % peers.nranks != peers.rank) return;
     int64_t y = 0;
     if (!SQUARE) {
         y = cur->index;
@@ -151,7 +164,12 @@ __global__ void __launch_bounds__(256) trigemv_kernel(const double *__restrict__
             }
         }
     }
-    *reinterpret_cast<double2 *>(partial + (int64_t)rb * n_pad + c) = make_double2(ax, ay);
+    double2 *dst = reinterpret_cast<double2 *>(partial + (int64_t)rb * n_pad + c);
+    if (peers.nranks > 1) {
+        for (int q = 0; q < peers.nranks; ++q) *(dst + (peers.delta[q] >> 1)) = make_double2(ax, ay);   // peers: NVLink
+    } else {
+        *dst = make_double2(ax, ay);
+    }
 }
 
 // d0[j] = sum over row blocks b >= j / RB of partial[b][j]   (mode 1: column norms of M = diag of M^T M)
@@ -366,6 +384,24 @@ __global__ void lazy_pad_identity_kernel(double *a, int64_t ld, int64_t n, int64
     if (i < n_pad) a[i * ld + i] = 1.0;
 }
 
+TrigemvPeers peers_of(const vgp_lazy *h, int parity) {
+    TrigemvPeers p;
+    if (h->dist && h->dist->ctx.nranks > 1) {
+        p.rank = h->dist->ctx.rank;
+        p.nranks = h->dist->ctx.nranks;
+        (void)parity;                       // the parity offset is the same in every replica: it is part of `partial`
+        for (int q = 0; q < p.nranks; ++q) p.delta[q] = h->dist->ctx.delta[q];
+    }
+    return p;
+}
+
+// every rank's blocks have landed in every rank's buffer (stream order, all ranks)
+int peers_barrier(vgp_lazy *h, cudaStream_t s) {
+    if (!h->dist || h->dist->ctx.nranks == 1) return VGP_OK;
+    ++h->launches;
+    return dense_dist_barrier(h->dist->ctx, s);
+}
+
 int check(vgp_lazy *h) {
     if (!h) {
         set_error("lazy greedy handle is NULL");
@@ -384,7 +420,29 @@ int check(vgp_lazy *h) {
 
 extern "C" {
 
+static int lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, double small, double jitter, int mode,
+                       vgp_dist *dist);
+
 int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, double small, double jitter, int mode) {
+    return lazy_create(handle, device, n, kmax, small, jitter, mode, nullptr);
+}
+
+/* Sharded form over the ranks of a connected vgp_dist (one box): the inverse factor M = L^-1 is the replica every
+ * rank already holds after vgp_dist_factor_inverse; the only O(n^2) work per selection, the triangular matrix-vector
+ * product M^T (M e_y), is split by 512-row blocks over the ranks, each rank storing its blocks' partial sums into
+ * every rank's buffer over NVLink (the tail behind the replicas), one flag barrier per selection.  The O(n t) step
+ * kernel runs replicated and sums the blocks in the single-device order, so every rank selects the same winner and
+ * scores are bitwise those of one device.  Call order: fill cov_dev (vgp_lazy_matrices) with Sigma and the replicas
+ * with Sigma, vgp_dist_factor_inverse, vgp_lazy_adopt_factor, vgp_lazy_run -- the same calls on every rank. */
+int vgp_lazy_create_dist(vgp_lazy **handle, vgp_dist *dist, int64_t n, int64_t kmax, double small, double jitter) {
+    VGP_REQUIRE(dist, "dist handle is NULL");
+    VGP_REQUIRE(dist->connected || dist->ctx.nranks == 1, "vgp_dist_connect first");
+    VGP_REQUIRE(round_up(n, TILE) == dist->n_pad, "size does not match the dist handle");
+    return lazy_create(handle, dist->device, n, kmax, small, jitter, 1, dist);
+}
+
+static int lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, double small, double jitter, int mode,
+                       vgp_dist *dist) {
     VGP_REQUIRE(handle, "handle is NULL");
     *handle = nullptr;
     VGP_REQUIRE(n > 0 && kmax > 0 && kmax <= n, "bad sizes n=%lld kmax=%lld", (long long)n, (long long)kmax);
@@ -392,6 +450,7 @@ int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, doub
     VGP_ENTER(device);
     vgp_lazy *h = new (std::nothrow) vgp_lazy();
     VGP_REQUIRE(h, "out of host memory");
+    h->dist = dist;
     h->device = device;
     h->n = n;
     h->kmax = kmax;
@@ -407,7 +466,7 @@ int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, doub
         size_t bytes;
     } allocs[] = {
         {(void **)&h->cov, mat},
-        {(void **)&h->fac, mat},
+        {(void **)&h->fac, dist ? 0 : mat},
         {(void **)&h->d, vec},
         {(void **)&h->d0, vec},
         {(void **)&h->num, vec},
@@ -415,7 +474,7 @@ int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, doub
         {(void **)&h->U, (size_t)kmax * vec},
         {(void **)&h->W, (size_t)kmax * vec},
         {(void **)&h->inv, (size_t)kmax * 8},
-        {(void **)&h->partial, (size_t)h->row_blocks * vec},
+        {(void **)&h->partial, dist ? 0 : (size_t)h->row_blocks * vec},
         {(void **)&h->partials, (size_t)h->blocks * sizeof(vgp_candidate)},
         {(void **)&h->cur, 2 * sizeof(vgp_candidate)},
         {(void **)&h->counter, sizeof(unsigned)},
@@ -423,6 +482,7 @@ int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, doub
         {(void **)&h->sel_score, (size_t)kmax * 8},
     };
     for (auto &al : allocs) {
+        if (al.bytes == 0) continue;
         cudaError_t e = cudaMalloc(al.p, al.bytes);
         if (e != cudaSuccess) {
             int rc = cuda_fail(e, "cudaMalloc (lazy greedy state)", __FILE__, __LINE__);
@@ -430,9 +490,16 @@ int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, doub
             return rc;
         }
     }
+    if (dist) {
+        VGP_REQUIRE(RB == DIST_TAIL_RB && dist->tail_rows >= 2 * h->row_blocks, "dist tail too small");
+        h->fac = dist->matrix;
+        h->partial = dist->matrix + (size_t)h->n_pad * h->n_pad;
+        h->partial_parity_stride = h->row_blocks * h->n_pad;
+        h->own_fac = h->own_partial = 0;
+    }
     cudaMemset(h->cov, 0, mat);
     cudaMemset(h->counter, 0, sizeof(unsigned));
-    cudaMemset(h->partial, 0, (size_t)h->row_blocks * vec);
+    if (!dist) cudaMemset(h->partial, 0, (size_t)h->row_blocks * vec);
     cudaMemset(h->sel, 0xff, (size_t)kmax * 8);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -447,8 +514,9 @@ int vgp_lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, doub
 int vgp_lazy_destroy(vgp_lazy *h) {
     if (!h) return VGP_OK;
     VGP_ENTER(h->device);
-    void *ptrs[] = {h->cov, h->fac, h->d, h->d0, h->num, h->taken, h->U, h->W, h->inv, h->partial, h->partials,
-                    h->cur, h->counter, h->sel, h->sel_score, h->step_scores, h->cache};
+    void *ptrs[] = {h->cov, h->own_fac ? h->fac : nullptr, h->d, h->d0, h->num, h->taken, h->U, h->W, h->inv,
+                    h->own_partial ? h->partial : nullptr, h->partials, h->cur, h->counter, h->sel, h->sel_score,
+                    h->step_scores, h->cache};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto &e : h->pe)
@@ -493,8 +561,9 @@ int vgp_lazy_adopt_factor(vgp_lazy *h, void *stream) {
         L_LAUNCH_CHECK(h);
     } else {
         dim3 grid((unsigned)h->row_blocks, (unsigned)h->row_blocks);
-        trigemv_kernel<true><<<grid, 256, 0, s>>>(h->fac, h->n_pad, h->n_pad, nullptr, h->partial);
+        trigemv_kernel<true><<<grid, 256, 0, s>>>(h->fac, h->n_pad, h->n_pad, nullptr, h->partial, peers_of(h, 0));
         L_LAUNCH_CHECK(h);
+        VGP_TRY(peers_barrier(h, s));
         colnorm_reduce_kernel<<<vb, 256, 0, s>>>(h->partial, h->n_pad, h->row_blocks, h->d0);
         L_LAUNCH_CHECK(h);
     }
@@ -524,6 +593,7 @@ static int lazy_factor_staged(vgp_lazy *h, int *info_host, cudaStream_t s);
 
 int vgp_lazy_factor(vgp_lazy *h, int *info_host, void *stream) {
     VGP_TRY(check(h));
+    VGP_REQUIRE(!h->dist, "sharded handle: factorise with vgp_dist_factor_inverse, then vgp_lazy_adopt_factor");
     VGP_ENTER(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     VGP_TRY(lazy_stage_rows(h, 0, h->n_pad, s));
@@ -564,8 +634,11 @@ int vgp_lazy_run(vgp_lazy *h, int64_t k, void *stream) {
         if (h->t > 0 && h->mode == 1) {
             dim3 grid((unsigned)h->row_blocks, (unsigned)h->row_blocks);
             if (h->profile) VGP_CUDA(cudaEventRecord(h->pe[0], s));
-            trigemv_kernel<false><<<grid, 256, 0, s>>>(h->fac, h->n_pad, h->n_pad, h->cur + ((h->t - 1) & 1), h->partial);
+            double *part = h->partial + (h->t & 1) * h->partial_parity_stride;      // peers may still read the other one
+            trigemv_kernel<false><<<grid, 256, 0, s>>>(h->fac, h->n_pad, h->n_pad, h->cur + ((h->t - 1) & 1), part,
+                                                       peers_of(h, (int)(h->t & 1)));
             L_LAUNCH_CHECK(h);
+            VGP_TRY(peers_barrier(h, s));
             if (h->profile) {
                 float ms = 0.f;
                 VGP_CUDA(cudaEventRecord(h->pe[1], s));
@@ -578,7 +651,7 @@ int vgp_lazy_run(vgp_lazy *h, int64_t k, void *stream) {
         StepArgs a;
         a.cov = h->cov;
         a.fac = h->fac;
-        a.partial = h->partial;
+        a.partial = h->partial + (h->t & 1) * h->partial_parity_stride;
         a.ld = h->n_pad;
         a.n = h->n;
         a.n_pad = h->n_pad;

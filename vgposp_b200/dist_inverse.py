@@ -95,6 +95,14 @@ class DistInverse:
         info = c_int(0)
         call("vgp_dist_spd_inverse", self.handle, ctypes.byref(info), self.stream)
 
+    def factor_inverse(self):
+        """potrf + trtri only: the replicas hold M = L^-1 afterwards (sharded lazy-column greedy)."""
+        info = c_int(0)
+        call("vgp_dist_factor_inverse", self.handle, ctypes.byref(info), self.stream)
+
+    def add_diag(self, value):
+        call("vgp_dist_add_diag", self.handle, self.n, float(value), self.stream)
+
     def stats(self):
         g, b = c_i64(0), c_i64(0)
         call("vgp_dist_stats", self.handle, ctypes.byref(g), ctypes.byref(b))

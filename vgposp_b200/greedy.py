@@ -198,6 +198,23 @@ class LazyGreedy:
         self.cov_ptr, self.fac_ptr, self.ld = cov.value, fac.value, ld.value
         self.n_pad = self.ld
 
+    @classmethod
+    def from_dist(cls, dist_inverse, kmax, small=GUARD_NUMPY, jitter=0.0):
+        """The sharded form (csrc/lazy.cu, vgp_lazy_create_dist) on the ranks of a connected DistInverse: the inverse
+        factor is that handle's replica, the triangular matrix-vector product of every selection is split over the
+        ranks.  Same calls on every rank; every rank returns the same selection."""
+        self = cls.__new__(cls)
+        self.n, self.kmax, self.device, self.stream, self.mode = dist_inverse.n, int(kmax), dist_inverse.device, \
+            dist_inverse.stream, 1
+        h = c_vp()
+        call("vgp_lazy_create_dist", ctypes.byref(h), dist_inverse.handle, self.n, self.kmax, float(small), float(jitter))
+        self.handle = h.value
+        cov, fac, ld = c_vp(), c_vp(), c_i64()
+        call("vgp_lazy_matrices", self.handle, ctypes.byref(cov), ctypes.byref(fac), ctypes.byref(ld))
+        self.cov_ptr, self.fac_ptr, self.ld = cov.value, fac.value, ld.value
+        self.n_pad = self.ld
+        return self
+
     def load_cov_host(self, cov_vv):
         a = np.asarray(cov_vv)
         if a.dtype != np.float64 or a.strides[1] != 8:
@@ -206,6 +223,11 @@ class LazyGreedy:
         call("vgp_memcpy2d_h2d", self.device, self.cov_ptr, self.ld * 8, a.ctypes.data, a.strides[0], self.n * 8,
              self.n, self.stream)
         call("vgp_stream_sync", self.device, self.stream)
+
+    def load_cov_device(self, src_ptr, src_ld):
+        """Sigma from a device matrix [n, src_ld] (e.g. the replica of the distributed inverse before it is factorised)."""
+        call("vgp_memcpy2d_d2d", self.device, self.cov_ptr, self.ld * 8, src_ptr, src_ld * 8, self.n * 8, self.n,
+             self.stream)
 
     def build_cov_expquad(self, x_dev_ptr, d, amplitude, length_scale, nugget):
         call("vgp_expquad_matrix", self.device, x_dev_ptr, self.n, x_dev_ptr, self.n, d, float(amplitude),
@@ -336,21 +358,38 @@ class ShardedPlacer:
     distributed inverse (csrc/dist.cu), the column panels cut from the replica, k selections with the peer-memory
     exchange and D2H of the result.  `dist` is torch.distributed (used only for the IPC handle exchange)."""
 
-    def __init__(self, n, kmax, rank, world, dist, device, stream=None, small=GUARD_NUMPY, jitter=0.0):
+    def __init__(self, n, kmax, rank, world, dist, device, stream=None, small=GUARD_NUMPY, jitter=0.0,
+                 formulation="auto"):
+        """formulation: "lazy" = sharded lazy-column greedy on the inverse Cholesky factor (potrf + trtri, 2/3 of the
+        inverse's flops; per selection a sharded triangular matrix-vector product, csrc/lazy.cu) -- needs the replica
+        plus a copy of Sigma on every GPU (16 n^2 bytes); "dense" = full inverse + precision downdate on column panels
+        (the north-star formulation; 8 n^2 + 24 n^2 / G bytes); "auto" = lazy when it fits in 150 GB."""
         import time
         from .dist_inverse import DistInverse
         t0 = time.perf_counter()
         self.n, self.kmax, self.rank, self.world = int(n), int(kmax), int(rank), int(world)
         self.device, self.stream = device, stream
+        self.small, self.jitter = small, jitter
+        if formulation == "auto":
+            formulation = "lazy" if 16.0 * self.n * self.n < 150e9 else "dense"
+        assert formulation in ("lazy", "dense")
+        self.formulation = formulation
         self.bounds = shard_bounds(self.n, self.world)
         self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         dev_name = "cuda:%d" % device
         self.inv = DistInverse(self.n, self.rank, self.world, device, stream=stream)
-        self.shard = GreedyShard(self.n, self.r0, self.r1, self.kmax, device, small=small, jitter=jitter, stream=stream)
         self.inv.connect_torch(dist, dev_name)
-        connect_peers_torch(self.shard, self.rank, self.world, dist, dev_name)
+        if formulation == "dense":
+            self.shard = GreedyShard(self.n, self.r0, self.r1, self.kmax, device, small=small, jitter=jitter,
+                                     stream=stream)
+            connect_peers_torch(self.shard, self.rank, self.world, dist, dev_name)
+            self.lazy = None
+        else:
+            self.shard = None
+            self.lazy = LazyGreedy.from_dist(self.inv, self.kmax, small=small, jitter=jitter)
         self.inv.fill_padding()
-        self.shard.sync()
+        call("vgp_stream_sync", device, stream)
+        dist.barrier()
         self.connect_seconds = time.perf_counter() - t0
 
     def place(self, cov_rows, k=None):
@@ -365,32 +404,49 @@ class ShardedPlacer:
             a = a[r0:r1]
         assert a.shape == (r1 - r0, n) and a.dtype == np.float64 and a.strides[1] == 8, \
             "cov_rows must be this rank's row slab"
-        secs = {}
+        secs = {"formulation": self.formulation}
         t1 = time.perf_counter()
         call("vgp_memcpy2d_h2d", self.device, inv.ptr + r0 * inv.ld * 8, inv.ld * 8, a.ctypes.data, a.strides[0], n * 8,
              r1 - r0, self.stream)
         inv.push_rows(r0, r1)
         inv.barrier()                                     # every slab has landed in every replica
-        call("vgp_memcpy2d_d2d", self.device, shard.cov_ptr, shard.ld * 8, inv.ptr + r0 * 8, inv.ld * 8, (r1 - r0) * 8,
-             n, self.stream)
-        shard.sync()
+        if self.lazy is None:
+            call("vgp_memcpy2d_d2d", self.device, shard.cov_ptr, shard.ld * 8, inv.ptr + r0 * 8, inv.ld * 8,
+                 (r1 - r0) * 8, n, self.stream)
+        else:
+            self.lazy.load_cov_device(inv.ptr, inv.ld)     # Sigma stays read-only beside the factor
+            if self.jitter != 0.0:
+                inv.add_diag(self.jitter)
+        call("vgp_stream_sync", self.device, self.stream)
         secs["h2d_push"] = time.perf_counter() - t1
         t2 = time.perf_counter()
-        inv.invert()
+        if self.lazy is None:
+            inv.invert()
+        else:
+            inv.factor_inverse()
         secs["inverse"] = time.perf_counter() - t2
         t3 = time.perf_counter()
-        shard.load_prec_device(inv.ptr, inv.ld)
-        shard.reset()
-        shard.run_peer(k)
-        shard.comm_status()
-        sel, scores = shard.results()
+        if self.lazy is None:
+            shard.load_prec_device(inv.ptr, inv.ld)
+            shard.reset()
+            shard.run_peer(k)
+            shard.comm_status()
+            sel, scores = shard.results()
+        else:
+            self.lazy.adopt_factor()
+            self.lazy.run(k)
+            sel, scores = self.lazy.results()
+            sel, scores = sel[:k], scores[:k]
         secs["selections_and_d2h"] = time.perf_counter() - t3
         secs["total"] = time.perf_counter() - t1
         check_selection(sel)
         return sel, scores, secs
 
     def close(self):
-        self.shard.close()
+        if self.shard is not None:
+            self.shard.close()
+        if self.lazy is not None:
+            self.lazy.close()
         self.inv.close()
 
 
