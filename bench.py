@@ -330,7 +330,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_e2e:
         e2e = measure_e2e(args, shard, dev, sel)
     elif world > 1 and not args.no_e2e:
-        e2e = measure_e2e_sharded(args, shard, rank, world, dev, dist, sel)
+        e2e = measure_e2e_sharded(args, shard, rank, world, dev, dist, sel, xd, (amp, ls, nugget))
     shard.close()
     elbo_sharded = None
     if world > 1 and not args.no_elbo:
@@ -585,39 +585,42 @@ def measure_lazy(args, dev, hbm_peak):
     return out
 
 
-def measure_e2e_sharded(args, shard, rank, world, dev, dist, expect_sel):
-    """N > 1: every rank holds its ROW slab of Sigma in pinned host memory (n/G x n); one call to
-    vgposp_b200.greedy.place_sharded per rank does H2D, NVLink push, distributed inverse, k selections, D2H."""
+def measure_e2e_sharded(args, shard, rank, world, dev, dist, expect_sel, xd, kernel_params):
+    """N > 1: every rank holds its ROW slab of Sigma in pinned host memory (placer.r0:r1 x n); one call to
+    vgposp_b200.greedy.ShardedPlacer.place per rank does H2D, NVLink push, distributed factorisation, k selections,
+    D2H."""
     import torch
-    from vgposp_b200 import greedy
+    from vgposp_b200 import _ffi, greedy
     from vgposp_b200._ffi import call
     n, k = args.n, args.k
-    bounds = greedy.shard_bounds(n, world)
-    r0, r1 = bounds[rank], bounds[rank + 1]
+    amp, ls, nugget = kernel_params
+    shard.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tc = time.perf_counter()
+    form = {"auto": "auto", "dense": "dense"}.get(args.e2e_formulation, "lazy")
+    placer = greedy.ShardedPlacer(n, k, rank, world, dist, dev, stream=shard.stream, formulation=form)
+    torch.cuda.synchronize()
+    dist.barrier()
+    connect = time.perf_counter() - tc
+    r0, r1 = placer.r0, placer.r1
     rows = r1 - r0
     host = ctypes.c_void_p()
-    call("vgp_host_alloc", rows * n * 8, ctypes.byref(host))
+    call("vgp_host_alloc", max(rows, 1) * n * 8, ctypes.byref(host))
     try:
-        # Sigma is symmetric: this rank's row slab is the transpose of its column panel (outside the timed region)
-        # (chunks of 4096 panel rows: the temporary stays small next to the 8 n^2 / G byte slab)
+        # this rank's row slab of Sigma, built on the device in chunks and read back (outside the timed region)
         slab = np.ctypeslib.as_array(ctypes.cast(host, ctypes.POINTER(ctypes.c_double)), shape=(rows, n))
-        chunk = np.empty((4096, rows))
-        for i in range(0, n, 4096):
-            h = min(4096, n - i)
-            call("vgp_memcpy2d_d2h", dev, chunk.ctypes.data, rows * 8, shard.cov_ptr + i * shard.ld * 8,
-                 shard.ld * 8, rows * 8, h, shard.stream)
-            shard.sync()
-            slab[:, i:i + h] = chunk[:h].T
-        del chunk
-        shard.close()
+        tmp = _ffi.DeviceArray((min(4096, max(rows, 1)), n), np.float64, dev)
+        for a in range(r0, r1, 4096):
+            h = min(4096, r1 - a)
+            call("vgp_expquad_matrix", dev, xd.ptr + a * 3 * 8, h, xd.ptr, n, 3, float(amp), float(ls), float(nugget),
+                 -a, tmp.ptr, n, shard.stream)
+            call("vgp_memcpy2d_d2h", dev, slab.ctypes.data + (a - r0) * n * 8, n * 8, tmp.ptr, n * 8, n * 8, h,
+                 shard.stream)
+            call("vgp_stream_sync", dev, shard.stream)
+        tmp.free()
         torch.cuda.synchronize()
         dist.barrier()
-        tc = time.perf_counter()
-        form = {"auto": "auto", "dense": "dense"}.get(args.e2e_formulation, "lazy")
-        placer = greedy.ShardedPlacer(n, k, rank, world, dist, dev, stream=shard.stream, formulation=form)
-        torch.cuda.synchronize()
-        dist.barrier()
-        connect = time.perf_counter() - tc
         t0 = time.perf_counter()
         sel, sc, secs = placer.place(slab, k)
         torch.cuda.synchronize()
@@ -628,6 +631,7 @@ def measure_e2e_sharded(args, shard, rank, world, dev, dist, expect_sel):
         sel_b, _, secs_b = placer.place(slab, k)
         torch.cuda.synchronize()
         wall_b = time.perf_counter() - t1
+        placer_bounds = placer.bounds
         placer.close()
     finally:
         call("vgp_host_free", host)
@@ -635,8 +639,10 @@ def measure_e2e_sharded(args, shard, rank, world, dev, dist, expect_sel):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall, connect, wall_b = float(t[0].item()), float(t[1].item()), float(t[2].item())
     same = bool(np.array_equal(sel[:len(expect_sel)], expect_sel[:k])) and bool(np.array_equal(sel, sel_b))
-    return {"value": k / wall, "unit": "selections/s", "h2d_bytes_per_step": 8.0 * n * n / k, "d2h_bytes_per_step": 16,
-            "formulation": secs["formulation"],
+    lazy = secs["formulation"] == "lazy"
+    return {"value": k / wall, "unit": "selections/s",
+            "h2d_bytes_per_step": (4.0 * n * (n + 1) if lazy else 8.0 * n * n) / k, "d2h_bytes_per_step": 16,
+            "formulation": secs["formulation"], "row_slab_bounds": [int(b) for b in placer_bounds],
             "seconds": dict(secs, total_wall_max_over_ranks=wall, connect_once_max_over_ranks=connect),
             "second_call": {"value": k / wall_b, "seconds": dict(secs_b, total_wall_max_over_ranks=wall_b)},
             "cold_call_value": k / (wall + connect), "k": k, "selection_equals_resident_run": same,

@@ -404,6 +404,11 @@ int vgp_dist_destroy(vgp_dist *handle);
 int vgp_dist_matrix(vgp_dist *handle, double **matrix_dev, int64_t *ld);
 int vgp_dist_connect(vgp_dist *handle, const void *peers, int kind);
 int vgp_dist_push_rows(vgp_dist *handle, int64_t row0, int64_t row1, void *stream);
+/* Rows [row0, row1), columns [0, ncols) of a host matrix (host_ld doubles per row; pinned memory for full speed) into
+ * this replica and every other one: chunked upload with the peer copies of each chunk under the next upload.  ncols =
+ * row1 uploads just the lower triangle's share of the rows (all the factorisation and the lazy-column greedy read). */
+int vgp_dist_upload_rows(vgp_dist *handle, const double *host, int64_t host_ld, int64_t row0, int64_t row1,
+                         int64_t ncols, void *stream);
 int vgp_dist_barrier(vgp_dist *handle, void *stream);
 int vgp_dist_spd_inverse(vgp_dist *handle, int *info_host, void *stream);
 /* potrf + trtri only: the replicas end up holding M = L^-1 (lower triangle; 2/3 of the flops of the inverse) -- the

@@ -64,7 +64,7 @@ def main():
     want2, want2_scores = go.incremental_greedy_c(cov2, k - 3)
     for form in ("dense", "lazy", "auto"):
         placer = greedy.ShardedPlacer(n, k, rank, world, dist, local, stream=stream, formulation=form)
-        sel1, sc1, secs = placer.place(cov[bounds[rank]:bounds[rank + 1]], k)
+        sel1, sc1, secs = placer.place(cov[placer.r0:placer.r1], k)
         assert secs["formulation"] == ("dense" if form == "dense" else "lazy")
         assert [int(s) for s in sel1] == want_sel, (form, rank, sel1, want_sel)
         np.testing.assert_allclose(sc1, want_scores, rtol=1e-9)

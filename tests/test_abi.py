@@ -100,3 +100,14 @@ def test_shard_bounds_cover_everything():
         assert b[0] == 0 and b[-1] == n and len(b) == g + 1
         assert all(y >= x for x, y in zip(b[:-1], b[1:]))
         assert max(y - x for x, y in zip(b[:-1], b[1:])) - min(y - x for x, y in zip(b[:-1], b[1:])) <= 1
+
+
+def test_triangle_bounds_balance_the_lower_triangle():
+    from vgposp_b200.greedy import triangle_bounds
+    for n, g in ((10, 3), (50000, 8), (700, 2), (100000, 8), (5, 1), (1200, 4)):
+        b = triangle_bounds(n, g)
+        assert b[0] == 0 and b[-1] == n and len(b) == g + 1
+        assert all(y >= x for x, y in zip(b[:-1], b[1:]))
+    b = triangle_bounds(50000, 8)
+    share = [(y * (y + 1) - x * (x + 1)) / 2 for x, y in zip(b[:-1], b[1:])]       # lower-triangle entries per slab
+    assert max(share) / (50000 * 50001 / 2 / 8) < 1.03

@@ -117,11 +117,12 @@ def test_sharded_lazy_factor_greedy_threads(n, world, k, monkeypatch):
     for r in ranks:
         r.connect_pointers([q.pointers for q in ranks])
         r.fill_padding()
+        r.load_host(np.full((n, n), np.nan))        # poison: nothing may read the strict upper triangle
     lazies = [greedy.LazyGreedy.from_dist(r, k) for r in ranks]
     bounds = [(n * g) // world for g in range(world + 1)]
-    for r in ranks:
-        r.load_host(a, bounds[r.rank], bounds[r.rank + 1])
-        r.push_rows(bounds[r.rank], bounds[r.rank + 1])
+    for r in ranks:     # each rank uploads the lower-triangle share of its row slab; the peer copies ride along
+        r0, r1 = bounds[r.rank], bounds[r.rank + 1]
+        r.upload_rows(a[r0:r1], r0, r1, ncols=r1)
     errors, out = [], [None] * world
 
     def work(i):

@@ -167,6 +167,49 @@ int vgp_dist_push_rows(vgp_dist *h, int64_t r0, int64_t r1, void *stream) {
     return VGP_OK;
 }
 
+/* Rows [r0, r1), columns [0, ncols) of a HOST matrix (pinned for full speed) into this replica and on into every
+ * other replica: the upload runs in row chunks on `stream`, the peer copies of a chunk follow it on a side stream while
+ * the next chunk uploads, peers visited in a rank-staggered order (no two ranks start on the same destination).
+ * ncols < n_pad when only the lower triangle of a symmetric matrix is needed (ncols = r1).  Returns with the side
+ * stream joined back into `stream`; follow with vgp_dist_barrier on all ranks. */
+int vgp_dist_upload_rows(vgp_dist *h, const double *host, int64_t host_ld, int64_t r0, int64_t r1, int64_t ncols,
+                         void *stream) {
+    VGP_TRY(check(h));
+    VGP_REQUIRE(h->connected || h->ctx.nranks == 1, "vgp_dist_connect first");
+    VGP_REQUIRE(r0 >= 0 && r1 >= r0 && r1 <= h->n_pad && ncols >= 0 && ncols <= h->n_pad && host_ld >= ncols,
+                "bad row / column range");
+    if (r1 == r0 || ncols == 0) return VGP_OK;
+    VGP_REQUIRE(host, "host matrix is NULL");
+    VGP_ENTER(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->push_stream) {
+        VGP_CUDA(cudaStreamCreateWithFlags(&h->push_stream, cudaStreamNonBlocking));
+        VGP_CUDA(cudaEventCreateWithFlags(&h->push_event, cudaEventDisableTiming));
+    }
+    const int64_t chunk = 1024;
+    const int G = h->ctx.nranks, me = h->ctx.rank;
+    const size_t pitch = (size_t)h->n_pad * 8, width = (size_t)ncols * 8;
+    for (int64_t c0 = r0; c0 < r1; c0 += chunk) {
+        const int64_t rows = (r1 - c0 < chunk) ? r1 - c0 : chunk;
+        double *mine = h->matrix + (size_t)c0 * h->n_pad;
+        VGP_CUDA(cudaMemcpy2DAsync(mine, pitch, host + (size_t)(c0 - r0) * host_ld, (size_t)host_ld * 8, width,
+                                   (size_t)rows, cudaMemcpyHostToDevice, s));
+        if (G == 1) continue;
+        VGP_CUDA(cudaEventRecord(h->push_event, s));
+        VGP_CUDA(cudaStreamWaitEvent(h->push_stream, h->push_event, 0));
+        for (int i = 1; i < G; ++i) {
+            const int q = (me + i) % G;
+            VGP_CUDA(cudaMemcpy2DAsync(h->peer_matrix[q] + (size_t)c0 * h->n_pad, pitch, mine, pitch, width,
+                                       (size_t)rows, cudaMemcpyDefault, h->push_stream));
+        }
+    }
+    if (G > 1) {
+        VGP_CUDA(cudaEventRecord(h->push_event, h->push_stream));
+        VGP_CUDA(cudaStreamWaitEvent(s, h->push_event, 0));
+    }
+    return VGP_OK;
+}
+
 // replica[i][i] += value for i < n (every rank on its own replica: e.g. the TF-graph variant's jitter before factorising)
 int vgp_dist_add_diag(vgp_dist *h, int64_t n, double value, void *stream) {
     VGP_TRY(check(h));
@@ -236,6 +279,11 @@ int vgp_dist_stats(vgp_dist *h, int64_t *dist_gemms, int64_t *barriers) {
 int vgp_dist_destroy(vgp_dist *h) {
     if (!h) return VGP_OK;
     VGP_ENTER(h->device);
+    if (h->push_stream) {
+        cudaStreamSynchronize(h->push_stream);
+        cudaStreamDestroy(h->push_stream);
+        cudaEventDestroy(h->push_event);
+    }
     if (h->ipc && h->connected) {
         for (int q = 0; q < h->ctx.nranks; ++q) {
             if (q == h->ctx.rank) continue;

@@ -12,6 +12,8 @@ struct vgp_dist {
     unsigned long long *flags = nullptr;        // u64[DIST_MAX] barrier words + int error
     double *peer_matrix[vgp::DIST_MAX] = {nullptr};
     int ipc = 0, connected = 0;
+    cudaStream_t push_stream = nullptr;         // vgp_dist_upload_rows: peer copies of a chunk under the next upload
+    cudaEvent_t push_event = nullptr;
     vgp::DistContext ctx;
     vgp::DenseWorkspace ws;
 };

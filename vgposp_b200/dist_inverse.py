@@ -87,6 +87,15 @@ class DistInverse:
     def push_rows(self, row0, row1):
         call("vgp_dist_push_rows", self.handle, int(row0), int(row1), self.stream)
 
+    def upload_rows(self, rows_host, row0, row1, ncols=None):
+        """Host rows [row0, row1) (array [row1 - row0, >= ncols]) into every replica; ncols = row1 for the lower
+        triangle only."""
+        a = np.asarray(rows_host)
+        ncols = self.n if ncols is None else int(ncols)
+        assert a.dtype == np.float64 and a.strides[1] == 8 and a.shape[0] == row1 - row0 and a.shape[1] >= ncols
+        call("vgp_dist_upload_rows", self.handle, a.ctypes.data, a.strides[0] // 8, int(row0), int(row1), ncols,
+             self.stream)
+
     def barrier(self):
         call("vgp_dist_barrier", self.handle, self.stream)
 

@@ -34,6 +34,15 @@ def _ptr(x):
     return x.ptr
 
 
+def triangle_bounds(n, world):
+    """Row slabs with equal shares of the LOWER TRIANGLE (row i has i + 1 entries): r_g = n sqrt(g / G), multiples of
+    128 -- the slabs the sharded lazy path uploads, where only the lower triangle of Sigma travels."""
+    b = [min(n, int(round(n * (g / world) ** 0.5 / 128.0)) * 128) for g in range(world)] + [n]
+    for g in range(1, world + 1):
+        b[g] = max(b[g], b[g - 1])
+    return b
+
+
 def shard_bounds(n, world):
     """Contiguous column ranges of the ranks: bounds[g] .. bounds[g + 1]."""
     return [(n * g) // world for g in range(world + 1)]
@@ -374,7 +383,10 @@ class ShardedPlacer:
             formulation = "lazy" if 16.0 * self.n * self.n < 150e9 else "dense"
         assert formulation in ("lazy", "dense")
         self.formulation = formulation
-        self.bounds = shard_bounds(self.n, self.world)
+        # the row slab this rank uploads: `bounds` (equal column panels <-> equal row slabs for the dense path, equal
+        # lower-triangle shares for the lazy path)
+        self.bounds = shard_bounds(self.n, self.world) if formulation == "dense" else \
+            triangle_bounds(self.n, self.world)
         self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         dev_name = "cuda:%d" % device
         self.inv = DistInverse(self.n, self.rank, self.world, device, stream=stream)
@@ -393,8 +405,9 @@ class ShardedPlacer:
         self.connect_seconds = time.perf_counter() - t0
 
     def place(self, cov_rows, k=None):
-        """`cov_rows`: this rank's HOST row slab cov_vv[bounds[rank]:bounds[rank + 1], :] (a full [n, n] matrix is
-        accepted too).  Returns (selection, scores, seconds dict)."""
+        """`cov_rows`: this rank's HOST row slab cov_vv[self.r0:self.r1, :] (self.bounds; a full [n, n] matrix is
+        accepted too; the lazy formulation reads columns [0, r1) of it only).  Returns (selection, scores, seconds
+        dict)."""
         import time
         k = self.kmax if k is None else int(k)
         assert 0 < k <= self.kmax
@@ -406,9 +419,9 @@ class ShardedPlacer:
             "cov_rows must be this rank's row slab"
         secs = {"formulation": self.formulation}
         t1 = time.perf_counter()
-        call("vgp_memcpy2d_h2d", self.device, inv.ptr + r0 * inv.ld * 8, inv.ld * 8, a.ctypes.data, a.strides[0], n * 8,
-             r1 - r0, self.stream)
-        inv.push_rows(r0, r1)
+        # dense: whole rows (the column panels of Sigma and P are cut from them); lazy: Sigma is symmetric and both the
+        # factorisation and the selection kernels read its lower triangle only -> columns [0, r1) of the slab
+        inv.upload_rows(a, r0, r1, n if self.lazy is None else r1)
         inv.barrier()                                     # every slab has landed in every replica
         if self.lazy is None:
             call("vgp_memcpy2d_d2d", self.device, shard.cov_ptr, shard.ld * 8, inv.ptr + r0 * 8, inv.ld * 8,
