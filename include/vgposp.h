@@ -406,7 +406,9 @@ int vgp_dist_connect(vgp_dist *handle, const void *peers, int kind);
 int vgp_dist_push_rows(vgp_dist *handle, int64_t row0, int64_t row1, void *stream);
 /* Rows [row0, row1), columns [0, ncols) of a host matrix (host_ld doubles per row; pinned memory for full speed) into
  * this replica and every other one: chunked upload with the peer copies of each chunk under the next upload.  ncols =
- * row1 uploads just the lower triangle's share of the rows (all the factorisation and the lazy-column greedy read). */
+ * VGP_UPLOAD_LOWER uploads just the lower triangle's share of the rows, chunk by chunk (all that the factorisation and
+ * the lazy-column greedy read of a symmetric Sigma). */
+#define VGP_UPLOAD_LOWER (-1)
 int vgp_dist_upload_rows(vgp_dist *handle, const double *host, int64_t host_ld, int64_t row0, int64_t row1,
                          int64_t ncols, void *stream);
 int vgp_dist_barrier(vgp_dist *handle, void *stream);

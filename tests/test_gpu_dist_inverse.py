@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from vgposp_b200 import _ffi
-from vgposp_b200.dist_inverse import DistInverse
+from vgposp_b200.dist_inverse import UPLOAD_LOWER, DistInverse
 
 pytestmark = pytest.mark.gpu
 D = 0
@@ -122,7 +122,7 @@ def test_sharded_lazy_factor_greedy_threads(n, world, k, monkeypatch):
     bounds = [(n * g) // world for g in range(world + 1)]
     for r in ranks:     # each rank uploads the lower-triangle share of its row slab; the peer copies ride along
         r0, r1 = bounds[r.rank], bounds[r.rank + 1]
-        r.upload_rows(a[r0:r1], r0, r1, ncols=r1)
+        r.upload_rows(a[r0:r1], r0, r1, ncols=UPLOAD_LOWER)
     errors, out = [], [None] * world
 
     def work(i):

@@ -170,12 +170,15 @@ int vgp_dist_push_rows(vgp_dist *h, int64_t r0, int64_t r1, void *stream) {
 /* Rows [r0, r1), columns [0, ncols) of a HOST matrix (pinned for full speed) into this replica and on into every
  * other replica: the upload runs in row chunks on `stream`, the peer copies of a chunk follow it on a side stream while
  * the next chunk uploads, peers visited in a rank-staggered order (no two ranks start on the same destination).
- * ncols < n_pad when only the lower triangle of a symmetric matrix is needed (ncols = r1).  Returns with the side
- * stream joined back into `stream`; follow with vgp_dist_barrier on all ranks. */
+ * ncols = VGP_UPLOAD_LOWER when only the lower triangle of a symmetric matrix is needed: each chunk of rows [c0, c1)
+ * travels with columns [0, c1).  Returns with the side stream joined back into `stream`; follow with vgp_dist_barrier
+ * on all ranks. */
 int vgp_dist_upload_rows(vgp_dist *h, const double *host, int64_t host_ld, int64_t r0, int64_t r1, int64_t ncols,
                          void *stream) {
     VGP_TRY(check(h));
     VGP_REQUIRE(h->connected || h->ctx.nranks == 1, "vgp_dist_connect first");
+    const bool lower = ncols == VGP_UPLOAD_LOWER;        // every row chunk [c0, c1) travels with columns [0, c1)
+    if (lower) ncols = r1;
     VGP_REQUIRE(r0 >= 0 && r1 >= r0 && r1 <= h->n_pad && ncols >= 0 && ncols <= h->n_pad && host_ld >= ncols,
                 "bad row / column range");
     if (r1 == r0 || ncols == 0) return VGP_OK;
@@ -188,9 +191,10 @@ int vgp_dist_upload_rows(vgp_dist *h, const double *host, int64_t host_ld, int64
     }
     const int64_t chunk = 1024;
     const int G = h->ctx.nranks, me = h->ctx.rank;
-    const size_t pitch = (size_t)h->n_pad * 8, width = (size_t)ncols * 8;
+    const size_t pitch = (size_t)h->n_pad * 8;
     for (int64_t c0 = r0; c0 < r1; c0 += chunk) {
         const int64_t rows = (r1 - c0 < chunk) ? r1 - c0 : chunk;
+        const size_t width = (size_t)(lower ? c0 + rows : ncols) * 8;
         double *mine = h->matrix + (size_t)c0 * h->n_pad;
         VGP_CUDA(cudaMemcpy2DAsync(mine, pitch, host + (size_t)(c0 - r0) * host_ld, (size_t)host_ld * 8, width,
                                    (size_t)rows, cudaMemcpyHostToDevice, s));

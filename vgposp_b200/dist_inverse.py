@@ -14,6 +14,7 @@ from . import _ffi
 from ._ffi import call, c_i64, c_int, c_vp
 
 IPC_BYTES = 128
+UPLOAD_LOWER = -1          # VGP_UPLOAD_LOWER
 
 
 class DistInverse:
@@ -88,11 +89,12 @@ class DistInverse:
         call("vgp_dist_push_rows", self.handle, int(row0), int(row1), self.stream)
 
     def upload_rows(self, rows_host, row0, row1, ncols=None):
-        """Host rows [row0, row1) (array [row1 - row0, >= ncols]) into every replica; ncols = row1 for the lower
-        triangle only."""
+        """Host rows [row0, row1) (array [row1 - row0, >= ncols]) into every replica; ncols = UPLOAD_LOWER for the
+        lower triangle only."""
         a = np.asarray(rows_host)
         ncols = self.n if ncols is None else int(ncols)
-        assert a.dtype == np.float64 and a.strides[1] == 8 and a.shape[0] == row1 - row0 and a.shape[1] >= ncols
+        assert a.dtype == np.float64 and a.strides[1] == 8 and a.shape[0] == row1 - row0
+        assert a.shape[1] >= (row1 if ncols == UPLOAD_LOWER else ncols)
         call("vgp_dist_upload_rows", self.handle, a.ctypes.data, a.strides[0] // 8, int(row0), int(row1), ncols,
              self.stream)
 

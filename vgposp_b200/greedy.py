@@ -19,6 +19,7 @@ import numpy as np
 
 from . import _ffi
 from ._ffi import call, c_i64, c_int, c_vp
+from .dist_inverse import UPLOAD_LOWER
 
 GUARD_NUMPY = 1e-8        # placement_algorithm2.py:116,198
 GUARD_TF_GRAPH = 1e-7     # snippets_a2.py:480
@@ -235,8 +236,11 @@ class LazyGreedy:
 
     def load_cov_device(self, src_ptr, src_ld):
         """Sigma from a device matrix [n, src_ld] (e.g. the replica of the distributed inverse before it is factorised)."""
-        call("vgp_memcpy2d_d2d", self.device, self.cov_ptr, self.ld * 8, src_ptr, src_ld * 8, self.n * 8, self.n,
-             self.stream)
+        if src_ld == self.ld:           # one contiguous copy (3x the speed of the pitched form)
+            call("vgp_memcpy_d2d", self.device, self.cov_ptr, src_ptr, self.n * self.ld * 8, self.stream)
+        else:
+            call("vgp_memcpy2d_d2d", self.device, self.cov_ptr, self.ld * 8, src_ptr, src_ld * 8, self.n * 8, self.n,
+                 self.stream)
 
     def build_cov_expquad(self, x_dev_ptr, d, amplitude, length_scale, nugget):
         call("vgp_expquad_matrix", self.device, x_dev_ptr, self.n, x_dev_ptr, self.n, d, float(amplitude),
@@ -420,8 +424,8 @@ class ShardedPlacer:
         secs = {"formulation": self.formulation}
         t1 = time.perf_counter()
         # dense: whole rows (the column panels of Sigma and P are cut from them); lazy: Sigma is symmetric and both the
-        # factorisation and the selection kernels read its lower triangle only -> columns [0, r1) of the slab
-        inv.upload_rows(a, r0, r1, n if self.lazy is None else r1)
+        # factorisation and the selection kernels read its lower triangle only
+        inv.upload_rows(a, r0, r1, n if self.lazy is None else UPLOAD_LOWER)
         inv.barrier()                                     # every slab has landed in every replica
         if self.lazy is None:
             call("vgp_memcpy2d_d2d", self.device, shard.cov_ptr, shard.ld * 8, inv.ptr + r0 * 8, inv.ld * 8,
