@@ -419,6 +419,17 @@ int vgp_dist_factor_inverse(vgp_dist *handle, int *info_host, void *stream);
 int vgp_dist_add_diag(vgp_dist *handle, int64_t n, double value, void *stream);
 int vgp_dist_stats(vgp_dist *handle, int64_t *distributed_gemms, int64_t *barriers);
 
+/* ---------------------------------------------------------------- experimental: FP64 GEMM on the int8 tensor cores */
+/* NOT on any default path.  C[m][n] = alpha op(A) op(B) + beta C with FP64-class accuracy, the products taken exactly on
+ * tcgen05.mma kind::i8 after an error-free split of the operands into `slices` 7-bit digit planes (Ozaki scheme;
+ * csrc/emulated.cu, tools/ozaki_prototype.py).  Same operand convention as the dense layer: trans_a == 0: A stored
+ * [m][k], 1: [k][m]; trans_b == 0: B stored [k][n], 1: [n][k].  lower != 0: only the 128 x 128 tiles on or below the
+ * diagonal.  Candidate replacement for the DMMA products of potrf / trtri (placement_algorithm2.py:399-413 via the
+ * seed inverse); to be validated on the GPU before anything routes through it. */
+int vgp_gemm_emulated(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                      const double *a_dev, int64_t lda, const double *b_dev, int64_t ldb, double beta, double *c_dev,
+                      int64_t ldc, int slices, int lower, void *stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

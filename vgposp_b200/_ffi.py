@@ -118,6 +118,8 @@ SIGNATURES = {
     "vgp_dist_matrix": [c_vp, P(c_vp), P(c_i64)],
     "vgp_dist_connect": [c_vp, c_vp, c_int],
     "vgp_dist_push_rows": [c_vp, c_i64, c_i64, c_vp],
+    "vgp_gemm_emulated": [c_int, c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp,
+                          c_i64, c_int, c_int, c_vp],
     "vgp_dist_upload_rows": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
     "vgp_dist_barrier": [c_vp, c_vp],
     "vgp_dist_spd_inverse": [c_vp, P(c_int), c_vp],

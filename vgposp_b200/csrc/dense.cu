@@ -714,6 +714,12 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
         VGP_TRY(gate_wait(c, m, s));
     }
     DistContext *dc = g_dist;
+    // opt-in experiment: large products on the int8 tensor cores (emulated.cu); never taken unless the variable is set
+    static const int emu_slices = getenv("VGP_GEMM_EMULATE") ? atoi(getenv("VGP_GEMM_EMULATE")) : 0;
+    static const int64_t emu_min = getenv("VGP_GEMM_EMULATE_MIN") ? atoll(getenv("VGP_GEMM_EMULATE_MIN")) : 2048;
+    if (emu_slices >= 2 && !(dc && dc->nranks > 1) && m >= emu_min && n >= emu_min && 2 * k >= emu_min)
+        return emulated_gemm(trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, emu_slices,
+                             tiles == GEMM_LOWER ? 1 : 0, s);
     if (dc && dc->nranks > 1) {
         const int64_t tm = m / BM, tn = n / BN;
         const int64_t total = tiles == GEMM_LOWER ? tm * (tm + 1) / 2 : tm * tn;

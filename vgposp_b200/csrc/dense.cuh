@@ -61,6 +61,12 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
                int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, GemmTiles tiles,
                cudaStream_t s);
 
+// EXPERIMENTAL (emulated.cu): the same product on the int8 tensor cores after an error-free split into `slices` 7-bit
+// digit planes.  dense_gemm routes large products through it only when VGP_GEMM_EMULATE=<slices> is set.
+int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a, int64_t lda,
+                  const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int slices, int lower,
+                  cudaStream_t s);
+
 int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                       int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,
                       double *partial, cudaStream_t s, GemmTiles tiles = GEMM_FULL);

@@ -1,0 +1,488 @@
+// EXPERIMENTAL, not on any default path: FP64 GEMM on the int8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+// The factorisations behind the placement path (potrf / trtri: SURVEY.md section 8d, "Seed inverse") are bound by the
+// FP64 tensor pipe, which tops out at ~37 TFLOP/s on B200 (DMMA; profiles/r01_ncu_gemm_summary.txt).  The int8 path of
+// the 5th-generation tensor cores is two orders of magnitude wider.  Ozaki's error-free splitting carries an FP64
+// product on it: every operand row is scaled by a power of two to |x| < 1 and cut into s signed digits of W = 7 bits,
+//     A[i][:] = 2^ea[i] * sum_t QA_t[i][:] 2^(-W (t + 1)),      QA_t in [-127, 127],
+// (columns of B likewise), the digit planes are multiplied exactly in int32,
+//     C = 2^(ea[i] + eb[j]) * sum_{g < s} 2^(-W (g + 2)) * sum_{t <= g} QA_t QB_{g-t}^T,
+// and the s group sums are combined in FP64.  tools/ozaki_prototype.py measures what s buys on this workload's
+// matrices: s = 8 (36 integer products) gives a product within 1.4e-14 of exact (native FP64: 1.5e-15), identical
+// greedy selections and scores within 1.5e-13; s = 7: 1.4e-12 / 1.3e-11.
+//
+// Layout here: digit planes Q[t][rows_pad][k_pad] int8, k-contiguous, fetched by TMA (SWIZZLE_128B boxes of 128 rows x
+// 128 k).  One CTA per 128 x 128 tile of C: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 =
+// epilogue.  For group g the k loop runs over the concatenation [QA_0 | ... | QA_g] x [QB_g | ... | QB_0] into one
+// int32 accumulator (128 TMEM columns, double-buffered so the epilogue of one group overlaps the MMAs of the next); the
+// epilogue converts each group to FP64, scales it by 2^(-W (g + 2)) and adds it to register accumulators, smallest
+// group first; the last step applies 2^(ea + eb), alpha and beta.  int32 cannot overflow while s * k * 127^2 < 2^31;
+// the host splits k into chunks of 8192.
+//
+// Status: compiles for sm_100a; numerics and speed are to be validated on the GPU before anything routes through it
+// (tests/test_gpu_emulated_gemm.py runs only with VGP_TEST_EMULATED=1).
+#include <cuda.h>
+
+#include "dense.cuh"
+
+namespace vgp {
+namespace emu {
+
+constexpr int W = 7;
+constexpr int S_MAX = 9;
+constexpr int BM = 128, BN = 128, BKB = 128;          // C tile; k block in bytes (= int8 elements)
+constexpr int UMMA_K = 32;                            // k per tcgen05.mma.kind::i8
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 8, THREADS = 64 + 32 * EPI_WARPS;
+constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers
+constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 8;   // full[], empty[], tmem_full[2], tmem_empty[2], tmem base
+constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BN * 4;
+constexpr int64_t K_CHUNK = 8192;
+
+struct GemmArgs {
+    int64_t m, n;                 // real extent of C (stores are guarded)
+    int64_t m_pad, n_pad;         // rows per digit plane
+    int kblocks;                  // k_pad / BKB
+    int s;
+    const int *ea, *eb;           // [m_pad], [n_pad]
+    double *c;
+    int64_t ldc;
+    double alpha, beta;
+    int lower;                    // skip tiles strictly above the diagonal
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 8000000000LL) __trap();      // ~4 s: fail the launch instead of hanging the device
+    }
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+// shared-memory matrix descriptor: k-major operand tile, 128-byte rows, SWIZZLE_128B (8-row groups 1024 bytes apart)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);            // start address, 16-byte units
+    d |= (unsigned long long)1 << 16;                                // leading byte offset: unused for swizzled k-major
+    d |= (unsigned long long)(1024 >> 4) << 32;                      // stride byte offset between 8-row groups
+    d |= (unsigned long long)1 << 46;                                // descriptor version (sm_100)
+    d |= (unsigned long long)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::i8: D = s32, A = B = signed 8 bit, both k-major, N x M
+constexpr unsigned IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {      // arrives on `bar` once all MMAs issued so far are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned addr, int (&v)[32]) {   // this warp's 32 lanes x 32 columns
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ the GEMM
+__global__ void __launch_bounds__(THREADS, 1)
+    emu_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
+    extern __shared__ unsigned char raw[];
+    const unsigned raw_addr = smem_u32(raw);
+    unsigned char *sm = raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + STAGES * STAGE_BYTES);
+    unsigned long long *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * STAGES + 4);
+    int *eb_tile = reinterpret_cast<int *>(sm + STAGES * STAGE_BYTES + BAR_BYTES);
+
+    const int tm = blockIdx.y, tn = blockIdx.x;
+    if (p.lower && tn > tm) return;
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(&full[i]), 1);
+            mbar_init(smem_u32(&empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&tfull[i]), 1);
+            mbar_init(smem_u32(&tempty[i]), EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    if (warp == 1) {      // this warp owns the tensor memory: allocate, later free
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid >= 64 && tid < 64 + BN) eb_tile[tid - 64] = p.eb[n0 + tid - 64];
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+
+    const int KB = p.kblocks, S = p.s;
+    if (warp == 0) {
+        // ===== TMA producer: groups g = S-1 .. 0, inside a group the digit pairs (t, g - t), inside a pair the k blocks
+        if (elect_one()) {
+            int it = 0;
+            for (int g = S - 1; g >= 0; --g)
+                for (int t = 0; t <= g; ++t) {
+                    const int row_a = (int)((int64_t)t * p.m_pad + m0), row_b = (int)((int64_t)(g - t) * p.n_pad + n0);
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const int stage = it % STAGES;
+                        if (it >= STAGES) mbar_wait(smem_u32(&empty[stage]), ((it / STAGES) - 1) & 1);
+                        const unsigned bar = smem_u32(&full[stage]);
+                        const unsigned dst = smem_u32(sm + stage * STAGE_BYTES);
+                        mbar_expect_tx(bar, STAGE_BYTES);
+                        tma_load_2d(dst, &map_a, kb * BKB, row_a, bar);
+                        tma_load_2d(dst + A_BYTES, &map_b, kb * BKB, row_b, bar);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        int it = 0;
+        for (int g = S - 1, gi = 0; g >= 0; --g, ++gi) {
+            const int buf = gi & 1;
+            if (gi >= 2) mbar_wait(smem_u32(&tempty[buf]), ((gi >> 1) - 1) & 1);     // epilogue has drained this buffer
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const unsigned tmem_d = tmem_base + (unsigned)(buf * BN);
+            const int steps = (g + 1) * KB;
+            for (int st = 0; st < steps; ++st, ++it) {
+                const int stage = it % STAGES;
+                mbar_wait(smem_u32(&full[stage]), (it / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (elect_one()) {
+                    const unsigned a_addr = smem_u32(sm + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BKB / UMMA_K; ++k)
+                        umma_i8(tmem_d, umma_desc(a_addr + k * UMMA_K), umma_desc(b_addr + k * UMMA_K),
+                                (st > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(smem_u32(&empty[stage]));                            // frees the slot when the MMAs are done
+                    if (st == steps - 1) umma_commit(smem_u32(&tfull[buf]));         // group complete -> epilogue
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (one C row per thread), columns 64 half .. +63
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        double acc[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) acc[c] = 0.0;
+        for (int g = S - 1, gi = 0; g >= 0; --g, ++gi) {
+            const int buf = gi & 1;
+            mbar_wait(smem_u32(&tfull[buf]), (gi >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const double scale = scalbn(1.0, -W * (g + 2));
+            const unsigned addr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * BN + half * 64);
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                int v[32];
+                tmem_ld32(addr + part * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[part * 32 + c] = fma((double)v[c], scale, acc[part * 32 + c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty[buf]));
+        }
+        const int64_t i = m0 + row;
+        if (i < p.m) {
+            const int ea = p.ea[i];
+            double *crow = p.c + i * p.ldc + n0 + half * 64;
+#pragma unroll
+            for (int c = 0; c < 64; c += 2) {
+                const int64_t j = n0 + half * 64 + c;
+                if (j + 1 < p.n) {
+                    double2 o;
+                    o.x = p.alpha * scalbn(acc[c], ea + eb_tile[half * 64 + c]);
+                    o.y = p.alpha * scalbn(acc[c + 1], ea + eb_tile[half * 64 + c + 1]);
+                    if (p.beta != 0.0) {
+                        const double2 old = *reinterpret_cast<const double2 *>(crow + c);
+                        o.x = fma(p.beta, old.x, o.x);
+                        o.y = fma(p.beta, old.y, o.y);
+                    }
+                    *reinterpret_cast<double2 *>(crow + c) = o;
+                } else if (j < p.n) {
+                    double o = p.alpha * scalbn(acc[c], ea + eb_tile[half * 64 + c]);
+                    if (p.beta != 0.0) o = fma(p.beta, crow[c], o);
+                    crow[c] = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ digit planes
+// Element (r, k) of the operand lives at x[r * rs + k * ks] (one of rs, ks is 1).
+// e[r] = exponent with |x[r][:]| 2^-e < 1 (0 for an all-zero row).  One CTA per 32 rows.
+__global__ void __launch_bounds__(256) row_exponent_kernel(const double *__restrict__ x, int64_t rs, int64_t ks, int64_t rows,
+                                                           int64_t k, int64_t rows_pad, int *__restrict__ e) {
+    __shared__ double part[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    if (ks == 1) {                                   // k-contiguous: a warp walks along k, four rows per warp
+        for (int j = 0; j < 4; ++j) {
+            const int64_t r = r0 + warp * 4 + j;
+            double mx = 0.0;
+            if (r < rows)
+                for (int64_t c = lane; c < k; c += 32) mx = fmax(mx, fabs(x[r * rs + c]));
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) part[0][warp * 4 + j] = mx;
+        }
+        __syncthreads();
+    } else {                                         // row-contiguous: lanes along the rows, warps interleaved along k
+        const int64_t r = r0 + lane;
+        double mx = 0.0;
+        if (r < rows)
+            for (int64_t c = warp; c < k; c += 8) mx = fmax(mx, fabs(x[r * rs + c * ks]));
+        part[warp][lane] = mx;
+        __syncthreads();
+        if (warp == 0) {
+            for (int w = 1; w < 8; ++w) mx = fmax(mx, part[w][lane]);
+            part[0][lane] = mx;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        const int64_t r = r0 + threadIdx.x;
+        if (r < rows_pad) {
+            const double mx = part[0][threadIdx.x];
+            e[r] = (r < rows && mx > 0.0) ? ilogb(mx) + 1 : 0;
+        }
+    }
+}
+
+// q[t][r][c] (t < s, planes of rows_pad x k_pad bytes) = digit t of x[r][c] 2^-e[r]; zeros in the padding.
+// One CTA per 32 rows x 128 k.
+__global__ void __launch_bounds__(256) digit_planes_kernel(const double *__restrict__ x, int64_t rs, int64_t ks, int64_t rows,
+                                                           int64_t k, int64_t rows_pad, int64_t k_pad,
+                                                           const int *__restrict__ e, int s, signed char *__restrict__ q) {
+    __shared__ double tile[32][129];
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ks == 1) {
+        for (int rr = warp; rr < 32; rr += 8)
+            for (int cc = lane; cc < 128; cc += 32) {
+                const int64_t r = r0 + rr, c = c0 + cc;
+                tile[rr][cc] = (r < rows && c < k) ? x[r * rs + c] : 0.0;
+            }
+    } else {
+        for (int cc = warp; cc < 128; cc += 8) {
+            const int64_t r = r0 + lane, c = c0 + cc;
+            tile[lane][cc] = (r < rows && c < k) ? x[r * rs + c * ks] : 0.0;
+        }
+    }
+    __syncthreads();
+    const size_t plane = (size_t)rows_pad * (size_t)k_pad;
+    for (int rr = warp; rr < 32; rr += 8) {
+        const int64_t r = r0 + rr;
+        if (r >= rows_pad) break;
+        const int er = e[r];
+        for (int cc = lane; cc < 128; cc += 32) {
+            double v = scalbn(tile[rr][cc], -er);                  // |v| < 1, exact
+            signed char *dst = q + (size_t)r * (size_t)k_pad + (size_t)(c0 + cc);
+            for (int t = 0; t < s; ++t) {
+                v *= 128.0;
+                const int d = __double2int_rz(v);                  // |d| <= 127
+                v -= (double)d;
+                dst[(size_t)t * plane] = (signed char)d;
+            }
+        }
+    }
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (TensorMapEncodeFn)ptr;
+    }
+    return fn;
+}
+
+static int plane_map(CUtensorMap *map, const signed char *base, int64_t rows_total, int64_t k_pad) {
+    TensorMapEncodeFn enc = encoder();
+    VGP_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows_total};
+    const cuuint64_t strides[1] = {(cuuint64_t)k_pad};
+    const cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VGP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return VGP_OK;
+}
+
+static int slice_operand(const double *x, int64_t rs, int64_t ks, int64_t rows, int64_t k, int64_t rows_pad, int64_t k_pad,
+                         int s, int *e, signed char *q, cudaStream_t st) {
+    row_exponent_kernel<<<(unsigned)(rows_pad / 32), 256, 0, st>>>(x, rs, ks, rows, k, rows_pad, e);
+    VGP_LAUNCH_CHECK();
+    digit_planes_kernel<<<dim3((unsigned)(k_pad / 128), (unsigned)(rows_pad / 32)), 256, 0, st>>>(x, rs, ks, rows, k, rows_pad,
+                                                                                                   k_pad, e, s, q);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
+// Digit planes and exponents of one product, kept per host thread and device and only ever grown (the factorisations
+// issue hundreds of products of shrinking size; the first large one sizes it).
+struct Workspace {
+    int device = -1;
+    signed char *qa = nullptr, *qb = nullptr;
+    int *ea = nullptr, *eb = nullptr;
+    size_t qa_bytes = 0, qb_bytes = 0, ea_rows = 0, eb_rows = 0;
+};
+static thread_local Workspace g_ws[16];
+
+static int grow(void **ptr, size_t *have, size_t want, cudaStream_t st) {
+    if (*have >= want) return VGP_OK;
+    VGP_CUDA(cudaStreamSynchronize(st));                // earlier products may still read the old planes
+    if (*ptr) VGP_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *have = 0;
+    VGP_CUDA(cudaMalloc(ptr, want));
+    *have = want;
+    return VGP_OK;
+}
+
+}  // namespace emu
+
+// Asynchronous on `st`; same operand convention as dense_gemm.  C must not alias A or B (with k > K_CHUNK the second
+// chunk's planes would be cut from an already updated operand).
+int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a, int64_t lda,
+                  const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int slices, int lower,
+                  cudaStream_t st) {
+    using namespace emu;
+    VGP_REQUIRE(slices >= 2 && slices <= S_MAX, "slices must be in [2, %d]", S_MAX);
+    VGP_REQUIRE(ldc % 2 == 0 && ((uintptr_t)c & 15) == 0, "C must be 16-byte aligned with an even leading dimension");
+    VGP_REQUIRE((const double *)c != a && (const double *)c != b, "emulated_gemm: C aliases an operand");
+    if (m == 0 || n == 0) return VGP_OK;
+    int device = 0;
+    VGP_CUDA(cudaGetDevice(&device));
+    VGP_REQUIRE(device >= 0 && device < 16, "device ordinal out of range");
+    static bool configured[16] = {};
+    if (!configured[device]) {
+        VGP_CUDA(cudaFuncSetAttribute(emu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured[device] = true;
+    }
+    Workspace &ws = g_ws[device];
+    const int64_t m_pad = round_up(m, BM), n_pad = round_up(n, BN);
+    const int64_t kc_max = k < K_CHUNK ? round_up(k > 0 ? k : 1, BKB) : K_CHUNK;
+    VGP_TRY(grow((void **)&ws.qa, &ws.qa_bytes, (size_t)slices * m_pad * kc_max, st));
+    VGP_TRY(grow((void **)&ws.qb, &ws.qb_bytes, (size_t)slices * n_pad * kc_max, st));
+    size_t ea_bytes = ws.ea_rows * 4, eb_bytes = ws.eb_rows * 4;
+    VGP_TRY(grow((void **)&ws.ea, &ea_bytes, (size_t)m_pad * 4, st));
+    VGP_TRY(grow((void **)&ws.eb, &eb_bytes, (size_t)n_pad * 4, st));
+    ws.ea_rows = ea_bytes / 4;
+    ws.eb_rows = eb_bytes / 4;
+    const int64_t a_rs = trans_a ? 1 : lda, a_ks = trans_a ? lda : 1;
+    const int64_t b_rs = trans_b ? ldb : 1, b_ks = trans_b ? 1 : ldb;
+    for (int64_t k0 = 0; k0 < k || k0 == 0; k0 += K_CHUNK) {
+        const int64_t kc = k - k0 < K_CHUNK ? k - k0 : K_CHUNK;
+        const int64_t k_pad = round_up(kc > 0 ? kc : 1, BKB);
+        VGP_TRY(slice_operand(a + k0 * a_ks, a_rs, a_ks, m, kc, m_pad, k_pad, slices, ws.ea, ws.qa, st));
+        VGP_TRY(slice_operand(b + k0 * b_ks, b_rs, b_ks, n, kc, n_pad, k_pad, slices, ws.eb, ws.qb, st));
+        alignas(64) CUtensorMap ma, mb;
+        VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad));
+        VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad));
+        GemmArgs p;
+        p.m = m;
+        p.n = n;
+        p.m_pad = m_pad;
+        p.n_pad = n_pad;
+        p.kblocks = (int)(k_pad / BKB);
+        p.s = slices;
+        p.ea = ws.ea;
+        p.eb = ws.eb;
+        p.c = c;
+        p.ldc = ldc;
+        p.alpha = alpha;
+        p.beta = k0 == 0 ? beta : 1.0;
+        p.lower = lower;
+        emu_gemm_kernel<<<dim3((unsigned)(n_pad / BN), (unsigned)(m_pad / BM)), THREADS, SMEM, st>>>(ma, mb, p);
+        VGP_LAUNCH_CHECK();
+        if (k == 0) break;
+    }
+    return VGP_OK;
+}
+
+}  // namespace vgp
+
+using namespace vgp;
+
+/* EXPERIMENTAL.  C[m][n] = alpha op(A) op(B) + beta C in FP64 accuracy class, the products on the int8 tensor cores
+ * (see the header of this file).  trans_a == 0: A stored [m][k], 1: [k][m]; trans_b == 0: B stored [k][n], 1: [n][k]
+ * (dense_gemm's convention).  slices in [2, 9]; lower != 0 computes only the 128 x 128 tiles on or below the diagonal.
+ * The digit planes (slices * (m + n) * min(k, 8192) bytes) live in a grow-only workspace per host thread and device.
+ * Asynchronous on `stream`. */
+int vgp_gemm_emulated(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                      const double *a_dev, int64_t lda, const double *b_dev, int64_t ldb, double beta, double *c_dev,
+                      int64_t ldc, int slices, int lower, void *stream) {
+    VGP_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
+    VGP_REQUIRE(a_dev && b_dev && c_dev, "NULL matrix");
+    VGP_ENTER(device);
+    return emulated_gemm(trans_a, trans_b, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, slices, lower,
+                         (cudaStream_t)stream);
+}
