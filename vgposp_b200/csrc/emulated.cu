@@ -89,23 +89,30 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 // shared-memory matrix descriptor: k-major operand tile, 128-byte rows, SWIZZLE_128B (8-row groups 1024 bytes apart)
+// ROW_BYTES = 128: SWIZZLE_128B (layout code 2), 64: SWIZZLE_64B (code 4); 8-row groups are 8 * ROW_BYTES apart
+template <int ROW_BYTES>
 __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
+    static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "swizzle span");
     unsigned long long d = 0;
     d |= (unsigned long long)((smem_addr >> 4) & 0x3fff);            // start address, 16-byte units
     d |= (unsigned long long)1 << 16;                                // leading byte offset: unused for swizzled k-major
-    d |= (unsigned long long)(1024 >> 4) << 32;                      // stride byte offset between 8-row groups
+    d |= (unsigned long long)((8 * ROW_BYTES) >> 4) << 32;           // stride byte offset between 8-row groups
     d |= (unsigned long long)1 << 46;                                // descriptor version (sm_100)
-    d |= (unsigned long long)2 << 61;                                // SWIZZLE_128B
+    d |= (unsigned long long)(ROW_BYTES == 128 ? 2 : 4) << 61;
     return d;
 }
 // instruction descriptor, kind::i8: D = s32, A = B = signed 8 bit, both k-major, N x M
-constexpr unsigned IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(BM >> 4) << 24);
+constexpr unsigned idesc_i8(int m, int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+constexpr unsigned IDESC = idesc_i8(BM, BN);
 
-__device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+__device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
+                                        unsigned accumulate) {
     asm volatile(
         "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
         " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned bar) {      // arrives on `bar` once all MMAs issued so far are done
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     const unsigned a_addr = smem_u32(sm + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BKB / UMMA_K; ++k)
-                        umma_i8(tmem_d, umma_desc(a_addr + k * UMMA_K), umma_desc(b_addr + k * UMMA_K),
+                        umma_i8(tmem_d, umma_desc<128>(a_addr + k * UMMA_K), umma_desc<128>(b_addr + k * UMMA_K), IDESC,
                                 (st > 0 || k > 0) ? 1u : 0u);
                     umma_commit(smem_u32(&empty[stage]));                            // frees the slot when the MMAs are done
                     if (st == steps - 1) umma_commit(smem_u32(&tfull[buf]));         // group complete -> epilogue
@@ -265,6 +272,140 @@ __global__ void __launch_bounds__(THREADS, 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
+
+// ------------------------------------------------------------------------------------------------ variant 2
+// All digit planes of a k block resident: one CTA per 128 x 64 tile of C keeps the s group accumulators side by side in
+// tensor memory (s * 64 <= 512 columns) and, per 64-byte k block, loads the s plane tiles of A and of B once (16 TMA
+// boxes, SWIZZLE_64B) to feed all s (s + 1) / 2 plane pairs -- 96 KB for 72 MMAs (42 bytes per MMA cycle) where the
+// group-by-group kernel above moves 32 KB for 4 (128 bytes per cycle).  Same integer sums, same FP64 recombination
+// order: bitwise the same C.
+namespace v2 {
+constexpr int BN2 = 64, BKB2 = 64, STAGES2 = 2, S2_MAX = 8;
+constexpr int A2 = BM * BKB2, B2 = BN2 * BKB2;                    // one plane tile of A / B
+constexpr int STAGE2 = S2_MAX * (A2 + B2);
+constexpr int BAR2 = (2 * STAGES2 + 1) * 8 + 8;
+constexpr int SMEM2 = STAGES2 * STAGE2 + 1024 + BAR2 + BN2 * 4;
+constexpr unsigned IDESC2 = idesc_i8(BM, BN2);
+
+__global__ void __launch_bounds__(THREADS, 1)
+    emu_gemm_resident_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
+    extern __shared__ unsigned char raw[];
+    const unsigned raw_addr = smem_u32(raw);
+    unsigned char *sm = raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + STAGES2 * STAGE2);
+    unsigned long long *full = bars, *empty = bars + STAGES2, *tfull = bars + 2 * STAGES2;
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * STAGES2 + 1);
+    int *eb_tile = reinterpret_cast<int *>(sm + STAGES2 * STAGE2 + BAR2);
+
+    const int tm = blockIdx.y, tn = blockIdx.x;
+    if (p.lower && tn * BN2 > tm * BM + (BM - 1)) return;           // wholly above the diagonal
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = p.s, KB = p.kblocks * (BKB / BKB2);
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES2; ++i) {
+            mbar_init(smem_u32(&full[i]), 1);
+            mbar_init(smem_u32(&empty[i]), 1);
+        }
+        mbar_init(smem_u32(tfull), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid >= 64 && tid < 64 + BN2) eb_tile[tid - 64] = p.eb[n0 + tid - 64];
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int stage = kb % STAGES2;
+                if (kb >= STAGES2) mbar_wait(smem_u32(&empty[stage]), ((kb / STAGES2) - 1) & 1);
+                const unsigned bar = smem_u32(&full[stage]);
+                const unsigned dst = smem_u32(sm + stage * STAGE2);
+                mbar_expect_tx(bar, (unsigned)(S * (A2 + B2)));
+                for (int t = 0; t < S; ++t) {
+                    tma_load_2d(dst + t * A2, &map_a, kb * BKB2, (int)((int64_t)t * p.m_pad + m0), bar);
+                    tma_load_2d(dst + S2_MAX * A2 + t * B2, &map_b, kb * BKB2, (int)((int64_t)t * p.n_pad + n0), bar);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        for (int kb = 0; kb < KB; ++kb) {
+            const int stage = kb % STAGES2;
+            mbar_wait(smem_u32(&full[stage]), (kb / STAGES2) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (elect_one()) {
+                const unsigned a_addr = smem_u32(sm + stage * STAGE2), b_addr = a_addr + S2_MAX * A2;
+                for (int t = 0; t < S; ++t)
+                    for (int u = 0; t + u < S; ++u)
+#pragma unroll
+                        for (int k = 0; k < BKB2 / UMMA_K; ++k)
+                            umma_i8(tmem_base + (unsigned)((t + u) * BN2), umma_desc<64>(a_addr + t * A2 + k * UMMA_K),
+                                    umma_desc<64>(b_addr + u * B2 + k * UMMA_K), IDESC2,
+                                    (kb == 0 && t == 0 && k == 0) ? 0u : 1u);      // first touch of group t + u
+                umma_commit(smem_u32(&empty[stage]));
+                if (kb == KB - 1) umma_commit(smem_u32(tfull));
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;            // TMEM lane quarter; 32-column half of the tile
+        const int row = q * 32 + lane;
+        double acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+        mbar_wait(smem_u32(tfull), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        for (int g = S - 1; g >= 0; --g) {
+            const double scale = scalbn(1.0, -W * (g + 2));
+            int v[32];
+            tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(g * BN2 + half * 32), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c] = fma((double)v[c], scale, acc[c]);
+        }
+        const int64_t i = m0 + row;
+        if (i < p.m) {
+            const int ea = p.ea[i];
+            double *crow = p.c + i * p.ldc + n0 + half * 32;
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+                const int64_t j = n0 + half * 32 + c;
+                if (p.lower && j / BM > i / BM) continue;           // keep to the 128 x 128 tiles on or below the diagonal
+                if (j + 1 < p.n) {
+                    double2 o;
+                    o.x = p.alpha * scalbn(acc[c], ea + eb_tile[half * 32 + c]);
+                    o.y = p.alpha * scalbn(acc[c + 1], ea + eb_tile[half * 32 + c + 1]);
+                    if (p.beta != 0.0) {
+                        const double2 old = *reinterpret_cast<const double2 *>(crow + c);
+                        o.x = fma(p.beta, old.x, o.x);
+                        o.y = fma(p.beta, old.y, o.y);
+                    }
+                    *reinterpret_cast<double2 *>(crow + c) = o;
+                } else if (j < p.n) {
+                    double o = p.alpha * scalbn(acc[c], ea + eb_tile[half * 32 + c]);
+                    if (p.beta != 0.0) o = fma(p.beta, crow[c], o);
+                    crow[c] = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+}  // namespace v2
 
 // ------------------------------------------------------------------------------------------------ digit planes
 // Element (r, k) of the operand lives at x[r * rs + k * ks] (one of rs, ks is 1).
@@ -362,16 +503,17 @@ static TensorMapEncodeFn encoder() {
     return fn;
 }
 
-static int plane_map(CUtensorMap *map, const signed char *base, int64_t rows_total, int64_t k_pad) {
+static int plane_map(CUtensorMap *map, const signed char *base, int64_t rows_total, int64_t k_pad, int box_k = BKB,
+                     int box_rows = BM) {
     TensorMapEncodeFn enc = encoder();
     VGP_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows_total};
     const cuuint64_t strides[1] = {(cuuint64_t)k_pad};
-    const cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)BM};
+    const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char *>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VGP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return VGP_OK;
 }
@@ -425,8 +567,12 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
     static bool configured[16] = {};
     if (!configured[device]) {
         VGP_CUDA(cudaFuncSetAttribute(emu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        VGP_CUDA(cudaFuncSetAttribute(v2::emu_gemm_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM2));
         configured[device] = true;
     }
+    // VGP_GEMM_EMULATE_VARIANT=2: all planes of a k block resident (needs slices <= 8); read per call so tests can flip it
+    const char *var = getenv("VGP_GEMM_EMULATE_VARIANT");
+    const bool resident = var && atoi(var) == 2 && slices <= v2::S2_MAX;
     Workspace &ws = g_ws[device];
     const int64_t m_pad = round_up(m, BM), n_pad = round_up(n, BN);
     const int64_t kc_max = k < K_CHUNK ? round_up(k > 0 ? k : 1, BKB) : K_CHUNK;
@@ -445,8 +591,13 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
         VGP_TRY(slice_operand(a + k0 * a_ks, a_rs, a_ks, m, kc, m_pad, k_pad, slices, ws.ea, ws.qa, st));
         VGP_TRY(slice_operand(b + k0 * b_ks, b_rs, b_ks, n, kc, n_pad, k_pad, slices, ws.eb, ws.qb, st));
         alignas(64) CUtensorMap ma, mb;
-        VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad));
-        VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad));
+        if (resident) {
+            VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad, v2::BKB2, BM));
+            VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad, v2::BKB2, v2::BN2));
+        } else {
+            VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad));
+            VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad));
+        }
         GemmArgs p;
         p.m = m;
         p.n = n;
@@ -461,7 +612,11 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
         p.alpha = alpha;
         p.beta = k0 == 0 ? beta : 1.0;
         p.lower = lower;
-        emu_gemm_kernel<<<dim3((unsigned)(n_pad / BN), (unsigned)(m_pad / BM)), THREADS, SMEM, st>>>(ma, mb, p);
+        if (resident)
+            v2::emu_gemm_resident_kernel<<<dim3((unsigned)(n_pad / v2::BN2), (unsigned)(m_pad / BM)), THREADS, v2::SMEM2, st>>>(
+                ma, mb, p);
+        else
+            emu_gemm_kernel<<<dim3((unsigned)(n_pad / BN), (unsigned)(m_pad / BM)), THREADS, SMEM, st>>>(ma, mb, p);
         VGP_LAUNCH_CHECK();
         if (k == 0) break;
     }
