@@ -89,3 +89,29 @@ def test_both_kernels_give_the_same_bits(monkeypatch):
     monkeypatch.setenv("VGP_GEMM_EMULATE_VARIANT", "2")
     two = emulated(a, b, 0, 1, 384, 320, 640)
     np.testing.assert_array_equal(one, two)          # same integer sums, same FP64 recombination order
+
+
+def test_placement_on_emulated_factorisation_matches_the_oracle():
+    """The whole one-call placement with the large products of potrf + trtri routed through the int8 kernels
+    (VGP_GEMM_EMULATE is read once per process, hence the subprocess)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np, json, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from vgposp_b200 import greedy\n"
+        "x = np.random.default_rng(7).uniform(-2, 2, (3000, 3)); ls = 0.5 * (1000.0 / 3000) ** (1 / 3)\n"
+        "d = x[:, None, :] - x[None, :, :]\n"
+        "cov = np.exp(-np.einsum('ijk,ijk->ij', d, d) / (2 * ls * ls)) + 1e-2 * np.eye(3000)\n"
+        "sel, sc, _, _ = greedy.place_single(cov, 12, 0, formulation='lazy_factor')\n"
+        "print(json.dumps({'sel': [int(v) for v in sel], 'scores': [float(v) for v in sc]}))\n" % root)
+    outs = []
+    for emulate in ("0", "8"):
+        env = dict(os.environ, VGP_GEMM_EMULATE=emulate, VGP_GEMM_EMULATE_MIN="512")
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=root)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        import json
+        outs.append(json.loads(res.stdout.strip().splitlines()[-1]))
+    assert outs[0]["sel"] == outs[1]["sel"]
+    np.testing.assert_allclose(outs[1]["scores"], outs[0]["scores"], rtol=1e-10)

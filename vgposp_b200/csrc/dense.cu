@@ -691,6 +691,11 @@ static int gemm_dispatch(int trans_a, int trans_b, const GemmArgs &p, cudaStream
     return gemm_launch<false, true>(p, s);
 }
 
+static int emulate_slices() {       // VGP_GEMM_EMULATE=<digit planes>: 0 (default) keeps every product on the FP64 pipe
+    static const int slices = getenv("VGP_GEMM_EMULATE") ? atoi(getenv("VGP_GEMM_EMULATE")) : 0;
+    return slices;
+}
+
 int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, GemmTiles tiles,
                cudaStream_t s) {
@@ -715,9 +720,10 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
     }
     DistContext *dc = g_dist;
     // opt-in experiment: large products on the int8 tensor cores (emulated.cu); never taken unless the variable is set
-    static const int emu_slices = getenv("VGP_GEMM_EMULATE") ? atoi(getenv("VGP_GEMM_EMULATE")) : 0;
+    const int emu_slices = emulate_slices();
     static const int64_t emu_min = getenv("VGP_GEMM_EMULATE_MIN") ? atoll(getenv("VGP_GEMM_EMULATE_MIN")) : 2048;
-    if (emu_slices >= 2 && !(dc && dc->nranks > 1) && m >= emu_min && n >= emu_min && 2 * k >= emu_min)
+    const bool emulate = emu_slices >= 2 && m >= emu_min && n >= emu_min && 2 * k >= emu_min;
+    if (emulate && !(dc && dc->nranks > 1))
         return emulated_gemm(trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, emu_slices,
                              tiles == GEMM_LOWER ? 1 : 0, s);
     if (dc && dc->nranks > 1) {
@@ -732,6 +738,11 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
             for (int q = 0; q < dc->nranks; ++q) p.delta[q] = dc->delta[q];
             ++dc->dist_gemms;
             VGP_TRY(dense_dist_barrier(*dc, s));                  // every rank is done with all earlier work
+            if (emulate) {
+                VGP_TRY(emulated_gemm(trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, emu_slices,
+                                      tiles == GEMM_LOWER ? 1 : 0, s, dc));
+                return dense_dist_barrier(*dc, s);
+            }
             VGP_TRY(gemm_dispatch(trans_a, trans_b, p, s));
             return dense_dist_barrier(*dc, s);                    // every tile has landed in every replica
         }
@@ -1156,6 +1167,7 @@ int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream
     VGP_REQUIRE(n > 0 && n % NB == 0 && ld >= n && ld % 2 == 0, "dense_potrf: unpadded size %lld (ld %lld)",
                 (long long)n, (long long)ld);
     VGP_TRY(ws.ensure(n / NB));
+    if (emulate_slices() >= 2) VGP_TRY(emulated_reserve(n, emulate_slices(), s));
     VGP_CUDA(cudaMemsetAsync(ws.info, 0, sizeof(int), s));
     return potrf_rec(a, n, ld, 0, ws.dinv, ws, s);
 }

@@ -65,7 +65,9 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
 // digit planes.  dense_gemm routes large products through it only when VGP_GEMM_EMULATE=<slices> is set.
 int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a, int64_t lda,
                   const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int slices, int lower,
-                  cudaStream_t s);
+                  cudaStream_t s, const DistContext *dist = nullptr);
+
+int emulated_reserve(int64_t rows, int slices, cudaStream_t s);
 
 int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                       int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,

@@ -50,7 +50,39 @@ struct GemmArgs {
     int64_t ldc;
     double alpha, beta;
     int lower;                    // skip tiles strictly above the diagonal
+    // distributed form (dist.cu): tiles dealt round-robin to the ranks (linear tile = rank + dist_n * blockIdx.x), every
+    // finished tile stored into all dist_n replicas (delta[q] = replica q minus the local one, in doubles)
+    int dist_n, rank, tiles_n;
+    int64_t delta[DIST_MAX];
 };
+
+// tile coordinates of this CTA; false when it has no tile
+__device__ __forceinline__ bool tile_of_cta(const GemmArgs &p, int tiles_m, int &tm, int &tn) {
+    if (p.dist_n > 0) {
+        const int64_t lin = (int64_t)p.rank + (int64_t)p.dist_n * blockIdx.x;
+        if (lin >= (int64_t)tiles_m * p.tiles_n) return false;
+        tm = (int)(lin / p.tiles_n);
+        tn = (int)(lin % p.tiles_n);
+    } else {
+        tm = blockIdx.y;
+        tn = blockIdx.x;
+    }
+    return true;
+}
+__device__ __forceinline__ void store_pair(const GemmArgs &p, double *dst, double2 o) {
+    if (p.dist_n > 0) {
+        for (int q = 0; q < p.dist_n; ++q) *(reinterpret_cast<double2 *>(dst) + (p.delta[q] >> 1)) = o;    // peers: NVLink
+    } else {
+        *reinterpret_cast<double2 *>(dst) = o;
+    }
+}
+__device__ __forceinline__ void store_one(const GemmArgs &p, double *dst, double o) {
+    if (p.dist_n > 0) {
+        for (int q = 0; q < p.dist_n; ++q) dst[p.delta[q]] = o;
+    } else {
+        *dst = o;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -142,7 +174,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * STAGES + 4);
     int *eb_tile = reinterpret_cast<int *>(sm + STAGES * STAGE_BYTES + BAR_BYTES);
 
-    const int tm = blockIdx.y, tn = blockIdx.x;
+    int tm, tn;
+    if (!tile_of_cta(p, (int)(p.m_pad / BM), tm, tn)) return;
     if (p.lower && tn > tm) return;
     const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -256,11 +289,11 @@ __global__ void __launch_bounds__(THREADS, 1)
                         o.x = fma(p.beta, old.x, o.x);
                         o.y = fma(p.beta, old.y, o.y);
                     }
-                    *reinterpret_cast<double2 *>(crow + c) = o;
+                    store_pair(p, crow + c, o);
                 } else if (j < p.n) {
                     double o = p.alpha * scalbn(acc[c], ea + eb_tile[half * 64 + c]);
                     if (p.beta != 0.0) o = fma(p.beta, crow[c], o);
-                    crow[c] = o;
+                    store_one(p, crow + c, o);
                 }
             }
         }
@@ -297,7 +330,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * STAGES2 + 1);
     int *eb_tile = reinterpret_cast<int *>(sm + STAGES2 * STAGE2 + BAR2);
 
-    const int tm = blockIdx.y, tn = blockIdx.x;
+    int tm, tn;
+    if (!tile_of_cta(p, (int)(p.m_pad / BM), tm, tn)) return;
     if (p.lower && tn * BN2 > tm * BM + (BM - 1)) return;           // wholly above the diagonal
     const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -389,11 +423,11 @@ __global__ void __launch_bounds__(THREADS, 1)
                         o.x = fma(p.beta, old.x, o.x);
                         o.y = fma(p.beta, old.y, o.y);
                     }
-                    *reinterpret_cast<double2 *>(crow + c) = o;
+                    store_pair(p, crow + c, o);
                 } else if (j < p.n) {
                     double o = p.alpha * scalbn(acc[c], ea + eb_tile[half * 32 + c]);
                     if (p.beta != 0.0) o = fma(p.beta, crow[c], o);
-                    crow[c] = o;
+                    store_one(p, crow + c, o);
                 }
             }
         }
@@ -551,11 +585,32 @@ static int grow(void **ptr, size_t *have, size_t want, cudaStream_t st) {
 
 }  // namespace emu
 
+// Size the digit-plane workspace for products of up to rows x rows x K_CHUNK once, up front.  Growing frees the old planes
+// (cudaFree waits for the whole device): inside a distributed factorisation, with other ranks' barrier kernels possibly
+// spinning on this device, that must not happen -- dense_potrf calls this before its first launch.
+int emulated_reserve(int64_t rows, int slices, cudaStream_t st) {
+    using namespace emu;
+    if (slices < 2 || slices > S_MAX || rows <= 0) return VGP_OK;
+    int device = 0;
+    VGP_CUDA(cudaGetDevice(&device));
+    VGP_REQUIRE(device >= 0 && device < 16, "device ordinal out of range");
+    Workspace &ws = g_ws[device];
+    const int64_t r = round_up(rows, BM);
+    VGP_TRY(grow((void **)&ws.qa, &ws.qa_bytes, (size_t)slices * r * K_CHUNK, st));
+    VGP_TRY(grow((void **)&ws.qb, &ws.qb_bytes, (size_t)slices * r * K_CHUNK, st));
+    size_t ea_bytes = ws.ea_rows * 4, eb_bytes = ws.eb_rows * 4;
+    VGP_TRY(grow((void **)&ws.ea, &ea_bytes, (size_t)r * 4, st));
+    VGP_TRY(grow((void **)&ws.eb, &eb_bytes, (size_t)r * 4, st));
+    ws.ea_rows = ea_bytes / 4;
+    ws.eb_rows = eb_bytes / 4;
+    return VGP_OK;
+}
+
 // Asynchronous on `st`; same operand convention as dense_gemm.  C must not alias A or B (with k > K_CHUNK the second
 // chunk's planes would be cut from an already updated operand).
 int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a, int64_t lda,
                   const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int slices, int lower,
-                  cudaStream_t st) {
+                  cudaStream_t st, const DistContext *dc) {
     using namespace emu;
     VGP_REQUIRE(slices >= 2 && slices <= S_MAX, "slices must be in [2, %d]", S_MAX);
     VGP_REQUIRE(ldc % 2 == 0 && ((uintptr_t)c & 15) == 0, "C must be 16-byte aligned with an even leading dimension");
@@ -612,11 +667,21 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
         p.alpha = alpha;
         p.beta = k0 == 0 ? beta : 1.0;
         p.lower = lower;
+        p.dist_n = 0;
+        p.rank = 0;
+        const int64_t tiles_n = n_pad / (resident ? v2::BN2 : BN), tiles_m = m_pad / BM;
+        p.tiles_n = (int)tiles_n;
+        dim3 grid((unsigned)tiles_n, (unsigned)tiles_m);
+        if (dc && dc->nranks > 1) {          // every rank slices the whole operands (O(n^2)); the tiles are shared out
+            p.dist_n = dc->nranks;
+            p.rank = dc->rank;
+            for (int q = 0; q < dc->nranks; ++q) p.delta[q] = dc->delta[q];
+            grid = dim3((unsigned)((tiles_n * tiles_m + dc->nranks - 1) / dc->nranks), 1);
+        }
         if (resident)
-            v2::emu_gemm_resident_kernel<<<dim3((unsigned)(n_pad / v2::BN2), (unsigned)(m_pad / BM)), THREADS, v2::SMEM2, st>>>(
-                ma, mb, p);
+            v2::emu_gemm_resident_kernel<<<grid, THREADS, v2::SMEM2, st>>>(ma, mb, p);
         else
-            emu_gemm_kernel<<<dim3((unsigned)(n_pad / BN), (unsigned)(m_pad / BM)), THREADS, SMEM, st>>>(ma, mb, p);
+            emu_gemm_kernel<<<grid, THREADS, SMEM, st>>>(ma, mb, p);
         VGP_LAUNCH_CHECK();
         if (k == 0) break;
     }
@@ -639,5 +704,5 @@ int vgp_gemm_emulated(int device, int trans_a, int trans_b, int64_t m, int64_t n
     VGP_REQUIRE(a_dev && b_dev && c_dev, "NULL matrix");
     VGP_ENTER(device);
     return emulated_gemm(trans_a, trans_b, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, slices, lower,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, nullptr);
 }
