@@ -75,3 +75,32 @@ def test_session_run_fetches_and_batch_of_two():
     amp_assign([2.0, 3.0])
     np.testing.assert_allclose(amp.numpy(), [2.0, 3.0], rtol=1e-14)
     assert np.allclose(gpf.do_assign(sess, amp, amp_assign, amp_p, [0.5, 0.6]), [0.5, 0.6])
+
+
+def test_likelihood_surfaces_walk_the_reference_grids(monkeypatch):
+    """calc_H / calc_H_1d (gp_functions.py:864-889): (length_scale, amplitude) = span (1+i)/X, span (1+j)/Y with span 40
+    and 2; calc_H feeds the observations, calc_H_1d evaluates the node as it stands."""
+    class FakeGP:
+        def __init__(self):
+            self.calls = []
+
+        def log_prob(self, obs):
+            self.calls.append((float(lensc), float(amp), None if obs is None else np.asarray(obs).copy()))
+            return np.array([float(lensc) * 100 + float(amp)])
+
+    amp, amp_assign, amp_p, lensc, lensc_assign, lensc_p, _, _, _, _ = \
+        gpf.tf_Placeholder_assign_test(np.array([0.54]), np.array([0.54]), np.array([0.1]))
+    gp = FakeGP()
+    obs = gpf.placeholder(np.float64, (1, 3))
+    node = gpf.LogProb(gp, obs)
+    y = np.array([1.0, 2.0, 3.0])
+    H = gpf.calc_H(3, 2, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, node, None, obs, y)
+    want = np.array([[40 * (1 + i) / 3 * 100 + 40 * (1 + j) / 2 for j in range(2)] for i in range(3)])
+    np.testing.assert_allclose(H, want, rtol=1e-12)
+    assert all(np.array_equal(c[2], y) for c in gp.calls)
+    gp.calls.clear()
+    obs.value = y
+    H1 = gpf.calc_H_1d(4, 3, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, node, None)
+    want1 = np.array([[2 * (1 + i) / 4 * 100 + 2 * (1 + j) / 3 for j in range(3)] for i in range(4)])
+    np.testing.assert_allclose(H1, want1, rtol=1e-12)
+    assert len(gp.calls) == 12 and all(np.array_equal(c[2], y) for c in gp.calls)

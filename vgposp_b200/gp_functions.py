@@ -534,6 +534,18 @@ def calc_H(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p,
     The reference issues X * Y session runs, each a kernel build + Cholesky (25 600 of them at main.py:400-401).  When
     the GP is known and has at most 127 observations the whole sweep is ONE launch -- one CTA per grid point, kernel
     matrix, Cholesky and solve in registers (vgp_gp_logprob_batch_k); otherwise the evaluations run one by one."""
+    return _likelihood_surface(40.0, XEDGES, YEDGES, lensc, lensc_assign, amp, amp_assign, log_likelihood,
+                               obs_train_dataset)
+
+
+def calc_H_1d(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, log_likelihood, sess=None):
+    """The same sweep on (length_scale, amplitude) = 2 (1+i)/X, 2 (1+j)/Y with the observations already bound to the
+    `log_likelihood` node (gp_functions.py:879-889: nothing but the two parameters is fed)."""
+    y = log_likelihood.placeholder.value if isinstance(log_likelihood, LogProb) else None
+    return _likelihood_surface(2.0, XEDGES, YEDGES, lensc, lensc_assign, amp, amp_assign, log_likelihood, y)
+
+
+def _likelihood_surface(span, XEDGES, YEDGES, lensc, lensc_assign, amp, amp_assign, log_likelihood, obs_train_dataset):
     H = np.zeros([XEDGES, YEDGES])
     y = None if obs_train_dataset is None else np.asarray(obs_train_dataset, dtype=np.float64)
     gp = log_likelihood.gp if isinstance(log_likelihood, LogProb) else getattr(log_likelihood, "__self__", None)
@@ -541,8 +553,8 @@ def calc_H(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p,
             gp.kernel.amplitude is amp and gp.kernel.length_scale is lensc:
         n, d = gp._x.shape
         y0 = _vector(gp._rows(y)[0])
-        ls_grid = 40.0 * (1.0 + np.arange(XEDGES)) / XEDGES
-        amp_grid = 40.0 * (1.0 + np.arange(YEDGES)) / YEDGES
+        ls_grid = span * (1.0 + np.arange(XEDGES)) / XEDGES
+        amp_grid = span * (1.0 + np.arange(YEDGES)) / YEDGES
         params = np.empty((XEDGES, YEDGES, 3))
         params[:, :, 0] = amp_grid[None, :]
         params[:, :, 1] = ls_grid[:, None]
@@ -555,8 +567,8 @@ def calc_H(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p,
         return out.reshape(XEDGES, YEDGES)
     for i in range(XEDGES):
         for j in range(YEDGES):
-            lensc_assign([40 * np.double((1 + i) / XEDGES)])
-            amp_assign([40 * np.double((1 + j) / YEDGES)])
+            lensc_assign([span * np.double((1 + i) / XEDGES)])
+            amp_assign([span * np.double((1 + j) / YEDGES)])
             H[i, j] = np.atleast_1d(log_likelihood(y) if y is not None else log_likelihood())[0]      # :875, L[0]
     return H
 
