@@ -104,3 +104,12 @@ def test_likelihood_surfaces_walk_the_reference_grids(monkeypatch):
     want1 = np.array([[2 * (1 + i) / 4 * 100 + 2 * (1 + j) / 3 for j in range(3)] for i in range(4)])
     np.testing.assert_allclose(H1, want1, rtol=1e-12)
     assert len(gp.calls) == 12 and all(np.array_equal(c[2], y) for c in gp.calls)
+
+
+def test_vgp_input_rows_for_one_location():
+    """gp_functions.py:995-1016: columns (x, y, z, t, p) with t = vec_pt[:, 1], p = vec_pt[:, 0]."""
+    vec_pt = np.array([[10.0, 1.0], [20.0, 2.0], [30.0, 3.0]])
+    got = gpf.graph_get_vgp_input_xyztp([0.5, -1.0, 2.0], vec_pt)
+    want = np.array([[0.5, -1.0, 2.0, 1.0, 10.0], [0.5, -1.0, 2.0, 2.0, 20.0], [0.5, -1.0, 2.0, 3.0, 30.0]])
+    assert got.dtype == np.float64
+    np.testing.assert_array_equal(got, want)

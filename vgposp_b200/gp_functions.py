@@ -517,12 +517,35 @@ def denormalize_coord(sel_norm_coord):
     return sel_norm_coord
 
 
+def graph_get_vgp_input_xyztp(loc_xyz, vec_pt):
+    """[S, 5] VGP inputs (x, y, z, t, p) for one location and S (pressure, temperature) samples: the location repeated,
+    then column 1 of `vec_pt`, then column 0 (gp_functions.py:995-1016; call site main_architecture_2.py:341)."""
+    vec_pt = np.asarray(vec_pt, dtype=np.float64)
+    out = np.empty((vec_pt.shape[0], 5))
+    out[:, 0], out[:, 1], out[:, 2] = float(loc_xyz[0]), float(loc_xyz[1]), float(loc_xyz[2])
+    out[:, 3] = vec_pt[:, 1]
+    out[:, 4] = vec_pt[:, 0]
+    return out
+
+
 def create_cov_matrix(minmax_x, minmax_y, minmax_z, minmax_pressure, minmax_temperature, SPATIAL_COVER,
                       SPATIAL_COV_PR_TEMP, encoder, sess=None):
     """gp_functions.py:1019-1057 (see vgposp_b200.cov_producer.create_cov_matrix)."""
     from .cov_producer import create_cov_matrix as impl
     return impl(minmax_x, minmax_y, minmax_z, minmax_pressure, minmax_temperature, SPATIAL_COVER,
                 SPATIAL_COV_PR_TEMP, encoder, sess)
+
+
+def create_cov_matrix_while_loops(minmax_x, minmax_y, minmax_z, minmax_pressure, minmax_temperature, SPATIAL_COVER,
+                                  SPATIAL_COV_PR_TEMP, encoder, sess=None):
+    """gp_functions.py:1060-1117: the same matrix as create_cov_matrix written with while loops."""
+    return create_cov_matrix(minmax_x, minmax_y, minmax_z, minmax_pressure, minmax_temperature, SPATIAL_COVER,
+                             SPATIAL_COV_PR_TEMP, encoder, sess)
+
+
+def tf_create_cov_matrix(mm_x, mm_y, mm_z, mm_p, mm_t, sptl_const, sptl_pt_const, encoder, sess=None):
+    """gp_functions.py:1120-1179: again the same matrix (the reference's third copy of the loop nest)."""
+    return create_cov_matrix(mm_x, mm_y, mm_z, mm_p, mm_t, sptl_const, sptl_pt_const, encoder, sess)
 
 
 def calc_H(XEDGES, YEDGES, lensc, lensc_assign, lensc_p, amp, amp_assign, amp_p, log_likelihood, sess=None,
