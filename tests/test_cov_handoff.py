@@ -69,3 +69,11 @@ def test_host_helpers_of_gp_functions():
     c = np.ones((2, 3))
     out = gpf.denormalize_coord(c)
     assert out is c and c[0, 0] == pytest.approx(0.0007434639347162126 * 3000000 + 0.0018159087825037148)
+
+
+def test_reference_module_names_resolve():
+    """`import snippets_save`, `import cache_plot_gen_idxs` in the reference's scripts map to modules of the same name."""
+    from vgposp_b200 import cache_plot_gen_idxs, cov_producer, snippets_save
+    assert snippets_save.load_cov_vv is cov_producer.load_cov_vv
+    assert snippets_save.save_cov_vv is cov_producer.save_cov_vv
+    assert cache_plot_gen_idxs.gen_idxs is cov_producer.gen_idxs
