@@ -17,3 +17,10 @@ for v in 1 2; do
     VGP_GEMM_EMULATE=8 VGP_GEMM_EMULATE_VARIANT=$v timeout 300 python tools/e2e_only.py 2 auto 2>&1 | grep overlap \
         | tee gpurun_out/e2e_emulated_v$v.log
 done
+# slab kernels for the triangular solves (csrc/slab.cu)
+VGP_TEST_SLAB=1 timeout 600 python -m pytest tests/test_gpu_slab_solves.py -x -q --timeout 240 -p no:cacheprovider \
+    > gpurun_out/slab_tests.log 2>&1
+tail -15 gpurun_out/slab_tests.log
+for w in 512 1024 2048; do
+    VGP_TRSM_SLAB=$w timeout 300 python tools/e2e_only.py 2 auto 2>&1 | grep overlap | tee gpurun_out/e2e_slab_$w.log
+done

@@ -1067,9 +1067,41 @@ static inline const double *dinv_at(const double *dinv, int64_t rows) {
 // =====================================================================================================
 // triangular solves (recursive), all in place on B.  `dinv`: cached inverses of L's diagonal blocks or NULL.
 // =====================================================================================================
+// Opt-in experiment (slab.cu): VGP_TRSM_SLAB=<width> lets one launch solve a whole triangle of up to <width> columns per
+// 128-wide slab of right-hand sides instead of recursing down to 128 x 128 leaves.  Needs the cached diagonal-block
+// inverses.  *done tells the caller whether the solve was taken over.
+static int slab_solve(int form, int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
+                      double *b, int64_t ldb, cudaStream_t s, bool *done) {
+    *done = false;
+    const char *env = getenv("VGP_TRSM_SLAB");           // read per call: tests flip it
+    const int64_t width = env ? atoll(env) : 0;
+    if (width <= 0 || n <= NB || n > width || !dinv || m == 0) return VGP_OK;
+    *done = true;
+    if (g_gate) {
+        VGP_TRY(gate_wait(l, n, s));
+        VGP_TRY(gate_wait(b, form == 2 ? n : m, s));
+    }
+    DistContext *dc = g_dist;
+    if (dc && dc->nranks > 1) {
+        const int64_t rows = form == 2 ? n : m, cols = form == 2 ? m : n;
+        const char *b0 = (const char *)b, *b1 = (const char *)(b + (rows - 1) * ldb + cols);
+        const bool inside = b0 >= (const char *)dc->base && b1 <= (const char *)dc->base + dc->bytes;
+        if (inside && m / NB >= 2 * dc->nranks) {
+            ++dc->dist_gemms;
+            VGP_TRY(dense_dist_barrier(*dc, s));
+            VGP_TRY(slab_trsm(form, m, n, alpha, l, ldl, dinv, b, ldb, dc, s));
+            return dense_dist_barrier(*dc, s);
+        }
+    }
+    return slab_trsm(form, m, n, alpha, l, ldl, dinv, b, ldb, nullptr, s);
+}
+
 // X L^T = alpha B,  B [m][n]
 static int trsm_right_t(int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
                         double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
+    bool done;
+    VGP_TRY(slab_solve(0, m, n, alpha, l, ldl, dinv, b, ldb, s, &done));
+    if (done) return VGP_OK;
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1085,6 +1117,9 @@ static int trsm_right_t(int64_t m, int64_t n, double alpha, const double *l, int
 // X L = alpha B,  B [m][n]
 static int trsm_right_n(int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
                         double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
+    bool done;
+    VGP_TRY(slab_solve(1, m, n, alpha, l, ldl, dinv, b, ldb, s, &done));
+    if (done) return VGP_OK;
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1100,6 +1135,9 @@ static int trsm_right_n(int64_t m, int64_t n, double alpha, const double *l, int
 // L X = alpha B,  B [n][nrhs]
 static int trsm_left_n(int64_t n, int64_t nrhs, double alpha, const double *l, int64_t ldl, const double *dinv,
                        double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
+    bool done;
+    VGP_TRY(slab_solve(2, nrhs, n, alpha, l, ldl, dinv, b, ldb, s, &done));
+    if (done) return VGP_OK;
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));

@@ -69,6 +69,11 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
 
 int emulated_reserve(int64_t rows, int slices, cudaStream_t s);
 
+// EXPERIMENTAL (slab.cu): a whole triangular solve of width n per 128-wide slab of right-hand sides in one launch.
+// form 0: X L^T = alpha B, B [m][n];  1: X L = alpha B, B [m][n];  2: L X = alpha B, B [n][m].
+int slab_trsm(int form, int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv, double *b,
+              int64_t ldb, const DistContext *dist, cudaStream_t s);
+
 int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                       int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,
                       double *partial, cudaStream_t s, GemmTiles tiles = GEMM_FULL);
