@@ -23,14 +23,22 @@ def split(n):
 
 
 class Trace:
-    def __init__(self):
-        self.gemms, self.leaves = [], 0
+    def __init__(self, slab_width=0):
+        self.gemms, self.leaves, self.slabs, self.slab_width = [], 0, [], slab_width
+
+    def slab(self, m, n):                       # one launch: m / 128 slabs, each walks an n-wide triangle (slab.cu)
+        if self.slab_width and NB < n <= self.slab_width:
+            self.slabs.append((m, n))
+            return True
+        return False
 
     def gemm(self, m, n, k, lower=False):
         self.gemms.append((m, n, k, lower))
 
     # -- the recursions of dense.cu (shapes only)
     def trsm_right(self, m, n):                 # both right-side forms: leaves m x 128 x 128, updates m x n2 x n1
+        if self.slab(m, n):
+            return
         if n == NB:
             return self.gemm(m, NB, NB)
         n1 = split(n)
@@ -39,6 +47,8 @@ class Trace:
         self.trsm_right(m, n - n1)
 
     def trsm_left(self, n, nrhs):
+        if self.slab(nrhs, n):
+            return
         if n == NB:
             return self.gemm(NB, nrhs, NB)
         n1 = split(n)
@@ -96,15 +106,20 @@ def gemm_us(m, n, k, lower, t0, tk, share=1):
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
-    ranks = [int(v) for v in sys.argv[2:]] or [1, 2, 4, 8]
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    opts = dict(a[2:].split("=") for a in sys.argv[1:] if a.startswith("--"))
+    slab_width = int(opts.get("slab", 0))              # --slab=1024: solves of up to that width in one launch
+    emulate = float(opts.get("emulate", 1.0))          # --emulate=2.5: products with m, n >= 2048, k >= 1024 that much faster
+    n = int(argv[0]) if argv else 50000
+    ranks = [int(v) for v in argv[1:]] or [1, 2, 4, 8]
     n_pad = (n + NB - 1) // NB * NB
     t0, tk = fit()
-    tr = Trace()
+    tr = Trace(slab_width)
     tr.potrf(n_pad)
     tr.trtri(n_pad)
     launch_us, leaf_us, barrier_us = 3.0, 45.0, 12.0     # launch gap of a short kernel; potf2 + block inverse; flag barrier
-    out = {"n": n, "n_pad": n_pad, "gemm_launches": len(tr.gemms), "diagonal_block_leaves": tr.leaves,
+    out = {"n": n, "n_pad": n_pad, "options": {"slab_width": slab_width, "emulated_speedup": emulate},
+           "gemm_launches": len(tr.gemms), "slab_launches": len(tr.slabs), "diagonal_block_leaves": tr.leaves,
            "wave_model_us": {"t0": t0, "per_k": tk}, "ranks": {}}
     flops = sum((m * (m + 128) if lo else 2 * m * nn) * k for m, nn, k, lo in tr.gemms)
     out["gemm_flop"] = flops
@@ -115,7 +130,10 @@ def main():
         for m, nn, k, lo in tr.gemms:
             tiles128 = (m // 128) * (m // 128 + 1) // 2 if lo else (m // 128) * (nn // 128)
             distributed = g > 1 and tiles128 >= 96 and k >= 256
-            t = gemm_us(m, nn, k, lo, t0, tk, g if distributed else 1) + launch_us
+            t = gemm_us(m, nn, k, lo, t0, tk, g if distributed else 1)
+            if emulate != 1.0 and m >= 2048 and nn >= 2048 and 2 * k >= 2048:
+                t /= emulate
+            t += launch_us
             key = "k<=128" if k <= 128 else ("128<k<=1024" if k <= 1024 else "k>1024")
             classes[key][0] += 1
             classes[key][1] += t
@@ -124,11 +142,21 @@ def main():
                 dist_t += t
             else:
                 repl_t += t
-        total = dist_t + repl_t + tr.leaves * leaf_us + 2 * ndist * barrier_us
+        # slab launches: one CTA per SM at the full per-SM DMMA rate (35.5 TF / 148), 128 (n^2 + 128 n) flop per slab,
+        # slabs shared out over the ranks when there are at least two per rank
+        slab_t, slab_barriers = 0.0, 0
+        for m, nn in tr.slabs:
+            slabs = m // 128
+            share = g if (g > 1 and slabs >= 2 * g) else 1
+            slab_barriers += 2 if share > 1 else 0
+            per_cta_us = 128.0 * (nn * nn + 128.0 * nn) / (35.5e12 / 148) * 1e6
+            slab_t += math.ceil(math.ceil(slabs / share) / 148) * (t0 + per_cta_us) + launch_us
+        total = dist_t + repl_t + slab_t + tr.leaves * leaf_us + (2 * ndist + slab_barriers) * barrier_us
         out["ranks"][str(g)] = {
             "modelled_seconds": total / 1e6,
             "distributed_products": ndist, "distributed_seconds": dist_t / 1e6,
             "replicated_products_seconds": repl_t / 1e6,
+            "slab_solves_seconds": slab_t / 1e6,
             "diagonal_blocks_seconds": tr.leaves * leaf_us / 1e6,
             "barrier_seconds": 2 * ndist * barrier_us / 1e6,
             "by_k": {k: {"launches": v[0], "seconds": v[1] / 1e6} for k, v in classes.items()},
