@@ -189,3 +189,25 @@ def test_time_steps_stack_like_gp_pvtk(tmp_path):
     assert feats["Velocity"].shape == (len(xyz), 3) and feats["Pressure"].shape == (len(xyz), 1)
     xyz2, _, used2 = mesh_ingest.load_time_steps(files, max_steps=2)
     assert len(used2) == 2 and len(xyz2) == len(want_xyz[0]) + len(want_xyz[1])
+
+
+def test_several_pieces_in_one_file(tmp_path):
+    """A .vtu may hold more than one <Piece>; points, point data and cells are concatenated (cells renumbered)."""
+    a, b = room(11, n=12), room(12, n=9)
+    fa, fb = str(tmp_path / "a.vtu"), str(tmp_path / "b.vtu")
+    write_vtu(fa, *a, mode="ascii")
+    write_vtu(fb, *b, mode="ascii")
+
+    def piece(fn):
+        text = open(fn).read()
+        return text[text.index("<Piece"):text.index("</Piece>") + len("</Piece>")]
+
+    both = str(tmp_path / "both.vtu")
+    with open(both, "w") as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="1.0" byte_order="LittleEndian" '
+                'header_type="UInt32">\n<UnstructuredGrid>\n' + piece(fa) + "\n" + piece(fb) +
+                "\n</UnstructuredGrid>\n</VTKFile>\n")
+    g = mesh_ingest.vtu(both)
+    np.testing.assert_array_equal(g.GetLocations(), np.vstack([a[0], b[0]]).astype(np.float64))
+    np.testing.assert_array_equal(g.GetVectorField("Velocity"), np.vstack([a[1]["Velocity"], b[1]["Velocity"]]))
+    np.testing.assert_array_equal(g.GetCellPoints(101), b[2][0][4:8] + 12)
