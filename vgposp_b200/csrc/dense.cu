@@ -1067,14 +1067,20 @@ static inline const double *dinv_at(const double *dinv, int64_t rows) {
 // =====================================================================================================
 // triangular solves (recursive), all in place on B.  `dinv`: cached inverses of L's diagonal blocks or NULL.
 // =====================================================================================================
+// VGP_TRSM_SLAB, read at the entry of every public factorisation / solve (tests flip it between calls)
+static thread_local int64_t g_slab_width = 0;
+static void read_slab_width() {
+    const char *env = getenv("VGP_TRSM_SLAB");
+    g_slab_width = env ? atoll(env) : 0;
+}
+
 // Opt-in experiment (slab.cu): VGP_TRSM_SLAB=<width> lets one launch solve a whole triangle of up to <width> columns per
 // 128-wide slab of right-hand sides instead of recursing down to 128 x 128 leaves.  Needs the cached diagonal-block
 // inverses.  *done tells the caller whether the solve was taken over.
 static int slab_solve(int form, int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
                       double *b, int64_t ldb, cudaStream_t s, bool *done) {
     *done = false;
-    const char *env = getenv("VGP_TRSM_SLAB");           // read per call: tests flip it
-    const int64_t width = env ? atoll(env) : 0;
+    const int64_t width = g_slab_width;
     if (width <= 0 || n <= NB || n > width || !dinv || m == 0) return VGP_OK;
     *done = true;
     if (g_gate) {
@@ -1171,6 +1177,7 @@ int dense_trsm(int side, int trans, int64_t n, int64_t nrhs, double alpha, const
     VGP_REQUIRE(n % NB == 0 && nrhs % NB == 0, "dense_trsm: unpadded size n=%lld nrhs=%lld", (long long)n,
                 (long long)nrhs);
     VGP_TRY(ws.ensure(0));
+    read_slab_width();
     const double *dinv = nullptr;
     if (use_cached_inverses) {
         VGP_REQUIRE(ws.dinv && ws.dinv_blocks >= n / NB, "dense_trsm: no cached diagonal-block inverses");
@@ -1205,6 +1212,7 @@ int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream
     VGP_REQUIRE(n > 0 && n % NB == 0 && ld >= n && ld % 2 == 0, "dense_potrf: unpadded size %lld (ld %lld)",
                 (long long)n, (long long)ld);
     VGP_TRY(ws.ensure(n / NB));
+    read_slab_width();
     if (emulate_slices() >= 2) VGP_TRY(emulated_reserve(n, emulate_slices(), s));
     VGP_CUDA(cudaMemsetAsync(ws.info, 0, sizeof(int), s));
     return potrf_rec(a, n, ld, 0, ws.dinv, ws, s);
@@ -1234,6 +1242,7 @@ static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, Dense
 int dense_trtri(double *l, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
     VGP_REQUIRE(n > 0 && n % NB == 0, "dense_trtri: unpadded size");
     VGP_REQUIRE(ws.dinv && ws.dinv_blocks >= n / NB, "dense_trtri: call dense_potrf on this workspace first");
+    read_slab_width();
     return trtri_rec(l, n, ld, ws.dinv, ws, s);
 }
 
