@@ -24,3 +24,7 @@ tail -15 gpurun_out/slab_tests.log
 for w in 512 1024 2048; do
     VGP_TRSM_SLAB=$w timeout 300 python tools/e2e_only.py 2 auto 2>&1 | grep overlap | tee gpurun_out/e2e_slab_$w.log
 done
+# wide leaves for the triangular solves (dense.cu, VGP_TRSM_LEAF)
+for w in 256 512; do
+    VGP_TRSM_LEAF=$w timeout 300 python tools/e2e_only.py 2 auto 2>&1 | grep overlap | tee gpurun_out/e2e_leaf_$w.log
+done

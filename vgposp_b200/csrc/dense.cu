@@ -1033,13 +1033,43 @@ int DenseWorkspace::ensure(int64_t nblocks) {
     return VGP_OK;
 }
 
+int DenseWorkspace::ensure_wide(int64_t n, int64_t width) {
+    leaf = width > NB ? width : NB;
+    wide_count = 0;
+    wide_used = 0;
+    if (leaf <= NB) return VGP_OK;
+    const size_t want_wide = (size_t)n * (size_t)leaf;                       // sum of n_i^2 <= leaf * sum of n_i
+    const size_t want_tmp = (size_t)(n / 2 + 2 * NB) * (size_t)leaf;        // the widest right-hand side: half the matrix
+    if (wide_doubles < want_wide) {
+        if (wide) cudaFree(wide);
+        wide = nullptr;
+        wide_doubles = 0;
+        VGP_CUDA(cudaMalloc((void **)&wide, want_wide * 8));
+        wide_doubles = want_wide;
+    }
+    if (tmp_doubles < want_tmp) {
+        if (tmp) cudaFree(tmp);
+        tmp = nullptr;
+        tmp_doubles = 0;
+        VGP_CUDA(cudaMalloc((void **)&tmp, want_tmp * 8));
+        tmp_doubles = want_tmp;
+    }
+    return VGP_OK;
+}
+
 void DenseWorkspace::release() {
     if (winv) cudaFree(winv);
     if (info) cudaFree(info);
     if (dinv) cudaFree(dinv);
+    if (wide) cudaFree(wide);
+    if (tmp) cudaFree(tmp);
     winv = nullptr;
     info = nullptr;
     dinv = nullptr;
+    wide = tmp = nullptr;
+    wide_doubles = wide_used = tmp_doubles = 0;
+    wide_count = 0;
+    leaf = NB;
     dinv_blocks = 0;
     device = -1;
 }
@@ -1067,6 +1097,61 @@ static inline const double *dinv_at(const double *dinv, int64_t rows) {
 // =====================================================================================================
 // triangular solves (recursive), all in place on B.  `dinv`: cached inverses of L's diagonal blocks or NULL.
 // =====================================================================================================
+// ---- wide leaves (opt-in, VGP_TRSM_LEAF=<width>) -----------------------------------------------------------------
+// The solves recurse down to 128-wide leaves: 8 107 of the 9 262 products of potrf + trtri at n = 50 000 have k <= 128,
+// take 0.26 s and are too thin to distribute (tools/factor_schedule_model.py).  With the explicit inverse W of every
+// diagonal node of size in (128, width] at hand, a solve against such a node is one dense product (X = alpha B W^T,
+// alpha B W or alpha W B) with k = the node size -- fewer, fatter, distributable launches for twice the flops of the
+// node's own triangle.  The product cannot run in place (every tile reads whole rows / columns of B): it goes to
+// scratch and is copied back.
+static int64_t wide_leaf_env() {
+    const char *env = getenv("VGP_TRSM_LEAF");
+    return env ? atoll(env) : 0;
+}
+static const double *wide_lookup(const DenseWorkspace &ws, const double *dinv, int64_t n) {
+    if (ws.leaf <= NB || !dinv || !ws.dinv || n <= NB || n > ws.leaf) return nullptr;
+    const int64_t block0 = (dinv - ws.dinv) / (NB * NB);
+    for (int i = 0; i < ws.wide_count; ++i)
+        if (ws.wide_nodes[i].block0 == block0 && ws.wide_nodes[i].n == n) return ws.wide + ws.wide_nodes[i].offset;
+    return nullptr;
+}
+static double *wide_scratch(DenseWorkspace &ws, size_t doubles) {
+    DistContext *dc = g_dist;
+    if (dc && dc->nranks > 1 && dc->tmp && dc->tmp_doubles >= doubles) return dc->tmp;     // peer-mapped: distributable
+    return ws.tmp_doubles >= doubles ? ws.tmp : nullptr;
+}
+static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, DenseWorkspace &ws, cudaStream_t s);
+// W = inv(L_node) for the node at `a` (n x n, first diagonal block index block0), dense with zeros above the diagonal
+static int wide_build(const double *a, int64_t n, int64_t ld, int64_t block0, const double *dinv, DenseWorkspace &ws,
+                      cudaStream_t s) {
+    if (ws.leaf <= NB || n <= NB || n > ws.leaf) return VGP_OK;
+    VGP_REQUIRE(ws.wide_count < DenseWorkspace::MAX_WIDE && ws.wide_used + (size_t)n * n <= ws.wide_doubles,
+                "wide-leaf cache is full");
+    double *w = ws.wide + ws.wide_used;
+    VGP_CUDA(cudaMemcpy2DAsync(w, (size_t)n * 8, a, (size_t)ld * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToDevice, s));
+    VGP_TRY(dense_zero_strict_upper(w, n, n, s));
+    VGP_TRY(trtri_rec(w, n, n, dinv, ws, s));          // sub-nodes are not in the cache: plain recursion
+    ws.wide_nodes[ws.wide_count++] = {block0, n, ws.wide_used};
+    ws.wide_used += (size_t)n * n;
+    return VGP_OK;
+}
+// B [rows][cols] <- scratch product; form 0: alpha B W^T, 1: alpha B W (B [m][n]), 2: alpha W B (B [n][m])
+static int wide_solve(int form, int64_t m, int64_t n, double alpha, const double *w, double *b, int64_t ldb,
+                      DenseWorkspace &ws, cudaStream_t s, bool *done) {
+    *done = false;
+    double *t = wide_scratch(ws, (size_t)m * (size_t)n);
+    if (!t) return VGP_OK;
+    *done = true;
+    if (form == 2) {
+        VGP_TRY(dense_gemm(0, 0, n, m, n, alpha, w, n, b, ldb, 0.0, t, m, GEMM_FULL, s));
+        VGP_CUDA(cudaMemcpy2DAsync(b, (size_t)ldb * 8, t, (size_t)m * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToDevice, s));
+    } else {
+        VGP_TRY(dense_gemm(0, form == 0 ? 1 : 0, m, n, n, alpha, b, ldb, w, n, 0.0, t, n, GEMM_FULL, s));
+        VGP_CUDA(cudaMemcpy2DAsync(b, (size_t)ldb * 8, t, (size_t)n * 8, (size_t)n * 8, (size_t)m, cudaMemcpyDeviceToDevice, s));
+    }
+    return VGP_OK;
+}
+
 // VGP_TRSM_SLAB, read at the entry of every public factorisation / solve (tests flip it between calls)
 static thread_local int64_t g_slab_width = 0;
 static void read_slab_width() {
@@ -1108,6 +1193,10 @@ static int trsm_right_t(int64_t m, int64_t n, double alpha, const double *l, int
     bool done;
     VGP_TRY(slab_solve(0, m, n, alpha, l, ldl, dinv, b, ldb, s, &done));
     if (done) return VGP_OK;
+    if (const double *w = wide_lookup(ws, dinv, n)) {
+        VGP_TRY(wide_solve(0, m, n, alpha, w, b, ldb, ws, s, &done));
+        if (done) return VGP_OK;
+    }
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1126,6 +1215,10 @@ static int trsm_right_n(int64_t m, int64_t n, double alpha, const double *l, int
     bool done;
     VGP_TRY(slab_solve(1, m, n, alpha, l, ldl, dinv, b, ldb, s, &done));
     if (done) return VGP_OK;
+    if (const double *w = wide_lookup(ws, dinv, n)) {
+        VGP_TRY(wide_solve(1, m, n, alpha, w, b, ldb, ws, s, &done));
+        if (done) return VGP_OK;
+    }
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1144,6 +1237,10 @@ static int trsm_left_n(int64_t n, int64_t nrhs, double alpha, const double *l, i
     bool done;
     VGP_TRY(slab_solve(2, nrhs, n, alpha, l, ldl, dinv, b, ldb, s, &done));
     if (done) return VGP_OK;
+    if (const double *w = wide_lookup(ws, dinv, n)) {
+        VGP_TRY(wide_solve(2, nrhs, n, alpha, w, b, ldb, ws, s, &done));
+        if (done) return VGP_OK;
+    }
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1202,10 +1299,15 @@ static int potrf_rec(double *a, int64_t n, int64_t ld, int64_t row_offset, doubl
     }
     const int64_t n1 = split(n), n2 = n - n1;
     double *a21 = a + n1 * ld, *a22 = a21 + n1;
+    double *dinv2 = dinv + (n1 / NB) * NB * NB;
+    const bool wide = ws.leaf > NB && n > ws.leaf;      // children no larger than the leaf width are the cached nodes
     VGP_TRY(potrf_rec(a, n1, ld, row_offset, dinv, ws, s));
+    if (wide) VGP_TRY(wide_build(a, n1, ld, row_offset / NB, dinv, ws, s));
     VGP_TRY(trsm_right_t(n2, n1, 1.0, a, ld, dinv, a21, ld, ws, s));                               // A21 <- A21 L11^-T
     VGP_TRY(dense_gemm(0, 1, n2, n2, n1, -1.0, a21, ld, a21, ld, 1.0, a22, ld, GEMM_LOWER, s));    // A22 -= A21 A21^T
-    return potrf_rec(a22, n2, ld, row_offset + n1, dinv + (n1 / NB) * NB * NB, ws, s);
+    VGP_TRY(potrf_rec(a22, n2, ld, row_offset + n1, dinv2, ws, s));
+    if (wide) VGP_TRY(wide_build(a22, n2, ld, (row_offset + n1) / NB, dinv2, ws, s));
+    return VGP_OK;
 }
 
 int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
@@ -1213,6 +1315,7 @@ int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream
                 (long long)n, (long long)ld);
     VGP_TRY(ws.ensure(n / NB));
     read_slab_width();
+    VGP_TRY(ws.ensure_wide(n, wide_leaf_env()));
     if (emulate_slices() >= 2) VGP_TRY(emulated_reserve(n, emulate_slices(), s));
     VGP_CUDA(cudaMemsetAsync(ws.info, 0, sizeof(int), s));
     return potrf_rec(a, n, ld, 0, ws.dinv, ws, s);
@@ -1225,6 +1328,12 @@ __global__ void __launch_bounds__(256) block_copy_kernel(const double *src, doub
 }
 
 static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, DenseWorkspace &ws, cudaStream_t s) {
+    if (const double *w = wide_lookup(ws, dinv, n)) {      // the node's inverse is in the wide-leaf cache: copy it in
+        if (w != l)
+            VGP_CUDA(cudaMemcpy2DAsync(l, (size_t)ld * 8, w, (size_t)n * 8, (size_t)n * 8, (size_t)n,
+                                       cudaMemcpyDeviceToDevice, s));
+        return VGP_OK;
+    }
     if (n == NB) {
         block_copy_kernel<<<16, 256, 0, s>>>(dinv, l, ld);
         VGP_LAUNCH_CHECK();

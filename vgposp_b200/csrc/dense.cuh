@@ -12,7 +12,21 @@ struct DenseWorkspace {
     int *info = nullptr;        // device flag: 0, or 1 + row of the first non-positive pivot
     double *dinv = nullptr;     // [dinv_blocks][TILE][TILE]: inverses of the diagonal blocks of the last potrf
     int64_t dinv_blocks = 0;
+    // Opt-in (VGP_TRSM_LEAF=<width>, dense.cu "wide leaves"): explicit inverses of the diagonal nodes of the last
+    // potrf whose size is in (128, width], kept densely ([n][n], zeros above the diagonal) so that a solve against such
+    // a node is ONE product; `tmp` receives that product before it is copied over the right-hand sides.
+    struct WideNode {
+        int64_t block0, n;
+        size_t offset;
+    };
+    static constexpr int MAX_WIDE = 1024;
+    double *wide = nullptr, *tmp = nullptr;
+    size_t wide_doubles = 0, wide_used = 0, tmp_doubles = 0;
+    WideNode wide_nodes[MAX_WIDE];
+    int wide_count = 0;
+    int64_t leaf = 128;
     int ensure(int64_t nblocks);
+    int ensure_wide(int64_t n, int64_t width);      // sizes `wide` / `tmp` for an n x n factorisation, forgets old nodes
     void release();
 };
 
@@ -35,6 +49,8 @@ struct DistContext {
     // 1.26 s, 96 / 256 (1157 products, two flag barriers each) in 1.07 s (profiles/r01_bench_n50k_g8_thresholds.json)
     int64_t min_tiles = 96, min_k = 256;
     int64_t dist_gemms = 0, barriers = 0;
+    double *tmp = nullptr;                  // peer-mapped scratch behind the replica (wide-leaf solves), inside `bytes`
+    size_t tmp_doubles = 0;
 };
 void dense_set_dist(DistContext *ctx);      // thread-local; nullptr switches distribution off
 int dense_dist_barrier(DistContext &ctx, cudaStream_t s);

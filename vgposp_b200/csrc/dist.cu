@@ -56,6 +56,13 @@ int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t
     // the tail behind the replica (peer-mapped with it): two parity buffers of [row blocks][n_pad] partial sums for the
     // sharded lazy-column greedy (lazy.cu)
     h->tail_rows = 2 * ((h->n_pad + DIST_TAIL_RB - 1) / DIST_TAIL_RB);
+    // opt-in wide-leaf solves (dense.cu, VGP_TRSM_LEAF): their scratch products must be peer-visible to be distributed
+    const char *leaf_env = getenv("VGP_TRSM_LEAF");
+    const int64_t leaf = leaf_env ? atoll(leaf_env) : 0;
+    if (leaf > TILE) {
+        const int64_t rows = ((h->n_pad / 2 + 2 * TILE) * leaf + h->n_pad - 1) / h->n_pad;
+        if (rows > h->tail_rows) h->tail_rows = rows;
+    }
     cudaError_t e = cudaMalloc((void **)&h->matrix, bytes + (size_t)h->tail_rows * h->n_pad * 8);
     if (e == cudaSuccess) e = cudaMemset(h->matrix + (size_t)h->n_pad * h->n_pad, 0, (size_t)h->tail_rows * h->n_pad * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->flags, FLAG_BYTES);
@@ -68,6 +75,11 @@ int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t
     }
     h->ctx.base = h->matrix;
     h->ctx.bytes = bytes;
+    if (leaf > TILE) {
+        h->ctx.tmp = h->matrix + (size_t)h->n_pad * h->n_pad;
+        h->ctx.tmp_doubles = (size_t)h->tail_rows * h->n_pad;
+        h->ctx.bytes = bytes + h->ctx.tmp_doubles * 8;         // products into the scratch are distributed like any other
+    }
     // thresholds: DistContext defaults (dense.cuh) -- measured on 8 GPUs; the NVLink egress of the tile stores
     // (64 KB per 128x64 tile and peer) stays below a rank's 900 GB/s share down to k = 256
     // everything that could allocate, free or load a module later happens now, before any rank can be spinning
