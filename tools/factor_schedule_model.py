@@ -23,8 +23,16 @@ def split(n):
 
 
 class Trace:
-    def __init__(self, slab_width=0):
-        self.gemms, self.leaves, self.slabs, self.slab_width = [], 0, [], slab_width
+    def __init__(self, slab_width=0, leaf=0):
+        self.gemms, self.leaves, self.slabs, self.slab_width, self.leaf = [], 0, [], slab_width, leaf
+        self.copies = 0                         # doubles copied back from scratch by the wide-leaf solves
+
+    def wide(self, m, n, left=False):           # VGP_TRSM_LEAF: one product with the node's cached explicit inverse
+        if self.leaf and NB < n <= self.leaf:
+            self.gemm(n, m, n) if left else self.gemm(m, n, n)
+            self.copies += m * n
+            return True
+        return False
 
     def slab(self, m, n):                       # one launch: m / 128 slabs, each walks an n-wide triangle (slab.cu)
         if self.slab_width and NB < n <= self.slab_width:
@@ -37,7 +45,7 @@ class Trace:
 
     # -- the recursions of dense.cu (shapes only)
     def trsm_right(self, m, n):                 # both right-side forms: leaves m x 128 x 128, updates m x n2 x n1
-        if self.slab(m, n):
+        if self.slab(m, n) or self.wide(m, n):
             return
         if n == NB:
             return self.gemm(m, NB, NB)
@@ -47,7 +55,7 @@ class Trace:
         self.trsm_right(m, n - n1)
 
     def trsm_left(self, n, nrhs):
-        if self.slab(nrhs, n):
+        if self.slab(nrhs, n) or self.wide(nrhs, n, left=True):
             return
         if n == NB:
             return self.gemm(NB, nrhs, NB)
@@ -110,15 +118,16 @@ def main():
     opts = dict(a[2:].split("=") for a in sys.argv[1:] if a.startswith("--"))
     slab_width = int(opts.get("slab", 0))              # --slab=1024: solves of up to that width in one launch
     emulate = float(opts.get("emulate", 1.0))          # --emulate=2.5: products with m, n >= 2048, k >= 1024 that much faster
+    leaf = int(opts.get("leaf", 0))                    # --leaf=512: solves against nodes of up to that size as one product
     n = int(argv[0]) if argv else 50000
     ranks = [int(v) for v in argv[1:]] or [1, 2, 4, 8]
     n_pad = (n + NB - 1) // NB * NB
     t0, tk = fit()
-    tr = Trace(slab_width)
+    tr = Trace(slab_width, leaf)
     tr.potrf(n_pad)
     tr.trtri(n_pad)
     launch_us, leaf_us, barrier_us = 3.0, 45.0, 12.0     # launch gap of a short kernel; potf2 + block inverse; flag barrier
-    out = {"n": n, "n_pad": n_pad, "options": {"slab_width": slab_width, "emulated_speedup": emulate},
+    out = {"n": n, "n_pad": n_pad, "options": {"slab_width": slab_width, "emulated_speedup": emulate, "wide_leaf": leaf},
            "gemm_launches": len(tr.gemms), "slab_launches": len(tr.slabs), "diagonal_block_leaves": tr.leaves,
            "wave_model_us": {"t0": t0, "per_k": tk}, "ranks": {}}
     flops = sum((m * (m + 128) if lo else 2 * m * nn) * k for m, nn, k, lo in tr.gemms)
@@ -151,7 +160,8 @@ def main():
             slab_barriers += 2 if share > 1 else 0
             per_cta_us = 128.0 * (nn * nn + 128.0 * nn) / (35.5e12 / 148) * 1e6
             slab_t += math.ceil(math.ceil(slabs / share) / 148) * (t0 + per_cta_us) + launch_us
-        total = dist_t + repl_t + slab_t + tr.leaves * leaf_us + (2 * ndist + slab_barriers) * barrier_us
+        copy_t = tr.copies * 16 / 2.0e12 * 1e6            # pitched device copies: ~2 TB/s of read + write
+        total = dist_t + repl_t + slab_t + copy_t + tr.leaves * leaf_us + (2 * ndist + slab_barriers) * barrier_us
         out["ranks"][str(g)] = {
             "modelled_seconds": total / 1e6,
             "distributed_products": ndist, "distributed_seconds": dist_t / 1e6,
