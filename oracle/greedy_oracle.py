@@ -384,12 +384,24 @@ def _load_c():
     lib.oracle_segments.argtypes = [vp, vp, i64, i64, i64, vp, i64, i64, dbl, i64, dbl, vp, vp]
     lib.oracle_apply.restype = None
     lib.oracle_apply.argtypes = [vp, i64, i64, i64, i64, vp, vp, i64, vp, vp]
+    lib.oracle_set_threads.restype = ctypes.c_int
+    lib.oracle_set_threads.argtypes = [ctypes.c_int]
     return lib
 
 
-def incremental_greedy_c(cov_vv, k, small=GUARD_NUMPY, jitter=0.0, prec=None, timings=None):
+def set_threads(n):
+    """Thread count of the C/OpenMP step (omp_set_num_threads: overrides an OMP_NUM_THREADS=1 exported by a launcher
+    such as torch.distributed.run).  Returns the count in effect, or None without the C library."""
+    lib = _load_c()
+    if lib is None:
+        return None
+    return int(lib.oracle_set_threads(int(n)))
+
+
+def incremental_greedy_c(cov_vv, k, small=GUARD_NUMPY, jitter=0.0, prec=None, timings=None, all_scores=None):
     """Single-block incremental greedy with the per-step work in C/OpenMP.  Returns (selection, scores).
-    `timings`, if a dict, receives 'setup_s' (inverse) and 'steps_s' (list of per-selection seconds)."""
+    `timings`, if a dict, receives 'setup_s' (inverse) and 'steps_s' (list of per-selection seconds); `all_scores`, if
+    a list, receives every step's full score vector (NaN where taken), as incremental_greedy(return_all_scores=True)."""
     import ctypes
     import time
     lib = _load_c()
@@ -418,6 +430,8 @@ def incremental_greedy_c(cov_vv, k, small=GUARD_NUMPY, jitter=0.0, prec=None, ti
         y = lib.oracle_scores(ptr(P), n, 0, n, ptr(num), ptr(taken), small, jitter, ptr(scores), ctypes.byref(bs))
         if y < 0:
             raise ValueError("list.remove(x): x not in list")
+        if all_scores is not None:
+            all_scores.append(scores.copy())
         lib.oracle_segments(ptr(cov), ptr(P), n, 0, n, ptr(wfull), n, t, jitter, y, float(num[y]), ptr(w_seg),
                             ptr(p_seg))
         wfull[t] = w_seg

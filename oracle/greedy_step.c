@@ -10,7 +10,15 @@
  * Built by oracle/build_oracle.py with gcc -O3 -fopenmp; no product code links or loads it.
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
+
+/* explicit thread count (a launcher's OMP_NUM_THREADS=1 must not silently make the CPU arm single-threaded);
+ * n <= 0 only queries.  Returns the count the next parallel region will use. */
+int oracle_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
 
 /* scores[j] for j < nloc (NaN where taken); returns the local first strict maximum above -1 or -1 */
 int64_t oracle_scores(const double *prec, int64_t ld, int64_t c0, int64_t nloc, const double *num,
