@@ -12,7 +12,9 @@
  *   - pointers named *_dev are device pointers on `device`; pointers named *_host are host pointers;
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
  *     asynchronous on that stream unless stated otherwise;
- *   - no hidden global state: handles are per device and not thread-safe;
+ *   - handles are per device and not thread-safe; the only process-wide state is the option table below
+ *     (vgp_set_option) and the per-device workspace cache (vgp_workspace_trim).  The library never reads
+ *     environment variables;
  *   - there is no CPU fallback anywhere: without a CUDA device every compute call fails with
  *     VGP_ERR_CUDA.
  */
@@ -44,6 +46,39 @@ const char *vgp_last_error(void);
 int vgp_device_count(int *count);
 /* name[<=len], SM count, total/free bytes of HBM */
 int vgp_device_info(int device, char *name, int len, int *sm_count, size_t *total_bytes, size_t *free_bytes);
+
+/* Process-wide options.  Every rank of a multi-GPU run must hold the same values (vgp_dist_connect verifies the ones
+ * that change numerics or buffer sizes).  Defaults in brackets.
+ *   GEMM_EMULATE_SLICES  [8]  products of the O(n^3) factorisations (potrf / trtri / lauum) with m, n >= EMULATE_MIN and
+ *                             2 k >= EMULATE_MIN run on the int8 tensor cores (tcgen05.mma kind::i8) after an error-free
+ *                             split of the FP64 operands into this many 7-bit digit planes (csrc/emulated.cu): 8 planes
+ *                             = 36 exact integer products, result within 1e-14 of the FP64 DMMA product.  0 = every
+ *                             product on the FP64 tensor pipe (mma.sync DMMA).
+ *   GEMM_EMULATE_MIN     [2048]
+ *   H2D_OVERLAP          [1]  one-call placement: factorise behind the arriving host matrix (0: copy first)
+ *   GEMM_TILE_CONFIG     [-1] measurement knob: force the DMMA tile configuration (0 base, 1 pair, 2 tma)
+ *   GEMM_SMALL_BELOW     [74] products with fewer 128 x 64 tiles use the 64 x 64 tile shape
+ *   DIST_MIN_TILES / DIST_MIN_K [96 / 256] smallest product the distributed factorisation shares out over the ranks
+ *   ELBO_OVERLAP         [3]  side streams of the ELBO step (0: single stream)
+ *   WORKSPACE_CACHE_BYTES [-1] cap of the per-device workspace cache; -1 = half of the device memory, 0 = no caching */
+enum {
+    VGP_OPT_GEMM_EMULATE_SLICES = 0,
+    VGP_OPT_GEMM_EMULATE_MIN = 1,
+    VGP_OPT_H2D_OVERLAP = 2,
+    VGP_OPT_GEMM_TILE_CONFIG = 3,
+    VGP_OPT_GEMM_SMALL_BELOW = 4,
+    VGP_OPT_DIST_MIN_TILES = 5,
+    VGP_OPT_DIST_MIN_K = 6,
+    VGP_OPT_ELBO_OVERLAP = 7,
+    VGP_OPT_WORKSPACE_CACHE_BYTES = 8,
+    VGP_OPT_COUNT = 9
+};
+int vgp_set_option(int option, int64_t value);
+int vgp_get_option(int option, int64_t *value);
+/* The one-call placement entries (vgp_placement_host*) keep their device matrices (2 x 8 n^2 bytes) and the digit-plane
+ * workspace of the emulated products in a per-device cache between calls; this hands all of it back to the driver.
+ * Any allocation of the library that runs out of memory trims the cache by itself and retries. */
+int vgp_workspace_trim(int device, size_t *released_bytes);
 
 int vgp_malloc(int device, size_t bytes, void **ptr_dev);
 int vgp_free(int device, void *ptr_dev);
@@ -386,6 +421,10 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
 int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
                        double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
                        double *seconds_host);
+/* Host wall-clock breakdown of the calling thread's last vgp_placement_host_ex (lazy formulations), in seconds:
+ * [0] state allocation + initialisation (a hit in the per-device workspace cache after the first call), [1] enqueue of
+ * copies, factorisation and selections, [2] release of the state (back into the cache), [3] the whole call. */
+int vgp_placement_host_wall(double *seconds4);
 
 /* ---------------------------------------------------------------- distributed SPD inverse (setup, 8e) ------- */
 /* P = Sigma^-1 over the GPUs of one box, one rank per GPU (process or thread).  Stands for the same pseudo-inverses
@@ -419,13 +458,14 @@ int vgp_dist_factor_inverse(vgp_dist *handle, int *info_host, void *stream);
 int vgp_dist_add_diag(vgp_dist *handle, int64_t n, double value, void *stream);
 int vgp_dist_stats(vgp_dist *handle, int64_t *distributed_gemms, int64_t *barriers);
 
-/* ---------------------------------------------------------------- experimental: FP64 GEMM on the int8 tensor cores */
-/* NOT on any default path.  C[m][n] = alpha op(A) op(B) + beta C with FP64-class accuracy, the products taken exactly on
- * tcgen05.mma kind::i8 after an error-free split of the operands into `slices` 7-bit digit planes (Ozaki scheme;
- * csrc/emulated.cu, tools/ozaki_prototype.py).  Same operand convention as the dense layer: trans_a == 0: A stored
+/* ---------------------------------------------------------------- FP64-class GEMM on the int8 tensor cores ---- */
+/* C[m][n] = alpha op(A) op(B) + beta C with FP64-class accuracy, the products taken exactly on tcgen05.mma kind::i8
+ * (int32 accumulators in tensor memory) after an error-free split of the operands into `slices` (2..8) 7-bit digit
+ * planes (Ozaki scheme; csrc/emulated.cu).  Same operand convention as vgp_dgemm's internals: trans_a == 0: A stored
  * [m][k], 1: [k][m]; trans_b == 0: B stored [k][n], 1: [n][k].  lower != 0: only the 128 x 128 tiles on or below the
- * diagonal.  Candidate replacement for the DMMA products of potrf / trtri (placement_algorithm2.py:399-413 via the
- * seed inverse); to be validated on the GPU before anything routes through it. */
+ * diagonal.  C must not overlap A or B.  This is what the large products of potrf / trtri / lauum run on by default
+ * (VGP_OPT_GEMM_EMULATE_SLICES; the seed inverse behind placement_algorithm2.py:399-413): 59 TFLOP/s FP64-equivalent
+ * at 8192^3 against 36 for DGEMM on the FP64 pipe, max relative difference 1e-14 (profiles/r02_*). */
 int vgp_gemm_emulated(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
                       const double *a_dev, int64_t lda, const double *b_dev, int64_t ldb, double beta, double *c_dev,
                       int64_t ldc, int slices, int lower, void *stream);

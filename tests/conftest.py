@@ -62,3 +62,20 @@ def golden():
 def pytest_generate_tests(metafunc):
     if "golden_name" in metafunc.fixturenames:
         metafunc.parametrize("golden_name", Golden().names())
+
+
+@pytest.fixture
+def vgp_options():
+    """Set process-wide library options (vgp_set_option) for one test and restore them afterwards:
+    vgp_options(dist_min_tiles=2, gemm_emulate_min=512)."""
+    from vgposp_b200 import _ffi
+    saved = {}
+
+    def set_(**kw):
+        for name, value in kw.items():
+            old = _ffi.set_option(name, value)
+            saved.setdefault(name, old)
+
+    yield set_
+    for name, old in saved.items():
+        _ffi.set_option(name, old)

@@ -16,8 +16,9 @@ def main():
     from oracle import greedy_oracle as go
     from vgposp_b200 import _ffi, greedy
     from vgposp_b200.dist_inverse import DistInverse
-    os.environ["VGP_DIST_MIN_TILES"] = "2"
-    os.environ["VGP_DIST_MIN_K"] = "256"
+    _ffi.set_option("dist_min_tiles", 2)
+    _ffi.set_option("dist_min_k", 256)
+    _ffi.set_option("gemm_emulate_min", 512)       # small n: still exercise the int8 products, distributed
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

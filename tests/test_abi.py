@@ -111,3 +111,23 @@ def test_triangle_bounds_balance_the_lower_triangle():
     b = triangle_bounds(50000, 8)
     share = [(y * (y + 1) - x * (x + 1)) / 2 for x, y in zip(b[:-1], b[1:])]       # lower-triangle entries per slab
     assert max(share) / (50000 * 50001 / 2 / 8) < 1.03
+
+
+def test_options_table_roundtrip_and_validation():
+    """vgp_set_option / vgp_get_option (no device needed): defaults as documented in the header, bad values refused,
+    and the library does not read the environment."""
+    assert _ffi.get_option("gemm_emulate_slices") == 8
+    assert _ffi.get_option("gemm_emulate_min") == 2048
+    assert _ffi.get_option("dist_min_tiles") == 96 and _ffi.get_option("dist_min_k") == 256
+    old = _ffi.set_option("gemm_emulate_slices", 0)
+    assert old == 8 and _ffi.get_option("gemm_emulate_slices") == 0
+    _ffi.set_option("gemm_emulate_slices", old)
+    for bad in (1, 9, -3):
+        with pytest.raises(_ffi.VgpError):
+            _ffi.set_option("gemm_emulate_slices", bad)
+    with pytest.raises(_ffi.VgpError):
+        _ffi.call("vgp_set_option", 99, 1)
+    assert sorted(_ffi.OPTIONS.values()) == list(range(len(_ffi.OPTIONS)))
+    src = "".join(open(os.path.join(ROOT, "vgposp_b200", "csrc", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "vgposp_b200", "csrc")))
+    assert "getenv" not in src

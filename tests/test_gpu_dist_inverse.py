@@ -36,11 +36,11 @@ def single_inverse(a):
 
 
 @pytest.mark.timeout(240)
+@pytest.mark.parametrize("emulate_min", [2048, 512], ids=["fp64_products", "int8_products"])
 @pytest.mark.parametrize("n,world", [(1000, 2), (1664, 3), (2050, 4)])
-def test_ranks_as_threads_one_device(n, world, monkeypatch):
+def test_ranks_as_threads_one_device(n, world, emulate_min, vgp_options):
     """G ranks as threads of this process on one device (each with its own stream and replica)."""
-    monkeypatch.setenv("VGP_DIST_MIN_TILES", "2")
-    monkeypatch.setenv("VGP_DIST_MIN_K", "256")
+    vgp_options(dist_min_tiles=2, dist_min_k=256, gemm_emulate_min=emulate_min)
     a = spd(n, n)
     want = single_inverse(a)
     streams = []
@@ -97,15 +97,15 @@ def test_two_processes_ipc():
 
 
 @pytest.mark.timeout(240)
+@pytest.mark.parametrize("emulate_min", [2048, 512], ids=["fp64_products", "int8_products"])
 @pytest.mark.parametrize("n,world,k", [(1000, 2, 12), (1664, 3, 20), (2050, 4, 9), (700, 2, 600)])
-def test_sharded_lazy_factor_greedy_threads(n, world, k, monkeypatch):
+def test_sharded_lazy_factor_greedy_threads(n, world, k, emulate_min, vgp_options):
     """The one-call path on G ranks: replicas factorised to L^-1 by the distributed potrf + trtri, the triangular
     matrix-vector product of every selection split over the ranks (csrc/lazy.cu, vgp_lazy_create_dist).  Every rank
     must return the single-device lazy-factor result bit for bit, and the CPU oracle's selection."""
     from oracle import greedy_oracle as go
     from vgposp_b200 import greedy
-    monkeypatch.setenv("VGP_DIST_MIN_TILES", "2")
-    monkeypatch.setenv("VGP_DIST_MIN_K", "256")
+    vgp_options(dist_min_tiles=2, dist_min_k=256, gemm_emulate_min=emulate_min)
     a = spd(n, n + 1)
     want = greedy.place_single(a, k, D, want_step_scores=True, formulation="lazy_factor")
     streams = []

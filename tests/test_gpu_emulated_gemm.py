@@ -1,8 +1,7 @@
-"""GPU check of the experimental FP64-on-int8 GEMM (csrc/emulated.cu, vgp_gemm_emulated): the digit-plane product must
-agree with a float64 matmul to the accuracy tools/ozaki_prototype.py predicts for the slice count.
-
-The kernel is not on any default path and has not been validated on hardware yet, so these tests only run with
-VGP_TEST_EMULATED=1 (first thing to do with a GPU at hand: VGP_TEST_EMULATED=1 pytest tests/test_gpu_emulated_gemm.py)."""
+"""GPU check of the FP64-class GEMM on the int8 tensor cores (csrc/emulated.cu, vgp_gemm_emulated; the default route of the
+large products of potrf / trtri / lauum): the digit-plane product must agree with a float64 matmul to the accuracy
+tools/ozaki_prototype.py predicts for the slice count, and a factorisation built on it must leave the placement
+unchanged.  First validated on a B200 in round 2 (profiles/r02_first_contact_experimental_paths.md)."""
 import os
 
 import numpy as np
@@ -10,16 +9,8 @@ import pytest
 
 from vgposp_b200 import _ffi
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VGP_TEST_EMULATED") != "1", reason="experimental kernel: opt in")]
+pytestmark = pytest.mark.gpu
 D = 0
-
-
-@pytest.fixture(params=[1, 2], ids=["by_group", "planes_resident"], autouse=True)
-def variant(request, monkeypatch):
-    """Both kernels: group by group (128 x 128 tiles) and all planes of a k block resident (128 x 64 tiles)."""
-    monkeypatch.setenv("VGP_GEMM_EMULATE_VARIANT", str(request.param))
-    return request.param
 
 
 def emulated(a, b, trans_a, trans_b, m, n, k, alpha=1.0, beta=0.0, c=None, slices=8, lower=0):
@@ -46,10 +37,8 @@ def test_matches_float64_matmul(m, n, k, trans_a, trans_b):
     assert np.max(np.abs(got - want) / scale) < 1e-13
 
 
-@pytest.mark.parametrize("slices,tol", [(6, 1e-9), (7, 1e-11), (8, 1e-13), (9, 1e-15)])
-def test_accuracy_follows_the_slice_count(slices, tol, variant):
-    if slices == 9 and variant == 2:
-        pytest.skip("nine group accumulators do not fit the 512 TMEM columns: falls back to the by-group kernel")
+@pytest.mark.parametrize("slices,tol", [(4, 1e-5), (6, 1e-9), (7, 1e-11), (8, 1e-13)])
+def test_accuracy_follows_the_slice_count(slices, tol):
     rng = np.random.default_rng(slices)
     a, b = rng.standard_normal((256, 1024)), rng.standard_normal((256, 1024))
     want = (a.astype(np.longdouble) @ b.T.astype(np.longdouble)).astype(np.float64)
@@ -81,37 +70,72 @@ def test_workload_product_keeps_the_selection():
     assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < 1e-13
 
 
-def test_both_kernels_give_the_same_bits(monkeypatch):
+def test_result_is_independent_of_the_k_split():
+    """Integer partial sums: splitting k (here: two calls with beta = 1 against one call) changes nothing but the
+    order of the final FP64 additions of two exact group sums -- agreement to the last few ulps, and the single call
+    is run-to-run bitwise reproducible."""
     rng = np.random.default_rng(11)
     a, b = rng.standard_normal((384, 640)), rng.standard_normal((320, 640))
-    monkeypatch.setenv("VGP_GEMM_EMULATE_VARIANT", "1")
     one = emulated(a, b, 0, 1, 384, 320, 640)
-    monkeypatch.setenv("VGP_GEMM_EMULATE_VARIANT", "2")
-    two = emulated(a, b, 0, 1, 384, 320, 640)
-    np.testing.assert_array_equal(one, two)          # same integer sums, same FP64 recombination order
+    again = emulated(a, b, 0, 1, 384, 320, 640)
+    np.testing.assert_array_equal(one, again)
+    first = emulated(np.ascontiguousarray(a[:, :256]), np.ascontiguousarray(b[:, :256]), 0, 1, 384, 320, 256)
+    c = np.zeros((384, 320))
+    c[:, :] = first
+    two = emulated(np.ascontiguousarray(a[:, 256:]), np.ascontiguousarray(b[:, 256:]), 0, 1, 384, 320, 384, beta=1.0, c=c)
+    np.testing.assert_allclose(two, one, rtol=0, atol=1e-13)
 
 
-def test_placement_on_emulated_factorisation_matches_the_oracle():
-    """The whole one-call placement with the large products of potrf + trtri routed through the int8 kernels
-    (VGP_GEMM_EMULATE is read once per process, hence the subprocess)."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import numpy as np, json, sys\n"
-        "sys.path.insert(0, %r)\n"
-        "from vgposp_b200 import greedy\n"
-        "x = np.random.default_rng(7).uniform(-2, 2, (3000, 3)); ls = 0.5 * (1000.0 / 3000) ** (1 / 3)\n"
-        "d = x[:, None, :] - x[None, :, :]\n"
-        "cov = np.exp(-np.einsum('ijk,ijk->ij', d, d) / (2 * ls * ls)) + 1e-2 * np.eye(3000)\n"
-        "sel, sc, _, _ = greedy.place_single(cov, 12, 0, formulation='lazy_factor')\n"
-        "print(json.dumps({'sel': [int(v) for v in sel], 'scores': [float(v) for v in sc]}))\n" % root)
+def test_rejects_bad_arguments():
+    a = _ffi.DeviceArray.from_host(np.zeros((128, 128)), D)
+    c = _ffi.DeviceArray.from_host(np.zeros((128, 128)), D)
+    with pytest.raises(_ffi.VgpError, match="slices"):           # more planes than tensor memory holds
+        _ffi.call("vgp_gemm_emulated", D, 0, 1, 128, 128, 128, 1.0, a.ptr, 128, a.ptr, 128, 0.0, c.ptr, 128, 9, 0, None)
+    with pytest.raises(_ffi.VgpError, match="aliases"):          # C aliases A
+        _ffi.call("vgp_gemm_emulated", D, 0, 1, 128, 128, 128, 1.0, a.ptr, 128, a.ptr, 128, 0.0, a.ptr, 128, 8, 0, None)
+    a.free()
+    c.free()
+
+
+@pytest.mark.parametrize("formulation", ["lazy_factor", "lazy_precision", "dense"])
+def test_placement_on_emulated_factorisation_matches_the_fp64_pipe_and_the_oracle(formulation, vgp_options):
+    """The whole one-call placement with the large products of potrf + trtri (+ lauum) on the int8 tensor cores
+    (threshold lowered so that n = 3000 has such products) against the same call on the FP64 pipe and the CPU oracle."""
+    from oracle import greedy_oracle as go
+    from vgposp_b200 import greedy
+    n, k = 3000, 12
+    x = np.random.default_rng(7).uniform(-2, 2, (n, 3))
+    ls = 0.5 * (1000.0 / n) ** (1 / 3)
+    d = x[:, None, :] - x[None, :, :]
+    cov = np.exp(-np.einsum("ijk,ijk->ij", d, d) / (2 * ls * ls)) + 1e-2 * np.eye(n)
+    vgp_options(gemm_emulate_slices=0)
+    sel0, sc0, _, _ = greedy.place_single(cov, k, D, formulation=formulation)
+    vgp_options(gemm_emulate_slices=8, gemm_emulate_min=512)
+    sel1, sc1, _, _ = greedy.place_single(cov, k, D, formulation=formulation)
+    want_sel, want_scores = go.incremental_greedy_c(cov, k)
+    assert [int(v) for v in sel0] == [int(v) for v in sel1] == want_sel
+    np.testing.assert_allclose(sc1, sc0, rtol=1e-11)
+    np.testing.assert_allclose(sc1, want_scores, rtol=1e-9)
+    assert not np.array_equal(sc1, sc0), "the int8 route was not taken"
+
+
+def test_spd_inverse_on_emulated_products(vgp_options):
+    import ctypes
+    n = 4096
+    x = np.random.default_rng(3).uniform(-2, 2, (n, 3))
+    ls = 0.5 * (1000.0 / n) ** (1 / 3)
+    cov = np.empty((n, n))
+    for i in range(0, n, 512):
+        dd = x[i:i + 512, None, :] - x[None, :, :]
+        cov[i:i + 512] = np.exp(-np.einsum("ijk,ijk->ij", dd, dd) / (2 * ls * ls))
+    cov[np.diag_indices(n)] += 1e-2
     outs = []
-    for emulate in ("0", "8"):
-        env = dict(os.environ, VGP_GEMM_EMULATE=emulate, VGP_GEMM_EMULATE_MIN="512")
-        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=root)
-        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-        import json
-        outs.append(json.loads(res.stdout.strip().splitlines()[-1]))
-    assert outs[0]["sel"] == outs[1]["sel"]
-    np.testing.assert_allclose(outs[1]["scores"], outs[0]["scores"], rtol=1e-10)
+    for slices in (0, 8):
+        vgp_options(gemm_emulate_slices=slices, gemm_emulate_min=1024)
+        dev = _ffi.DeviceArray.from_host(cov, D)
+        info = ctypes.c_int(0)
+        _ffi.call("vgp_spd_inverse", D, dev.ptr, n, n, ctypes.byref(info), None)
+        outs.append(dev.to_host())
+        dev.free()
+    np.testing.assert_allclose(outs[1], outs[0], rtol=0, atol=1e-11 * np.abs(outs[0]).max())
+    np.testing.assert_allclose(outs[1] @ cov, np.eye(n), atol=1e-9)

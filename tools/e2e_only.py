@@ -1,5 +1,7 @@
 """The one-call host path alone (vgp_placement_host_ex on a pinned host covariance), repeated; prints the event
-breakdown of every call.  VGP_H2D_OVERLAP=0 finishes the copy before the factorisation starts (comparison knob)."""
+breakdown of every call.  Options through the environment of this tool (VGP_OPT_<NAME>, _ffi.apply_env_options):
+VGP_OPT_H2D_OVERLAP=0 finishes the copy before the factorisation starts; VGP_OPT_GEMM_EMULATE_SLICES=0 keeps every
+product on the FP64 pipe."""
 import ctypes
 import os
 import sys
@@ -13,6 +15,7 @@ from vgposp_b200 import _ffi  # noqa: E402
 from vgposp_b200._ffi import call  # noqa: E402
 from vgposp_b200.greedy import FORMULATIONS  # noqa: E402
 
+print("options", _ffi.apply_env_options(), flush=True)
 n = int(os.environ.get("VGP_BENCH_N", 50000))
 k = 100
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
@@ -34,6 +37,9 @@ for form in sys.argv[2:] or ["auto"]:
         call("vgp_placement_host_ex", 0, host, n, n, k, 1e-8, 0.0, FORMULATIONS[form], sel.ctypes.data, sc.ctypes.data,
              None, secs.ctypes.data)
         wall = time.perf_counter() - t0
-        print(form, "overlap=%s" % os.environ.get("VGP_H2D_OVERLAP", "1"), "h2d %.3f factor %.3f select %.3f total %.3f"
-              % tuple(secs), "wall %.3f" % wall, "sel", sel[:4], flush=True)
+        hw = np.zeros(4)
+        call("vgp_placement_host_wall", hw.ctypes.data)
+        print(form, "overlap=%d" % _ffi.get_option("h2d_overlap"), "h2d %.3f factor %.3f select %.3f total %.3f"
+              % tuple(secs), "wall %.3f" % wall, "(alloc %.3f enqueue %.3f release %.3f)" % tuple(hw[:3]), "sel", sel[:4],
+              flush=True)
 call("vgp_host_free", host)

@@ -47,6 +47,9 @@ SIGNATURES = {
     "vgp_last_error": [],
     "vgp_device_count": [P(c_int)],
     "vgp_device_info": [c_int, ctypes.c_char_p, c_int, P(c_int), P(c_sz), P(c_sz)],
+    "vgp_set_option": [c_int, c_i64],
+    "vgp_get_option": [c_int, P(c_i64)],
+    "vgp_workspace_trim": [c_int, P(c_sz)],
     "vgp_malloc": [c_int, c_sz, P(c_vp)],
     "vgp_free": [c_int, c_vp],
     "vgp_host_alloc": [c_sz, P(c_vp)],
@@ -139,6 +142,7 @@ SIGNATURES = {
     "vgp_greedy_profile_read": [c_vp, P(c_dbl), P(c_i64)],
     "vgp_placement_host": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp],
     "vgp_placement_host_ex": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp],
+    "vgp_placement_host_wall": [c_vp],
     "vgp_lazy_create": [P(c_vp), c_int, c_i64, c_i64, c_dbl, c_dbl, c_int],
     "vgp_lazy_destroy": [c_vp],
     "vgp_lazy_matrices": [c_vp, P(c_vp), P(c_vp), P(c_i64)],
@@ -156,25 +160,39 @@ SIGNATURES = {
 _RESTYPES = {"vgp_last_error": ctypes.c_char_p}
 _NO_STATUS = {"vgp_abi_version", "vgp_last_error"}
 
+# vgp_set_option identifiers (include/vgposp.h)
+OPTIONS = {"gemm_emulate_slices": 0, "gemm_emulate_min": 1, "h2d_overlap": 2, "gemm_tile_config": 3,
+           "gemm_small_below": 4, "dist_min_tiles": 5, "dist_min_k": 6, "elbo_overlap": 7, "workspace_cache_bytes": 8}
+
 _lib = None
+LOADED = {"path": None, "stamp": None, "stamp_matches_sources": None}     # what load() bound; bench/tests print it
 
 
 def load(build_if_missing=True):
-    """Load (once) and type libvgposp.so.  Builds it in-tree when absent and nvcc is available."""
+    """Load (once) and type libvgposp.so.  Builds it in-tree when absent or stale and nvcc is available; a build
+    that fails while the sources no longer match the existing binary is an error, never a silent stale load."""
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if build_if_missing:
         # no-op when the in-tree library matches the sources (stamp); rebuilds after an edit
-        from . import build as _build
         try:
             _build.build()
         except Exception:
-            if not os.path.exists(LIB_PATH):
-                raise
+            if not os.path.exists(LIB_PATH) or _build.nvcc_available():
+                raise                    # nvcc is here and the build failed: do not run against the old binary
     if not os.path.exists(LIB_PATH):
         raise VgpError(VGP_ERR_STATE, "libvgposp.so not built (run python -m vgposp_b200.build)")
-    lib = ctypes.CDLL(os.environ.get("VGP_LIB", LIB_PATH))        # VGP_LIB: A/B comparisons of two builds
+    path = os.environ.get("VGP_LIB", LIB_PATH)                     # VGP_LIB: A/B comparisons of two builds
+    built = _build.built_stamp()
+    LOADED.update(path=path, stamp=built, stamp_matches_sources=(built == _build.source_stamp()) if path == LIB_PATH
+                  else None)
+    if path == LIB_PATH and built != _build.source_stamp():
+        import warnings
+        warnings.warn("libvgposp.so was built from different sources (stamp %s...): rebuild with python -m "
+                      "vgposp_b200.build" % (built or "none")[:12])
+    lib = ctypes.CDLL(path)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -197,6 +215,39 @@ def call(name, *args):
             raise NotPositiveDefiniteError(status, msg)
         raise VgpError(status, msg)
     return status
+
+
+def set_option(name, value):
+    """vgp_set_option by name (OPTIONS); returns the previous value."""
+    old = c_i64(0)
+    call("vgp_get_option", OPTIONS[name], ctypes.byref(old))
+    call("vgp_set_option", OPTIONS[name], int(value))
+    return old.value
+
+
+def get_option(name):
+    v = c_i64(0)
+    call("vgp_get_option", OPTIONS[name], ctypes.byref(v))
+    return v.value
+
+
+def apply_env_options():
+    """For the measurement tools only (the library itself never reads the environment): VGP_OPT_<NAME>=<int> for
+    every name in OPTIONS, e.g. VGP_OPT_GEMM_EMULATE_SLICES=0.  Returns what was applied."""
+    applied = {}
+    for name in OPTIONS:
+        v = os.environ.get("VGP_OPT_" + name.upper())
+        if v not in (None, ""):
+            set_option(name, int(v))
+            applied[name] = int(v)
+    return applied
+
+
+def workspace_trim(device=0):
+    """Hand the cached device workspace (matrices of the one-call placement, digit planes) back to the driver."""
+    out = c_sz(0)
+    call("vgp_workspace_trim", device, ctypes.byref(out))
+    return out.value
 
 
 def device_count():

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvgposp.so")
-SOURCES = ["runtime.cu", "expquad.cu", "dense.cu", "dense_api.cu", "greedy.cu", "gp.cu", "elbo.cu", "dist.cu", "lazy.cu", "emulated.cu", "slab.cu"]
+SOURCES = ["runtime.cu", "expquad.cu", "dense.cu", "dense_api.cu", "greedy.cu", "gp.cu", "elbo.cu", "dist.cu", "lazy.cu", "emulated.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -36,6 +36,23 @@ def _stamp():
                     h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
+
+
+def source_stamp():
+    return _stamp()
+
+
+def built_stamp():
+    try:
+        with open(os.path.join(LIBDIR, "build.stamp")) as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
+def nvcc_available():
+    import shutil
+    return os.path.exists(_nvcc()) or shutil.which("nvcc") is not None
 
 
 def build(force=False, verbose=False):

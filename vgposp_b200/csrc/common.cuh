@@ -22,6 +22,20 @@ struct DeviceGuard {
     ~DeviceGuard();
 };
 
+// Process-wide options (vgp_set_option): the library's only global state; it never reads the environment.
+int64_t option(int which);
+
+// cudaMalloc that, when the device is out of memory, first hands the cached workspace blocks back and retries.
+cudaError_t device_malloc(void **ptr, size_t bytes);
+// Workspace cache of the CURRENT device: the multi-gigabyte matrices of the one-call placement paths are kept across
+// calls (allocating and releasing 2 x 20 GB per call cost 0.03 - 3.5 s of host time at n = 50 000, erratically).
+// cache_alloc hands out a cached block of at least `bytes` (at most 1/8 larger) or allocates; cache_free waits for
+// the device and keeps the block unless the cache limit (VGP_OPT_WORKSPACE_CACHE_BYTES) would be exceeded.
+cudaError_t cache_alloc(void **ptr, size_t bytes);
+void cache_free(void *ptr);
+size_t cache_trim_current(size_t *cached_before);
+size_t emulated_release();      // emulated.cu: digit-plane workspace of the current device
+
 constexpr int64_t TILE = 128;   // every dense matrix the library owns is padded to a multiple of this
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

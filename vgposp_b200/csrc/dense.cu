@@ -604,21 +604,10 @@ static int gemm_launch_tma(const GemmArgs &p, cudaStream_t s) {
 // own all 128 rows of its column block: every shape with 128-row tiles, i.e. not tma::Small -- a 64-row tile there let
 // two CTAs overwrite rows the other was still reading, an intermittent wrong K^-1 in the ELBO step until it was
 // excluded).
-// VGP_GEMM_CFG = base | pair | tma forces one for every product that may legally use it (measurement knob).
+// VGP_OPT_GEMM_TILE_CONFIG = 0 base | 1 pair | 2 tma forces one for every product that may legally use it
+// (measurement knob; -1 = automatic).
 enum GemmChoice { CHOICE_BASE = 0, CHOICE_PAIR = 1, CHOICE_TMA = 2 };
-static int gemm_forced_choice() {
-    static int forced = -2;
-    if (forced == -2) {
-        const char *e = getenv("VGP_GEMM_CFG");
-        forced = -1;
-        if (e) {
-            if (!strcmp(e, "base")) forced = CHOICE_BASE;
-            if (!strcmp(e, "pair")) forced = CHOICE_PAIR;
-            if (!strcmp(e, "tma")) forced = CHOICE_TMA;
-        }
-    }
-    return forced;
-}
+static int gemm_forced_choice() { return (int)option(VGP_OPT_GEMM_TILE_CONFIG); }
 static GemmChoice gemm_choose(const GemmArgs &p) {
     if (p.in_place & 1) return CHOICE_BASE;
     const int f = gemm_forced_choice();
@@ -673,7 +662,7 @@ static int gemm_launch(const GemmArgs &p, cudaStream_t s) {
         // (the lower-tile mode stays Big: its tile enumeration assumes TM = 128 row blocks)
         int64_t big_tiles = (p.m / tma::Big::TM) * (p.n / tma::Big::TN) * ((p.k + p.k_split - 1) / p.k_split);
         if (p.dist_n > 0) big_tiles /= p.tiles_n;         // distributed product: this rank's share (tiles_n = ranks here)
-        static const int small_below = getenv("VGP_GEMM_SMALL_BELOW") ? atoi(getenv("VGP_GEMM_SMALL_BELOW")) : 74;
+        const int64_t small_below = option(VGP_OPT_GEMM_SMALL_BELOW);
         if (!p.lower && !p.in_place && big_tiles < small_below) return gemm_launch_tma<tma::Small, AKC, BKC>(p, s);
         // a k-strided A arrives as eight 2 KB boxes per stage: measured equal to (B k-strided) or 1.5 % behind
         // (B k-contiguous) the cp.async ring on large products, so those keep the ring; 34.1-34.6 vs 34.3-35.1 TFLOP/s
@@ -691,10 +680,24 @@ static int gemm_dispatch(int trans_a, int trans_b, const GemmArgs &p, cudaStream
     return gemm_launch<false, true>(p, s);
 }
 
-static int emulate_slices() {       // VGP_GEMM_EMULATE=<digit planes>: 0 (default) keeps every product on the FP64 pipe
-    static const int slices = getenv("VGP_GEMM_EMULATE") ? atoi(getenv("VGP_GEMM_EMULATE")) : 0;
-    return slices;
-}
+// Digit planes of the int8 tensor-core product (emulated.cu) for the large products; 0 = FP64 DMMA only.  Only the
+// factorisation entry points (potrf / trtri / lauum and what is built on them) switch it on for their own products:
+// thread-local, set by EmulateScope.
+static thread_local int g_emulate_slices = 0;
+static thread_local EmuWorkspace *g_emu_ws = nullptr;
+struct EmulateScope {
+    int prev;
+    EmuWorkspace *prev_ws;
+    explicit EmulateScope(DenseWorkspace &ws) : prev(g_emulate_slices), prev_ws(g_emu_ws) {
+        g_emulate_slices = (int)option(VGP_OPT_GEMM_EMULATE_SLICES);
+        g_emu_ws = &ws.emu;
+    }
+    ~EmulateScope() {
+        g_emulate_slices = prev;
+        g_emu_ws = prev_ws;
+    }
+};
+static int emulate_slices() { return g_emulate_slices; }
 
 int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, GemmTiles tiles,
@@ -719,12 +722,13 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
         VGP_TRY(gate_wait(c, m, s));
     }
     DistContext *dc = g_dist;
-    // opt-in experiment: large products on the int8 tensor cores (emulated.cu); never taken unless the variable is set
+    // large products of the factorisations: int8 tensor cores (emulated.cu), exact integer partial products
     const int emu_slices = emulate_slices();
-    static const int64_t emu_min = getenv("VGP_GEMM_EMULATE_MIN") ? atoll(getenv("VGP_GEMM_EMULATE_MIN")) : 2048;
-    const bool emulate = emu_slices >= 2 && m >= emu_min && n >= emu_min && 2 * k >= emu_min;
+    const int64_t emu_min = option(VGP_OPT_GEMM_EMULATE_MIN);
+    const bool emulate = emu_slices >= 2 && g_emu_ws && m >= emu_min && n >= emu_min && 2 * k >= emu_min && c != a &&
+                         c != b;
     if (emulate && !(dc && dc->nranks > 1))
-        return emulated_gemm(trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, emu_slices,
+        return emulated_gemm(*g_emu_ws, trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, emu_slices,
                              tiles == GEMM_LOWER ? 1 : 0, s);
     if (dc && dc->nranks > 1) {
         const int64_t tm = m / BM, tn = n / BN;
@@ -739,8 +743,8 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
             ++dc->dist_gemms;
             VGP_TRY(dense_dist_barrier(*dc, s));                  // every rank is done with all earlier work
             if (emulate) {
-                VGP_TRY(emulated_gemm(trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, emu_slices,
-                                      tiles == GEMM_LOWER ? 1 : 0, s, dc));
+                VGP_TRY(emulated_gemm(*g_emu_ws, trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc,
+                                      emu_slices, tiles == GEMM_LOWER ? 1 : 0, s, dc));
                 return dense_dist_barrier(*dc, s);
             }
             VGP_TRY(gemm_dispatch(trans_a, trans_b, p, s));
@@ -1018,8 +1022,8 @@ int DenseWorkspace::ensure(int64_t nblocks) {
     if (winv && device != dev) release();
     device = dev;
     if (!winv) {
-        VGP_CUDA(cudaMalloc((void **)&winv, (size_t)NB * NB * 8));
-        VGP_CUDA(cudaMalloc((void **)&info, sizeof(int)));
+        VGP_CUDA(device_malloc((void **)&winv, (size_t)NB * NB * 8));
+        VGP_CUDA(device_malloc((void **)&info, sizeof(int)));
         VGP_CUDA(cudaMemset(info, 0, sizeof(int)));
         VGP_TRY(block_kernels_configure());
     }
@@ -1027,32 +1031,8 @@ int DenseWorkspace::ensure(int64_t nblocks) {
         if (dinv) cudaFree(dinv);
         dinv = nullptr;
         dinv_blocks = 0;
-        VGP_CUDA(cudaMalloc((void **)&dinv, (size_t)nblocks * NB * NB * 8));
+        VGP_CUDA(device_malloc((void **)&dinv, (size_t)nblocks * NB * NB * 8));
         dinv_blocks = nblocks;
-    }
-    return VGP_OK;
-}
-
-int DenseWorkspace::ensure_wide(int64_t n, int64_t width) {
-    leaf = width > NB ? width : NB;
-    wide_count = 0;
-    wide_used = 0;
-    if (leaf <= NB) return VGP_OK;
-    const size_t want_wide = (size_t)n * (size_t)leaf;                       // sum of n_i^2 <= leaf * sum of n_i
-    const size_t want_tmp = (size_t)(n / 2 + 2 * NB) * (size_t)leaf;        // the widest right-hand side: half the matrix
-    if (wide_doubles < want_wide) {
-        if (wide) cudaFree(wide);
-        wide = nullptr;
-        wide_doubles = 0;
-        VGP_CUDA(cudaMalloc((void **)&wide, want_wide * 8));
-        wide_doubles = want_wide;
-    }
-    if (tmp_doubles < want_tmp) {
-        if (tmp) cudaFree(tmp);
-        tmp = nullptr;
-        tmp_doubles = 0;
-        VGP_CUDA(cudaMalloc((void **)&tmp, want_tmp * 8));
-        tmp_doubles = want_tmp;
     }
     return VGP_OK;
 }
@@ -1061,15 +1041,10 @@ void DenseWorkspace::release() {
     if (winv) cudaFree(winv);
     if (info) cudaFree(info);
     if (dinv) cudaFree(dinv);
-    if (wide) cudaFree(wide);
-    if (tmp) cudaFree(tmp);
     winv = nullptr;
     info = nullptr;
     dinv = nullptr;
-    wide = tmp = nullptr;
-    wide_doubles = wide_used = tmp_doubles = 0;
-    wide_count = 0;
-    leaf = NB;
+    emu.release();
     dinv_blocks = 0;
     device = -1;
 }
@@ -1097,106 +1072,9 @@ static inline const double *dinv_at(const double *dinv, int64_t rows) {
 // =====================================================================================================
 // triangular solves (recursive), all in place on B.  `dinv`: cached inverses of L's diagonal blocks or NULL.
 // =====================================================================================================
-// ---- wide leaves (opt-in, VGP_TRSM_LEAF=<width>) -----------------------------------------------------------------
-// The solves recurse down to 128-wide leaves: 8 107 of the 9 262 products of potrf + trtri at n = 50 000 have k <= 128,
-// take 0.26 s and are too thin to distribute (tools/factor_schedule_model.py).  With the explicit inverse W of every
-// diagonal node of size in (128, width] at hand, a solve against such a node is one dense product (X = alpha B W^T,
-// alpha B W or alpha W B) with k = the node size -- fewer, fatter, distributable launches for twice the flops of the
-// node's own triangle.  The product cannot run in place (every tile reads whole rows / columns of B): it goes to
-// scratch and is copied back.
-static int64_t wide_leaf_env() {
-    const char *env = getenv("VGP_TRSM_LEAF");
-    return env ? atoll(env) : 0;
-}
-static const double *wide_lookup(const DenseWorkspace &ws, const double *dinv, int64_t n) {
-    if (ws.leaf <= NB || !dinv || !ws.dinv || n <= NB || n > ws.leaf) return nullptr;
-    const int64_t block0 = (dinv - ws.dinv) / (NB * NB);
-    for (int i = 0; i < ws.wide_count; ++i)
-        if (ws.wide_nodes[i].block0 == block0 && ws.wide_nodes[i].n == n) return ws.wide + ws.wide_nodes[i].offset;
-    return nullptr;
-}
-static double *wide_scratch(DenseWorkspace &ws, size_t doubles) {
-    DistContext *dc = g_dist;
-    if (dc && dc->nranks > 1 && dc->tmp && dc->tmp_doubles >= doubles) return dc->tmp;     // peer-mapped: distributable
-    return ws.tmp_doubles >= doubles ? ws.tmp : nullptr;
-}
-static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, DenseWorkspace &ws, cudaStream_t s);
-// W = inv(L_node) for the node at `a` (n x n, first diagonal block index block0), dense with zeros above the diagonal
-static int wide_build(const double *a, int64_t n, int64_t ld, int64_t block0, const double *dinv, DenseWorkspace &ws,
-                      cudaStream_t s) {
-    if (ws.leaf <= NB || n <= NB || n > ws.leaf) return VGP_OK;
-    VGP_REQUIRE(ws.wide_count < DenseWorkspace::MAX_WIDE && ws.wide_used + (size_t)n * n <= ws.wide_doubles,
-                "wide-leaf cache is full");
-    double *w = ws.wide + ws.wide_used;
-    VGP_CUDA(cudaMemcpy2DAsync(w, (size_t)n * 8, a, (size_t)ld * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToDevice, s));
-    VGP_TRY(dense_zero_strict_upper(w, n, n, s));
-    VGP_TRY(trtri_rec(w, n, n, dinv, ws, s));          // sub-nodes are not in the cache: plain recursion
-    ws.wide_nodes[ws.wide_count++] = {block0, n, ws.wide_used};
-    ws.wide_used += (size_t)n * n;
-    return VGP_OK;
-}
-// B [rows][cols] <- scratch product; form 0: alpha B W^T, 1: alpha B W (B [m][n]), 2: alpha W B (B [n][m])
-static int wide_solve(int form, int64_t m, int64_t n, double alpha, const double *w, double *b, int64_t ldb,
-                      DenseWorkspace &ws, cudaStream_t s, bool *done) {
-    *done = false;
-    double *t = wide_scratch(ws, (size_t)m * (size_t)n);
-    if (!t) return VGP_OK;
-    *done = true;
-    if (form == 2) {
-        VGP_TRY(dense_gemm(0, 0, n, m, n, alpha, w, n, b, ldb, 0.0, t, m, GEMM_FULL, s));
-        VGP_CUDA(cudaMemcpy2DAsync(b, (size_t)ldb * 8, t, (size_t)m * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToDevice, s));
-    } else {
-        VGP_TRY(dense_gemm(0, form == 0 ? 1 : 0, m, n, n, alpha, b, ldb, w, n, 0.0, t, n, GEMM_FULL, s));
-        VGP_CUDA(cudaMemcpy2DAsync(b, (size_t)ldb * 8, t, (size_t)n * 8, (size_t)n * 8, (size_t)m, cudaMemcpyDeviceToDevice, s));
-    }
-    return VGP_OK;
-}
-
-// VGP_TRSM_SLAB, read at the entry of every public factorisation / solve (tests flip it between calls)
-static thread_local int64_t g_slab_width = 0;
-static void read_slab_width() {
-    const char *env = getenv("VGP_TRSM_SLAB");
-    g_slab_width = env ? atoll(env) : 0;
-}
-
-// Opt-in experiment (slab.cu): VGP_TRSM_SLAB=<width> lets one launch solve a whole triangle of up to <width> columns per
-// 128-wide slab of right-hand sides instead of recursing down to 128 x 128 leaves.  Needs the cached diagonal-block
-// inverses.  *done tells the caller whether the solve was taken over.
-static int slab_solve(int form, int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
-                      double *b, int64_t ldb, cudaStream_t s, bool *done) {
-    *done = false;
-    const int64_t width = g_slab_width;
-    if (width <= 0 || n <= NB || n > width || !dinv || m == 0) return VGP_OK;
-    *done = true;
-    if (g_gate) {
-        VGP_TRY(gate_wait(l, n, s));
-        VGP_TRY(gate_wait(b, form == 2 ? n : m, s));
-    }
-    DistContext *dc = g_dist;
-    if (dc && dc->nranks > 1) {
-        const int64_t rows = form == 2 ? n : m, cols = form == 2 ? m : n;
-        const char *b0 = (const char *)b, *b1 = (const char *)(b + (rows - 1) * ldb + cols);
-        const bool inside = b0 >= (const char *)dc->base && b1 <= (const char *)dc->base + dc->bytes;
-        if (inside && m / NB >= 2 * dc->nranks) {
-            ++dc->dist_gemms;
-            VGP_TRY(dense_dist_barrier(*dc, s));
-            VGP_TRY(slab_trsm(form, m, n, alpha, l, ldl, dinv, b, ldb, dc, s));
-            return dense_dist_barrier(*dc, s);
-        }
-    }
-    return slab_trsm(form, m, n, alpha, l, ldl, dinv, b, ldb, nullptr, s);
-}
-
 // X L^T = alpha B,  B [m][n]
 static int trsm_right_t(int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
                         double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
-    bool done;
-    VGP_TRY(slab_solve(0, m, n, alpha, l, ldl, dinv, b, ldb, s, &done));
-    if (done) return VGP_OK;
-    if (const double *w = wide_lookup(ws, dinv, n)) {
-        VGP_TRY(wide_solve(0, m, n, alpha, w, b, ldb, ws, s, &done));
-        if (done) return VGP_OK;
-    }
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1212,13 +1090,6 @@ static int trsm_right_t(int64_t m, int64_t n, double alpha, const double *l, int
 // X L = alpha B,  B [m][n]
 static int trsm_right_n(int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv,
                         double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
-    bool done;
-    VGP_TRY(slab_solve(1, m, n, alpha, l, ldl, dinv, b, ldb, s, &done));
-    if (done) return VGP_OK;
-    if (const double *w = wide_lookup(ws, dinv, n)) {
-        VGP_TRY(wide_solve(1, m, n, alpha, w, b, ldb, ws, s, &done));
-        if (done) return VGP_OK;
-    }
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1234,13 +1105,6 @@ static int trsm_right_n(int64_t m, int64_t n, double alpha, const double *l, int
 // L X = alpha B,  B [n][nrhs]
 static int trsm_left_n(int64_t n, int64_t nrhs, double alpha, const double *l, int64_t ldl, const double *dinv,
                        double *b, int64_t ldb, DenseWorkspace &ws, cudaStream_t s) {
-    bool done;
-    VGP_TRY(slab_solve(2, nrhs, n, alpha, l, ldl, dinv, b, ldb, s, &done));
-    if (done) return VGP_OK;
-    if (const double *w = wide_lookup(ws, dinv, n)) {
-        VGP_TRY(wide_solve(2, nrhs, n, alpha, w, b, ldb, ws, s, &done));
-        if (done) return VGP_OK;
-    }
     if (n == NB) {
         const double *w;
         VGP_TRY(block_inverse(l, ldl, dinv, ws, s, &w));
@@ -1274,7 +1138,6 @@ int dense_trsm(int side, int trans, int64_t n, int64_t nrhs, double alpha, const
     VGP_REQUIRE(n % NB == 0 && nrhs % NB == 0, "dense_trsm: unpadded size n=%lld nrhs=%lld", (long long)n,
                 (long long)nrhs);
     VGP_TRY(ws.ensure(0));
-    read_slab_width();
     const double *dinv = nullptr;
     if (use_cached_inverses) {
         VGP_REQUIRE(ws.dinv && ws.dinv_blocks >= n / NB, "dense_trsm: no cached diagonal-block inverses");
@@ -1300,23 +1163,19 @@ static int potrf_rec(double *a, int64_t n, int64_t ld, int64_t row_offset, doubl
     const int64_t n1 = split(n), n2 = n - n1;
     double *a21 = a + n1 * ld, *a22 = a21 + n1;
     double *dinv2 = dinv + (n1 / NB) * NB * NB;
-    const bool wide = ws.leaf > NB && n > ws.leaf;      // children no larger than the leaf width are the cached nodes
     VGP_TRY(potrf_rec(a, n1, ld, row_offset, dinv, ws, s));
-    if (wide) VGP_TRY(wide_build(a, n1, ld, row_offset / NB, dinv, ws, s));
     VGP_TRY(trsm_right_t(n2, n1, 1.0, a, ld, dinv, a21, ld, ws, s));                               // A21 <- A21 L11^-T
     VGP_TRY(dense_gemm(0, 1, n2, n2, n1, -1.0, a21, ld, a21, ld, 1.0, a22, ld, GEMM_LOWER, s));    // A22 -= A21 A21^T
     VGP_TRY(potrf_rec(a22, n2, ld, row_offset + n1, dinv2, ws, s));
-    if (wide) VGP_TRY(wide_build(a22, n2, ld, (row_offset + n1) / NB, dinv2, ws, s));
     return VGP_OK;
 }
 
 int dense_potrf(double *a, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
+    EmulateScope emulate_large_products(ws);
     VGP_REQUIRE(n > 0 && n % NB == 0 && ld >= n && ld % 2 == 0, "dense_potrf: unpadded size %lld (ld %lld)",
                 (long long)n, (long long)ld);
     VGP_TRY(ws.ensure(n / NB));
-    read_slab_width();
-    VGP_TRY(ws.ensure_wide(n, wide_leaf_env()));
-    if (emulate_slices() >= 2) VGP_TRY(emulated_reserve(n, emulate_slices(), s));
+    if (emulate_slices() >= 2 && n >= option(VGP_OPT_GEMM_EMULATE_MIN)) VGP_TRY(ws.emu.reserve(largest_half(n), emulate_slices(), s));
     VGP_CUDA(cudaMemsetAsync(ws.info, 0, sizeof(int), s));
     return potrf_rec(a, n, ld, 0, ws.dinv, ws, s);
 }
@@ -1328,12 +1187,6 @@ __global__ void __launch_bounds__(256) block_copy_kernel(const double *src, doub
 }
 
 static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, DenseWorkspace &ws, cudaStream_t s) {
-    if (const double *w = wide_lookup(ws, dinv, n)) {      // the node's inverse is in the wide-leaf cache: copy it in
-        if (w != l)
-            VGP_CUDA(cudaMemcpy2DAsync(l, (size_t)ld * 8, w, (size_t)n * 8, (size_t)n * 8, (size_t)n,
-                                       cudaMemcpyDeviceToDevice, s));
-        return VGP_OK;
-    }
     if (n == NB) {
         block_copy_kernel<<<16, 256, 0, s>>>(dinv, l, ld);
         VGP_LAUNCH_CHECK();
@@ -1349,9 +1202,9 @@ static int trtri_rec(double *l, int64_t n, int64_t ld, const double *dinv, Dense
 
 // Needs the diagonal-block inverses cached by dense_potrf on the same workspace.
 int dense_trtri(double *l, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
+    EmulateScope emulate_large_products(ws);
     VGP_REQUIRE(n > 0 && n % NB == 0, "dense_trtri: unpadded size");
     VGP_REQUIRE(ws.dinv && ws.dinv_blocks >= n / NB, "dense_trtri: call dense_potrf on this workspace first");
-    read_slab_width();
     return trtri_rec(l, n, ld, ws.dinv, ws, s);
 }
 
@@ -1381,6 +1234,7 @@ static int lauum_rec(double *x, int64_t n, int64_t ld, cudaStream_t s) {
 }
 
 int dense_lauum(double *x, int64_t n, int64_t ld, DenseWorkspace &ws, cudaStream_t s) {
+    EmulateScope emulate_large_products(ws);
     VGP_REQUIRE(n > 0 && n % NB == 0, "dense_lauum: unpadded size");
     VGP_TRY(ws.ensure(0));
     return lauum_rec(x, n, ld, s);
@@ -1432,6 +1286,7 @@ int dense_preload() {
     VGP_CUDA(cudaFuncGetAttributes(&fa, add_diag_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, splitk_reduce_kernel));
     VGP_CUDA(cudaFuncGetAttributes(&fa, dist_barrier_kernel));
+    if (option(VGP_OPT_GEMM_EMULATE_SLICES) >= 2) VGP_TRY(emulated_preload());
     return VGP_OK;
 }
 

@@ -6,27 +6,29 @@
 
 namespace vgp {
 
+// Digit planes and row exponents of the int8 tensor-core products (emulated.cu); grown on demand, blocks from the
+// per-device workspace cache.
+struct EmuWorkspace {
+    signed char *qa = nullptr, *qb = nullptr;
+    int *ea = nullptr, *eb = nullptr;
+    size_t qa_bytes = 0, qb_bytes = 0, ea_bytes = 0, eb_bytes = 0;
+    // Size for products of up to rows x rows x 8192 once, up front: growing later waits for the device, which inside
+    // a distributed factorisation (other ranks' barrier kernels possibly spinning on this device) must not happen.
+    int reserve(int64_t rows, int slices, cudaStream_t s);
+    void release();
+};
+
+// the larger half of the recursive 2 x 2 split (dense.cu `split`): the largest product dimension of a factorisation
+inline int64_t largest_half(int64_t n) { return n - (n / TILE / 2) * TILE; }
+
 struct DenseWorkspace {
     int device = -1;
+    EmuWorkspace emu;
     double *winv = nullptr;     // TILE x TILE scratch: explicit inverse of a diagonal block
     int *info = nullptr;        // device flag: 0, or 1 + row of the first non-positive pivot
     double *dinv = nullptr;     // [dinv_blocks][TILE][TILE]: inverses of the diagonal blocks of the last potrf
     int64_t dinv_blocks = 0;
-    // Opt-in (VGP_TRSM_LEAF=<width>, dense.cu "wide leaves"): explicit inverses of the diagonal nodes of the last
-    // potrf whose size is in (128, width], kept densely ([n][n], zeros above the diagonal) so that a solve against such
-    // a node is ONE product; `tmp` receives that product before it is copied over the right-hand sides.
-    struct WideNode {
-        int64_t block0, n;
-        size_t offset;
-    };
-    static constexpr int MAX_WIDE = 1024;
-    double *wide = nullptr, *tmp = nullptr;
-    size_t wide_doubles = 0, wide_used = 0, tmp_doubles = 0;
-    WideNode wide_nodes[MAX_WIDE];
-    int wide_count = 0;
-    int64_t leaf = 128;
     int ensure(int64_t nblocks);
-    int ensure_wide(int64_t n, int64_t width);      // sizes `wide` / `tmp` for an n x n factorisation, forgets old nodes
     void release();
 };
 
@@ -49,8 +51,6 @@ struct DistContext {
     // 1.26 s, 96 / 256 (1157 products, two flag barriers each) in 1.07 s (profiles/r01_bench_n50k_g8_thresholds.json)
     int64_t min_tiles = 96, min_k = 256;
     int64_t dist_gemms = 0, barriers = 0;
-    double *tmp = nullptr;                  // peer-mapped scratch behind the replica (wide-leaf solves), inside `bytes`
-    size_t tmp_doubles = 0;
 };
 void dense_set_dist(DistContext *ctx);      // thread-local; nullptr switches distribution off
 int dense_dist_barrier(DistContext &ctx, cudaStream_t s);
@@ -77,18 +77,13 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
                int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, GemmTiles tiles,
                cudaStream_t s);
 
-// EXPERIMENTAL (emulated.cu): the same product on the int8 tensor cores after an error-free split into `slices` 7-bit
-// digit planes.  dense_gemm routes large products through it only when VGP_GEMM_EMULATE=<slices> is set.
-int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a, int64_t lda,
-                  const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int slices, int lower,
-                  cudaStream_t s, const DistContext *dist = nullptr);
-
-int emulated_reserve(int64_t rows, int slices, cudaStream_t s);
-
-// EXPERIMENTAL (slab.cu): a whole triangular solve of width n per 128-wide slab of right-hand sides in one launch.
-// form 0: X L^T = alpha B, B [m][n];  1: X L = alpha B, B [m][n];  2: L X = alpha B, B [n][m].
-int slab_trsm(int form, int64_t m, int64_t n, double alpha, const double *l, int64_t ldl, const double *dinv, double *b,
-              int64_t ldb, const DistContext *dist, cudaStream_t s);
+// emulated.cu: the same product on the int8 tensor cores (tcgen05.mma kind::i8) after an error-free split into `slices`
+// 7-bit digit planes.  dense_gemm routes the large products of potrf / trtri / lauum through it
+// (VGP_OPT_GEMM_EMULATE_SLICES, VGP_OPT_GEMM_EMULATE_MIN).
+int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                  const double *a, int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc,
+                  int slices, int lower, cudaStream_t s, const DistContext *dist = nullptr);
+int emulated_preload();                     // load the kernels, set the shared-memory opt-in (current device)
 
 int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,
                       int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int splits,

@@ -154,6 +154,17 @@ int vgp_dgemm(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_
     VGP_REQUIRE(a_dev && b_dev && c_dev, "NULL pointer");
     const int64_t ar = trans_a ? k : m, ac = trans_a ? m : k, br = trans_b ? n : k, bc = trans_b ? k : n;
     VGP_REQUIRE(lda >= ac && ldb >= bc && ldc >= n, "leading dimension too small");
+    {
+        // C may not share memory with an operand: tiles of C are written while other CTAs still read A and B
+        auto overlaps = [](const double *x, int64_t rows, int64_t cols, int64_t ld, const double *y, int64_t yrows,
+                           int64_t ycols, int64_t yld) {
+            if (rows == 0 || cols == 0 || yrows == 0 || ycols == 0) return false;
+            const double *x1 = x + (rows - 1) * ld + cols, *y1 = y + (yrows - 1) * yld + ycols;
+            return x < y1 && y < x1;
+        };
+        VGP_REQUIRE(!overlaps(c_dev, m, n, ldc, a_dev, ar, ac, lda) && !overlaps(c_dev, m, n, ldc, b_dev, br, bc, ldb),
+                    "vgp_dgemm: C overlaps an operand");
+    }
     VGP_ENTER(device);
     cudaStream_t s = (cudaStream_t)stream;
     if (m % TILE == 0 && n % TILE == 0 && k % 16 == 0 && k > 0 && lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0 &&

@@ -25,7 +25,18 @@ using namespace vgp;
 #include "dist.cuh"
 
 namespace {
-constexpr size_t FLAG_BYTES = 8 * (DIST_MAX + 1);
+constexpr size_t FLAG_BYTES = 8 * (DIST_MAX + 2);
+
+// The options every rank must agree on: they decide which kernel produces a tile (replicas must stay bitwise equal)
+// and how large the buffers behind the replica are.  Never 0 (0 = "peer has not created its handle").
+unsigned long long options_fingerprint(int64_t n_pad, int64_t tail_rows) {
+    unsigned long long h = 1469598103934665603ull;
+    const int64_t words[] = {VGP_ABI_VERSION, n_pad, tail_rows, option(VGP_OPT_GEMM_EMULATE_SLICES),
+                             option(VGP_OPT_GEMM_EMULATE_MIN), option(VGP_OPT_DIST_MIN_TILES), option(VGP_OPT_DIST_MIN_K),
+                             option(VGP_OPT_GEMM_TILE_CONFIG), option(VGP_OPT_GEMM_SMALL_BELOW)};
+    for (int64_t w : words) h = (h ^ (unsigned long long)w) * 1099511628211ull;
+    return h | 1ull;
+}
 
 int check(vgp_dist *h) {
     if (!h) {
@@ -56,17 +67,12 @@ int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t
     // the tail behind the replica (peer-mapped with it): two parity buffers of [row blocks][n_pad] partial sums for the
     // sharded lazy-column greedy (lazy.cu)
     h->tail_rows = 2 * ((h->n_pad + DIST_TAIL_RB - 1) / DIST_TAIL_RB);
-    // opt-in wide-leaf solves (dense.cu, VGP_TRSM_LEAF): their scratch products must be peer-visible to be distributed
-    const char *leaf_env = getenv("VGP_TRSM_LEAF");
-    const int64_t leaf = leaf_env ? atoll(leaf_env) : 0;
-    if (leaf > TILE) {
-        const int64_t rows = ((h->n_pad / 2 + 2 * TILE) * leaf + h->n_pad - 1) / h->n_pad;
-        if (rows > h->tail_rows) h->tail_rows = rows;
-    }
-    cudaError_t e = cudaMalloc((void **)&h->matrix, bytes + (size_t)h->tail_rows * h->n_pad * 8);
+    cudaError_t e = device_malloc((void **)&h->matrix, bytes + (size_t)h->tail_rows * h->n_pad * 8);
     if (e == cudaSuccess) e = cudaMemset(h->matrix + (size_t)h->n_pad * h->n_pad, 0, (size_t)h->tail_rows * h->n_pad * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->flags, FLAG_BYTES);
+    if (e == cudaSuccess) e = device_malloc((void **)&h->flags, FLAG_BYTES);
     if (e == cudaSuccess) e = cudaMemset(h->flags, 0, FLAG_BYTES);
+    h->fingerprint = options_fingerprint(h->n_pad, h->tail_rows);
+    if (e == cudaSuccess) e = cudaMemcpy(h->flags + DIST_MAX + 1, &h->fingerprint, 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         int rc = cuda_fail(e, "replica allocation", __FILE__, __LINE__);
@@ -75,16 +81,13 @@ int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t
     }
     h->ctx.base = h->matrix;
     h->ctx.bytes = bytes;
-    if (leaf > TILE) {
-        h->ctx.tmp = h->matrix + (size_t)h->n_pad * h->n_pad;
-        h->ctx.tmp_doubles = (size_t)h->tail_rows * h->n_pad;
-        h->ctx.bytes = bytes + h->ctx.tmp_doubles * 8;         // products into the scratch are distributed like any other
-    }
     // thresholds: DistContext defaults (dense.cuh) -- measured on 8 GPUs; the NVLink egress of the tile stores
     // (64 KB per 128x64 tile and peer) stays below a rank's 900 GB/s share down to k = 256
     // everything that could allocate, free or load a module later happens now, before any rank can be spinning
     int rc0 = dense_preload();
     if (rc0 == VGP_OK) rc0 = h->ws.ensure(h->n_pad / TILE);
+    if (rc0 == VGP_OK && option(VGP_OPT_GEMM_EMULATE_SLICES) >= 2 && h->n_pad >= option(VGP_OPT_GEMM_EMULATE_MIN))
+        rc0 = h->ws.emu.reserve(largest_half(h->n_pad), (int)option(VGP_OPT_GEMM_EMULATE_SLICES), nullptr);
     if (rc0 != VGP_OK) {
         vgp_dist_destroy(h);
         return rc0;
@@ -151,6 +154,17 @@ int vgp_dist_connect(vgp_dist *h, const void *peers, int kind) {
             VGP_CUDA(cudaIpcOpenMemHandle(&vb, b, cudaIpcMemLazyEnablePeerAccess));
             pm = (double *)va;
             pf = (unsigned long long *)vb;
+        }
+        if (q != me) {
+            // a rank created with other options (or another size) would run other kernels on its tiles, or store into
+            // buffers of another size: refuse to connect
+            unsigned long long theirs = 0;
+            VGP_CUDA(cudaMemcpy(&theirs, pf + DIST_MAX + 1, 8, cudaMemcpyDefault));
+            if (theirs != h->fingerprint) {
+                set_error("rank %d was created with different options or sizes than rank %d (vgp_set_option must be "
+                          "identical on all ranks before vgp_dist_create)", q, me);
+                return VGP_ERR_STATE;
+            }
         }
         h->peer_matrix[q] = pm;
         h->ctx.delta[q] = pm - h->matrix;
@@ -256,10 +270,12 @@ static int dist_run(vgp_dist *h, int *info_host, void *stream, bool factor_only)
     if (info_host) *info_host = 0;
     VGP_ENTER(h->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const char *env = getenv("VGP_DIST_MIN_TILES");
-    if (env && *env) h->ctx.min_tiles = atoll(env);
-    env = getenv("VGP_DIST_MIN_K");
-    if (env && *env) h->ctx.min_k = atoll(env);
+    if (options_fingerprint(h->n_pad, h->tail_rows) != h->fingerprint) {
+        set_error("options changed since vgp_dist_create: set them before creating the handle, identically on all ranks");
+        return VGP_ERR_STATE;
+    }
+    h->ctx.min_tiles = option(VGP_OPT_DIST_MIN_TILES);
+    h->ctx.min_k = option(VGP_OPT_DIST_MIN_K);
     if (h->ctx.min_k < 2 * TILE) h->ctx.min_k = 2 * TILE;      // the k = 128 leaf GEMMs update their operand in place
     dense_set_dist(h->ctx.nranks > 1 ? &h->ctx : nullptr);
     int rc = VGP_OK;

@@ -9,7 +9,8 @@ struct vgp_dist {
     int64_t n_pad = 0;
     double *matrix = nullptr;                   // [n_pad + tail_rows][n_pad]: the replica, then the peer-visible tail
     int64_t tail_rows = 0;
-    unsigned long long *flags = nullptr;        // u64[DIST_MAX] barrier words + int error
+    unsigned long long *flags = nullptr;        // u64[DIST_MAX] barrier words + int error + u64 option fingerprint
+    unsigned long long fingerprint = 0;         // of the options that change numerics / buffer sizes, at create
     double *peer_matrix[vgp::DIST_MAX] = {nullptr};
     int ipc = 0, connected = 0;
     cudaStream_t push_stream = nullptr;         // vgp_dist_upload_rows: peer copies of a chunk under the next upload

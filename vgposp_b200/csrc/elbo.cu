@@ -323,7 +323,7 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     };
     auto mm = [&](const double *A, const double *B, double *C) { return mm_on(s, A, B, C); };
     // measurement knob: bit 0 = the K/Q/Gb products on a side stream, bit 1 = the minibatch push-through on a side stream
-    static const int overlap = getenv("VGP_ELBO_OVERLAP") ? atoi(getenv("VGP_ELBO_OVERLAP")) : 3;
+    const int overlap = (int)option(VGP_OPT_ELBO_OVERLAP);
     cudaStream_t sb = (overlap & 1) ? h->side[0] : s;       // products that need only K, Q, Gb
     cudaStream_t sd = (overlap & 2) ? h->side[1] : s;       // minibatch / K_zz push-through
     VGP_CUDA(cudaMemsetAsync(h->rowacc, 0, (size_t)m * (2 + h->d) * 8, s));
@@ -553,7 +553,7 @@ int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const do
         {(void **)&h->gradz, (size_t)m * d * 8},         {(void **)&h->rowacc2, (size_t)m * (2 + d) * 8},
     };
     for (auto &al : allocs) {
-        cudaError_t e = cudaMalloc(al.p, al.bytes);
+        cudaError_t e = device_malloc(al.p, al.bytes);
         if (e == cudaSuccess) e = cudaMemset(*al.p, 0, al.bytes);
         if (e != cudaSuccess) {
             int rc = cuda_fail(e, "cudaMalloc (ELBO state)", __FILE__, __LINE__);

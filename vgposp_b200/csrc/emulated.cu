@@ -1,26 +1,25 @@
-// EXPERIMENTAL, not on any default path: FP64 GEMM on the int8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+// FP64 GEMM on the int8 tensor cores (tcgen05.mma kind::i8, int32 accumulators in TMEM): the large products of the
+// factorisations behind the placement path (potrf / trtri / lauum: SURVEY.md section 8d, "Seed inverse").
 //
-// The factorisations behind the placement path (potrf / trtri: SURVEY.md section 8d, "Seed inverse") are bound by the
-// FP64 tensor pipe, which tops out at ~37 TFLOP/s on B200 (DMMA; profiles/r01_ncu_gemm_summary.txt).  The int8 path of
-// the 5th-generation tensor cores is two orders of magnitude wider.  Ozaki's error-free splitting carries an FP64
-// product on it: every operand row is scaled by a power of two to |x| < 1 and cut into s signed digits of W = 7 bits,
+// Those products are bound by the FP64 tensor pipe, which tops out at ~37 TFLOP/s on B200 (DMMA, 97 % pipe-active in
+// dense.cu's kernel: profiles/r01_ncu_gemm_summary.txt); tcgen05 has no f64 kind, but its int8 path is two orders of
+// magnitude wider.  Ozaki's error-free splitting carries an FP64 product on it: every operand row is scaled by a power
+// of two to |x| < 1 and cut into s signed digits of W = 7 bits,
 //     A[i][:] = 2^ea[i] * sum_t QA_t[i][:] 2^(-W (t + 1)),      QA_t in [-127, 127],
 // (columns of B likewise), the digit planes are multiplied exactly in int32,
 //     C = 2^(ea[i] + eb[j]) * sum_{g < s} 2^(-W (g + 2)) * sum_{t <= g} QA_t QB_{g-t}^T,
-// and the s group sums are combined in FP64.  tools/ozaki_prototype.py measures what s buys on this workload's
-// matrices: s = 8 (36 integer products) gives a product within 1.4e-14 of exact (native FP64: 1.5e-15), identical
-// greedy selections and scores within 1.5e-13; s = 7: 1.4e-12 / 1.3e-11.
+// and the s group sums are combined in FP64, smallest group first.  s = 8 (36 integer products): within 1e-14 of the
+// exact product (native FP64: 1.5e-15); the result does not depend on tile shape, k split or rank count (integer sums).
 //
-// Layout here: digit planes Q[t][rows_pad][k_pad] int8, k-contiguous, fetched by TMA (SWIZZLE_128B boxes of 128 rows x
-// 128 k).  One CTA per 128 x 128 tile of C: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 =
-// epilogue.  For group g the k loop runs over the concatenation [QA_0 | ... | QA_g] x [QB_g | ... | QB_0] into one
-// int32 accumulator (128 TMEM columns, double-buffered so the epilogue of one group overlaps the MMAs of the next); the
-// epilogue converts each group to FP64, scales it by 2^(-W (g + 2)) and adds it to register accumulators, smallest
-// group first; the last step applies 2^(ea + eb), alpha and beta.  int32 cannot overflow while s * k * 127^2 < 2^31;
-// the host splits k into chunks of 8192.
+// Layout: digit planes Q[t][rows_pad][k_pad] int8, k-contiguous, fetched by TMA (SWIZZLE_64B boxes of 64 k).  One CTA per
+// 128 x 64 tile of C keeps the s group accumulators side by side in tensor memory (s * 64 <= 512 columns) and, per
+// 64-byte k block, loads the s plane tiles of A and of B once (16 TMA boxes) to feed all s (s + 1) / 2 plane pairs:
+// warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = epilogue (TMEM -> registers, FP64
+// recombination, 2^(ea + eb), alpha / beta).  int32 cannot overflow while s * k * 127^2 < 2^31: the host splits k into
+// chunks of 8192.
 //
-// Status: compiles for sm_100a; numerics and speed are to be validated on the GPU before anything routes through it
-// (tests/test_gpu_emulated_gemm.py runs only with VGP_TEST_EMULATED=1).
+// Measured on B200 (profiles/r02_first_contact_experimental_paths.md): 59 TFLOP/s FP64-equivalent at 8192^3 against 36
+// for cuBLAS DGEMM; an earlier group-by-group kernel (128 x 128 tiles, one accumulator) reached 47 and was removed.
 #include <cuda.h>
 
 #include "dense.cuh"
@@ -29,15 +28,10 @@ namespace vgp {
 namespace emu {
 
 constexpr int W = 7;
-constexpr int S_MAX = 9;
-constexpr int BM = 128, BN = 128, BKB = 128;          // C tile; k block in bytes (= int8 elements)
+constexpr int S_MAX = 8;
+constexpr int BM = 128, BN = 128, BKB = 128;          // padding granularity of the digit planes (rows, rows, k bytes)
 constexpr int UMMA_K = 32;                            // k per tcgen05.mma.kind::i8
-constexpr int STAGES = 6;
-constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8, THREADS = 64 + 32 * EPI_WARPS;
-constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers
-constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 8;   // full[], empty[], tmem_full[2], tmem_empty[2], tmem base
-constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + BN * 4;
 constexpr int64_t K_CHUNK = 8192;
 
 struct GemmArgs {
@@ -120,7 +114,6 @@ __device__ __forceinline__ bool elect_one() {
         "{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
     return pred != 0;
 }
-// shared-memory matrix descriptor: k-major operand tile, 128-byte rows, SWIZZLE_128B (8-row groups 1024 bytes apart)
 // ROW_BYTES = 128: SWIZZLE_128B (layout code 2), 64: SWIZZLE_64B (code 4); 8-row groups are 8 * ROW_BYTES apart
 template <int ROW_BYTES>
 __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
@@ -137,7 +130,6 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
 constexpr unsigned idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
-constexpr unsigned IDESC = idesc_i8(BM, BN);
 
 __device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
                                         unsigned accumulate) {
@@ -164,154 +156,7 @@ __device__ __forceinline__ void tmem_ld32(unsigned addr, int (&v)[32]) {   // th
 }
 
 // ------------------------------------------------------------------------------------------------ the GEMM
-__global__ void __launch_bounds__(THREADS, 1)
-    emu_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
-    extern __shared__ unsigned char raw[];
-    const unsigned raw_addr = smem_u32(raw);
-    unsigned char *sm = raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + STAGES * STAGE_BYTES);
-    unsigned long long *full = bars, *empty = bars + STAGES, *tfull = bars + 2 * STAGES, *tempty = bars + 2 * STAGES + 2;
-    unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * STAGES + 4);
-    int *eb_tile = reinterpret_cast<int *>(sm + STAGES * STAGE_BYTES + BAR_BYTES);
-
-    int tm, tn;
-    if (!tile_of_cta(p, (int)(p.m_pad / BM), tm, tn)) return;
-    if (p.lower && tn > tm) return;
-    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&full[i]), 1);
-            mbar_init(smem_u32(&empty[i]), 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&tfull[i]), 1);
-            mbar_init(smem_u32(&tempty[i]), EPI_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    }
-    if (warp == 1) {      // this warp owns the tensor memory: allocate, later free
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)),
-                     "n"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    if (tid >= 64 && tid < 64 + BN) eb_tile[tid - 64] = p.eb[n0 + tid - 64];
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const unsigned tmem_base = *tmem_slot;
-
-    const int KB = p.kblocks, S = p.s;
-    if (warp == 0) {
-        // ===== TMA producer: groups g = S-1 .. 0, inside a group the digit pairs (t, g - t), inside a pair the k blocks
-        if (elect_one()) {
-            int it = 0;
-            for (int g = S - 1; g >= 0; --g)
-                for (int t = 0; t <= g; ++t) {
-                    const int row_a = (int)((int64_t)t * p.m_pad + m0), row_b = (int)((int64_t)(g - t) * p.n_pad + n0);
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        const int stage = it % STAGES;
-                        if (it >= STAGES) mbar_wait(smem_u32(&empty[stage]), ((it / STAGES) - 1) & 1);
-                        const unsigned bar = smem_u32(&full[stage]);
-                        const unsigned dst = smem_u32(sm + stage * STAGE_BYTES);
-                        mbar_expect_tx(bar, STAGE_BYTES);
-                        tma_load_2d(dst, &map_a, kb * BKB, row_a, bar);
-                        tma_load_2d(dst + A_BYTES, &map_b, kb * BKB, row_b, bar);
-                    }
-                }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer
-        int it = 0;
-        for (int g = S - 1, gi = 0; g >= 0; --g, ++gi) {
-            const int buf = gi & 1;
-            if (gi >= 2) mbar_wait(smem_u32(&tempty[buf]), ((gi >> 1) - 1) & 1);     // epilogue has drained this buffer
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const unsigned tmem_d = tmem_base + (unsigned)(buf * BN);
-            const int steps = (g + 1) * KB;
-            for (int st = 0; st < steps; ++st, ++it) {
-                const int stage = it % STAGES;
-                mbar_wait(smem_u32(&full[stage]), (it / STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                if (elect_one()) {
-                    const unsigned a_addr = smem_u32(sm + stage * STAGE_BYTES), b_addr = a_addr + A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < BKB / UMMA_K; ++k)
-                        umma_i8(tmem_d, umma_desc<128>(a_addr + k * UMMA_K), umma_desc<128>(b_addr + k * UMMA_K), IDESC,
-                                (st > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(smem_u32(&empty[stage]));                            // frees the slot when the MMAs are done
-                    if (st == steps - 1) umma_commit(smem_u32(&tfull[buf]));         // group complete -> epilogue
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (one C row per thread), columns 64 half .. +63
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;
-        double acc[64];
-#pragma unroll
-        for (int c = 0; c < 64; ++c) acc[c] = 0.0;
-        for (int g = S - 1, gi = 0; g >= 0; --g, ++gi) {
-            const int buf = gi & 1;
-            mbar_wait(smem_u32(&tfull[buf]), (gi >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const double scale = scalbn(1.0, -W * (g + 2));
-            const unsigned addr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(buf * BN + half * 64);
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                int v[32];
-                tmem_ld32(addr + part * 32, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-                for (int c = 0; c < 32; ++c) acc[part * 32 + c] = fma((double)v[c], scale, acc[part * 32 + c]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty[buf]));
-        }
-        const int64_t i = m0 + row;
-        if (i < p.m) {
-            const int ea = p.ea[i];
-            double *crow = p.c + i * p.ldc + n0 + half * 64;
-#pragma unroll
-            for (int c = 0; c < 64; c += 2) {
-                const int64_t j = n0 + half * 64 + c;
-                if (j + 1 < p.n) {
-                    double2 o;
-                    o.x = p.alpha * scalbn(acc[c], ea + eb_tile[half * 64 + c]);
-                    o.y = p.alpha * scalbn(acc[c + 1], ea + eb_tile[half * 64 + c + 1]);
-                    if (p.beta != 0.0) {
-                        const double2 old = *reinterpret_cast<const double2 *>(crow + c);
-                        o.x = fma(p.beta, old.x, o.x);
-                        o.y = fma(p.beta, old.y, o.y);
-                    }
-                    store_pair(p, crow + c, o);
-                } else if (j < p.n) {
-                    double o = p.alpha * scalbn(acc[c], ea + eb_tile[half * 64 + c]);
-                    if (p.beta != 0.0) o = fma(p.beta, crow[c], o);
-                    store_one(p, crow + c, o);
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ variant 2
-// All digit planes of a k block resident: one CTA per 128 x 64 tile of C keeps the s group accumulators side by side in
-// tensor memory (s * 64 <= 512 columns) and, per 64-byte k block, loads the s plane tiles of A and of B once (16 TMA
-// boxes, SWIZZLE_64B) to feed all s (s + 1) / 2 plane pairs -- 96 KB for 72 MMAs (42 bytes per MMA cycle) where the
-// group-by-group kernel above moves 32 KB for 4 (128 bytes per cycle).  Same integer sums, same FP64 recombination
-// order: bitwise the same C.
+// All digit planes of a k block resident: 96 KB per stage feed 72 MMAs (42 bytes of shared-memory fill per MMA cycle).
 namespace v2 {
 constexpr int BN2 = 64, BKB2 = 64, STAGES2 = 2, S2_MAX = 8;
 constexpr int A2 = BM * BKB2, B2 = BN2 * BKB2;                    // one plane tile of A / B
@@ -537,8 +382,7 @@ static TensorMapEncodeFn encoder() {
     return fn;
 }
 
-static int plane_map(CUtensorMap *map, const signed char *base, int64_t rows_total, int64_t k_pad, int box_k = BKB,
-                     int box_rows = BM) {
+static int plane_map(CUtensorMap *map, const signed char *base, int64_t rows_total, int64_t k_pad, int box_k, int box_rows) {
     TensorMapEncodeFn enc = encoder();
     VGP_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows_total};
@@ -546,7 +390,7 @@ static int plane_map(CUtensorMap *map, const signed char *base, int64_t rows_tot
     const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<signed char *>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VGP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return VGP_OK;
@@ -562,82 +406,68 @@ static int slice_operand(const double *x, int64_t rs, int64_t ks, int64_t rows, 
     return VGP_OK;
 }
 
-// Digit planes and exponents of one product, kept per host thread and device and only ever grown (the factorisations
-// issue hundreds of products of shrinking size; the first large one sizes it).
-struct Workspace {
-    int device = -1;
-    signed char *qa = nullptr, *qb = nullptr;
-    int *ea = nullptr, *eb = nullptr;
-    size_t qa_bytes = 0, qb_bytes = 0, ea_rows = 0, eb_rows = 0;
-};
-static thread_local Workspace g_ws[16];
-
+// grow-only: the factorisations issue hundreds of products of shrinking size; the first large one sizes the planes
 static int grow(void **ptr, size_t *have, size_t want, cudaStream_t st) {
     if (*have >= want) return VGP_OK;
     VGP_CUDA(cudaStreamSynchronize(st));                // earlier products may still read the old planes
-    if (*ptr) VGP_CUDA(cudaFree(*ptr));
+    cache_free(*ptr);
     *ptr = nullptr;
     *have = 0;
-    VGP_CUDA(cudaMalloc(ptr, want));
+    VGP_CUDA(cache_alloc(ptr, want));
     *have = want;
     return VGP_OK;
+}
+static int grow_for(EmuWorkspace &ws, int64_t m_pad, int64_t n_pad, int64_t kc, int slices, cudaStream_t st) {
+    VGP_TRY(grow((void **)&ws.qa, &ws.qa_bytes, (size_t)slices * m_pad * kc, st));
+    VGP_TRY(grow((void **)&ws.qb, &ws.qb_bytes, (size_t)slices * n_pad * kc, st));
+    VGP_TRY(grow((void **)&ws.ea, &ws.ea_bytes, (size_t)m_pad * 4, st));
+    return grow((void **)&ws.eb, &ws.eb_bytes, (size_t)n_pad * 4, st);
 }
 
 }  // namespace emu
 
-// Size the digit-plane workspace for products of up to rows x rows x K_CHUNK once, up front.  Growing frees the old planes
-// (cudaFree waits for the whole device): inside a distributed factorisation, with other ranks' barrier kernels possibly
-// spinning on this device, that must not happen -- dense_potrf calls this before its first launch.
-int emulated_reserve(int64_t rows, int slices, cudaStream_t st) {
+int EmuWorkspace::reserve(int64_t rows, int slices, cudaStream_t st) {
     using namespace emu;
     if (slices < 2 || slices > S_MAX || rows <= 0) return VGP_OK;
+    const int64_t r = round_up(rows, BM);
+    return grow_for(*this, r, r, r < K_CHUNK ? r : K_CHUNK, slices, st);
+}
+
+void EmuWorkspace::release() {
+    for (void *p : {(void *)qa, (void *)qb, (void *)ea, (void *)eb}) cache_free(p);
+    *this = EmuWorkspace();
+}
+
+int emulated_preload() {
+    using namespace emu;
     int device = 0;
     VGP_CUDA(cudaGetDevice(&device));
-    VGP_REQUIRE(device >= 0 && device < 16, "device ordinal out of range");
-    Workspace &ws = g_ws[device];
-    const int64_t r = round_up(rows, BM);
-    VGP_TRY(grow((void **)&ws.qa, &ws.qa_bytes, (size_t)slices * r * K_CHUNK, st));
-    VGP_TRY(grow((void **)&ws.qb, &ws.qb_bytes, (size_t)slices * r * K_CHUNK, st));
-    size_t ea_bytes = ws.ea_rows * 4, eb_bytes = ws.eb_rows * 4;
-    VGP_TRY(grow((void **)&ws.ea, &ea_bytes, (size_t)r * 4, st));
-    VGP_TRY(grow((void **)&ws.eb, &eb_bytes, (size_t)r * 4, st));
-    ws.ea_rows = ea_bytes / 4;
-    ws.eb_rows = eb_bytes / 4;
+    VGP_REQUIRE(device >= 0 && device < 64, "device ordinal out of range");
+    static bool configured[64] = {};
+    if (!configured[device]) {
+        VGP_CUDA(cudaFuncSetAttribute(v2::emu_gemm_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM2));
+        cudaFuncAttributes fa;
+        VGP_CUDA(cudaFuncGetAttributes(&fa, row_exponent_kernel));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, digit_planes_kernel));
+        configured[device] = true;
+    }
     return VGP_OK;
 }
 
 // Asynchronous on `st`; same operand convention as dense_gemm.  C must not alias A or B (with k > K_CHUNK the second
 // chunk's planes would be cut from an already updated operand).
-int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a, int64_t lda,
-                  const double *b, int64_t ldb, double beta, double *c, int64_t ldc, int slices, int lower,
-                  cudaStream_t st, const DistContext *dc) {
+int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                  const double *a, int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc,
+                  int slices, int lower, cudaStream_t st, const DistContext *dc) {
     using namespace emu;
     VGP_REQUIRE(slices >= 2 && slices <= S_MAX, "slices must be in [2, %d]", S_MAX);
     VGP_REQUIRE(ldc % 2 == 0 && ((uintptr_t)c & 15) == 0, "C must be 16-byte aligned with an even leading dimension");
     VGP_REQUIRE((const double *)c != a && (const double *)c != b, "emulated_gemm: C aliases an operand");
     if (m == 0 || n == 0) return VGP_OK;
-    int device = 0;
-    VGP_CUDA(cudaGetDevice(&device));
-    VGP_REQUIRE(device >= 0 && device < 16, "device ordinal out of range");
-    static bool configured[16] = {};
-    if (!configured[device]) {
-        VGP_CUDA(cudaFuncSetAttribute(emu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        VGP_CUDA(cudaFuncSetAttribute(v2::emu_gemm_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM2));
-        configured[device] = true;
-    }
-    // VGP_GEMM_EMULATE_VARIANT=2: all planes of a k block resident (needs slices <= 8); read per call so tests can flip it
-    const char *var = getenv("VGP_GEMM_EMULATE_VARIANT");
-    const bool resident = var && atoi(var) == 2 && slices <= v2::S2_MAX;
-    Workspace &ws = g_ws[device];
+    VGP_TRY(emulated_preload());
     const int64_t m_pad = round_up(m, BM), n_pad = round_up(n, BN);
     const int64_t kc_max = k < K_CHUNK ? round_up(k > 0 ? k : 1, BKB) : K_CHUNK;
-    VGP_TRY(grow((void **)&ws.qa, &ws.qa_bytes, (size_t)slices * m_pad * kc_max, st));
-    VGP_TRY(grow((void **)&ws.qb, &ws.qb_bytes, (size_t)slices * n_pad * kc_max, st));
-    size_t ea_bytes = ws.ea_rows * 4, eb_bytes = ws.eb_rows * 4;
-    VGP_TRY(grow((void **)&ws.ea, &ea_bytes, (size_t)m_pad * 4, st));
-    VGP_TRY(grow((void **)&ws.eb, &eb_bytes, (size_t)n_pad * 4, st));
-    ws.ea_rows = ea_bytes / 4;
-    ws.eb_rows = eb_bytes / 4;
+    VGP_TRY(grow_for(ws, m_pad, n_pad, kc_max, slices, st));
     const int64_t a_rs = trans_a ? 1 : lda, a_ks = trans_a ? lda : 1;
     const int64_t b_rs = trans_b ? ldb : 1, b_ks = trans_b ? 1 : ldb;
     for (int64_t k0 = 0; k0 < k || k0 == 0; k0 += K_CHUNK) {
@@ -646,13 +476,8 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
         VGP_TRY(slice_operand(a + k0 * a_ks, a_rs, a_ks, m, kc, m_pad, k_pad, slices, ws.ea, ws.qa, st));
         VGP_TRY(slice_operand(b + k0 * b_ks, b_rs, b_ks, n, kc, n_pad, k_pad, slices, ws.eb, ws.qb, st));
         alignas(64) CUtensorMap ma, mb;
-        if (resident) {
-            VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad, v2::BKB2, BM));
-            VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad, v2::BKB2, v2::BN2));
-        } else {
-            VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad));
-            VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad));
-        }
+        VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad, v2::BKB2, BM));
+        VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad, v2::BKB2, v2::BN2));
         GemmArgs p;
         p.m = m;
         p.n = n;
@@ -669,7 +494,7 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
         p.lower = lower;
         p.dist_n = 0;
         p.rank = 0;
-        const int64_t tiles_n = n_pad / (resident ? v2::BN2 : BN), tiles_m = m_pad / BM;
+        const int64_t tiles_n = n_pad / v2::BN2, tiles_m = m_pad / BM;
         p.tiles_n = (int)tiles_n;
         dim3 grid((unsigned)tiles_n, (unsigned)tiles_m);
         if (dc && dc->nranks > 1) {          // every rank slices the whole operands (O(n^2)); the tiles are shared out
@@ -678,10 +503,7 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
             for (int q = 0; q < dc->nranks; ++q) p.delta[q] = dc->delta[q];
             grid = dim3((unsigned)((tiles_n * tiles_m + dc->nranks - 1) / dc->nranks), 1);
         }
-        if (resident)
-            v2::emu_gemm_resident_kernel<<<grid, THREADS, v2::SMEM2, st>>>(ma, mb, p);
-        else
-            emu_gemm_kernel<<<grid, THREADS, SMEM, st>>>(ma, mb, p);
+        v2::emu_gemm_resident_kernel<<<grid, THREADS, v2::SMEM2, st>>>(ma, mb, p);
         VGP_LAUNCH_CHECK();
         if (k == 0) break;
     }
@@ -692,9 +514,21 @@ int emulated_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, dou
 
 using namespace vgp;
 
-/* EXPERIMENTAL.  C[m][n] = alpha op(A) op(B) + beta C in FP64 accuracy class, the products on the int8 tensor cores
+static thread_local EmuWorkspace g_public_ws[16];
+namespace vgp {
+size_t emulated_release() {         // vgp_workspace_trim: this thread's planes of the current device go back to the cache
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess || device < 0) return 0;
+    EmuWorkspace &ws = g_public_ws[device & 15];
+    const size_t bytes = ws.qa_bytes + ws.qb_bytes + ws.ea_bytes + ws.eb_bytes;
+    ws.release();
+    return bytes;
+}
+}  // namespace vgp
+
+/* C[m][n] = alpha op(A) op(B) + beta C in FP64 accuracy class, the products on the int8 tensor cores
  * (see the header of this file).  trans_a == 0: A stored [m][k], 1: [k][m]; trans_b == 0: B stored [k][n], 1: [n][k]
- * (dense_gemm's convention).  slices in [2, 9]; lower != 0 computes only the 128 x 128 tiles on or below the diagonal.
+ * (dense_gemm's convention).  slices in [2, 8]; lower != 0 computes only the 128 x 128 tiles on or below the diagonal.
  * The digit planes (slices * (m + n) * min(k, 8192) bytes) live in a grow-only workspace per host thread and device.
  * Asynchronous on `stream`. */
 int vgp_gemm_emulated(int device, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
@@ -703,6 +537,7 @@ int vgp_gemm_emulated(int device, int trans_a, int trans_b, int64_t m, int64_t n
     VGP_REQUIRE(m >= 0 && n >= 0 && k >= 0, "negative size");
     VGP_REQUIRE(a_dev && b_dev && c_dev, "NULL matrix");
     VGP_ENTER(device);
-    return emulated_gemm(trans_a, trans_b, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev, ldc, slices, lower,
-                         (cudaStream_t)stream, nullptr);
+    // the public entry keeps its digit planes per host thread and device until vgp_workspace_trim
+    return emulated_gemm(g_public_ws[device & 15], trans_a, trans_b, m, n, k, alpha, a_dev, lda, b_dev, ldb, beta, c_dev,
+                         ldc, slices, lower, (cudaStream_t)stream, nullptr);
 }

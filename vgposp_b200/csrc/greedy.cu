@@ -478,11 +478,6 @@ int check_handle(vgp_greedy *h) {
     return VGP_OK;
 }
 
-int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
 }  // namespace
 
 #define H_LAUNCH_CHECK(h)      \
@@ -493,9 +488,7 @@ int env_int(const char *name, int dflt) {
 
 // The dominant kernel: one streaming read-modify-write pass over the local precision panel.
 static int launch_downdate(vgp_greedy *h, cudaStream_t s) {
-    static const int rows_per_block = env_int("VGP_DOWNDATE_ROWS", 32);
-    static const int waves = env_int("VGP_DOWNDATE_WAVES", 4);
-    static const int unroll = env_int("VGP_DOWNDATE_UNROLL", 4);
+    constexpr int rows_per_block = 32, waves = 4, unroll = 4;     // tuned on B200 (profiles/r01_kernel_bench_n50000.json)
     const unsigned gx = (unsigned)((h->ld + 511) / 512);
     const int64_t row_tiles = (h->n_pad + rows_per_block - 1) / rows_per_block;
     int64_t gy = ((int64_t)h->sm_count * 8 * waves + gx - 1) / gx;
@@ -509,12 +502,7 @@ static int launch_downdate(vgp_greedy *h, cudaStream_t s) {
         VGP_CUDA(cudaEventCreate(&pe1));
         VGP_CUDA(cudaEventRecord(pe0, s));
     }
-    if (unroll >= 8)
-        downdate_kernel<8><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
-    else if (unroll >= 4)
-        downdate_kernel<4><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
-    else
-        downdate_kernel<2><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
+    downdate_kernel<unroll><<<grid, 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->pfull, h->ploc, h->c0, h->cur, rows_per_block);
     H_LAUNCH_CHECK(h);
     if (h->profile) {
         VGP_CUDA(cudaEventRecord(pe1, s));
@@ -569,7 +557,8 @@ int vgp_greedy_create(vgp_greedy **handle, int device, int64_t n, int64_t c0, in
         {(void **)&h->sel_score, (size_t)kmax * 8},
     };
     for (auto &a : allocs) {
-        e = cudaMalloc(a.p, a.bytes);
+        // the two panels come from (and go back to) the per-device workspace cache: see common.cuh
+        e = a.bytes == panel ? cache_alloc(a.p, a.bytes) : device_malloc(a.p, a.bytes);
         if (e != cudaSuccess) {
             int rc = cuda_fail(e, "cudaMalloc (greedy state)", __FILE__, __LINE__);
             vgp_greedy_destroy(h);
@@ -595,10 +584,11 @@ int vgp_greedy_create(vgp_greedy **handle, int device, int64_t n, int64_t c0, in
 int vgp_greedy_destroy(vgp_greedy *h) {
     if (!h) return VGP_OK;
     VGP_ENTER(h->device);
-    void *ptrs[] = {h->cov, h->prec, h->prec_saved, h->num, h->ploc, h->taken, h->wfull, h->pfull, h->seg,
+    void *ptrs[] = {h->num, h->ploc, h->taken, h->wfull, h->pfull, h->seg,
                     h->partials, h->cur, h->best, h->counter, h->sel, h->sel_score, h->step_scores};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (void *p : {(void *)h->cov, (void *)h->prec, (void *)h->prec_saved}) cache_free(p);
     if (h->comm_ipc)
         for (int q = 0; q < h->comm_nranks; ++q)
             if (q != h->comm_rank && h->peer_mb[q]) cudaIpcCloseMemHandle(h->peer_mb[q]);
@@ -657,7 +647,7 @@ int vgp_greedy_save_precision(vgp_greedy *h, void *stream) {
     VGP_TRY(check_handle(h));
     VGP_ENTER(h->device);
     const size_t panel = (size_t)h->n_pad * h->ld * sizeof(double);
-    if (!h->prec_saved) VGP_CUDA(cudaMalloc((void **)&h->prec_saved, panel));
+    if (!h->prec_saved) VGP_CUDA(cache_alloc((void **)&h->prec_saved, panel));
     VGP_CUDA(cudaMemcpyAsync(h->prec_saved, h->prec, panel, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return VGP_OK;
 }
@@ -800,10 +790,10 @@ int vgp_greedy_comm_create(vgp_greedy *h, int rank, int nranks, const int64_t *b
     h->comm_stride = stride;
     for (int g = 0; g <= nranks; ++g) h->comm_bounds[g] = bounds_host[g];
     h->mailbox_bytes = MB_SEGS + (size_t)2 * nranks * 2 * stride * 8;
-    VGP_CUDA(cudaMalloc((void **)&h->mailbox, h->mailbox_bytes));
+    VGP_CUDA(device_malloc((void **)&h->mailbox, h->mailbox_bytes));
     VGP_CUDA(cudaMemset(h->mailbox, 0, h->mailbox_bytes));
     if (!h->counter2) {
-        VGP_CUDA(cudaMalloc((void **)&h->counter2, sizeof(unsigned)));
+        VGP_CUDA(device_malloc((void **)&h->counter2, sizeof(unsigned)));
         VGP_CUDA(cudaMemset(h->counter2, 0, sizeof(unsigned)));
     }
     VGP_CUDA(cudaDeviceSynchronize());
@@ -928,7 +918,7 @@ int vgp_greedy_record_scores(vgp_greedy *h, int enable) {
     VGP_TRY(check_handle(h));
     VGP_ENTER(h->device);
     if (enable && !h->step_scores)
-        VGP_CUDA(cudaMalloc((void **)&h->step_scores, (size_t)h->kmax * h->nloc * 8));
+        VGP_CUDA(device_malloc((void **)&h->step_scores, (size_t)h->kmax * h->nloc * 8));
     h->record = enable ? 1 : 0;
     return VGP_OK;
 }

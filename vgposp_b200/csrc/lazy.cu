@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <new>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -483,7 +484,8 @@ static int lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, d
     };
     for (auto &al : allocs) {
         if (al.bytes == 0) continue;
-        cudaError_t e = cudaMalloc(al.p, al.bytes);
+        // the two matrices come from (and go back to) the per-device workspace cache: see common.cuh
+        cudaError_t e = al.bytes == mat ? cache_alloc(al.p, al.bytes) : device_malloc(al.p, al.bytes);
         if (e != cudaSuccess) {
             int rc = cuda_fail(e, "cudaMalloc (lazy greedy state)", __FILE__, __LINE__);
             vgp_lazy_destroy(h);
@@ -514,11 +516,13 @@ static int lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, d
 int vgp_lazy_destroy(vgp_lazy *h) {
     if (!h) return VGP_OK;
     VGP_ENTER(h->device);
-    void *ptrs[] = {h->cov, h->own_fac ? h->fac : nullptr, h->d, h->d0, h->num, h->taken, h->U, h->W, h->inv,
+    void *ptrs[] = {h->d, h->d0, h->num, h->taken, h->U, h->W, h->inv,
                     h->own_partial ? h->partial : nullptr, h->partials, h->cur, h->counter, h->sel, h->sel_score,
                     h->step_scores, h->cache};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    cache_free(h->cov);
+    if (h->own_fac) cache_free(h->fac);
     for (auto &e : h->pe)
         if (e) cudaEventDestroy(e);
     h->ws.release();
@@ -713,7 +717,7 @@ int vgp_lazy_set_local(vgp_lazy *h, int64_t i0, int64_t i1, int64_t i2, int64_t 
                 (long long)i0, (long long)i1, (long long)i2, (long long)h->n);
     VGP_REQUIRE(h->t == 0, "set the local mode before the first selection");
     VGP_ENTER(h->device);
-    if (!h->cache) VGP_CUDA(cudaMalloc((void **)&h->cache, (size_t)h->n_pad * 8));
+    if (!h->cache) VGP_CUDA(device_malloc((void **)&h->cache, (size_t)h->n_pad * 8));
     h->loc_i1 = i1;
     h->loc_i2 = i2;
     h->loc_cutoff = cutoff;
@@ -723,7 +727,7 @@ int vgp_lazy_set_local(vgp_lazy *h, int64_t i0, int64_t i1, int64_t i2, int64_t 
 int vgp_lazy_record_scores(vgp_lazy *h, int enable) {
     VGP_TRY(check(h));
     VGP_ENTER(h->device);
-    if (enable && !h->step_scores) VGP_CUDA(cudaMalloc((void **)&h->step_scores, (size_t)h->kmax * h->n * 8));
+    if (enable && !h->step_scores) VGP_CUDA(device_malloc((void **)&h->step_scores, (size_t)h->kmax * h->n * 8));
     h->record = enable ? 1 : 0;
     return VGP_OK;
 }
@@ -769,6 +773,15 @@ int vgp_placement_host_dense(int device, const double *cov_host, int64_t n, int6
                              double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
                              double *seconds_host);
 
+// host wall-clock breakdown of this thread's last vgp_placement_host_ex call (lazy formulations):
+// [0] state allocation + init, [1] enqueue, [2] release, [3] whole call
+static thread_local double g_call_stats[4] = {0, 0, 0, 0};
+int vgp_placement_host_wall(double *seconds4) {
+    VGP_REQUIRE(seconds4, "NULL argument");
+    for (int i = 0; i < 4; ++i) seconds4[i] = g_call_stats[i];
+    return VGP_OK;
+}
+
 int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
                           double jitter, int formulation, int64_t *selection_host, double *scores_host,
                           double *step_scores_host, double *seconds_host) {
@@ -784,15 +797,24 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
         return vgp_placement_host_dense(device, cov_host, n, ld_host, k, small, jitter, selection_host, scores_host,
                                         step_scores_host, seconds_host);
     VGP_ENTER(device);
+    const auto wall0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
+    };
+    for (double &v : g_call_stats) v = 0.0;
     vgp_lazy *h = nullptr;
     VGP_TRY(vgp_lazy_create(&h, device, n, k, small, jitter, formulation == VGP_FORMULATION_LAZY_FACTOR ? 1 : 0));
+    g_call_stats[0] = since(wall0);                  // state allocation (workspace cache hit or cudaMalloc) + init
     cudaStream_t s = nullptr;
     cudaEvent_t ev[4];
     for (auto &e : ev) cudaEventCreate(&e);
     int rc = VGP_OK;
     auto fail = [&](int code) {
         for (auto &e : ev) cudaEventDestroy(e);
+        const auto t = std::chrono::steady_clock::now();
         vgp_lazy_destroy(h);
+        g_call_stats[2] = since(t);                  // release (back into the workspace cache)
+        g_call_stats[3] = since(wall0);
         return code;
     };
     // H2D of the lower triangle in row chunks on a copy stream; the factorisation starts at once on `s` and every
@@ -837,8 +859,8 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
     gate.chunk_rows = CHUNK_ROWS;
     gate.events = chunk_ev.data();
     gate.nchunks = nchunks;
-    const char *ov = getenv("VGP_H2D_OVERLAP");          // measurement knob: "0" = finish the copy before factorising
-    if (ov && ov[0] == '0') gate.waited = nchunks, cudaStreamWaitEvent(s, chunk_ev[(size_t)nchunks - 1], 0);
+    if (option(VGP_OPT_H2D_OVERLAP) == 0)                // measurement knob: finish the copy before factorising
+        gate.waited = nchunks, cudaStreamWaitEvent(s, chunk_ev[(size_t)nchunks - 1], 0);
     dense_set_gate(&gate);
     int info = 0;
     rc = lazy_factor_staged(h, &info, s);
@@ -848,20 +870,21 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
     cudaEventRecord(ev[2], s);
     if (step_scores_host) {
         rc = vgp_lazy_record_scores(h, 1);
-        if (rc != VGP_OK) return fail(rc);
+        if (rc != VGP_OK) return fail2(rc);
     }
     rc = vgp_lazy_run(h, k, s);
-    if (rc != VGP_OK) return fail(rc);
+    if (rc != VGP_OK) return fail2(rc);
     int64_t count = 0;
     rc = vgp_lazy_results(h, &count, selection_host, scores_host, k, s);
-    if (rc != VGP_OK) return fail(rc);
+    if (rc != VGP_OK) return fail2(rc);
     if (step_scores_host) {
         rc = vgp_lazy_step_scores(h, step_scores_host, k, s);
-        if (rc != VGP_OK) return fail(rc);
+        if (rc != VGP_OK) return fail2(rc);
     }
     cudaEventRecord(ev[3], s);
+    g_call_stats[1] = since(wall0) - g_call_stats[0];         // host time to enqueue everything
     ce = cudaEventSynchronize(ev[3]);
-    if (ce != cudaSuccess) return fail(cuda_fail(ce, "placement", __FILE__, __LINE__));
+    if (ce != cudaSuccess) return fail2(cuda_fail(ce, "placement", __FILE__, __LINE__));
     if (seconds_host) {
         float ms;
         cudaEventElapsedTime(&ms, ev[0], ev[1]);

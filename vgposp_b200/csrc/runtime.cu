@@ -2,6 +2,11 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 #include "common.cuh"
 
 namespace vgp {
@@ -36,6 +41,132 @@ static void keep_pool_memory(int device) {
     }
     cudaGetLastError();
     done[device] = true;
+}
+
+// ---- options ------------------------------------------------------------------------------------------------------
+static std::atomic<int64_t> g_options[VGP_OPT_COUNT] = {
+    {8},       // VGP_OPT_GEMM_EMULATE_SLICES
+    {2048},    // VGP_OPT_GEMM_EMULATE_MIN
+    {1},       // VGP_OPT_H2D_OVERLAP
+    {-1},      // VGP_OPT_GEMM_TILE_CONFIG
+    {74},      // VGP_OPT_GEMM_SMALL_BELOW
+    {96},      // VGP_OPT_DIST_MIN_TILES
+    {256},     // VGP_OPT_DIST_MIN_K
+    {3},       // VGP_OPT_ELBO_OVERLAP
+    {-1},      // VGP_OPT_WORKSPACE_CACHE_BYTES (-1: half of the device's memory)
+};
+int64_t option(int which) { return which >= 0 && which < VGP_OPT_COUNT ? g_options[which].load() : 0; }
+
+// ---- workspace cache ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int MAX_DEV = 64;
+constexpr size_t GRANULE = 2u << 20;
+struct Block {
+    void *ptr;
+    size_t bytes;
+};
+std::mutex g_cache_mu;
+std::vector<Block> g_cache_free[MAX_DEV];
+std::unordered_map<void *, size_t> g_cache_live[MAX_DEV];
+size_t g_cache_bytes[MAX_DEV];
+
+int current_device() {
+    int d = -1;
+    return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < MAX_DEV ? d : -1;
+}
+size_t cache_limit(int device) {
+    const int64_t v = option(VGP_OPT_WORKSPACE_CACHE_BYTES);
+    if (v >= 0) return (size_t)v;
+    size_t f = 0, t = 0;
+    if (cudaMemGetInfo(&f, &t) != cudaSuccess) return 0;
+    (void)device;
+    return t / 2;
+}
+size_t trim_locked(int device) {
+    size_t freed = 0;
+    for (Block &b : g_cache_free[device]) {
+        cudaFree(b.ptr);
+        freed += b.bytes;
+    }
+    g_cache_free[device].clear();
+    g_cache_bytes[device] = 0;
+    return freed;
+}
+}  // namespace
+
+size_t cache_trim_current(size_t *cached_before) {
+    const int d = current_device();
+    if (d < 0) return 0;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (cached_before) *cached_before = g_cache_bytes[d];
+    return trim_locked(d);
+}
+
+cudaError_t device_malloc(void **ptr, size_t bytes) {
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaErrorMemoryAllocation) return e;
+    cudaGetLastError();
+    const int d = current_device();
+    if (d < 0) return e;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        if (trim_locked(d) == 0) return e;
+    }
+    return cudaMalloc(ptr, bytes);
+}
+
+cudaError_t cache_alloc(void **ptr, size_t bytes) {
+    *ptr = nullptr;
+    const int d = current_device();
+    if (d < 0) return cudaErrorInvalidDevice;
+    bytes = (bytes + GRANULE - 1) / GRANULE * GRANULE;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    std::vector<Block> &fr = g_cache_free[d];
+    int best = -1;
+    for (int i = 0; i < (int)fr.size(); ++i)
+        if (fr[i].bytes >= bytes && fr[i].bytes <= bytes + bytes / 8 && (best < 0 || fr[i].bytes < fr[best].bytes)) best = i;
+    if (best >= 0) {
+        *ptr = fr[best].ptr;
+        g_cache_live[d][*ptr] = fr[best].bytes;
+        g_cache_bytes[d] -= fr[best].bytes;
+        fr.erase(fr.begin() + best);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        if (trim_locked(d) > 0) e = cudaMalloc(ptr, bytes);
+    }
+    if (e == cudaSuccess) g_cache_live[d][*ptr] = bytes;
+    return e;
+}
+
+void cache_free(void *ptr) {
+    if (!ptr) return;
+    const int d = current_device();
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        if (d >= 0) {
+            auto it = g_cache_live[d].find(ptr);
+            if (it != g_cache_live[d].end()) {
+                bytes = it->second;
+                g_cache_live[d].erase(it);
+            }
+        }
+    }
+    if (bytes == 0 || d < 0) {           // not one of ours (or allocated on another device): plain release
+        cudaFree(ptr);
+        return;
+    }
+    cudaDeviceSynchronize();             // what cudaFree would have done: nothing in flight still uses the block
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (g_cache_bytes[d] + bytes <= cache_limit(d)) {
+        g_cache_free[d].push_back({ptr, bytes});
+        g_cache_bytes[d] += bytes;
+    } else {
+        cudaFree(ptr);
+    }
 }
 
 DeviceGuard::DeviceGuard(int device) {
@@ -96,11 +227,49 @@ int vgp_device_info(int device, char *name, int len, int *sm_count, size_t *tota
     return VGP_OK;
 }
 
+int vgp_set_option(int option_id, int64_t value) {
+    VGP_REQUIRE(option_id >= 0 && option_id < VGP_OPT_COUNT, "unknown option %d", option_id);
+    switch (option_id) {
+        case VGP_OPT_GEMM_EMULATE_SLICES:
+            VGP_REQUIRE(value == 0 || (value >= 2 && value <= 8), "digit planes must be 0 (off) or 2..8");
+            break;
+        case VGP_OPT_GEMM_EMULATE_MIN:
+            VGP_REQUIRE(value >= 128, "smallest emulated product must be >= 128");
+            break;
+        case VGP_OPT_GEMM_TILE_CONFIG:
+            VGP_REQUIRE(value >= -1 && value <= 2, "tile configuration: -1 auto, 0 base, 1 pair, 2 tma");
+            break;
+        case VGP_OPT_DIST_MIN_TILES:
+        case VGP_OPT_DIST_MIN_K:
+        case VGP_OPT_GEMM_SMALL_BELOW:
+            VGP_REQUIRE(value >= 0, "negative threshold");
+            break;
+        default:
+            break;
+    }
+    g_options[option_id].store(value);
+    return VGP_OK;
+}
+
+int vgp_get_option(int option_id, int64_t *value) {
+    VGP_REQUIRE(option_id >= 0 && option_id < VGP_OPT_COUNT && value, "unknown option %d", option_id);
+    *value = g_options[option_id].load();
+    return VGP_OK;
+}
+
+int vgp_workspace_trim(int device, size_t *released_bytes) {
+    VGP_ENTER(device);
+    VGP_CUDA(cudaDeviceSynchronize());
+    const size_t freed = cache_trim_current(nullptr) + emulated_release();
+    if (released_bytes) *released_bytes = freed;
+    return VGP_OK;
+}
+
 int vgp_malloc(int device, size_t bytes, void **ptr_dev) {
     VGP_REQUIRE(ptr_dev, "ptr is NULL");
     VGP_ENTER(device);
     *ptr_dev = nullptr;
-    VGP_CUDA(cudaMalloc(ptr_dev, bytes ? bytes : 1));
+    VGP_CUDA(device_malloc(ptr_dev, bytes ? bytes : 1));
     return VGP_OK;
 }
 
