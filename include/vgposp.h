@@ -421,6 +421,20 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
 int vgp_placement_host(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
                        double jitter, int64_t *selection_host, double *scores_host, double *step_scores_host,
                        double *seconds_host);
+/* The same call for a positive SEMI-definite cov_vv of numerical rank r < n (e.g. an empirical covariance M M^T / S
+ * over n > S locations: main_architecture_2.py:391-444, gp_functions.py:1019-1057), where the reference's
+ * np.linalg.pinv (placement_algorithm2.py:399-405) is a true pseudo-inverse and vgp_placement_host* return
+ * VGP_ERR_NOT_PD (their Cholesky meets a pivot below 1e-12 of the largest variance).  Conditional variances are taken
+ * in the factor space of a pivoted Cholesky (csrc/pinv.cu): sigma^2(y | A) as the distance of f_y from span F_A,
+ * sigma^2(y | Abar \ y) = 0 unless y is essential for the span of Abar (then 1 / (Sigma_AbarAbar^+)_yy), guard and
+ * first-strict-maximum rule as in the reference (:116-123).  algorithm = 1: placement_algorithm_1 (fresh deltas every
+ * selection); 2: placement_algorithm_2 (its lazy cache, :151-219 -- on these inputs the two differ, because a delta can
+ * rise from 0 to a positive value between selections).  The whole symmetric matrix is read.  max_rank <= 0: n.
+ * rank_host (optional) receives r; seconds_host [4] = [0, H2D + factor, selections, total] (CUDA events).
+ * In the reference's own regime (r << n) every delta is 0 and the selection is [0, 1, ..., k - 1], as the reference's. */
+int vgp_placement_host_pinv(int device, const double *cov_host, int64_t n, int64_t ld_host, int64_t k, double small,
+                            int algorithm, int64_t max_rank, int64_t *selection_host, double *scores_host, double *step_scores_host,
+                            int64_t *rank_host, double *seconds_host);
 /* Host wall-clock breakdown of the calling thread's last vgp_placement_host_ex (lazy formulations), in seconds:
  * [0] state allocation + initialisation (a hit in the per-device workspace cache after the first call), [1] enqueue of
  * copies, factorisation and selections, [2] release of the state (back into the cache), [3] the whole call. */

@@ -441,3 +441,68 @@ def incremental_greedy_c(cov_vv, k, small=GUARD_NUMPY, jitter=0.0, prec=None, ti
         if timings is not None:
             timings["steps_s"].append(time.perf_counter() - t1)
     return selection, np.array(win)
+
+
+# --------------------------------------------------------------------------------------------------
+# rank-deficient covariances: the reference's pinv semantics in closed form
+# --------------------------------------------------------------------------------------------------
+def pinv_step_scores(cov_vv, A, small=GUARD_NUMPY, rank_tol=1e-12, leverage_tol=1e-6):
+    """delta_y for every y not in A on a positive SEMI-definite cov_vv, as the reference computes them with
+    np.linalg.pinv (placement_algorithm2.py:371-413), from two symmetric eigendecompositions instead of one SVD per
+    candidate:
+
+      nominator    sigma^2(y | A)        = Sigma_yy - Sigma_yA pinv(Sigma_AA) Sigma_Ay
+      denominator  sigma^2(y | Abar \\ y) = 0 when e_y is not in the range of Sigma_AbarAbar (y's factor-space vector lies
+                   in the span of the others: leverage (Sigma Sigma^+)_yy < 1), else 1 / (Sigma_AbarAbar^+)_yy
+
+    (block-inverse identity on the range of Sigma_AbarAbar).  Eigenvalues below rank_tol x the largest are treated as
+    zero -- on exactly rank-deficient inputs they are rounding noise ~1e-17, far below either this cut or pinv's 1e-15."""
+    cov = np.asarray(cov_vv, dtype=np.float64)
+    n = cov.shape[0]
+    A = [int(a) for a in A]
+    rest = np.array([v for v in range(n) if v not in A], dtype=np.int64)
+    scale = float(np.max(np.diag(cov)))
+    nom = np.diag(cov)[rest].copy()
+    if A:
+        w, v = np.linalg.eigh(cov[np.ix_(A, A)])
+        keep = w > rank_tol * max(w.max(), 0.0) if w.max() > 0 else np.zeros_like(w, dtype=bool)
+        proj = (v[:, keep].T @ cov[np.ix_(A, rest)]) / np.sqrt(w[keep])[:, None]
+        nom = nom - np.sum(proj * proj, axis=0)
+    w, v = np.linalg.eigh(cov[np.ix_(rest, rest)])
+    keep = w > rank_tol * scale
+    lev = np.sum(v[:, keep] ** 2, axis=1)
+    pinv_diag = np.sum(v[:, keep] ** 2 / w[keep][None, :], axis=1)
+    den = np.where((lev >= 1.0 - leverage_tol) & (pinv_diag > 0), 1.0 / np.where(pinv_diag > 0, pinv_diag, 1.0), 0.0)
+    out = np.full(n, np.nan)
+    out[rest] = guarded_scores(nom, den, small)
+    return out
+
+
+def pinv_greedy(cov_vv, k, algorithm=1, small=GUARD_NUMPY):
+    """placement_algorithm_1 (algorithm=1: first strict maximum of the fresh scores, :128-145) or placement_algorithm_2
+    (algorithm=2: the lazy cache, :151-219 -- NOT equivalent to alg. 1 here, because on rank-deficient inputs a delta
+    can rise from 0 to a positive value between steps, which the stale cache never sees) on a rank-deficient PSD
+    matrix.  Returns (selection, winning deltas, per-step score vectors [k, n])."""
+    n = np.asarray(cov_vv).shape[0]
+    A, win, steps = [], [], []
+    cache = np.full(n, np.inf)
+    taken = np.zeros(n, dtype=bool)
+    for _ in range(k):
+        scores = pinv_step_scores(cov_vv, A, small)
+        steps.append(scores)
+        if algorithm == 1:
+            y = first_argmax(np.nan_to_num(scores, nan=-np.inf), taken)
+        else:
+            fresh = np.zeros(n, dtype=bool)
+            while True:
+                y = first_argmax(cache, taken)
+                if y < 0 or fresh[y]:
+                    break
+                cache[y] = scores[y]
+                fresh[y] = True
+        if y < 0:
+            raise ValueError("list.remove(x): x not in list")
+        win.append(float(scores[y]))
+        A.append(int(y))
+        taken[y] = True
+    return A, np.array(win), np.array(steps)

@@ -73,8 +73,10 @@ def test_dropin_error_behaviour():
     with pytest.raises(ValueError, match="not in list"):                  # reference: A_bar.remove(-1), :144
         alg2.placement_algorithm_1(cov, 5)
     assert alg2.placement_algorithm_1(cov, 0) == []
-    with pytest.raises(np.linalg.LinAlgError):                             # rank-deficient: reference would pinv
-        alg2.placement_algorithm_1(np.ones((6, 6)), 2)
+    # rank-deficient PSD input: the pseudo-inverse path gives what the reference's pinv gives (all deltas 0 -> [0, 1])
+    assert alg2.placement_algorithm_1(np.ones((6, 6)), 2) == [0, 1]
+    with pytest.raises(np.linalg.LinAlgError):                             # indefinite: neither path applies
+        alg2.placement_algorithm_1(np.array([[1.0, 2.0, 0.0], [2.0, 1.0, 0.0], [0.0, 0.0, 1.0]]), 2)
     with pytest.raises(ValueError):
         alg2.placement_algorithm_1(np.ones((3, 4)), 1)
 

@@ -143,6 +143,7 @@ SIGNATURES = {
     "vgp_placement_host": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp],
     "vgp_placement_host_ex": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgp_placement_host_wall": [c_vp],
+    "vgp_placement_host_pinv": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_int, c_i64, c_vp, c_vp, c_vp, P(c_i64), c_vp],
     "vgp_lazy_create": [P(c_vp), c_int, c_i64, c_i64, c_dbl, c_dbl, c_int],
     "vgp_lazy_destroy": [c_vp],
     "vgp_lazy_matrices": [c_vp, P(c_vp), P(c_vp), P(c_i64)],

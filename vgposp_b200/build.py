@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvgposp.so")
-SOURCES = ["runtime.cu", "expquad.cu", "dense.cu", "dense_api.cu", "greedy.cu", "gp.cu", "elbo.cu", "dist.cu", "lazy.cu", "emulated.cu"]
+SOURCES = ["runtime.cu", "expquad.cu", "dense.cu", "dense_api.cu", "greedy.cu", "gp.cu", "elbo.cu", "dist.cu", "lazy.cu", "emulated.cu", "pinv.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -14,7 +14,7 @@ constexpr int NB = 128;
 
 template <int SJ>
 __device__ __forceinline__ void potf2_panel(double (&v)[8][8], double (*colbuf)[NB], int ti, int tc, int *info,
-                                            int row_offset) {
+                                            int row_offset, double pivot_floor = 0.0) {
 #pragma unroll 1
     for (int jj = 0; jj < 16; ++jj) {
         const int j = 16 * SJ + jj, jb = j & 1;
@@ -24,7 +24,8 @@ __device__ __forceinline__ void potf2_panel(double (&v)[8][8], double (*colbuf)[
         }
         __syncthreads();
         const double d = colbuf[jb][j];
-        if (!(d > 0.0) && threadIdx.x == 0) atomicCAS(info, 0, row_offset + j + 1);
+        // pivot_floor > 0: a conditional variance this far below the matrix scale means numerical rank deficiency
+        if (!(d > pivot_floor) && threadIdx.x == 0) atomicCAS(info, 0, row_offset + j + 1);
         const double piv = sqrt(d);
         const double inv = 1.0 / piv;
         double lr[8], lc[8];

@@ -865,7 +865,8 @@ constexpr int BLOCK_SMEM = NB * SLD * 8;    // 132 096 B
 // which rows / columns lie behind the pivot (and need no update) are then compile-time facts, and the trailing
 // update shrinks with the panel -- the first version carried them as run-time selects (374 FSEL per column, 200 us
 // per block, issue-bound; ncu launch list of the ELBO step).
-__global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, int *info, int row_offset) {
+__global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, int *info, int row_offset,
+                                                       double pivot_floor) {
     __shared__ double colbuf[2][NB];
     const int ti = threadIdx.x >> 4, tc = threadIdx.x & 15;
     double v[8][8];
@@ -876,14 +877,14 @@ __global__ void __launch_bounds__(256, 1) potf2_kernel(double *a, int64_t ld, in
             const int i = ti + 16 * r, c = tc + 16 * s;
             v[r][s] = c <= i ? a[(int64_t)i * ld + c] : 0.0;
         }
-    potf2_panel<0>(v, colbuf, ti, tc, info, row_offset);
-    potf2_panel<1>(v, colbuf, ti, tc, info, row_offset);
-    potf2_panel<2>(v, colbuf, ti, tc, info, row_offset);
-    potf2_panel<3>(v, colbuf, ti, tc, info, row_offset);
-    potf2_panel<4>(v, colbuf, ti, tc, info, row_offset);
-    potf2_panel<5>(v, colbuf, ti, tc, info, row_offset);
-    potf2_panel<6>(v, colbuf, ti, tc, info, row_offset);
-    potf2_panel<7>(v, colbuf, ti, tc, info, row_offset);
+    potf2_panel<0>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
+    potf2_panel<1>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
+    potf2_panel<2>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
+    potf2_panel<3>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
+    potf2_panel<4>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
+    potf2_panel<5>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
+    potf2_panel<6>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
+    potf2_panel<7>(v, colbuf, ti, tc, info, row_offset, pivot_floor);
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -1049,6 +1050,12 @@ void DenseWorkspace::release() {
     device = -1;
 }
 
+// Pivots at or below this count as "not positive definite" in dense_potrf (thread-local; 0 = only non-positive pivots).
+// The one-call placement entries set it to 1e-12 x the largest diagonal entry of cov_vv: below that the Cholesky of
+// a covariance is numerically rank deficient and the reference's pinv semantics apply (pinv.cu).
+static thread_local double g_pivot_floor = 0.0;
+void dense_set_pivot_floor(double floor) { g_pivot_floor = floor > 0.0 ? floor : 0.0; }
+
 static inline int64_t split(int64_t n) {
     int64_t n1 = (n / NB / 2) * NB;
     return n1 < NB ? NB : n1;
@@ -1156,7 +1163,7 @@ static int potrf_rec(double *a, int64_t n, int64_t ld, int64_t row_offset, doubl
                      cudaStream_t s) {
     if (n == NB) {
         VGP_TRY(gate_wait(a, NB, s));
-        potf2_kernel<<<1, 256, 0, s>>>(a, ld, ws.info, (int)row_offset);
+        potf2_kernel<<<1, 256, 0, s>>>(a, ld, ws.info, (int)row_offset, g_pivot_floor);
         VGP_LAUNCH_CHECK();
         return block_trtri(a, ld, dinv, NB, 0, s);          // cache inv(L_ii) for every later solve
     }
@@ -1296,8 +1303,8 @@ int dense_read_info(DenseWorkspace &ws, int *info_host, cudaStream_t s) {
     VGP_CUDA(cudaStreamSynchronize(s));
     if (info_host) *info_host = info;
     if (info != 0) {
-        set_error("matrix is not positive definite: non-positive pivot at row %d "
-                  "(the reference would take a pseudo-inverse here; this path needs an SPD input)",
+        set_error("matrix is not positive definite: non-positive (or numerically zero) pivot at row %d "
+                  "(the reference takes a pseudo-inverse here: vgp_placement_host_pinv; this path needs an SPD input)",
                   info - 1);
         return VGP_ERR_NOT_PD;
     }

@@ -68,6 +68,7 @@ struct RowGate {
     int nchunks = 0, waited = 0;            // chunks [0, waited) are already ordered before the compute stream
 };
 void dense_set_gate(RowGate *gate);         // thread-local; nullptr switches it off
+void dense_set_pivot_floor(double floor);   // thread-local; pivots <= floor fail dense_potrf (0: only non-positive ones)
 
 enum GemmTiles { GEMM_FULL = 0, GEMM_LOWER = 1 };   // LOWER: only tiles with tile_row >= tile_col
 

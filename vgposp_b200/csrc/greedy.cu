@@ -558,7 +558,8 @@ int vgp_greedy_create(vgp_greedy **handle, int device, int64_t n, int64_t c0, in
     };
     for (auto &a : allocs) {
         // the two panels come from (and go back to) the per-device workspace cache: see common.cuh
-        e = a.bytes == panel ? cache_alloc(a.p, a.bytes) : device_malloc(a.p, a.bytes);
+        const bool is_panel = a.p == (void **)&h->cov || a.p == (void **)&h->prec;
+        e = is_panel ? cache_alloc(a.p, a.bytes) : device_malloc(a.p, a.bytes);
         if (e != cudaSuccess) {
             int rc = cuda_fail(e, "cudaMalloc (greedy state)", __FILE__, __LINE__);
             vgp_greedy_destroy(h);
@@ -961,10 +962,16 @@ int vgp_placement_host_dense(int device, const double *cov_host, int64_t n, int6
     for (auto &e : ev) cudaEventCreate(&e);
     int rc = VGP_OK;
     auto fail = [&](int code) {
+        dense_set_pivot_floor(0.0);
         for (auto &e : ev) cudaEventDestroy(e);
         vgp_greedy_destroy(h);
         return code;
     };
+    {   // numerical rank deficiency counts as "not positive definite": pivots below 1e-12 of the largest variance
+        double scale = 0.0;
+        for (int64_t i = 0; i < n; ++i) scale = std::max(scale, fabs(cov_host[i * ld_host + i]));
+        dense_set_pivot_floor(1e-12 * scale);
+    }
     cudaEventRecord(ev[0], s);
     cudaError_t ce = cudaMemcpy2DAsync(h->cov, (size_t)h->ld * 8, cov_host, (size_t)ld_host * 8, (size_t)n * 8,
                                        (size_t)n, cudaMemcpyHostToDevice, s);

@@ -485,7 +485,8 @@ static int lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, d
     for (auto &al : allocs) {
         if (al.bytes == 0) continue;
         // the two matrices come from (and go back to) the per-device workspace cache: see common.cuh
-        cudaError_t e = al.bytes == mat ? cache_alloc(al.p, al.bytes) : device_malloc(al.p, al.bytes);
+        const bool is_matrix = al.p == (void **)&h->cov || al.p == (void **)&h->fac;
+        cudaError_t e = is_matrix ? cache_alloc(al.p, al.bytes) : device_malloc(al.p, al.bytes);
         if (e != cudaSuccess) {
             int rc = cuda_fail(e, "cudaMalloc (lazy greedy state)", __FILE__, __LINE__);
             vgp_lazy_destroy(h);
@@ -805,11 +806,17 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
     vgp_lazy *h = nullptr;
     VGP_TRY(vgp_lazy_create(&h, device, n, k, small, jitter, formulation == VGP_FORMULATION_LAZY_FACTOR ? 1 : 0));
     g_call_stats[0] = since(wall0);                  // state allocation (workspace cache hit or cudaMalloc) + init
+    {   // numerical rank deficiency counts as "not positive definite": pivots below 1e-12 of the largest variance
+        double scale = 0.0;
+        for (int64_t i = 0; i < n; ++i) scale = std::max(scale, fabs(cov_host[i * ld_host + i]));
+        dense_set_pivot_floor(1e-12 * scale);
+    }
     cudaStream_t s = nullptr;
     cudaEvent_t ev[4];
     for (auto &e : ev) cudaEventCreate(&e);
     int rc = VGP_OK;
     auto fail = [&](int code) {
+        dense_set_pivot_floor(0.0);
         for (auto &e : ev) cudaEventDestroy(e);
         const auto t = std::chrono::steady_clock::now();
         vgp_lazy_destroy(h);

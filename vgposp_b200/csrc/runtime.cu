@@ -102,8 +102,16 @@ size_t cache_trim_current(size_t *cached_before) {
     return trim_locked(d);
 }
 
+static void forget_live(void *ptr) {      // an address cudaMalloc hands out is not (or no longer) a cache block
+    const int d = current_device();
+    if (d < 0 || !ptr) return;
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    g_cache_live[d].erase(ptr);
+}
+
 cudaError_t device_malloc(void **ptr, size_t bytes) {
     cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaSuccess) forget_live(*ptr);
     if (e != cudaErrorMemoryAllocation) return e;
     cudaGetLastError();
     const int d = current_device();
@@ -112,7 +120,9 @@ cudaError_t device_malloc(void **ptr, size_t bytes) {
         std::lock_guard<std::mutex> lock(g_cache_mu);
         if (trim_locked(d) == 0) return e;
     }
-    return cudaMalloc(ptr, bytes);
+    e = cudaMalloc(ptr, bytes);
+    if (e == cudaSuccess) forget_live(*ptr);
+    return e;
 }
 
 cudaError_t cache_alloc(void **ptr, size_t bytes) {

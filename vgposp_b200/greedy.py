@@ -319,7 +319,8 @@ def check_selection(sel):
 FORMULATIONS = {"auto": -1, "dense": 0, "lazy_precision": 1, "lazy_factor": 2}     # VGP_FORMULATION_*
 
 
-def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_scores=False, formulation="auto"):
+def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_scores=False, formulation="auto",
+                 pinv_fallback=True, algorithm=1):
     """placement_algorithm_1/2(cov_vv, k) for a host matrix on one device: one C-ABI call
     (H2D, factorisation, k selections, D2H).  Returns (selection, scores, step_scores or None, seconds).
     formulation: "dense" (precision downdate, north-star formulation), "lazy_precision", "lazy_factor"
@@ -340,10 +341,44 @@ def place_single(cov_vv, k, device=0, small=GUARD_NUMPY, jitter=0.0, want_step_s
     sc = np.zeros(k)
     steps = np.empty((k, n)) if want_step_scores else None
     secs = np.zeros(4)
-    call("vgp_placement_host_ex", device, a.ctypes.data, n, a.strides[0] // 8, k, float(small), float(jitter),
-         FORMULATIONS[formulation], sel.ctypes.data, sc.ctypes.data,
-         steps.ctypes.data if want_step_scores else None, secs.ctypes.data)
+    try:
+        call("vgp_placement_host_ex", device, a.ctypes.data, n, a.strides[0] // 8, k, float(small), float(jitter),
+             FORMULATIONS[formulation], sel.ctypes.data, sc.ctypes.data,
+             steps.ctypes.data if want_step_scores else None, secs.ctypes.data)
+    except _ffi.NotPositiveDefiniteError:
+        if jitter != 0.0 or not pinv_fallback:
+            raise
+        # numerically rank-deficient covariance: the reference's pinv semantics (csrc/pinv.cu).  Raises
+        # NotPositiveDefiniteError itself when the matrix is not positive semi-definite either.
+        return place_single_pinv(a, k, device, small, want_step_scores, algorithm=algorithm)
     check_selection(sel)
+    return sel, sc, steps, secs
+
+
+def place_single_pinv(cov_vv, k, device=0, small=GUARD_NUMPY, want_step_scores=False, max_rank=0, algorithm=1):
+    """placement_algorithm_<algorithm>(cov_vv, k) for a positive semi-definite matrix of numerical rank r < n through
+    vgp_placement_host_pinv.  Returns (selection, scores, step_scores or None, seconds) like place_single;
+    `place_single_pinv.last_rank` holds r of the last call."""
+    _ffi.require_device(device)
+    a = np.ascontiguousarray(np.asarray(cov_vv), dtype=np.float64)
+    n = a.shape[0]
+    if not np.allclose(a, a.T, rtol=0, atol=1e-10 * max(float(np.abs(np.diag(a)).max()), 1e-300)):
+        raise ValueError("cov_vv must be symmetric for the pseudo-inverse path")
+    k = int(k)
+    sel = np.full(k, -1, dtype=np.int64)
+    sc = np.zeros(k)
+    steps = np.empty((k, n)) if want_step_scores else None
+    secs = np.zeros(4)
+    rank = _ffi.c_i64(0)
+    try:
+        call("vgp_placement_host_pinv", device, a.ctypes.data, n, n, k, float(small), int(algorithm), int(max_rank),
+             sel.ctypes.data,
+             sc.ctypes.data, steps.ctypes.data if want_step_scores else None, ctypes.byref(rank), secs.ctypes.data)
+    except _ffi.VgpError as e:
+        if "list.remove" in str(e):
+            raise ValueError("list.remove(x): x not in list") from None
+        raise
+    place_single_pinv.last_rank = int(rank.value)
     return sel, sc, steps, secs
 
 

@@ -9,12 +9,17 @@ kernels; this module only moves arrays and mirrors the reference's host-visible 
 np.int64 out, the per-evaluation prints of alg. 2, the ValueError when candidates run out).  There is no CPU
 fallback: without a GPU every function that needs arithmetic raises.
 
-Deviations from the reference, all deliberate and documented in DESIGN.md:
-  * the reference takes `np.linalg.pinv` of Sigma_AA and of Sigma_{Abar\\y}; this path needs cov_vv to be
-    symmetric positive definite (pinv == inv there) and raises `NotPositiveDefiniteError` otherwise;
-  * alg. 1 and alg. 2 return the same selection (the lazy evaluation of alg. 2 is an optimisation of the
-    same arg-max; the reference's two functions agree on every input tried), so both
-    are served by the dense per-step scores; alg. 2's print trace is replayed from them on the host;
+Semantics, documented in DESIGN.md:
+  * the reference takes `np.linalg.pinv` of Sigma_AA and of Sigma_{Abar\\y}.  A symmetric positive definite cov_vv
+    (pinv == inv) runs on the Cholesky-based kernels; when that factorisation meets a pivot below 1e-12 of the
+    largest variance -- a rank-deficient covariance such as the empirical M M^T / S the reference really feeds
+    (main_architecture_2.py:391-444) -- the call continues on the pseudo-inverse path (csrc/pinv.cu), which
+    reproduces the reference's results there (golden vectors: tests/golden/greedy_lowrank_golden.json).  A matrix
+    that is not even positive semi-definite raises `NotPositiveDefiniteError`;
+  * on positive definite inputs alg. 1 and alg. 2 return the same selection (the lazy evaluation of alg. 2 is an
+    optimisation of the same arg-max while deltas only fall), so both are served by the dense per-step scores and
+    alg. 2's print trace is replayed from them on the host; on rank-deficient inputs the two DIFFER in the reference
+    (a delta can rise from the guarded 0), and the pseudo-inverse path follows each algorithm's own rule;
   * `argmax_` needs A_bar == V \\ A (every caller in the reference passes that).
 """
 import time
@@ -179,7 +184,7 @@ def step_scores_given(A, cov_vv, small=_greedy.GUARD_NUMPY, jitter=0.0):
 # --------------------------------------------------------------------------------------------------
 def placement_algorithm_1(cov_vv, k):
     """Naive greedy MI placement (placement_algorithm2.py:128-145): list of k np.int64, selection order."""
-    sel, _, _, _ = _greedy.place_single(cov_vv, k, DEVICE)
+    sel, _, _, _ = _greedy.place_single(cov_vv, k, DEVICE, algorithm=1)
     return [np.int64(s) for s in sel]
 
 
@@ -188,8 +193,9 @@ def placement_algorithm_2(cov_vv, k):
     set the reference's evaluation trace ('delta_y= .. y_st= ..' / 'y*= ..', :188,205) is replayed from the
     per-step scores computed on the device."""
     if not PRINTS:
-        return placement_algorithm_1(cov_vv, k)
-    sel, _, steps, _ = _greedy.place_single(cov_vv, k, DEVICE, want_step_scores=True)
+        sel, _, _, _ = _greedy.place_single(cov_vv, k, DEVICE, algorithm=2)
+        return [np.int64(s) for s in sel]
+    sel, _, steps, _ = _greedy.place_single(cov_vv, k, DEVICE, want_step_scores=True, algorithm=2)
     for line in lazy_trace_lines(steps, sel):
         print(line)
     return [np.int64(s) for s in sel]
