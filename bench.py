@@ -596,8 +596,8 @@ def measure_elbo(dev, with_cpu, n=200000, m=512, b=4096, steps=10, warmup=3, dis
            "loss_first_last": [losses[0], losses[-1]], "roofline_bound": "fp64 tensor pipe (DMMA)"}
     tr.close()
     peak = dgemm_peak_tflops(dev)
-    out["roofline"] = {"bound": "tensor", "achieved": flop / dt / 1e12, "peak": peak, "unit": "TFLOP/s",
-                       "frac": flop / dt / 1e12 / peak, "traffic": None,
+    out["roofline"] = {"bound": "tensor", "achieved": flop / dt / 1e12 / world, "peak": peak, "unit": "TFLOP/s per GPU",
+                       "frac": flop / dt / 1e12 / world / peak, "traffic": None,
                        "peak_kind": "cuBLAS DGEMM 8192^3 measured in this run (FP64 tensor pipe; MEASURED_PEAKS.json "
                                     "holds no FP64 figure)"}
     if with_cpu:

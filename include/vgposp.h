@@ -263,6 +263,9 @@ typedef struct vgp_elbo vgp_elbo;
 int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const double *y_dev, int64_t n_obs, int d,
                     const double *z_init_host, int64_t m, int64_t batch, double v_amplitude, double v_length_scale,
                     double v_noise, double length_scale_offset, double jitter, double learning_rate);
+/* Kernel family of the training step: VGP_KERNEL_EXPQUAD (default), MATERN32 or MATERN52 -- the reference's VGP trains
+ * tfkern.MaternFiveHalves over 5-D (x, y, z, t, p) inputs (main_architecture_2.py:184-249).  Call before the first step. */
+int vgp_elbo_set_kernel(vgp_elbo *handle, int kind);
 int vgp_elbo_destroy(vgp_elbo *handle);
 /* Loss and gradient at the current parameters (blocking).  grads_host[3] = d loss / d v; gradz_host [m, d] and
  * terms_host are optional. */

@@ -16,9 +16,26 @@ import torch
 LOG_2PI = math.log(2.0 * math.pi)
 
 
+KERNEL = "expquad"      # module switch read by `expquad` below: "expquad", "matern32" or "matern52" (TFP's forms)
+
+
 def expquad(x1, x2, amp, ls):
+    """The kernel matrix of the model (ExpQuad unless KERNEL says otherwise; the name is kept for the call sites).
+    The Matern forms take r through a square root whose gradient at r = 0 is defined as 0 (the kernels are smooth
+    there; TFP uses a finite-gradient sqrt for the same purpose)."""
     d = x1[:, None, :] - x2[None, :, :]
-    return amp ** 2 * torch.exp((d * d).sum(-1) * (-0.5 / ls ** 2))
+    r2 = (d * d).sum(-1)
+    if KERNEL == "expquad":
+        return amp ** 2 * torch.exp(r2 * (-0.5 / ls ** 2))
+    pos = r2 > 0
+    r = torch.where(pos, torch.sqrt(torch.where(pos, r2, torch.ones_like(r2))), torch.zeros_like(r2))
+    if KERNEL == "matern32":
+        u = math.sqrt(3.0) * r / ls
+        return amp ** 2 * (1.0 + u) * torch.exp(-u)
+    if KERNEL == "matern52":
+        u = math.sqrt(5.0) * r / ls
+        return amp ** 2 * (1.0 + u + u * u / 3.0) * torch.exp(-u)
+    raise ValueError(KERNEL)
 
 
 def constrained(v_amp, v_ls, v_noise, ls_offset=1e-5):
@@ -68,7 +85,16 @@ def training_loss(params, x, y, xb, yb, jitter=1e-6, ls_offset=1e-5):
     return vgp_loss(z, loc, scale, xb, yb, amp, ls, noise, xb.shape[0] / x.shape[0], jitter)
 
 
-def loss_and_grads(v_amp, v_ls, v_noise, z, x, y, xb, yb, jitter=1e-6, ls_offset=1e-5):
+def loss_and_grads(v_amp, v_ls, v_noise, z, x, y, xb, yb, jitter=1e-6, ls_offset=1e-5, kernel="expquad"):
+    global KERNEL
+    previous, KERNEL = KERNEL, kernel
+    try:
+        return _loss_and_grads(v_amp, v_ls, v_noise, z, x, y, xb, yb, jitter, ls_offset)
+    finally:
+        KERNEL = previous
+
+
+def _loss_and_grads(v_amp, v_ls, v_noise, z, x, y, xb, yb, jitter=1e-6, ls_offset=1e-5):
     t = lambda a: torch.as_tensor(a, dtype=torch.float64)  # noqa: E731
     params = [t(v_amp).clone().requires_grad_(True), t(v_ls).clone().requires_grad_(True),
               t(v_noise).clone().requires_grad_(True), t(z).clone().requires_grad_(True)]

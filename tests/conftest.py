@@ -79,3 +79,13 @@ def vgp_options():
     yield set_
     for name, old in saved.items():
         _ffi.set_option(name, old)
+
+
+@pytest.fixture
+def quiet_alg2():
+    """placement_algorithm_2 without its per-evaluation prints, module state restored afterwards."""
+    import vgposp_b200.placement_algorithm2 as alg2
+    saved = alg2.PRINTS
+    alg2.PRINTS = False
+    yield alg2
+    alg2.PRINTS = saved

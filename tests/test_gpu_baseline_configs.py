@@ -47,7 +47,7 @@ def check_against_c_oracle(cov, k, label):
     return want_sel
 
 
-def test_cfg2_mesh_cloud_n10768_k50_all_formulations():
+def test_cfg2_mesh_cloud_n10768_k50_all_formulations(quiet_alg2):
     x, amp, ls, nugget = workloads.mesh_cloud()
     assert x.shape == (10768, 3) and abs(ls - 0.226) < 1e-3
     cov = gpf.ExponentiatedQuadratic(amp, ls).matrix(x, x)                  # the device builder (row a1)
@@ -55,8 +55,7 @@ def test_cfg2_mesh_cloud_n10768_k50_all_formulations():
     host_rows = workloads.expquad_cov_host(x[:512], amp, ls, 0.0)
     np.testing.assert_allclose(cov[:512, :512] - nugget * np.eye(512), host_rows, rtol=1e-13)
     sel = check_against_c_oracle(cov, 50, "cfg2 n=10768 k=50")
-    alg2.PRINTS = False
-    assert alg2.placement_algorithm_2(cov, 50) == sel                       # the drop-in call itself
+    assert quiet_alg2.placement_algorithm_2(cov, 50) == sel                 # the drop-in call itself
 
 
 def test_cfg4_cloud_prefix_n8192_matches_bench_cpu_arm():
@@ -90,10 +89,8 @@ def test_cfg1_sin_wave_n1000_vgp_m32_then_placement_k10():
     amp, ls, noise, zfit = tr.parameters()
     xt = np.random.default_rng(1).uniform(-2, 2, (200, 3))
     loc, scale = gpo.optimal_variational_posterior(zfit, x, y, amp, ls, noise)
-    want_mean = gpo.vgp_predict(zfit, loc, scale, xt, amp, ls)[0] if hasattr(gpo, "vgp_predict") else None
-    mean = tr.vgp(xt).mean()
-    if want_mean is not None:
-        np.testing.assert_allclose(mean, want_mean, rtol=1e-8, atol=1e-10)
+    want_mean = gpo.vgp_predict(zfit, loc, scale, xt, amp, ls)[0]
+    np.testing.assert_allclose(tr.vgp(xt).mean(), want_mean, rtol=1e-8, atol=1e-10)
     tr.close()
     # placement on the ExpQuad covariance of the same points
     cov = gpf.ExponentiatedQuadratic(1.0, 0.5).matrix(x, x) + 1e-2 * np.eye(n)

@@ -44,6 +44,45 @@ def test_loss_and_gradient_match_autograd(n, m, b, d, v_ls):
     tr.close()
 
 
+@pytest.mark.parametrize("kernel,name,n,m,b,d,v_ls", [
+    (gpf.MaternFiveHalves, "matern52", 1500, 40, 128, 5, 0.54),       # the reference's VGP: 5-D (x, y, z, t, p) inputs
+    (gpf.MaternFiveHalves, "matern52", 4000, 128, 256, 5, 0.0),
+    (gpf.MaternFiveHalves, "matern52", 2000, 64, 200, 3, -0.5),
+    (gpf.MaternThreeHalves, "matern32", 1500, 40, 128, 5, 0.54),
+])
+def test_matern_training_step_matches_autograd(kernel, name, n, m, b, d, v_ls):
+    """main_architecture_2.py:184-249 trains tfkern.MaternFiveHalves over 5-D inputs with jitter 1e-6: hand-derived
+    gradient (csrc/elbo.cu, kernel_q) against torch autograd of the same loss with TFP's kernel form."""
+    x, y, z, idx = problem(n, m, b, d, n + m + d)
+    tr = gpf.VgpTrainer(x, y, z, b, v_length_scale=v_ls, kernel=kernel, jitter=1e-6)
+    loss, g, gz, _ = tr.loss_and_grad(x[idx], y[idx])
+    want_loss, want = gt.loss_and_grads(0.54, v_ls, 0.54, z, x, y, x[idx], y[idx], kernel=name)
+    assert loss == pytest.approx(want_loss, rel=1e-9)
+    for i in range(3):
+        assert g[i] == pytest.approx(float(want[i]), rel=1e-6, abs=1e-8 * abs(want_loss))
+    np.testing.assert_allclose(gz, want[3], rtol=1e-5, atol=1e-6 * np.abs(want[3]).max())
+    # two Adam steps follow the oracle optimiser
+    params = [np.array(0.54), np.array(v_ls), np.array(0.54), z.copy()]
+    opt = gt.TfAdamTorch([p.shape for p in params], lr=0.01)
+    for it in range(2):
+        got = tr.step(x[idx], y[idx])
+        wl, grads = gt.loss_and_grads(params[0], params[1], params[2], params[3], x, y, x[idx], y[idx], kernel=name)
+        assert got == pytest.approx(wl, rel=1e-7), it
+        params = opt.step(params, grads)
+    v, zz = tr.variables()
+    np.testing.assert_allclose(v, [float(p) for p in params[:3]], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(zz, params[3], rtol=1e-6, atol=1e-8)
+    mean = tr.vgp(x[:50]).mean()
+    assert np.all(np.isfinite(mean))
+    tr.close()
+
+
+def test_matern12_training_is_refused():
+    x, y, z, _ = problem(300, 8, 32, 3, 1)
+    with pytest.raises(Exception, match="MATERN"):
+        gpf.VgpTrainer(x, y, z, 32, kernel=gpf.MaternOneHalf)
+
+
 def test_training_steps_follow_tf_adam():
     n, m, b, d = 800, 20, 64, 3
     x, y, z, _ = problem(n, m, b, d, 5)

@@ -77,7 +77,9 @@ def test_tf_graph_compat_mode(formulation):
 @pytest.mark.parametrize("formulation", LAZY)
 def test_errors_like_the_dense_path(formulation):
     with pytest.raises(np.linalg.LinAlgError):
-        greedy.place_single(np.ones((6, 6)), 2, D, formulation=formulation)
+        greedy.place_single(np.ones((6, 6)), 2, D, formulation=formulation, pinv_fallback=False)
+    sel, *_ = greedy.place_single(np.ones((6, 6)), 2, D, formulation=formulation)      # pseudo-inverse path takes over
+    assert [int(v) for v in sel] == [0, 1]
     with pytest.raises(ValueError, match="not in list"):
         greedy.place_single(cloud_cov(4, 0), 5, D, formulation=formulation)
 

@@ -28,9 +28,8 @@ def golden_steps(case):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_reference_goldens_through_the_dropin(name):
+def test_reference_goldens_through_the_dropin(name, quiet_alg2):
     case, cov = CASES[name], INPUTS[name]
-    alg2.PRINTS = False
     assert alg2.placement_algorithm_1(cov, case["k"]) == case["alg1_selection"]
     assert alg2.placement_algorithm_2(cov, case["k"]) == case["alg2_selection"]
     sel, scores, steps, _ = greedy.place_single(cov, case["k"], D, want_step_scores=True)      # falls through to pinv
@@ -47,12 +46,12 @@ def test_alg2_print_trace_on_a_rank_deficient_input():
     """placement_algorithm_2 prints per evaluation (placement_algorithm2.py:188,205); compare with the oracle's cache
     walk on the device's step scores."""
     case, cov = CASES["midrank_n30_s22"], INPUTS["midrank_n30_s22"]
-    alg2.PRINTS = True
+    saved, alg2.PRINTS = alg2.PRINTS, True
     try:
         with contextlib.redirect_stdout(io.StringIO()) as out:
             sel = alg2.placement_algorithm_2(cov, case["k"])
     finally:
-        alg2.PRINTS = False
+        alg2.PRINTS = saved
     assert sel == case["alg2_selection"]
     lines = out.getvalue().splitlines()
     assert [ln for ln in lines if ln.startswith("y*= ")] == ["y*= %d" % y for y in case["alg2_selection"]]
@@ -88,7 +87,7 @@ def test_mid_rank_matches_the_oracle(n, s, k, alg):
     np.testing.assert_allclose(scores, want_scores, rtol=1e-7, atol=1e-12)
 
 
-def test_producer_feeds_the_placement_without_a_nugget():
+def test_producer_feeds_the_placement_without_a_nugget(quiet_alg2):
     """f-1 -> a8/a9: create_cov_matrix over more locations than samples (rank-deficient by construction) straight into
     placement_algorithm_2 -- the chain of main_architecture_2.py:391-444 -> :722."""
     from vgposp_b200 import cov_producer
@@ -96,7 +95,6 @@ def test_producer_feeds_the_placement_without_a_nugget():
     fields = rng.standard_normal((4, 5, 6, 30))                 # 120 locations, 30 samples each
     cov = cov_producer.empirical_cov(fields.reshape(120, 30))
     np.testing.assert_allclose(cov, np.cov(fields.reshape(120, 30), bias=True), rtol=1e-10, atol=1e-14)
-    alg2.PRINTS = False
     sel = alg2.placement_algorithm_2(cov, 7)
     assert sel == go.pinv_greedy(cov, 7, algorithm=2)[0] == list(range(7))
 

@@ -1,4 +1,4 @@
-"""Time the experimental int8-tensor-core FP64 GEMM (vgp_gemm_emulated) against cuBLAS DGEMM on one shape.
+"""Time the int8-tensor-core FP64 GEMM (vgp_gemm_emulated) against cuBLAS DGEMM on one shape.
     python tools/emulated_gemm_bench.py [n] [slices]
 The emulated entry allocates and slices per call; the slicing share is reported by timing a k = 128 call."""
 import json

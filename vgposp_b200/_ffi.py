@@ -97,6 +97,7 @@ SIGNATURES = {
                           c_vp, c_vp],
     "vgp_elbo_create": [P(c_vp), c_int, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl,
                         c_dbl],
+    "vgp_elbo_set_kernel": [c_vp, c_int],
     "vgp_elbo_destroy": [c_vp],
     "vgp_elbo_loss_grad": [c_vp, c_vp, c_vp, P(c_dbl), c_vp, c_vp, P(VgpTerms), c_vp],
     "vgp_elbo_step": [c_vp, c_vp, c_vp, P(c_dbl), c_vp],

@@ -96,15 +96,27 @@ __global__ void axpby_vec_kernel(const double *a, double ca, const double *b, do
     if (i < n) z[i] = ca * a[i] + (b ? cb * b[i] : 0.0);
 }
 
-// Push an adjoint W of a kernel block K_ij = k(z_i, x_j) through the ExpQuad kernel.  t_ij = (W_ij + vbar_i y_j) K_ij;
-// rowacc[i] += ( sum_j t_ij,  sum_j t_ij r_ij^2,  zscale * sum_j t_ij (x_j - z_i) ).  One CTA per inducing point,
-// fixed reduction tree, launches accumulate in stream order: deterministic.
-template <int D>
+// Push an adjoint W of a kernel block K_ij = k(z_i, x_j) through the kernel.  t_ij = (W_ij + vbar_i y_j) K_ij;
+// rowacc[i] += ( sum_j t_ij,  sum_j q_ij t_ij r_ij^2,  zscale * sum_j q_ij t_ij (x_j - z_i) ).  One CTA per inducing
+// point, fixed reduction tree, launches accumulate in stream order: deterministic.
+// q carries the kernel family: every stationary kernel here has  dK/dl = q K r^2 / l^3  and  dK/dz_i = q K (x_j - z_i)
+// / l^2  with   ExpQuad q = 1;   Matern-3/2 (u = sqrt(3) r / l) q = 3 / (1 + u);   Matern-5/2 (u = sqrt(5) r / l)
+// q = 5 (1 + u) / (3 + 3 u + u^2)   -- ratios of the kernel's own polynomial factors, so the stored K is reused and no
+// second exponential is needed (main_architecture_2.py:184 trains Matern-5/2 over 5-D inputs).
+template <int KIND>
+__device__ __forceinline__ double kernel_q(double r2, double ucoef) {
+    if (KIND == VGP_KERNEL_EXPQUAD) return 1.0;
+    const double u = ucoef * sqrt(r2);
+    if (KIND == VGP_KERNEL_MATERN32) return 3.0 / (1.0 + u);
+    return 5.0 * (1.0 + u) / (3.0 + u * (3.0 + u));
+}
+
+template <int D, int KIND>
 __global__ void __launch_bounds__(256) kernback_kernel(const double *__restrict__ w, const double *__restrict__ kmat,
                                                        int64_t ld, const double *__restrict__ z,
                                                        const double *__restrict__ x, int64_t n2,
                                                        const double *__restrict__ vbar,
-                                                       const double *__restrict__ yvec, double zscale,
+                                                       const double *__restrict__ yvec, double zscale, double ucoef,
                                                        double *rowacc) {
     __shared__ double sh[2 + D][256];
     const int64_t i = blockIdx.x;
@@ -119,15 +131,17 @@ __global__ void __launch_bounds__(256) kernback_kernel(const double *__restrict_
         double wij = w[i * ld + j];
         if (vbar) wij = fma(vb, yvec[j], wij);
         const double t = wij * kmat[i * ld + j];
-        double r2 = 0.0;
+        double r2 = 0.0, dk[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-            const double dk = x[j * D + k] - zi[k];
-            r2 = fma(dk, dk, r2);
-            acc[2 + k] = fma(t, dk, acc[2 + k]);
+            dk[k] = x[j * D + k] - zi[k];
+            r2 = fma(dk[k], dk[k], r2);
         }
+        const double tq = t * kernel_q<KIND>(r2, ucoef);
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc[2 + k] = fma(tq, dk[k], acc[2 + k]);
         acc[0] += t;
-        acc[1] = fma(t, r2, acc[1]);
+        acc[1] = fma(tq, r2, acc[1]);
     }
 #pragma unroll
     for (int k = 0; k < 2 + D; ++k) sh[k][threadIdx.x] = acc[k];
@@ -202,6 +216,8 @@ struct vgp_elbo {
     cudaEvent_t ev_gb = nullptr, ev_bar = nullptr, ev_mini = nullptr;
     double *rowacc2 = nullptr;                      // push-through sums of the minibatch / K_zz parts (side stream)
     int64_t launches = 0;
+    int kind = VGP_KERNEL_EXPQUAD;                  // vgp_elbo_set_kernel
+    double cur_length_scale = 1.0;                  // of the step in flight (kernback's u = c r / l)
     double last_terms[5] = {0, 0, 0, 0, 0};
     double *mat(int id) const { return mats + (size_t)id * mp * mp; }
     double *vec(int id) const { return vecs + (size_t)id * mp; }
@@ -213,7 +229,16 @@ namespace elbo_detail {
 template <int D>
 int launch_kernback(vgp_elbo *h, const double *w, const double *kmat, int64_t ld, const double *x2, int64_t n2,
                     const double *vbar, const double *yvec, double zscale, double *acc, cudaStream_t s) {
-    kernback_kernel<D><<<(unsigned)h->m, 256, 0, s>>>(w, kmat, ld, h->z, x2, n2, vbar, yvec, zscale, acc);
+    const unsigned grid = (unsigned)h->m;
+    const double l = h->cur_length_scale;
+    if (h->kind == VGP_KERNEL_EXPQUAD)
+        kernback_kernel<D, VGP_KERNEL_EXPQUAD><<<grid, 256, 0, s>>>(w, kmat, ld, h->z, x2, n2, vbar, yvec, zscale, 0.0, acc);
+    else if (h->kind == VGP_KERNEL_MATERN32)
+        kernback_kernel<D, VGP_KERNEL_MATERN32><<<grid, 256, 0, s>>>(w, kmat, ld, h->z, x2, n2, vbar, yvec, zscale,
+                                                                      sqrt(3.0) / l, acc);
+    else
+        kernback_kernel<D, VGP_KERNEL_MATERN52><<<grid, 256, 0, s>>>(w, kmat, ld, h->z, x2, n2, vbar, yvec, zscale,
+                                                                      sqrt(5.0) / l, acc);
     VGP_LAUNCH_CHECK();
     return VGP_OK;
 }
@@ -331,7 +356,8 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_CUDA(cudaMemsetAsync(h->vecs, 0, (size_t)NVEC_ * mp * 8, s));
 
     // ---- kernel blocks and sufficient statistics ---------------------------------------------------
-    VGP_TRY(expquad_dispatch_public(h->z, m, h->z, m, h->d, a, l, 0.0, 0, M(K_), mp, s));
+    h->cur_length_scale = l;
+    VGP_TRY(kernel_matrix_dispatch(h->kind, h->z, m, h->z, m, h->d, a, l, 0.0, 0, M(K_), mp, s));
     // fork: (K + eps I)^-1 and K^-1 depend on K_zz only; their latency-bound chains of small kernels run on two side
     // streams underneath the K_zx build and the m x m x N SYRK
     VGP_CUDA(cudaEventRecord(h->ev_fork, s));
@@ -340,8 +366,8 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(invert(h, M(K_), eps, M(Q_), h->ws[0], red, S_LDKT, h->side[0]));
     VGP_TRY(invert(h, M(K_), 0.0, M(KINV_), h->ws[2], red, S_LDK, h->side[1]));
     VGP_CUDA(cudaEventRecord(h->ev_join[1], h->side[1]));
-    VGP_TRY(expquad_dispatch_public(h->z, m, h->x, n, h->d, a, l, 0.0, -1 - n, h->kzx, h->np_, s));
-    VGP_TRY(expquad_dispatch_public(h->z, m, xb, b, h->d, a, l, 0.0, -1 - b, h->kzb, h->bp, s));
+    VGP_TRY(kernel_matrix_dispatch(h->kind, h->z, m, h->x, n, h->d, a, l, 0.0, -1 - n, h->kzx, h->np_, s));
+    VGP_TRY(kernel_matrix_dispatch(h->kind, h->z, m, xb, b, h->d, a, l, 0.0, -1 - b, h->kzb, h->bp, s));
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->np_, 1.0, h->kzx, h->np_, h->kzx, h->np_, 0.0, M(G_), mp, h->splits_n,
                               h->partial, s, GEMM_LOWER));
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->bp, 1.0, h->kzb, h->bp, h->kzb, h->bp, 0.0, M(GB_), mp, h->splits_b,
@@ -575,6 +601,18 @@ int vgp_elbo_create(vgp_elbo **handle, int device, const double *x_dev, const do
         return rc;
     }
     *handle = h;
+    return VGP_OK;
+}
+
+/* Kernel family of the training step (default EXPQUAD): MATERN32 and MATERN52 as well -- the reference's VGP trains
+ * tfkern.MaternFiveHalves over 5-D inputs (main_architecture_2.py:184-249).  MATERN12 is refused: its gradient with
+ * respect to the inducing points is singular on the diagonal of K_zz (r = 0). */
+int vgp_elbo_set_kernel(vgp_elbo *h, int kind) {
+    VGP_REQUIRE(h, "handle is NULL");
+    VGP_REQUIRE(kind == VGP_KERNEL_EXPQUAD || kind == VGP_KERNEL_MATERN32 || kind == VGP_KERNEL_MATERN52,
+                "ELBO training supports EXPQUAD, MATERN32 and MATERN52 (kind %d: the gradient of Matern-1/2 with respect "
+                "to the inducing points is singular at r = 0)", kind);
+    h->kind = kind;
     return VGP_OK;
 }
 

@@ -91,16 +91,17 @@ __global__ void __launch_bounds__(1024) first_argmax_kernel(const double *v, con
 }
 
 // One step of the conditioning recurrence shared by the pivoted Cholesky and the numerator update:
-//   row[i] = (cov[p][i] - sum_{s < j} panel[s][i] panel[s][p]) / sqrt(resid[p]);   resid[i] -= row[i]^2
+//   row[i] = (cov[p][i] - sum_{s < j} panel[s][i] panel[s][p]) / sqrt(resid_p);   resid[i] -= row[i]^2
+// resid_p = resid[p] comes by value: the thread that owns p overwrites resid[p] while the others still need it.
 // zero_taken: entries of taken candidates are stored as 0 and their residual is left alone (factor on Abar only).
 __global__ void __launch_bounds__(256) condition_row_kernel(const double *cov, int64_t ld, int64_t n, double *panel,
-                                                            int64_t ldp, int64_t j, int64_t p, double *resid,
-                                                            const int *taken, int zero_taken) {
+                                                            int64_t ldp, int64_t j, int64_t p, double resid_p,
+                                                            double *resid, const int *taken, int zero_taken) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     double acc = cov[p * ld + i];
     for (int64_t s = 0; s < j; ++s) acc -= panel[s * ldp + i] * panel[s * ldp + p];
-    double f = acc / sqrt(resid[p]);
+    double f = acc / sqrt(resid_p);
     if (zero_taken && taken[i]) f = 0.0;
     panel[j * ldp + i] = f;
     if (!(zero_taken && taken[i])) resid[i] = (i == p) ? 0.0 : resid[i] - f * f;
@@ -193,7 +194,8 @@ int factorise(State &st, cudaStream_t s) {
         Best b;
         VGP_TRY(read_best(st, s, &b));
         if (b.index < 0) break;                         // every remaining residual is below the rank tolerance
-        condition_row_kernel<<<vb, 256, 0, s>>>(st.cov, st.n_pad, st.n, st.ft, st.n_pad, j, b.index, st.resid, st.taken, 1);
+        condition_row_kernel<<<vb, 256, 0, s>>>(st.cov, st.n_pad, st.n, st.ft, st.n_pad, j, b.index, b.value, st.resid,
+                                                st.taken, 1);
         VGP_LAUNCH_CHECK();
         st.r = j + 1;
     }
@@ -373,7 +375,8 @@ int vgp_placement_host_pinv(int device, const double *cov_host, int64_t n, int64
         VGP_CUDA(cudaMemcpyAsync(&num_y, st.num + b.index, 8, cudaMemcpyDeviceToHost, s));
         VGP_CUDA(cudaStreamSynchronize(s));
         if (num_y > RANK_TOL * st.scale) {
-            condition_row_kernel<<<vb, 256, 0, s>>>(st.cov, st.n_pad, n, st.w, st.n_pad, wrows, b.index, st.num, st.taken, 0);
+            condition_row_kernel<<<vb, 256, 0, s>>>(st.cov, st.n_pad, n, st.w, st.n_pad, wrows, b.index, num_y, st.num,
+                                                    st.taken, 0);
             VGP_LAUNCH_CHECK();
             ++wrows;
         }

@@ -683,8 +683,10 @@ class VgpTrainer:
 
     def __init__(self, x_train, y_train, inducing_index_points, batch_size, v_amplitude=0.54, v_length_scale=0.54,
                  v_noise=0.54, length_scale_offset=1e-5, jitter=DEFAULT_JITTER, learning_rate=0.01, allreduce=None,
-                 n_total=None):
-        """`allreduce(device_view)`: sum-all-reduce over the ranks of a 1-D float64 device buffer, in place and in stream
+                 n_total=None, kernel=None):
+        """`kernel`: the kernel CLASS of the model -- ExponentiatedQuadratic (default, the example script),
+        MaternFiveHalves (main_architecture_2.py:184: the VGP over 5-D (x, y, z, t, p) inputs) or MaternThreeHalves.
+        `allreduce(device_view)`: sum-all-reduce over the ranks of a 1-D float64 device buffer, in place and in stream
         order (e.g. `lambda t: torch.distributed.all_reduce(t)`); then (x_train, y_train) is THIS rank's slice of the
         observations, `n_total` their number over all ranks, and every rank must feed the same minibatches."""
         self._x, self._y = _points(x_train), _vector(y_train)          # kept alive: the handle borrows them
@@ -699,6 +701,9 @@ class VgpTrainer:
              self.m, self.batch, float(v_amplitude), float(v_length_scale), float(v_noise),
              float(length_scale_offset), float(jitter), float(learning_rate))
         self.handle = h.value
+        self.kernel_class = ExponentiatedQuadratic if kernel is None else kernel
+        if self.kernel_class.KIND != 0:
+            call("vgp_elbo_set_kernel", self.handle, self.kernel_class.KIND)
         self.length_scale_offset, self.jitter = length_scale_offset, jitter
         self._cb = None
         if allreduce is not None:
@@ -763,7 +768,7 @@ class VgpTrainer:
     def vgp(self, index_points=None):
         """The VariationalGaussianProcess at the current parameters (for `.mean()` etc., :141-142)."""
         amp, ls, noise, z = self.parameters()
-        k = ExponentiatedQuadratic(amp, ls)
+        k = self.kernel_class(amp, ls)
         loc, scale = VariationalGaussianProcess.optimal_variational_posterior(k, z, self._x, self._y, noise,
                                                                               jitter=self.jitter, as_device=True)
         return VariationalGaussianProcess(k, index_points, z, loc, scale, noise, jitter=self.jitter)
