@@ -52,6 +52,7 @@ struct vgp_greedy {
     size_t mailbox_bytes = 0;
     int comm_rank = -1, comm_nranks = 0, comm_ipc = 0;
     int64_t comm_stride = 0;
+    size_t comm_seg_off = 0;
     int64_t comm_bounds[65] = {0};
     char *peer_mb[64] = {nullptr};                      // peers' mailboxes mapped into this process
     unsigned *counter2 = nullptr;
@@ -306,24 +307,37 @@ __global__ void __launch_bounds__(256) downdate_kernel(double *__restrict__ prec
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Peer-memory exchange: the two small per-selection exchanges are done by the kernels
-// themselves with stores into the peers' mailboxes over NVLink/NVSwitch and system-scope release/acquire flags --
-// no collective launch, no host involvement; k selections are enqueued back to back on every rank.
+// Peer-memory exchange: the per-selection exchanges are done by the step kernels themselves
+// with stores into the peers' mailboxes over NVLink/NVSwitch and system-scope release/acquire flags -- no collective
+// launch, no host involvement; k selections are enqueued back to back on every rank, TWO launches per selection:
+//
+//   peer_step_kernel      scores of the local candidates -> local winner -> its record and its conditioning history
+//                         W[0..t)[y] stored into every rank's mailbox -> wait for all ranks' records -> global winner
+//                         (same rule on every rank) -> conditioning row of the LOCAL candidates (needs only the
+//                         winner's history, so the rows themselves never travel) -> numerators updated -> this rank's
+//                         segment of the precision row P[y, J] stored into every rank's mailbox;
+//   downdate_peer_kernel  waits for all segments, then the rank-1 downdate of the local panel reading p straight from
+//                         the mailbox.
+//
+// (The first version had five launches -- score, publish, exchange, unpack, downdate -- and sent [w_J | p_J]: 0.17 ms
+// of a 0.95 ms selection at 8 GPUs, profiles/r01_bench_n50k_g8_final.json.)
 //
 // Mailbox of one rank (written by its peers, read by its own kernels):
 //   [0, 512)        rec_flag[64]   u64: exchange sequence number of the record stored by rank q
-//   [512, 1024)     seg_flag[64]   u64: same for the [w_J | p_J] segment of rank q
+//   [512, 1024)     seg_flag[64]   u64: same for the precision-row segment of rank q
 //   [1024, 1032)    error          int: set when a wait timed out
 //   [2048, 6144)    recs[2][64]    vgp_candidate, double-buffered by sequence parity
-//   [8192, ...)     segs[2][nranks][2][stride] doubles
+//   [8192, ...)     hist[2][nranks][kmax] doubles, then (256-byte aligned) segs[2][nranks][stride] doubles
 // ------------------------------------------------------------------------------------------------------------
-constexpr size_t MB_REC_FLAG = 0, MB_SEG_FLAG = 512, MB_ERROR = 1024, MB_RECS = 2048, MB_SEGS = 8192;
+constexpr size_t MB_REC_FLAG = 0, MB_SEG_FLAG = 512, MB_ERROR = 1024, MB_RECS = 2048, MB_HIST = 8192;
 constexpr long long SPIN_LIMIT_CYCLES = 20000000000LL;      // ~10 s at 1.9 GHz: a dead peer fails the run, no hang
+constexpr int HIST_SMEM = 2048;                             // history entries staged in shared memory
 
 struct PeerTable {
     char *mb[MAX_RANKS];
     int nranks, rank;
-    int64_t stride;
+    int64_t stride, kmax;
+    size_t seg_off;                 // byte offset of segs[] in a mailbox
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -337,8 +351,11 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
 __device__ __forceinline__ vgp_candidate *mb_rec(char *mb, unsigned long long seq, int r) {
     return reinterpret_cast<vgp_candidate *>(mb + MB_RECS) + (seq & 1) * MAX_RANKS + r;
 }
-__device__ __forceinline__ double *mb_seg(char *mb, unsigned long long seq, int nranks, int64_t stride, int r) {
-    return reinterpret_cast<double *>(mb + MB_SEGS) + ((int64_t)(seq & 1) * nranks + r) * 2 * stride;
+__device__ __forceinline__ double *mb_hist(const PeerTable &pt, char *mb, unsigned long long seq, int r) {
+    return reinterpret_cast<double *>(mb + MB_HIST) + ((int64_t)(seq & 1) * pt.nranks + r) * pt.kmax;
+}
+__device__ __forceinline__ double *mb_seg(const PeerTable &pt, char *mb, unsigned long long seq, int r) {
+    return reinterpret_cast<double *>(mb + pt.seg_off) + ((int64_t)(seq & 1) * pt.nranks + r) * pt.stride;
 }
 // Thread q < nranks waits until rank q's flag in the local mailbox reaches `seq`.
 __device__ __forceinline__ void wait_flags(char *mb, size_t flag_off, int nranks, unsigned long long seq) {
@@ -355,27 +372,114 @@ __device__ __forceinline__ void wait_flags(char *mb, size_t flag_off, int nranks
     __syncthreads();
 }
 
-// Publish this rank's local winner to every rank's mailbox (one thread per destination).
-__global__ void publish_record_kernel(PeerTable pt, unsigned long long seq, const vgp_candidate *best) {
-    const int q = threadIdx.x;
-    if (q >= pt.nranks) return;
-    *mb_rec(pt.mb[q], seq, pt.rank) = *best;
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned long long *>(pt.mb[q] + MB_REC_FLAG) + pt.rank, seq);
-}
+struct StepArgs {
+    const double *cov, *prec;
+    int64_t ld, c0, nloc, n_pad, t;
+    double *num;
+    int *taken;
+    double small_, jitter;
+    vgp_candidate *partials, *cur;
+    unsigned *counter, *counter2;
+    int64_t *sel;
+    double *sel_score, *step_row, *wfull, *ploc;
+};
 
-// Exchange 1 (receive) + winner rule + this rank's segments + exchange 2 (send).
-__global__ void __launch_bounds__(256) exchange_kernel(PeerTable pt, unsigned long long seq,
-                                                       const double *__restrict__ cov, const double *__restrict__ prec,
-                                                       int64_t ld, int64_t c0, int64_t nloc,
-                                                       const double *__restrict__ wfull, int64_t n_pad, int64_t t,
-                                                       double jitter, vgp_candidate *cur, int64_t *sel,
-                                                       double *sel_score, unsigned *counter) {
-    char *me = pt.mb[pt.rank];
-    wait_flags(me, MB_REC_FLAG, pt.nranks, seq);
+// One selection up to the point where the precision row is on its way to every rank.  At most one CTA per SM
+// (grid <= SM count, grid-stride over the local candidates): every CTA waits for flags, so all must be resident.
+__global__ void __launch_bounds__(256) peer_step_kernel(PeerTable pt, unsigned long long seq, StepArgs a) {
+    __shared__ double hist[HIST_SMEM];
     __shared__ vgp_candidate win;
+    __shared__ bool last;
+    char *me = pt.mb[pt.rank];
+    const int64_t span = pt.stride > a.ld ? pt.stride : a.ld;
+    // ---- 1. scores of the local candidates, this CTA's first strict maximum (placement_algorithm2.py:105-125)
+    double s = NEG_INF, nm = 0.0, pd = 0.0;
+    int64_t idx = INT64_MAX;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < a.nloc; j += (int64_t)gridDim.x * 256) {
+        const double pdj = a.prec[(a.c0 + j) * a.ld + j], nmj = a.num[j];
+        if (!a.taken[j]) {
+            const double den = 1.0 / pdj - a.jitter;        // sigma^2(y | Abar \ y)
+            const double nom = nmj - a.jitter;              // sigma^2(y | A)
+            double d = nom / den;
+            if (fabs(den) < a.small_ || fabs(nom) < a.small_) d = 0.0;    // :116-119
+            if (a.step_row) a.step_row[j] = d;
+            if (d > -1.0 && better(s, idx, d, a.c0 + j)) {  // running best starts at -1, strict '<' (:106,:121)
+                s = d;
+                idx = a.c0 + j;
+                nm = nmj;
+                pd = pdj;
+            }
+        } else if (a.step_row) {
+            a.step_row[j] = nan("");
+        }
+    }
+    {
+        double rs = s;
+        int64_t ri = idx;
+        int slot = 0;
+        block_argmax(rs, ri, slot);
+        if (threadIdx.x == 0) {
+            win.index = ri;
+            win.score = rs;
+        }
+    }
+    __syncthreads();
+    if (win.index == INT64_MAX) {
+        if (threadIdx.x == 0) a.partials[blockIdx.x] = vgp_candidate{NEG_INF, -1, 0.0, 0.0};
+    } else if (idx == win.index) {
+        a.partials[blockIdx.x] = vgp_candidate{win.score, idx, nm, pd};
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicInc(a.counter, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        // ---- 2. local winner over the CTAs' partials; publish its record and its history to every rank
+        __threadfence();
+        double rs = NEG_INF;
+        int64_t ri = INT64_MAX;
+        int slot = -1;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) {
+            const double cs = __ldcg(&a.partials[b].score);
+            const int64_t ci = __ldcg((const long long *)&a.partials[b].index);
+            if (ci >= 0 && better(rs, ri, cs, ci)) {
+                rs = cs;
+                ri = ci;
+                slot = b;
+            }
+        }
+        __syncthreads();
+        block_argmax(rs, ri, slot);
+        __shared__ vgp_candidate mine;
+        if (threadIdx.x == 0) {
+            vgp_candidate w{NEG_INF, -1, 0.0, 0.0};
+            if (slot >= 0) {
+                w.score = rs;
+                w.index = ri;
+                w.num = __ldcg(&a.partials[slot].num);
+                w.pdiag = __ldcg(&a.partials[slot].pdiag);
+            }
+            mine = w;
+        }
+        __syncthreads();
+        for (int q = 0; q < pt.nranks; ++q) {
+            if (mine.index >= 0) {
+                double *dst = mb_hist(pt, pt.mb[q], seq, pt.rank);
+                for (int64_t h = threadIdx.x; h < a.t; h += 256) dst[h] = a.wfull[h * a.n_pad + mine.index];
+            }
+            if (threadIdx.x == 0) *mb_rec(pt.mb[q], seq, pt.rank) = mine;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < pt.nranks)
+            st_release_sys(reinterpret_cast<unsigned long long *>(pt.mb[threadIdx.x] + MB_REC_FLAG) + pt.rank, seq);
+    }
+    // ---- 3. every CTA: all ranks' records have arrived (own rank's included) -> the same winner everywhere
+    wait_flags(me, MB_REC_FLAG, pt.nranks, seq);
+    __shared__ int win_rank;
     if (threadIdx.x == 0) {
         vgp_candidate w{NEG_INF, -1, 0.0, 0.0};
+        int wr = 0;
         for (int r = 0; r < pt.nranks; ++r) {
             const vgp_candidate *src = mb_rec(me, seq, r);
             vgp_candidate c;
@@ -384,37 +488,48 @@ __global__ void __launch_bounds__(256) exchange_kernel(PeerTable pt, unsigned lo
             c.num = __ldcg(&src->num);
             c.pdiag = __ldcg(&src->pdiag);
             if (c.index < 0) continue;
-            if (w.index < 0 || c.score > w.score || (c.score == w.score && c.index < w.index)) w = c;
+            if (w.index < 0 || c.score > w.score || (c.score == w.score && c.index < w.index)) {
+                w = c;
+                wr = r;
+            }
         }
         win = w;
+        win_rank = wr;
         if (blockIdx.x == 0) {
-            *cur = w;
-            sel[t] = w.index;
-            sel_score[t] = w.score;
+            *a.cur = w;
+            a.sel[a.t] = w.index;
+            a.sel_score[a.t] = w.score;
         }
     }
     __syncthreads();
-    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (j < pt.stride) {
-        const int64_t y = win.index;
-        double w = 0.0, p = 0.0;
-        if (y >= 0 && j < nloc) {
-            double acc = cov[y * ld + j];
-            if (c0 + j == y) acc += jitter;
-            for (int64_t s = 0; s < t; ++s) acc = fma(-wfull[s * n_pad + c0 + j], wfull[s * n_pad + y], acc);
-            w = acc / sqrt(win.num);
-            p = prec[y * ld + j];
+    const int64_t y = win.index;
+    const double *whist = mb_hist(pt, me, seq, win_rank);
+    if (y >= 0)
+        for (int64_t h = threadIdx.x; h < a.t && h < HIST_SMEM; h += 256) hist[h] = __ldcg(whist + h);
+    __syncthreads();
+    // ---- 4. conditioning row of the local candidates, numerators, precision-row segment to every rank
+    const double root = y >= 0 ? sqrt(win.num) : 1.0;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < span; j += (int64_t)gridDim.x * 256) {
+        double p = 0.0;
+        if (y >= 0 && j < a.nloc) {
+            double acc = a.cov[y * a.ld + j];
+            if (a.c0 + j == y) acc += a.jitter;
+            const int64_t ts = a.t < HIST_SMEM ? a.t : HIST_SMEM;
+            for (int64_t h = 0; h < ts; ++h) acc = fma(-a.wfull[h * a.n_pad + a.c0 + j], hist[h], acc);
+            for (int64_t h = ts; h < a.t; ++h) acc = fma(-a.wfull[h * a.n_pad + a.c0 + j], __ldcg(whist + h), acc);
+            const double w = acc / root;
+            a.wfull[a.t * a.n_pad + a.c0 + j] = w;
+            a.num[j] = fma(-w, w, a.num[j]);
+            if (a.c0 + j == y) a.taken[j] = 1;
+            p = a.prec[y * a.ld + j];
         }
-        for (int q = 0; q < pt.nranks; ++q) {
-            double *dst = mb_seg(pt.mb[q], seq, pt.nranks, pt.stride, pt.rank);
-            dst[j] = w;
-            dst[pt.stride + j] = p;
-        }
+        if (j < a.ld) a.ploc[j] = p;
+        if (j < pt.stride)
+            for (int q = 0; q < pt.nranks; ++q) mb_seg(pt, pt.mb[q], seq, pt.rank)[j] = p;
     }
     __threadfence_system();
-    __shared__ bool last;
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicInc(a.counter2, gridDim.x - 1) == gridDim.x - 1;
     __syncthreads();
     if (last && (int)threadIdx.x < pt.nranks) {
         __threadfence_system();
@@ -422,35 +537,53 @@ __global__ void __launch_bounds__(256) exchange_kernel(PeerTable pt, unsigned lo
     }
 }
 
-// Exchange 2 (receive): unpack_kernel reading the local mailbox once every rank's segment has arrived.
-__global__ void __launch_bounds__(256) unpack_peer_kernel(PeerTable pt, unsigned long long seq, Bounds bounds,
-                                                          int64_t n, int64_t n_pad, int64_t c0, int64_t nloc,
-                                                          int64_t ld, double *wrow, double *pfull, double *ploc,
-                                                          double *num, int *taken, const vgp_candidate *cur) {
+// downdate_kernel with the precision row read from the mailbox: p_i = segment of the rank that owns row i.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) downdate_peer_kernel(double *__restrict__ prec, int64_t ld, int64_t n_rows,
+                                                            int64_t n, PeerTable pt, unsigned long long seq,
+                                                            Bounds bounds, const double *__restrict__ ploc, int64_t c0,
+                                                            const vgp_candidate *cur, int rows_per_block) {
     char *me = pt.mb[pt.rank];
     wait_flags(me, MB_SEG_FLAG, pt.nranks, seq);
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t y = cur->index;
     if (y < 0) return;
-    if (i < n_pad) {
-        double w = 0.0, p = 0.0;
-        if (i < n) {
-            int g = 0;
-            while (g + 1 < bounds.nranks && i >= bounds.b[g + 1]) ++g;
-            const double *base = mb_seg(me, seq, pt.nranks, pt.stride, g);
-            w = __ldcg(base + (i - bounds.b[g]));
-            p = __ldcg(base + pt.stride + (i - bounds.b[g]));
-        }
-        wrow[i] = w;
-        pfull[i] = p;
-        if (i >= c0 && i < c0 + nloc) {
-            const int64_t j = i - c0;
-            num[j] = fma(-w, w, num[j]);
-            ploc[j] = p;
-            if (i == y) taken[j] = 1;
+    const int64_t col = (int64_t)blockIdx.x * 512 + 2 * threadIdx.x;
+    if (col >= ld) return;
+    const double inv = 1.0 / cur->pdiag;                 // = P[y][y], the same bits on every rank
+    const double pj0 = ploc[col], pj1 = ploc[col + 1];
+    const int64_t yl = y - c0;
+    const bool z0 = col == yl, z1 = col + 1 == yl;
+    const double *segs = mb_seg(pt, me, seq, 0);
+    for (int64_t rb = (int64_t)blockIdx.y * rows_per_block; rb < n_rows; rb += (int64_t)gridDim.y * rows_per_block) {
+        const int64_t rend = min(rb + rows_per_block, n_rows);
+        int g = 0;
+        while (g + 1 < bounds.nranks && rb >= bounds.b[g + 1]) ++g;
+        for (int64_t r = rb; r < rend; r += UNROLL) {
+            double2 v[UNROLL];
+            double pi[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (r + u < rend) {
+                    v[u] = *reinterpret_cast<const double2 *>(prec + (r + u) * ld + col);
+                    const int64_t row = r + u;
+                    while (g + 1 < bounds.nranks && row >= bounds.b[g + 1]) ++g;
+                    pi[u] = row < n ? __ldcg(segs + (int64_t)g * pt.stride + (row - bounds.b[g])) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (r + u < rend) {
+                    double2 o;
+                    o.x = fma(-(pi[u] * pj0), inv, v[u].x);
+                    o.y = fma(-(pi[u] * pj1), inv, v[u].y);
+                    if (r + u == y) o = make_double2(0.0, 0.0);
+                    if (z0) o.x = 0.0;
+                    if (z1) o.y = 0.0;
+                    *reinterpret_cast<double2 *>(prec + (r + u) * ld + col) = o;
+                }
+            }
         }
     }
-    if (i >= nloc && i < ld) ploc[i] = 0.0;
 }
 
 // num = diag(Sigma) (+ jitter); nothing taken
@@ -549,7 +682,7 @@ int vgp_greedy_create(vgp_greedy **handle, int device, int64_t n, int64_t c0, in
         {(void **)&h->wfull, (size_t)kmax * h->n_pad * 8},
         {(void **)&h->pfull, (size_t)h->n_pad * 8},
         {(void **)&h->seg, (size_t)2 * h->n_pad * 8},
-        {(void **)&h->partials, (size_t)h->score_blocks * sizeof(vgp_candidate)},
+        {(void **)&h->partials, (size_t)(h->score_blocks + 256) * sizeof(vgp_candidate)},   // + the peer step's CTAs
         {(void **)&h->cur, sizeof(vgp_candidate)},
         {(void **)&h->best, sizeof(vgp_candidate)},
         {(void **)&h->counter, sizeof(unsigned)},
@@ -790,7 +923,8 @@ int vgp_greedy_comm_create(vgp_greedy *h, int rank, int nranks, const int64_t *b
     h->comm_nranks = nranks;
     h->comm_stride = stride;
     for (int g = 0; g <= nranks; ++g) h->comm_bounds[g] = bounds_host[g];
-    h->mailbox_bytes = MB_SEGS + (size_t)2 * nranks * 2 * stride * 8;
+    h->comm_seg_off = (MB_HIST + (size_t)2 * nranks * h->kmax * 8 + 255) / 256 * 256;
+    h->mailbox_bytes = h->comm_seg_off + (size_t)2 * nranks * stride * 8;
     VGP_CUDA(device_malloc((void **)&h->mailbox, h->mailbox_bytes));
     VGP_CUDA(cudaMemset(h->mailbox, 0, h->mailbox_bytes));
     if (!h->counter2) {
@@ -801,13 +935,8 @@ int vgp_greedy_comm_create(vgp_greedy *h, int rank, int nranks, const int64_t *b
     {   // Load every kernel of the exchange loop now: with lazy module loading a first launch can wait for the
         // device to drain, which must not happen while one of these kernels is spinning on a peer's flag.
         cudaFuncAttributes fa;
-        VGP_CUDA(cudaFuncGetAttributes(&fa, score_kernel));
-        VGP_CUDA(cudaFuncGetAttributes(&fa, publish_record_kernel));
-        VGP_CUDA(cudaFuncGetAttributes(&fa, exchange_kernel));
-        VGP_CUDA(cudaFuncGetAttributes(&fa, unpack_peer_kernel));
-        VGP_CUDA(cudaFuncGetAttributes(&fa, downdate_kernel<2>));
-        VGP_CUDA(cudaFuncGetAttributes(&fa, downdate_kernel<4>));
-        VGP_CUDA(cudaFuncGetAttributes(&fa, downdate_kernel<8>));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, peer_step_kernel));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, downdate_peer_kernel<4>));
     }
     if (ipc_handle_out) {
         cudaIpcMemHandle_t ipc;
@@ -860,24 +989,60 @@ int vgp_greedy_run_peer(vgp_greedy *h, int64_t k, void *stream) {
     pt.nranks = h->comm_nranks;
     pt.rank = h->comm_rank;
     pt.stride = h->comm_stride;
+    pt.kmax = h->kmax;
+    pt.seg_off = h->comm_seg_off;
     Bounds b;
     b.nranks = h->comm_nranks;
     for (int g = 0; g <= h->comm_nranks; ++g) b.b[g] = h->comm_bounds[g];
-    const int64_t span = h->n_pad > h->ld ? h->n_pad : h->ld;
+    const int64_t span = h->comm_stride > h->ld ? h->comm_stride : h->ld;
+    int64_t step_blocks = (span + 255) / 256;
+    if (step_blocks > h->sm_count) step_blocks = h->sm_count;       // every CTA waits on flags: all must be resident
+    if (step_blocks > 256) step_blocks = 256;                       // size of the partials buffer beyond score_blocks
+    constexpr int rows_per_block = 32, waves = 4;
+    const unsigned gx = (unsigned)((h->ld + 511) / 512);
+    const int64_t row_tiles = (h->n_pad + rows_per_block - 1) / rows_per_block;
+    int64_t gy = ((int64_t)h->sm_count * 8 * waves + gx - 1) / gx;
+    if (gy > row_tiles) gy = row_tiles;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
     for (int64_t i = 0; i < k; ++i) {
         const unsigned long long seq = ++h->epoch;
-        VGP_TRY(vgp_greedy_local_best(h, h->best, stream));
-        publish_record_kernel<<<1, MAX_RANKS, 0, s>>>(pt, seq, h->best);
+        StepArgs a;
+        a.cov = h->cov;
+        a.prec = h->prec;
+        a.ld = h->ld;
+        a.c0 = h->c0;
+        a.nloc = h->nloc;
+        a.n_pad = h->n_pad;
+        a.t = h->t;
+        a.num = h->num;
+        a.taken = h->taken;
+        a.small_ = h->small_;
+        a.jitter = h->jitter;
+        a.partials = h->partials;
+        a.cur = h->cur;
+        a.counter = h->counter;
+        a.counter2 = h->counter2;
+        a.sel = h->sel;
+        a.sel_score = h->sel_score;
+        a.step_row = (h->record && h->step_scores) ? h->step_scores + h->t * h->nloc : nullptr;
+        a.wfull = h->wfull;
+        a.ploc = h->ploc;
+        peer_step_kernel<<<(unsigned)step_blocks, 256, 0, s>>>(pt, seq, a);
         H_LAUNCH_CHECK(h);
-        exchange_kernel<<<(unsigned)((h->comm_stride + 255) / 256), 256, 0, s>>>(
-            pt, seq, h->cov, h->prec, h->ld, h->c0, h->nloc, h->wfull, h->n_pad, h->t, h->jitter, h->cur, h->sel,
-            h->sel_score, h->counter2);
+        cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+        if (h->profile) {
+            VGP_CUDA(cudaEventCreate(&pe0));
+            VGP_CUDA(cudaEventCreate(&pe1));
+            VGP_CUDA(cudaEventRecord(pe0, s));
+        }
+        downdate_peer_kernel<4><<<dim3(gx, (unsigned)gy), 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->n, pt, seq, b, h->ploc,
+                                                                       h->c0, h->cur, rows_per_block);
         H_LAUNCH_CHECK(h);
-        unpack_peer_kernel<<<(unsigned)((span + 255) / 256), 256, 0, s>>>(pt, seq, b, h->n, h->n_pad, h->c0, h->nloc,
-                                                                        h->ld, h->wfull + h->t * h->n_pad, h->pfull,
-                                                                        h->ploc, h->num, h->taken, h->cur);
-        H_LAUNCH_CHECK(h);
-        VGP_TRY(launch_downdate(h, s));
+        if (h->profile) {
+            VGP_CUDA(cudaEventRecord(pe1, s));
+            h->prof_events.emplace_back(pe0, pe1);
+        }
         ++h->t;
     }
     return VGP_OK;
