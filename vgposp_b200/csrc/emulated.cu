@@ -50,17 +50,21 @@ struct GemmArgs {
     int64_t delta[DIST_MAX];
 };
 
-// tile coordinates of this CTA; false when it has no tile
+// Tile coordinates of this CTA; false when it has no tile.  CTAs are dispatched in linear order, and a wave of 148 of them
+// should share operand strips in L2: tiles are walked in super-columns of SUPER tile columns, rows outermost inside one
+// (16 x ~9 tiles per wave: ~150 MB of digit planes per wave instead of one strip of A and ALL of B -- the row-major walk
+// read 34.9 GB from DRAM for 1.07 GB of planes at 8192^3, L2 hit rate 61 %: profiles/r02_ncu_emulated_gemm.txt).
+constexpr int SUPER = 16;
 __device__ __forceinline__ bool tile_of_cta(const GemmArgs &p, int tiles_m, int &tm, int &tn) {
-    if (p.dist_n > 0) {
-        const int64_t lin = (int64_t)p.rank + (int64_t)p.dist_n * blockIdx.x;
-        if (lin >= (int64_t)tiles_m * p.tiles_n) return false;
-        tm = (int)(lin / p.tiles_n);
-        tn = (int)(lin % p.tiles_n);
-    } else {
-        tm = blockIdx.y;
-        tn = blockIdx.x;
-    }
+    const int64_t lin = p.dist_n > 0 ? (int64_t)p.rank + (int64_t)p.dist_n * blockIdx.x
+                                     : (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (lin >= (int64_t)tiles_m * p.tiles_n) return false;
+    const int64_t per_super = (int64_t)SUPER * tiles_m;
+    const int sc = (int)(lin / per_super);
+    const int64_t rem = lin % per_super;
+    const int width = p.tiles_n - sc * SUPER < SUPER ? p.tiles_n - sc * SUPER : SUPER;
+    tm = (int)(rem / width);
+    tn = sc * SUPER + (int)(rem % width);
     return true;
 }
 __device__ __forceinline__ void store_pair(const GemmArgs &p, double *dst, double2 o) {
@@ -127,7 +131,7 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr) {
     return d;
 }
 // instruction descriptor, kind::i8: D = s32, A = B = signed 8 bit, both k-major, N x M
-constexpr unsigned idesc_i8(int m, int n) {
+__host__ __device__ constexpr unsigned idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
 
@@ -163,7 +167,6 @@ constexpr int A2 = BM * BKB2, B2 = BN2 * BKB2;                    // one plane t
 constexpr int STAGE2 = S2_MAX * (A2 + B2);
 constexpr int BAR2 = (2 * STAGES2 + 1) * 8 + 8;
 constexpr int SMEM2 = STAGES2 * STAGE2 + 1024 + BAR2 + BN2 * 4;
-constexpr unsigned IDESC2 = idesc_i8(BM, BN2);
 
 __global__ void __launch_bounds__(THREADS, 1)
     emu_gemm_resident_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs p) {
@@ -223,13 +226,21 @@ __global__ void __launch_bounds__(THREADS, 1)
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (elect_one()) {
                 const unsigned a_addr = smem_u32(sm + stage * STAGE2), b_addr = a_addr + S2_MAX * A2;
+                // Plane t of A against planes u = 0 .. S-1-t of B: their accumulators (groups t + u) are NEIGHBOURS in tensor
+                // memory and the B planes are neighbours in shared memory (64 rows of 64 bytes each, 8-row groups 512 bytes
+                // apart throughout), so up to four of them form ONE operand of N = 256: 12 wide MMAs per k step instead of
+                // 36 narrow ones, and A_t is read from shared memory once per wide MMA -- 104 bytes per MMA cycle instead of
+                // 192 against a 128-byte port (the N = 64 form kept the tensor pipe 55 % busy: profiles/r02_ncu_emulated_gemm.txt).
                 for (int t = 0; t < S; ++t)
-                    for (int u = 0; t + u < S; ++u)
+                    for (int u0 = 0; t + u0 < S; u0 += 4) {
+                        const int cnt = S - t - u0 < 4 ? S - t - u0 : 4;
+                        const unsigned idesc = idesc_i8(BM, cnt * BN2);
 #pragma unroll
                         for (int k = 0; k < BKB2 / UMMA_K; ++k)
-                            umma_i8(tmem_base + (unsigned)((t + u) * BN2), umma_desc<64>(a_addr + t * A2 + k * UMMA_K),
-                                    umma_desc<64>(b_addr + u * B2 + k * UMMA_K), IDESC2,
-                                    (kb == 0 && t == 0 && k == 0) ? 0u : 1u);      // first touch of group t + u
+                            umma_i8(tmem_base + (unsigned)((t + u0) * BN2), umma_desc<64>(a_addr + t * A2 + k * UMMA_K),
+                                    umma_desc<64>(b_addr + u0 * B2 + k * UMMA_K), idesc,
+                                    (kb == 0 && t == 0 && k == 0) ? 0u : 1u);      // t = 0 touches every group first
+                    }
                 umma_commit(smem_u32(&empty[stage]));
                 if (kb == KB - 1) umma_commit(smem_u32(tfull));
             }

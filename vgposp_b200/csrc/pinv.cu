@@ -226,7 +226,7 @@ int denominators(State &st, cudaStream_t s, bool *rank_lost) {
     VGP_CUDA(cudaMemcpy2DAsync(diag.data(), 8, st.g, (size_t)(rp + 1) * 8, 8, (size_t)st.r, cudaMemcpyDeviceToHost, s));
     VGP_CUDA(cudaStreamSynchronize(s));
     const double gmax = *std::max_element(diag.begin(), diag.end());
-    dense_set_pivot_floor(RANK_TOL * gmax);
+    dense_set_pivot_floor(1e-9 * gmax);              // safety net for non-generic inputs (see the n - t < r rule)
     int info = 0;
     int rc = dense_potrf(st.g, rp, rp, st.ws, s);
     if (rc == VGP_OK) rc = dense_read_info(st.ws, &info, s);
@@ -329,6 +329,12 @@ int vgp_placement_host_pinv(int device, const double *cov_host, int64_t n, int64
     }
     for (int64_t t = 0; t < k; ++t) {
         bool lost = false;
+        // Fewer candidates left than factor columns: G = sum of n - t rank-1 terms is singular for certain (an
+        // unpivoted Cholesky does not show it reliably: the zero turns up as a pivot of 1e-11, not 1e-16) -> rebuild.
+        if (n - t < st.r) {
+            ++st.refactors;
+            VGP_TRY(factorise(st, s));
+        }
         VGP_TRY(denominators(st, s, &lost));
         if (lost) {                       // the remaining candidates no longer span the factor space: rebuild on Abar
             ++st.refactors;
