@@ -305,26 +305,15 @@ def config_dict(args):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
+def resident_run(args, n, rank, world, dev, dist, stream, kmax):
+    """Setup (Sigma panel from coordinates, P = Sigma^-1) and the timed selections with Sigma and P resident in HBM,
+    for one problem size.  Returns a dict of raw measurements plus the live GreedyShard (caller closes it)."""
     import torch
     from vgposp_b200 import _ffi, greedy
     from vgposp_b200._ffi import call
-
-    dev = local_rank
-    torch.cuda.set_device(dev)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
-    n, k = args.n, args.k
     x, amp, ls, nugget = workload(n)
-    stream = torch.cuda.current_stream().cuda_stream
     bounds = greedy.shard_bounds(n, world)
     c0, c1 = bounds[rank], bounds[rank + 1]
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if \
-        os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    hbm_peak, peak_kind = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
     def ev():
         e = ctypes.c_void_p()
@@ -338,7 +327,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- setup: Sigma panel from coordinates, P = Sigma^-1 (untimed, reported) -----------------------
     xd = _ffi.DeviceArray.from_host(x, dev)
-    shard = greedy.GreedyShard(n, c0, c1, max(k, args.steps + args.warmup), dev, stream=stream)
+    shard = greedy.GreedyShard(n, c0, c1, kmax, dev, stream=stream)
     shard.build_cov_expquad(xd.ptr, 3, amp, ls, nugget)       # first launch pays CUDA's lazy module load
     e0 = ev()
     shard.build_cov_expquad(xd.ptr, 3, amp, ls, nugget)
@@ -361,7 +350,6 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         inv.invert()
         dist_stats = inv.stats()
-        factor_only_s = time.perf_counter() - t0
         shard.load_prec_device(inv.ptr, inv.ld)
         shard.reset()
         shard.sync()
@@ -371,8 +359,8 @@ def run_ours(args, rank, world, local_rank):
     shard.save_precision()
 
     if world > 1 and args.exchange == "peer":
-        # the two per-selection exchanges are stores into the peers' mailboxes over NVLink (CUDA IPC), signalled
-        # with release/acquire flags inside the kernels: no collective launch, k selections enqueued at once
+        # the per-selection exchanges are stores into the peers' mailboxes over NVLink (CUDA IPC), signalled with
+        # release/acquire flags inside the two step kernels: no collective launch, k selections enqueued at once
         greedy.connect_peers_torch(shard, rank, world, dist, "cuda:%d" % dev)
         run_steps = shard.run_peer
     elif world > 1:
@@ -416,6 +404,51 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     sel, scores = shard.results()
+    return {"shard": shard, "xd": xd, "kernel": (amp, ls, nugget), "c0": c0, "c1": c1, "ms": ms, "kms": kms.value,
+            "kcount": kcount.value, "launches": launches, "clocks": clocks.summary(), "sel": sel, "scores": scores,
+            "build_ms": build_ms, "factor_s": factor_s, "dist_stats": dist_stats}
+
+
+def roofline_of(r, n, hbm_peak, peak_kind, steps):
+    """`roofline` object of a resident run: the downdate kernel's algorithmic bytes (16 n nloc: the panel read and
+    written once) over its mean duration from CUDA events around every launch of the timed region."""
+    nloc = r["c1"] - r["c0"]
+    algo_bytes = 16.0 * n * nloc
+    kernel_ms = r["kms"] / max(r["kcount"], 1)
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    traffic, traffic_src = ncu_traffic(n, nloc)
+    return {"bound": "hbm", "kernel": "downdate_kernel", "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+            "peak_kind": "%s copy bandwidth (MEASURED_PEAKS.json)" % peak_kind, "traffic": traffic,
+            "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": kernel_ms,
+            "kernel_launches_timed": r["kcount"],
+            "kernel_share_of_step": r["kms"] / r["ms"] if r["ms"] > 0 else None,
+            "whole_step_frac": algo_bytes * steps / (r["ms"] * 1e-3) / 1e9 / hbm_peak if r["ms"] > 0 else None}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from vgposp_b200 import _ffi, greedy
+    from vgposp_b200._ffi import call
+
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    n, k = args.n, args.k
+    stream = torch.cuda.current_stream().cuda_stream
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if \
+        os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak, peak_kind = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    res = resident_run(args, n, rank, world, dev, dist, stream, max(k, args.steps + args.warmup))
+    shard, xd, ms, sel, scores = res["shard"], res["xd"], res["ms"], res["sel"], res["scores"]
+    amp, ls, nugget = res["kernel"]
+    c0, c1 = res["c0"], res["c1"]
     gaps_ok = bool(np.all(np.diff(scores) <= 1e-12 * np.abs(scores[:-1]))) if len(scores) > 1 else True
 
     # ---- e2e: host covariance in pinned memory through the one-call C-ABI -----------------------------
@@ -432,36 +465,52 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:      # noqa: BLE001
             elbo_sharded = {"error": repr(e)}
 
+    # ---- north-star configuration (BASELINE configs[4]): n = 100 000 on 8 GPUs, measured in the same run ------------
+    cfg5 = None
+    if world == 8 and not args.no_cfg5 and n != 100000:
+        # every rank must take the same decision (the run is collective): 80 GB replica + 3 x 10 GB panels + digit planes
+        _ffi.workspace_trim(dev)
+        free_b, total_b = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        call("vgp_device_info", dev, None, 0, None, ctypes.byref(total_b), ctypes.byref(free_b))
+        t = torch.tensor([float(free_b.value)], dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if float(t.item()) < 125e9:
+            cfg5 = {"skipped": "%.0f GB free on the fullest GPU, 125 GB needed" % (float(t.item()) / 1e9)}
+    if world == 8 and not args.no_cfg5 and n != 100000 and cfg5 is None:
+        try:
+            r5 = resident_run(args, 100000, rank, world, dev, dist, stream, args.steps + args.warmup)
+            r5["shard"].close()
+            r5["xd"].free()
+            cfg5 = {"workload": "greedy_mi_placement_n100000_k%d_expquad_cloud (BASELINE configs[4])" % args.steps,
+                    "value": args.steps / (r5["ms"] * 1e-3), "unit": "selections/s", "ms_per_step": r5["ms"] / args.steps,
+                    "roofline": roofline_of(r5, 100000, hbm_peak, peak_kind, args.steps),
+                    "target": "north_star: >= 70 % of the HBM roofline per selection (>= 229 selections/s)",
+                    "setup_s": {"inverse_potrf_potri": r5["factor_s"], "inverse_distribution": r5["dist_stats"]},
+                    "gpu_launches": int(r5["launches"]), "selection_head": [int(v) for v in r5["sel"][:8]]}
+        except Exception as e:      # noqa: BLE001 -- an extra: never lose the headline line over it
+            cfg5 = {"error": repr(e)}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
     nloc = c1 - c0
-    algo_bytes = 16.0 * n * nloc
-    kernel_ms = kms.value / max(kcount.value, 1)
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
-    traffic, traffic_src = ncu_traffic(n, nloc)
     line = {
         "metric": "greedy_mi_selections_per_s", "value": args.steps / (ms * 1e-3), "unit": "selections/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args),
-        "roofline": {"bound": "hbm", "kernel": "downdate_kernel", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                     "peak_kind": "%s copy bandwidth (MEASURED_PEAKS.json)" % peak_kind, "traffic": traffic,
-                     "traffic_source": traffic_src,
-                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": kernel_ms,
-                     "kernel_launches_timed": kcount.value,
-                     "kernel_share_of_step": kms.value / ms if ms > 0 else None},
-        "clocks": clocks.summary(),
+        "roofline": roofline_of(res, n, hbm_peak, peak_kind, args.steps),
+        "clocks": res["clocks"],
         "e2e": e2e,
-        "gpu_launches": int(launches),
-        "setup_s": {"expquad_panel_build": build_ms * 1e-3, "inverse_potrf_potri": factor_s,
-                    "expquad_GBps": 8.0 * n * nloc / (build_ms * 1e-3) / 1e9 if build_ms > 0 else None,
-                    "inverse_tflops": (float(n) ** 3) / factor_s / 1e12 if factor_s > 0 else None,
-                    "inverse_distribution": dist_stats},
+        "gpu_launches": int(res["launches"]),
+        "setup_s": {"expquad_panel_build": res["build_ms"] * 1e-3, "inverse_potrf_potri": res["factor_s"],
+                    "expquad_GBps": 8.0 * n * nloc / (res["build_ms"] * 1e-3) / 1e9 if res["build_ms"] > 0 else None,
+                    "inverse_tflops": (float(n) ** 3) / res["factor_s"] / 1e12 if res["factor_s"] > 0 else None,
+                    "inverse_distribution": res["dist_stats"]},
         "selection_head": [int(s) for s in sel[:8]], "scores_non_increasing": gaps_ok,
     }
+    if cfg5 is not None:
+        line["cfg5_n100k"] = cfg5
     line["library"] = dict(_ffi.LOADED, options={k: _ffi.get_option(k) for k in _ffi.OPTIONS})
     parity_failed = False
     if world == 1 and not args.no_cpu:
@@ -850,6 +899,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-elbo", action="store_true")
     ap.add_argument("--no-lazy", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true", help="8 GPUs: skip the extra n = 100 000 measurement")
     ap.add_argument("--e2e-formulation", default="auto", choices=["auto", "dense", "lazy_precision", "lazy_factor"])
     ap.add_argument("--no-e2e-pageable", dest="e2e_pageable", action="store_false",
                     help="skip the extra e2e call on a pageable NumPy copy of the covariance (20 GB at n = 50k)")

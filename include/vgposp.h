@@ -54,7 +54,7 @@ int vgp_device_info(int device, char *name, int len, int *sm_count, size_t *tota
  *                             split of the FP64 operands into this many 7-bit digit planes (csrc/emulated.cu): 8 planes
  *                             = 36 exact integer products, result within 1e-14 of the FP64 DMMA product.  0 = every
  *                             product on the FP64 tensor pipe (mma.sync DMMA).
- *   GEMM_EMULATE_MIN     [2048]
+ *   GEMM_EMULATE_MIN     [1024] (one-call placement at n = 50 000: factorisation 1.46 s against 1.51 s at 2048, 1.67 s at 4096)
  *   H2D_OVERLAP          [1]  one-call placement: factorise behind the arriving host matrix (0: copy first)
  *   GEMM_TILE_CONFIG     [-1] measurement knob: force the DMMA tile configuration (0 base, 1 pair, 2 tma)
  *   GEMM_SMALL_BELOW     [74] products with fewer 128 x 64 tiles use the 64 x 64 tile shape

@@ -506,3 +506,21 @@ def pinv_greedy(cov_vv, k, algorithm=1, small=GUARD_NUMPY):
         A.append(int(y))
         taken[y] = True
     return A, np.array(win), np.array(steps)
+
+
+def pinv_well_posed(cov_vv, selection, lo=1e-15, hi=1e-9):
+    """Is the pinv greedy numerically well-posed along `selection`?  Returns (True, -1), or (False, t) for the first
+    selection t at which Sigma_AbarAbar has an eigenvalue between `lo` and `hi` of the largest variance: whether such a
+    direction counts as part of the range decides denominators by orders of magnitude, and np.linalg.pinv's own answer
+    (rcond 1e-15 on singular values it computes to ~1e-16 absolute) is rounding noise there.  Typical place: the one
+    selection at which card Abar equals the rank.  Parity tests assert this on their inputs, like the top-2 gap."""
+    cov = np.asarray(cov_vv, dtype=np.float64)
+    n = cov.shape[0]
+    scale = float(np.max(np.diag(cov)))
+    for t in range(len(selection)):
+        taken = set(int(v) for v in selection[:t])
+        rest = [v for v in range(n) if v not in taken]
+        w = np.linalg.eigvalsh(cov[np.ix_(rest, rest)]) / scale
+        if np.any((w > lo) & (w < hi)):
+            return False, t
+    return True, -1

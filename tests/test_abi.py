@@ -117,7 +117,7 @@ def test_options_table_roundtrip_and_validation():
     """vgp_set_option / vgp_get_option (no device needed): defaults as documented in the header, bad values refused,
     and the library does not read the environment."""
     assert _ffi.get_option("gemm_emulate_slices") == 8
-    assert _ffi.get_option("gemm_emulate_min") == 2048
+    assert _ffi.get_option("gemm_emulate_min") == 1024
     assert _ffi.get_option("dist_min_tiles") == 96 and _ffi.get_option("dist_min_k") == 256
     old = _ffi.set_option("gemm_emulate_slices", 0)
     assert old == 8 and _ffi.get_option("gemm_emulate_slices") == 0

@@ -36,7 +36,7 @@ def single_inverse(a):
 
 
 @pytest.mark.timeout(240)
-@pytest.mark.parametrize("emulate_min", [2048, 512], ids=["fp64_products", "int8_products"])
+@pytest.mark.parametrize("emulate_min", [4096, 512], ids=["fp64_products", "int8_products"])
 @pytest.mark.parametrize("n,world", [(1000, 2), (1664, 3), (2050, 4)])
 def test_ranks_as_threads_one_device(n, world, emulate_min, vgp_options):
     """G ranks as threads of this process on one device (each with its own stream and replica)."""
@@ -102,7 +102,7 @@ def test_two_processes_ipc():
 # a script and as two processes on two GPUs -- the int8 products of the sharded path are covered by
 # test_two_processes_ipc (tests/dist_worker.py sets gemm_emulate_min = 512) and by test_ranks_as_threads_one_device.
 @pytest.mark.timeout(240)
-@pytest.mark.parametrize("emulate_min", [2048], ids=["fp64_products"])
+@pytest.mark.parametrize("emulate_min", [4096], ids=["fp64_products"])
 @pytest.mark.parametrize("n,world,k", [(1000, 2, 12), (1664, 3, 20), (2050, 4, 9), (700, 2, 600)])
 def test_sharded_lazy_factor_greedy_threads(n, world, k, emulate_min, vgp_options):
     """The one-call path on G ranks: replicas factorised to L^-1 by the distributed potrf + trtri, the triangular

@@ -8,12 +8,15 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vgposp_b200.gp_functions as gpf  # noqa: E402
+from vgposp_b200 import _ffi  # noqa: E402
+
+print("options", _ffi.apply_env_options(), flush=True)      # VGP_OPT_<NAME>=<int>: this tool only, not the library
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=200000)
 ap.add_argument("--m", type=int, default=512)
 ap.add_argument("--b", type=int, default=4096)
-ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--steps", type=int, default=6)
 args = ap.parse_args()
 rng = np.random.default_rng(1)
 x = rng.uniform(-2, 2, (args.n, 3))

@@ -12,6 +12,8 @@ struct EmuWorkspace {
     signed char *qa = nullptr, *qb = nullptr;
     int *ea = nullptr, *eb = nullptr;
     size_t qa_bytes = 0, qb_bytes = 0, ea_bytes = 0, eb_bytes = 0;
+    void *partial = nullptr;            // split-K partial products (emulated_gemm_splitk)
+    size_t partial_bytes = 0;
     // Size for products of up to rows x rows x 8192 once, up front: growing later waits for the device, which inside
     // a distributed factorisation (other ranks' barrier kernels possibly spinning on this device) must not happen.
     int reserve(int64_t rows, int slices, cudaStream_t s);
@@ -83,7 +85,13 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
 // (VGP_OPT_GEMM_EMULATE_SLICES, VGP_OPT_GEMM_EMULATE_MIN).
 int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
                   const double *a, int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc,
-                  int slices, int lower, cudaStream_t s, const DistContext *dist = nullptr);
+                  int slices, int lower, cudaStream_t s, const DistContext *dist = nullptr, double bound_a = 0.0,
+                  double bound_b = 0.0);
+// split-K form for short-and-wide products (one launch, partial sums per 8192 of k, fixed-order reduction); a == b with
+// (trans_a, trans_b) = (0, 1) shares one set of digit planes; bound_* > 0: known bounds on |A|, |B| (kernel matrices)
+int emulated_gemm_splitk(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                         const double *a, int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc,
+                         int slices, int lower, double bound_a, double bound_b, cudaStream_t s);
 int emulated_preload();                     // load the kernels, set the shared-memory opt-in (current device)
 
 int dense_gemm_splitk(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha, const double *a,

@@ -368,8 +368,20 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_CUDA(cudaEventRecord(h->ev_join[1], h->side[1]));
     VGP_TRY(kernel_matrix_dispatch(h->kind, h->z, m, h->x, n, h->d, a, l, 0.0, -1 - n, h->kzx, h->np_, s));
     VGP_TRY(kernel_matrix_dispatch(h->kind, h->z, m, xb, b, h->d, a, l, 0.0, -1 - b, h->kzb, h->bp, s));
-    VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->np_, 1.0, h->kzx, h->np_, h->kzx, h->np_, 0.0, M(G_), mp, h->splits_n,
-                              h->partial, s, GEMM_LOWER));
+    // The two observation-sized products (G = K_zx K_zx^T here, W = 2 G_bar K_zx below: 2.1e11 flop of the step's 2.2e11)
+    // run on the int8 tensor cores like the factorisations' large products (emulated.cu; k(x, y) <= a^2 bounds every
+    // entry of K_zx, so its row exponents need no pass over the data); VGP_OPT_GEMM_EMULATE_SLICES = 0 or a small
+    // problem keeps them on the FP64 pipe.
+    const int emu = (int)option(VGP_OPT_GEMM_EMULATE_SLICES);
+    const bool emulate = emu >= 2 && (double)mp * (double)mp * (double)h->np_ >= 4e9;
+    if (emulate) {
+        VGP_TRY(emulated_gemm_splitk(h->ws[1].emu, 0, 1, mp, mp, h->np_, 1.0, h->kzx, h->np_, h->kzx, h->np_, 0.0, M(G_), mp,
+                                     emu, 1, a * a, a * a, s));
+        VGP_TRY(dense_mirror_lower(M(G_), mp, mp, s));
+    } else {
+        VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->np_, 1.0, h->kzx, h->np_, h->kzx, h->np_, 0.0, M(G_), mp, h->splits_n,
+                                  h->partial, s, GEMM_LOWER));
+    }
     VGP_TRY(dense_gemm_splitk(0, 1, mp, mp, h->bp, 1.0, h->kzb, h->bp, h->kzb, h->bp, 0.0, M(GB_), mp, h->splits_b,
                               h->partial, s, GEMM_LOWER));
     // the six m^3 products that need only K, Q and Gb follow (K + eps I)^-1 on its side stream, underneath the
@@ -473,7 +485,12 @@ int loss_and_grad(vgp_elbo *h, const double *xb, const double *yb, double *loss_
     VGP_TRY(kernback(h, h->wzb, h->kzb, h->bp, xb, b, V(VBBAR_), yb, 1.0, h->rowacc2, sd));
     VGP_TRY(kernback(h, M(KBAR_), M(K_), mp, h->z, m, nullptr, nullptr, 2.0, h->rowacc2, sd));
     VGP_CUDA(cudaEventRecord(h->ev_mini, sd));
-    VGP_TRY(dense_gemm(0, 0, mp, h->np_, mp, 1.0, M(GBAR2_), mp, h->kzx, h->np_, 0.0, h->wzx, h->np_, GEMM_FULL, s));
+    if (emulate) {
+        VGP_TRY(emulated_gemm(h->ws[1].emu, 0, 0, mp, h->np_, mp, 1.0, M(GBAR2_), mp, h->kzx, h->np_, 0.0, h->wzx, h->np_, emu, 0,
+                              s, nullptr, 0.0, a * a));
+    } else {
+        VGP_TRY(dense_gemm(0, 0, mp, h->np_, mp, 1.0, M(GBAR2_), mp, h->kzx, h->np_, 0.0, h->wzx, h->np_, GEMM_FULL, s));
+    }
     VGP_TRY(kernback(h, h->wzx, h->kzx, h->np_, h->x, n, V(VBAR_), h->y, 1.0, h->rowacc, s));
     VGP_TRY(exchange(h->rowacc, m * (2 + h->d)));       // the observation-sized part of the push-through sums
     VGP_CUDA(cudaStreamWaitEvent(s, h->ev_mini, 0));

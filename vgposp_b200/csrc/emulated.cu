@@ -38,6 +38,8 @@ struct GemmArgs {
     int64_t m, n;                 // real extent of C (stores are guarded)
     int64_t m_pad, n_pad;         // rows per digit plane
     int kblocks;                  // k_pad / BKB
+    int kb_split;                 // split-K: 64-byte k blocks per blockIdx.z (0: no split); each split writes its own
+    int64_t split_stride;         // partial C at c + blockIdx.z * split_stride (beta must be 0 then)
     int s;
     const int *ea, *eb;           // [m_pad], [n_pad]
     double *c;
@@ -183,7 +185,11 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (p.lower && tn * BN2 > tm * BM + (BM - 1)) return;           // wholly above the diagonal
     const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = p.s, KB = p.kblocks * (BKB / BKB2);
+    const int S = p.s, KB_ALL = p.kblocks * (BKB / BKB2);
+    // split-K (blockIdx.z): this CTA's k blocks are [KB0, KB0 + KB)
+    const int KB0 = p.kb_split > 0 ? (int)blockIdx.z * p.kb_split : 0;
+    const int KB = p.kb_split > 0 ? (KB_ALL - KB0 < p.kb_split ? KB_ALL - KB0 : p.kb_split) : KB_ALL;
+    if (KB <= 0) return;
 
     if (tid == 0) {
         for (int i = 0; i < STAGES2; ++i) {
@@ -214,8 +220,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const unsigned dst = smem_u32(sm + stage * STAGE2);
                 mbar_expect_tx(bar, (unsigned)(S * (A2 + B2)));
                 for (int t = 0; t < S; ++t) {
-                    tma_load_2d(dst + t * A2, &map_a, kb * BKB2, (int)((int64_t)t * p.m_pad + m0), bar);
-                    tma_load_2d(dst + S2_MAX * A2 + t * B2, &map_b, kb * BKB2, (int)((int64_t)t * p.n_pad + n0), bar);
+                    tma_load_2d(dst + t * A2, &map_a, (KB0 + kb) * BKB2, (int)((int64_t)t * p.m_pad + m0), bar);
+                    tma_load_2d(dst + S2_MAX * A2 + t * B2, &map_b, (KB0 + kb) * BKB2, (int)((int64_t)t * p.n_pad + n0), bar);
                 }
             }
         }
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const int64_t i = m0 + row;
         if (i < p.m) {
             const int ea = p.ea[i];
-            double *crow = p.c + i * p.ldc + n0 + half * 32;
+            double *crow = p.c + (int64_t)blockIdx.z * p.split_stride + i * p.ldc + n0 + half * 32;
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
                 const int64_t j = n0 + half * 32 + c;
@@ -407,9 +413,19 @@ static int plane_map(CUtensorMap *map, const signed char *base, int64_t rows_tot
     return VGP_OK;
 }
 
+__global__ void constant_exponent_kernel(int *e, int64_t rows, int64_t rows_pad, int value) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r < rows_pad) e[r] = r < rows ? value : 0;
+}
+
+// bound > 0: every |x| <= bound is known (a kernel matrix: k(x, y) <= amplitude^2), no pass over the operand for the
+// row exponents.
 static int slice_operand(const double *x, int64_t rs, int64_t ks, int64_t rows, int64_t k, int64_t rows_pad, int64_t k_pad,
-                         int s, int *e, signed char *q, cudaStream_t st) {
-    row_exponent_kernel<<<(unsigned)(rows_pad / 32), 256, 0, st>>>(x, rs, ks, rows, k, rows_pad, e);
+                         int s, int *e, signed char *q, cudaStream_t st, double bound = 0.0) {
+    if (bound > 0.0)
+        constant_exponent_kernel<<<(unsigned)((rows_pad + 255) / 256), 256, 0, st>>>(e, rows, rows_pad, ilogb(bound) + 1);
+    else
+        row_exponent_kernel<<<(unsigned)(rows_pad / 32), 256, 0, st>>>(x, rs, ks, rows, k, rows_pad, e);
     VGP_LAUNCH_CHECK();
     digit_planes_kernel<<<dim3((unsigned)(k_pad / 128), (unsigned)(rows_pad / 32)), 256, 0, st>>>(x, rs, ks, rows, k, rows_pad,
                                                                                                    k_pad, e, s, q);
@@ -445,7 +461,7 @@ int EmuWorkspace::reserve(int64_t rows, int slices, cudaStream_t st) {
 }
 
 void EmuWorkspace::release() {
-    for (void *p : {(void *)qa, (void *)qb, (void *)ea, (void *)eb}) cache_free(p);
+    for (void *p : {(void *)qa, (void *)qb, (void *)ea, (void *)eb, (void *)partial}) cache_free(p);
     *this = EmuWorkspace();
 }
 
@@ -467,9 +483,79 @@ int emulated_preload() {
 
 // Asynchronous on `st`; same operand convention as dense_gemm.  C must not alias A or B (with k > K_CHUNK the second
 // chunk's planes would be cut from an already updated operand).
+// C = beta C + sum_z partial_z, fixed summation order; lower: only the 128 x 128 tiles on or below the diagonal
+__global__ void __launch_bounds__(256) emu_splitk_reduce_kernel(const double *partial, int64_t stride, int splits, double beta,
+                                                                double *c, int64_t ldc, int64_t m, int64_t n, int lower) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= m * n) return;
+    const int64_t i = e / n, j = e % n;
+    if (lower && j / emu::BM > i / emu::BM) return;
+    double acc = 0.0;
+    for (int z = 0; z < splits; ++z) acc += partial[(int64_t)z * stride + i * n + j];
+    c[i * ldc + j] = beta != 0.0 ? fma(beta, c[i * ldc + j], acc) : acc;
+}
+
+// Short-and-wide products (m, n small, k huge: K_zx K_zx^T over all observations): the k range is cut into pieces of
+// <= 8192 (the int32 bound), every piece is a blockIdx.z of ONE launch writing its own partial C, summed afterwards in
+// a fixed order.  The operands are cut into digit planes once, over the whole k range.  a == b with (trans_a, trans_b)
+// = (0, 1) is a SYRK: one set of planes serves both sides.  bound_a / bound_b > 0: known bounds on |A|, |B| (see
+// slice_operand).  lower: only the tiles on or below the diagonal (the caller mirrors).
+int emulated_gemm_splitk(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
+                         const double *a, int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc,
+                         int slices, int lower, double bound_a, double bound_b, cudaStream_t st) {
+    using namespace emu;
+    VGP_REQUIRE(slices >= 2 && slices <= S_MAX, "slices must be in [2, %d]", S_MAX);
+    VGP_REQUIRE((const double *)c != a && (const double *)c != b, "emulated_gemm_splitk: C aliases an operand");
+    VGP_REQUIRE(m > 0 && n > 0 && k > 0 && m % 2 == 0 && n % 2 == 0, "emulated_gemm_splitk: bad sizes");
+    VGP_TRY(emulated_preload());
+    const int64_t m_pad = round_up(m, BM), n_pad = round_up(n, BN), k_pad = round_up(k, BKB);
+    const bool syrk = a == b && lda == ldb && m == n && trans_a == 0 && trans_b == 1;
+    const int splits = (int)((k_pad + K_CHUNK - 1) / K_CHUNK);
+    VGP_TRY(grow((void **)&ws.qa, &ws.qa_bytes, (size_t)slices * m_pad * k_pad, st));
+    VGP_TRY(grow((void **)&ws.ea, &ws.ea_bytes, (size_t)m_pad * 4, st));
+    if (!syrk) {
+        VGP_TRY(grow((void **)&ws.qb, &ws.qb_bytes, (size_t)slices * n_pad * k_pad, st));
+        VGP_TRY(grow((void **)&ws.eb, &ws.eb_bytes, (size_t)n_pad * 4, st));
+    }
+    VGP_TRY(grow((void **)&ws.partial, &ws.partial_bytes, (size_t)splits * m * n * 8, st));
+    const int64_t a_rs = trans_a ? 1 : lda, a_ks = trans_a ? lda : 1;
+    const int64_t b_rs = trans_b ? ldb : 1, b_ks = trans_b ? 1 : ldb;
+    VGP_TRY(slice_operand(a, a_rs, a_ks, m, k, m_pad, k_pad, slices, ws.ea, ws.qa, st, bound_a));
+    if (!syrk) VGP_TRY(slice_operand(b, b_rs, b_ks, n, k, n_pad, k_pad, slices, ws.eb, ws.qb, st, bound_b));
+    alignas(64) CUtensorMap ma, mb;
+    VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad, v2::BKB2, BM));
+    VGP_TRY(plane_map(&mb, syrk ? ws.qa : ws.qb, (int64_t)slices * n_pad, k_pad, v2::BKB2, v2::BN2));
+    GemmArgs p;
+    p.m = m;
+    p.n = n;
+    p.m_pad = m_pad;
+    p.n_pad = n_pad;
+    p.kblocks = (int)(k_pad / BKB);
+    p.s = slices;
+    p.ea = ws.ea;
+    p.eb = syrk ? ws.ea : ws.eb;
+    p.c = reinterpret_cast<double *>(ws.partial);
+    p.ldc = n;
+    p.alpha = alpha;
+    p.beta = 0.0;
+    p.lower = lower;
+    p.dist_n = 0;
+    p.rank = 0;
+    p.kb_split = (int)(K_CHUNK / v2::BKB2);
+    p.split_stride = m * n;
+    p.tiles_n = (int)(n_pad / v2::BN2);
+    dim3 grid((unsigned)(n_pad / v2::BN2), (unsigned)(m_pad / BM), (unsigned)splits);
+    v2::emu_gemm_resident_kernel<<<grid, THREADS, v2::SMEM2, st>>>(ma, mb, p);
+    VGP_LAUNCH_CHECK();
+    emu_splitk_reduce_kernel<<<(unsigned)((m * n + 255) / 256), 256, 0, st>>>(reinterpret_cast<double *>(ws.partial), m * n,
+                                                                             splits, beta, c, ldc, m, n, lower);
+    VGP_LAUNCH_CHECK();
+    return VGP_OK;
+}
+
 int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double alpha,
                   const double *a, int64_t lda, const double *b, int64_t ldb, double beta, double *c, int64_t ldc,
-                  int slices, int lower, cudaStream_t st, const DistContext *dc) {
+                  int slices, int lower, cudaStream_t st, const DistContext *dc, double bound_a, double bound_b) {
     using namespace emu;
     VGP_REQUIRE(slices >= 2 && slices <= S_MAX, "slices must be in [2, %d]", S_MAX);
     VGP_REQUIRE(ldc % 2 == 0 && ((uintptr_t)c & 15) == 0, "C must be 16-byte aligned with an even leading dimension");
@@ -484,8 +570,8 @@ int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t
     for (int64_t k0 = 0; k0 < k || k0 == 0; k0 += K_CHUNK) {
         const int64_t kc = k - k0 < K_CHUNK ? k - k0 : K_CHUNK;
         const int64_t k_pad = round_up(kc > 0 ? kc : 1, BKB);
-        VGP_TRY(slice_operand(a + k0 * a_ks, a_rs, a_ks, m, kc, m_pad, k_pad, slices, ws.ea, ws.qa, st));
-        VGP_TRY(slice_operand(b + k0 * b_ks, b_rs, b_ks, n, kc, n_pad, k_pad, slices, ws.eb, ws.qb, st));
+        VGP_TRY(slice_operand(a + k0 * a_ks, a_rs, a_ks, m, kc, m_pad, k_pad, slices, ws.ea, ws.qa, st, bound_a));
+        VGP_TRY(slice_operand(b + k0 * b_ks, b_rs, b_ks, n, kc, n_pad, k_pad, slices, ws.eb, ws.qb, st, bound_b));
         alignas(64) CUtensorMap ma, mb;
         VGP_TRY(plane_map(&ma, ws.qa, (int64_t)slices * m_pad, k_pad, v2::BKB2, BM));
         VGP_TRY(plane_map(&mb, ws.qb, (int64_t)slices * n_pad, k_pad, v2::BKB2, v2::BN2));
@@ -505,6 +591,8 @@ int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t
         p.lower = lower;
         p.dist_n = 0;
         p.rank = 0;
+        p.kb_split = 0;
+        p.split_stride = 0;
         const int64_t tiles_n = n_pad / v2::BN2, tiles_m = m_pad / BM;
         p.tiles_n = (int)tiles_n;
         dim3 grid((unsigned)tiles_n, (unsigned)tiles_m);

@@ -46,7 +46,7 @@ static void keep_pool_memory(int device) {
 // ---- options ------------------------------------------------------------------------------------------------------
 static std::atomic<int64_t> g_options[VGP_OPT_COUNT] = {
     {8},       // VGP_OPT_GEMM_EMULATE_SLICES
-    {2048},    // VGP_OPT_GEMM_EMULATE_MIN
+    {1024},    // VGP_OPT_GEMM_EMULATE_MIN
     {1},       // VGP_OPT_H2D_OVERLAP
     {-1},      // VGP_OPT_GEMM_TILE_CONFIG
     {74},      // VGP_OPT_GEMM_SMALL_BELOW
