@@ -1023,25 +1023,25 @@ int DenseWorkspace::ensure(int64_t nblocks) {
     if (winv && device != dev) release();
     device = dev;
     if (!winv) {
-        VGP_CUDA(device_malloc((void **)&winv, (size_t)NB * NB * 8));
-        VGP_CUDA(device_malloc((void **)&info, sizeof(int)));
+        VGP_CUDA(cache_alloc((void **)&winv, (size_t)NB * NB * 8));
+        VGP_CUDA(cache_alloc((void **)&info, sizeof(int)));
         VGP_CUDA(cudaMemset(info, 0, sizeof(int)));
         VGP_TRY(block_kernels_configure());
     }
     if (nblocks > dinv_blocks) {
-        if (dinv) cudaFree(dinv);
+        cache_free(dinv);
         dinv = nullptr;
         dinv_blocks = 0;
-        VGP_CUDA(device_malloc((void **)&dinv, (size_t)nblocks * NB * NB * 8));
+        VGP_CUDA(cache_alloc((void **)&dinv, (size_t)nblocks * NB * NB * 8));
         dinv_blocks = nblocks;
     }
     return VGP_OK;
 }
 
 void DenseWorkspace::release() {
-    if (winv) cudaFree(winv);
-    if (info) cudaFree(info);
-    if (dinv) cudaFree(dinv);
+    cache_free(winv);
+    cache_free(info);
+    cache_free(dinv);
     winv = nullptr;
     info = nullptr;
     dinv = nullptr;

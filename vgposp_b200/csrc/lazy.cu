@@ -484,9 +484,9 @@ static int lazy_create(vgp_lazy **handle, int device, int64_t n, int64_t kmax, d
     };
     for (auto &al : allocs) {
         if (al.bytes == 0) continue;
-        // the two matrices come from (and go back to) the per-device workspace cache: see common.cuh
-        const bool is_matrix = al.p == (void **)&h->cov || al.p == (void **)&h->fac;
-        cudaError_t e = is_matrix ? cache_alloc(al.p, al.bytes) : device_malloc(al.p, al.bytes);
+        // everything comes from (and goes back to) the per-device workspace cache (common.cuh): the one-call path
+        // neither allocates nor frees device memory after its first call (cudaFree alone cost 0.2 - 0.9 s there)
+        cudaError_t e = cache_alloc(al.p, al.bytes);
         if (e != cudaSuccess) {
             int rc = cuda_fail(e, "cudaMalloc (lazy greedy state)", __FILE__, __LINE__);
             vgp_lazy_destroy(h);
@@ -520,8 +520,7 @@ int vgp_lazy_destroy(vgp_lazy *h) {
     void *ptrs[] = {h->d, h->d0, h->num, h->taken, h->U, h->W, h->inv,
                     h->own_partial ? h->partial : nullptr, h->partials, h->cur, h->counter, h->sel, h->sel_score,
                     h->step_scores, h->cache};
-    for (void *p : ptrs)
-        if (p) cudaFree(p);
+    for (void *p : ptrs) cache_free(p);
     cache_free(h->cov);
     if (h->own_fac) cache_free(h->fac);
     for (auto &e : h->pe)
@@ -718,7 +717,7 @@ int vgp_lazy_set_local(vgp_lazy *h, int64_t i0, int64_t i1, int64_t i2, int64_t 
                 (long long)i0, (long long)i1, (long long)i2, (long long)h->n);
     VGP_REQUIRE(h->t == 0, "set the local mode before the first selection");
     VGP_ENTER(h->device);
-    if (!h->cache) VGP_CUDA(device_malloc((void **)&h->cache, (size_t)h->n_pad * 8));
+    if (!h->cache) VGP_CUDA(cache_alloc((void **)&h->cache, (size_t)h->n_pad * 8));
     h->loc_i1 = i1;
     h->loc_i2 = i2;
     h->loc_cutoff = cutoff;
@@ -728,7 +727,7 @@ int vgp_lazy_set_local(vgp_lazy *h, int64_t i0, int64_t i1, int64_t i2, int64_t 
 int vgp_lazy_record_scores(vgp_lazy *h, int enable) {
     VGP_TRY(check(h));
     VGP_ENTER(h->device);
-    if (enable && !h->step_scores) VGP_CUDA(device_malloc((void **)&h->step_scores, (size_t)h->kmax * h->n * 8));
+    if (enable && !h->step_scores) VGP_CUDA(cache_alloc((void **)&h->step_scores, (size_t)h->kmax * h->n * 8));
     h->record = enable ? 1 : 0;
     return VGP_OK;
 }
