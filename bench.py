@@ -398,6 +398,8 @@ def resident_run(args, n, rank, world, dev, dist, stream, kmax):
         shard.comm_status()                 # raises if any wait on a peer's flag timed out
     kms, kcount = ctypes.c_double(), ctypes.c_int64()
     call("vgp_greedy_profile_read", shard.handle, ctypes.byref(kms), ctypes.byref(kcount))
+    step_ms = ctypes.c_double()
+    call("vgp_greedy_profile_step_ms", shard.handle, ctypes.byref(step_ms))
     call("vgp_greedy_profile", shard.handle, 0)
     if dist:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % dev)
@@ -405,7 +407,7 @@ def resident_run(args, n, rank, world, dev, dist, stream, kmax):
         ms = float(t.item())
     sel, scores = shard.results()
     return {"shard": shard, "xd": xd, "kernel": (amp, ls, nugget), "c0": c0, "c1": c1, "ms": ms, "kms": kms.value,
-            "kcount": kcount.value, "launches": launches, "clocks": clocks.summary(), "sel": sel, "scores": scores,
+            "kcount": kcount.value, "step_kernel_ms": step_ms.value, "launches": launches, "clocks": clocks.summary(), "sel": sel, "scores": scores,
             "build_ms": build_ms, "factor_s": factor_s, "dist_stats": dist_stats}
 
 
@@ -424,6 +426,7 @@ def roofline_of(r, n, hbm_peak, peak_kind, steps):
             "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms_avg": kernel_ms,
             "kernel_launches_timed": r["kcount"],
             "kernel_share_of_step": r["kms"] / r["ms"] if r["ms"] > 0 else None,
+            "peer_step_kernel_ms_avg": (r["step_kernel_ms"] / max(r["kcount"], 1)) if r.get("step_kernel_ms") else None,
             "whole_step_frac": algo_bytes * steps / (r["ms"] * 1e-3) / 1e9 / hbm_peak if r["ms"] > 0 else None}
 
 

@@ -28,7 +28,8 @@ def tracer_field(p):
     return np.sin(1.5 * p[:, 0] + 0.4 * p[:, 3]) * np.cos(p[:, 1]) + 0.3 * p[:, 2] * p[:, 4]
 
 
-def main(cover=6, samples=8, k=5, steps=60, n_obs=4000, m=64, batch=256, beta=0.0, out=None, seed=0, quiet=False):
+def main(cover=6, samples=8, k=5, steps=60, n_obs=4000, m=64, batch=256, beta=0.0, out=None, seed=0, quiet=False,
+         nugget=0.0):
     rng = np.random.default_rng(seed)
     x = rng.uniform(0.0, 2.0, (n_obs, 5))
     y = tracer_field(x) + 0.05 * rng.standard_normal(n_obs)
@@ -56,14 +57,16 @@ def main(cover=6, samples=8, k=5, steps=60, n_obs=4000, m=64, batch=256, beta=0.
     n = cov_vv.shape[0]
     # location index = i0 + i1 I0 + i2 I0 I1 (gp_functions.py:1041-1046)
     xyz_idxs = np.array([[i % cover, (i // cover) % cover, i // (cover * cover)] for i in range(n)], dtype=np.int32)
-    # 3. optional taper, then a nugget: S^2 samples give a rank-deficient covariance for n > S^2 locations, and the
-    #    path needs an SPD matrix where the reference takes pseudo-inverses (deviations)
+    # 3. optional taper.  S^2 samples give a rank-deficient covariance for n > S^2 locations: placement_algorithm_2 then
+    #    runs on the pseudo-inverse path and returns what the reference's np.linalg.pinv arithmetic returns -- with
+    #    rank < n / 2 that is [0, 1, ..., k - 1], every delta being 0.  `nugget` > 0 is the
+    #    TF-graph variant's way out (snippets_a2.py:161-163 adds 1e-6 to the diagonal): a full-rank matrix, real scores.
     if beta > 0.0:
         cov_vv = cov_producer.cov_taper(cov_vv, xyz_idxs, beta)
-    cov_spd = cov_vv + (1e-6 * np.trace(cov_vv) / n + 1e-12) * np.eye(n)
+    cov_in = cov_vv + (nugget * np.trace(cov_vv) / n) * np.eye(n) if nugget > 0.0 else cov_vv
     # 4. placement
     alg2.PRINTS = False
-    selection = alg2.placement_algorithm_2(cov_spd, k)
+    selection = alg2.placement_algorithm_2(cov_in, k)
     # 5. hand-off files
     if out:
         os.makedirs(out, exist_ok=True)
@@ -82,6 +85,7 @@ if __name__ == "__main__":
     ap.add_argument("--k", type=int, default=5)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--beta", type=float, default=0.0)
+    ap.add_argument("--nugget", type=float, default=0.0, help="relative diagonal shift (1e-6: full-rank matrix, real scores)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    main(a.cover, a.samples, a.k, a.steps, beta=a.beta, out=a.out)
+    main(a.cover, a.samples, a.k, a.steps, beta=a.beta, out=a.out, nugget=a.nugget)

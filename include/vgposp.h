@@ -367,6 +367,7 @@ int vgp_greedy_launch_count(vgp_greedy *handle, int64_t *launches);
 /* Timing of the dominant kernel (the precision downdate): when enabled, every downdate launch is bracketed by
  * CUDA events on its stream; profile_read returns their summed duration and count (blocking). */
 int vgp_greedy_profile(vgp_greedy *handle, int enable);
+int vgp_greedy_profile_step_ms(vgp_greedy *handle, double *total_ms);   /* peer path: the step kernel's share */
 int vgp_greedy_profile_read(vgp_greedy *handle, double *total_ms, int64_t *launches);
 
 /* ---------------------------------------------------------------- greedy placement, lazy-column formulation -- */

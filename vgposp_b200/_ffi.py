@@ -141,6 +141,7 @@ SIGNATURES = {
     "vgp_greedy_launch_count": [c_vp, P(c_i64)],
     "vgp_greedy_profile": [c_vp, c_int],
     "vgp_greedy_profile_read": [c_vp, P(c_dbl), P(c_i64)],
+    "vgp_greedy_profile_step_ms": [c_vp, P(c_dbl)],
     "vgp_placement_host": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp],
     "vgp_placement_host_ex": [c_int, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp, c_vp],
     "vgp_placement_host_wall": [c_vp],

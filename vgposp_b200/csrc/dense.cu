@@ -269,7 +269,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) gemm_kernel(GemmArgs p) {
             }
         }
     }
-    if (p.dist_n > 0) __threadfence_system();
+    if (p.dist_n > 0) {             // one system-scope fence per CTA after its barrier (fences are cumulative)
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------
@@ -482,7 +485,10 @@ __global__ void __launch_bounds__(tma::THREADS, S::MINB)
                 }
             }
         }
-        if (p.dist_n > 0) __threadfence_system();
+        if (p.dist_n > 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) __threadfence_system();
+        }
         return;
     }
 
@@ -519,7 +525,10 @@ __global__ void __launch_bounds__(tma::THREADS, S::MINB)
             }
         }
     }
-    if (p.dist_n > 0) __threadfence_system();
+    if (p.dist_n > 0) {             // one system-scope fence per CTA after its barrier (fences are cumulative)
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();
+    }
 }
 
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

@@ -137,6 +137,13 @@ __host__ __device__ constexpr unsigned idesc_i8(int m, int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
 
+// x * 2^e, exact like scalbn: the power of two is built from its bit pattern (one multiply instead of a libm call per
+// output element; the epilogue of a k = 512 tile was longer than its MMAs)
+__device__ __forceinline__ double mul_pow2(double x, int e) {
+    if (e >= -1022 && e <= 1023) return x * __longlong_as_double((long long)(e + 1023) << 52);
+    return scalbn(x, e);
+}
+
 __device__ __forceinline__ void umma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
                                         unsigned accumulate) {
     asm volatile(
@@ -278,8 +285,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                 if (p.lower && j / BM > i / BM) continue;           // keep to the 128 x 128 tiles on or below the diagonal
                 if (j + 1 < p.n) {
                     double2 o;
-                    o.x = p.alpha * scalbn(acc[c], ea + eb_tile[half * 32 + c]);
-                    o.y = p.alpha * scalbn(acc[c + 1], ea + eb_tile[half * 32 + c + 1]);
+                    o.x = p.alpha * mul_pow2(acc[c], ea + eb_tile[half * 32 + c]);
+                    o.y = p.alpha * mul_pow2(acc[c + 1], ea + eb_tile[half * 32 + c + 1]);
                     if (p.beta != 0.0) {
                         const double2 old = *reinterpret_cast<const double2 *>(crow + c);
                         o.x = fma(p.beta, old.x, o.x);
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     }
                     store_pair(p, crow + c, o);
                 } else if (j < p.n) {
-                    double o = p.alpha * scalbn(acc[c], ea + eb_tile[half * 32 + c]);
+                    double o = p.alpha * mul_pow2(acc[c], ea + eb_tile[half * 32 + c]);
                     if (p.beta != 0.0) o = fma(p.beta, crow[c], o);
                     store_one(p, crow + c, o);
                 }
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (p.dist_n > 0 && tid == 0) __threadfence_system();      // the tile's stores into the peers' replicas (cumulative)
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512) : "memory");

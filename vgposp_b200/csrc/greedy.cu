@@ -47,6 +47,7 @@ struct vgp_greedy {
     DenseWorkspace ws;
     int profile = 0;                                    // CUDA events around every downdate launch
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_step_events;     // peer path: around peer_step_kernel
     // peer-memory exchange (one box, NVLink): every rank owns a mailbox its peers store into
     char *mailbox = nullptr;                            // this rank's mailbox (plain cudaMalloc: IPC-exportable)
     size_t mailbox_bytes = 0;
@@ -469,10 +470,13 @@ __global__ void __launch_bounds__(256) peer_step_kernel(PeerTable pt, unsigned l
             }
             if (threadIdx.x == 0) *mb_rec(pt.mb[q], seq, pt.rank) = mine;
         }
-        __threadfence_system();
+        // one system-scope fence per releasing thread, after the CTA barrier (fences are cumulative: the other threads'
+        // stores, ordered before the barrier, are covered) -- 256 x membar.sys per site cost tens of microseconds
         __syncthreads();
-        if ((int)threadIdx.x < pt.nranks)
+        if ((int)threadIdx.x < pt.nranks) {
+            __threadfence_system();
             st_release_sys(reinterpret_cast<unsigned long long *>(pt.mb[threadIdx.x] + MB_REC_FLAG) + pt.rank, seq);
+        }
     }
     // ---- 3. every CTA: all ranks' records have arrived (own rank's included) -> the same winner everywhere
     wait_flags(me, MB_REC_FLAG, pt.nranks, seq);
@@ -527,9 +531,11 @@ __global__ void __launch_bounds__(256) peer_step_kernel(PeerTable pt, unsigned l
         if (j < pt.stride)
             for (int q = 0; q < pt.nranks; ++q) mb_seg(pt, pt.mb[q], seq, pt.rank)[j] = p;
     }
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicInc(a.counter2, gridDim.x - 1) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();                 // this CTA's peer stores (all threads', via the barrier) before the count
+        last = atomicInc(a.counter2, gridDim.x - 1) == gridDim.x - 1;
+    }
     __syncthreads();
     if (last && (int)threadIdx.x < pt.nranks) {
         __threadfence_system();
@@ -865,7 +871,26 @@ int vgp_greedy_profile(vgp_greedy *h, int enable) {
         cudaEventDestroy(pr.second);
     }
     h->prof_events.clear();
+    for (auto &pr : h->prof_step_events) cudaEventDestroy(pr.first);       // .second is a downdate event, freed above
+    h->prof_step_events.clear();
     h->profile = enable ? 1 : 0;
+    return VGP_OK;
+}
+
+/* Peer path: summed duration of the peer_step_kernel launches since profiling was enabled (includes its waits for the
+ * other ranks' records); the downdate_peer_kernel figure of vgp_greedy_profile_read includes its wait for the segments. */
+int vgp_greedy_profile_step_ms(vgp_greedy *h, double *total_ms) {
+    VGP_TRY(check_handle(h));
+    VGP_REQUIRE(total_ms, "NULL argument");
+    VGP_ENTER(h->device);
+    double sum = 0.0;
+    for (auto &pr : h->prof_step_events) {
+        float ms = 0.f;
+        VGP_CUDA(cudaEventSynchronize(pr.second));
+        VGP_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        sum += ms;
+    }
+    *total_ms = sum;
     return VGP_OK;
 }
 
@@ -1028,13 +1053,18 @@ int vgp_greedy_run_peer(vgp_greedy *h, int64_t k, void *stream) {
         a.step_row = (h->record && h->step_scores) ? h->step_scores + h->t * h->nloc : nullptr;
         a.wfull = h->wfull;
         a.ploc = h->ploc;
+        cudaEvent_t pe0 = nullptr, pe1 = nullptr, se0 = nullptr;
+        if (h->profile) {
+            VGP_CUDA(cudaEventCreate(&se0));
+            VGP_CUDA(cudaEventRecord(se0, s));
+        }
         peer_step_kernel<<<(unsigned)step_blocks, 256, 0, s>>>(pt, seq, a);
         H_LAUNCH_CHECK(h);
-        cudaEvent_t pe0 = nullptr, pe1 = nullptr;
         if (h->profile) {
             VGP_CUDA(cudaEventCreate(&pe0));
             VGP_CUDA(cudaEventCreate(&pe1));
             VGP_CUDA(cudaEventRecord(pe0, s));
+            h->prof_step_events.emplace_back(se0, pe0);
         }
         downdate_peer_kernel<4><<<dim3(gx, (unsigned)gy), 256, 0, s>>>(h->prec, h->ld, h->n_pad, h->n, pt, seq, b, h->ploc,
                                                                        h->c0, h->cur, rows_per_block);
