@@ -171,3 +171,34 @@ def test_tf_graph_algorithm_2_outputs():
     assert [int(v) for v in sel[:, 0]] == [int(v) for v in want_sel[:, 0]]
     np.testing.assert_allclose(sel[:, 1], want_sel[:, 1], rtol=1e-7)
     np.testing.assert_allclose(dci, want_dci, rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("formulation", ["lazy_factor", "lazy_precision"])
+def test_pinned_and_pageable_sources_give_the_same_bits(formulation, vgp_options):
+    """The one-call path copies the lower triangle in row chunks underneath the factorisation: from pinned memory this
+    thread issues every copy up front; from pageable memory (a NumPy array) a helper thread issues them while the
+    factorisation is enqueued and the row gate waits on the host for each chunk's event.  Same results, also with the
+    overlap switched off, and with several chunks (n > 2048)."""
+    import ctypes
+    from vgposp_b200 import _ffi
+    n, k = 5000, 9
+    cov = cloud_cov(n, 12)
+    want_sel, want_scores = go.incremental_greedy_c(cov, k)
+    host = ctypes.c_void_p()
+    _ffi.call("vgp_host_alloc", cov.nbytes, ctypes.byref(host))
+    try:
+        pinned = np.ctypeslib.as_array(ctypes.cast(host, ctypes.POINTER(ctypes.c_double)), shape=(n, n))
+        pinned[:] = cov
+        results = []
+        for overlap in (1, 0):
+            vgp_options(h2d_overlap=overlap)
+            for src in (cov, pinned):
+                sel, scores, steps, secs = greedy.place_single(src, k, D, want_step_scores=True, formulation=formulation)
+                results.append((sel, scores, steps))
+        for sel, scores, steps in results:
+            assert [int(v) for v in sel] == want_sel
+            np.testing.assert_array_equal(scores, results[0][1])
+            np.testing.assert_array_equal(steps, results[0][2])
+        np.testing.assert_allclose(results[0][1], want_scores, rtol=1e-9)
+    finally:
+        _ffi.call("vgp_host_free", host)

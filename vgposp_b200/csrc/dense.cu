@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <thread>
+
 #include "dense.cuh"
 #include "block128.cuh"
 
@@ -91,6 +93,15 @@ static int gate_wait(const double *p, int64_t rows, cudaStream_t s) {
     int chunk = (int)(last / g->chunk_rows);
     if (chunk >= g->nchunks) chunk = g->nchunks - 1;
     if (chunk >= g->waited) {
+        if (g->recorded) {
+            while (g->recorded->load(std::memory_order_acquire) <= chunk) {
+                if (g->failed && g->failed->load(std::memory_order_acquire)) {
+                    set_error("the host-to-device copy of cov_vv failed");
+                    return VGP_ERR_CUDA;
+                }
+                std::this_thread::yield();
+            }
+        }
         VGP_CUDA(cudaStreamWaitEvent(s, g->events[chunk], 0));
         g->waited = chunk + 1;
     }

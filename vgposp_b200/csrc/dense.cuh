@@ -2,6 +2,8 @@
 // handed to these functions is a multiple of vgp::TILE (128) -- callers pad (identity on the padding
 // diagonal), which removes every edge case from the kernels.
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 
 namespace vgp {
@@ -68,6 +70,11 @@ struct RowGate {
     int64_t ld = 0, rows = 0, chunk_rows = 0;
     cudaEvent_t *events = nullptr;
     int nchunks = 0, waited = 0;            // chunks [0, waited) are already ordered before the compute stream
+    // When another host thread issues the copies (pageable source: its copies block the issuing thread), the number
+    // of chunk events recorded so far; a wait on chunk c first waits on the host until recorded > c (waiting on an
+    // event that has not been recorded yet is a no-op).  nullptr: all events are recorded before the gate is set.
+    const std::atomic<int> *recorded = nullptr;
+    const std::atomic<int> *failed = nullptr;  // set by the copying thread on an error: waits give up
 };
 void dense_set_gate(RowGate *gate);         // thread-local; nullptr switches it off
 void dense_set_pivot_floor(double floor);   // thread-local; pivots <= floor fail dense_potrf (0: only non-positive ones)

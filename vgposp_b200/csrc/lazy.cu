@@ -22,6 +22,9 @@
 
 #include <algorithm>
 #include <new>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <chrono>
 #include <vector>
 
@@ -54,7 +57,8 @@ struct vgp_lazy {
     int64_t partial_parity_stride = 0;                // doubles between the two parity buffers (0: single buffer)
     int64_t loc_i1 = 0, loc_i2 = 0, loc_cutoff = 0;   // algorithm 3: grid strides I1, I2 and the index-box half-width
     double *cache = nullptr;                          // algorithm 3: the (partly stale) delta cache [n_pad]
-    int64_t t = 0, launches = 0;
+    int64_t t = 0;
+    std::atomic<int64_t> launches{0};      // the one-call path counts from two host threads (pageable source)
     int blocks = 0;
     DenseWorkspace ws;
     int profile = 0;
@@ -832,8 +836,10 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
     std::vector<cudaEvent_t> chunk_ev((size_t)nchunks, nullptr);
     cudaError_t ce = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
     if (ce != cudaSuccess) return fail(cuda_fail(ce, "copy stream", __FILE__, __LINE__));
+    std::function<void()> join_before_fail = [] {};
     auto fail2 = [&](int code) {
         dense_set_gate(nullptr);
+        join_before_fail();                              // the copy helper (pageable source) must be done with `h`
         cudaStreamSynchronize(cs);
         for (auto &e : chunk_ev)
             if (e) cudaEventDestroy(e);
@@ -845,19 +851,52 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
             return fail2(cuda_fail(cudaGetLastError(), "chunk events", __FILE__, __LINE__));
     cudaEventRecord(ev[0], s);
     cudaStreamWaitEvent(cs, ev[0], 0);
-    for (int c = 0; c < nchunks; ++c) {
-        const int64_t r0 = (int64_t)c * CHUNK_ROWS, r1 = std::min(r0 + CHUNK_ROWS, h->n_pad);
-        const int64_t rows = std::min(r1, n) - r0, cols = std::min(r1, n);
-        if (rows > 0) {
-            ce = cudaMemcpy2DAsync(h->cov + r0 * h->n_pad, (size_t)h->n_pad * 8, cov_host + r0 * ld_host,
-                                   (size_t)ld_host * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice, cs);
-            if (ce != cudaSuccess) return fail2(cuda_fail(ce, "H2D of cov_vv", __FILE__, __LINE__));
+    // A pageable source (a plain NumPy array: what the reference's callers pass) makes every copy block the issuing
+    // thread.  The copies are then issued by a helper thread while this one enqueues the factorisation; the gate waits on
+    // the host until the chunk's event has been recorded, then on the device for the event (pinned source: this thread
+    // issues everything up front, as before).
+    cudaPointerAttributes pattr;
+    const bool pageable = cudaPointerGetAttributes(&pattr, cov_host) != cudaSuccess || pattr.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    std::atomic<int> recorded{0}, copy_failed{0};
+    int copy_rc = VGP_OK;
+    auto copy_all = [&]() -> void {
+        if (pageable) cudaSetDevice(device);
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t r0 = (int64_t)c * CHUNK_ROWS, r1 = std::min(r0 + CHUNK_ROWS, h->n_pad);
+            const int64_t rows = std::min(r1, n) - r0, cols = std::min(r1, n);
+            if (rows > 0) {
+                cudaError_t e = cudaMemcpy2DAsync(h->cov + r0 * h->n_pad, (size_t)h->n_pad * 8, cov_host + r0 * ld_host,
+                                                  (size_t)ld_host * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice,
+                                                  cs);
+                if (e != cudaSuccess) {
+                    copy_rc = cuda_fail(e, "H2D of cov_vv", __FILE__, __LINE__);
+                    copy_failed.store(1, std::memory_order_release);
+                    return;
+                }
+            }
+            const int rc1 = lazy_stage_rows(h, r0, r1, cs);
+            if (rc1 != VGP_OK) {
+                copy_rc = rc1;
+                copy_failed.store(1, std::memory_order_release);
+                return;
+            }
+            cudaEventRecord(chunk_ev[(size_t)c], cs);
+            recorded.store(c + 1, std::memory_order_release);
         }
-        rc = lazy_stage_rows(h, r0, r1, cs);
-        if (rc != VGP_OK) return fail2(rc);
-        cudaEventRecord(chunk_ev[(size_t)c], cs);
+        cudaEventRecord(ev[1], cs);                 // the last byte has arrived (overlaps the factorisation)
+    };
+    std::thread copier;
+    auto join_copier = [&]() {
+        if (copier.joinable()) copier.join();
+    };
+    join_before_fail = join_copier;
+    if (pageable) {
+        copier = std::thread(copy_all);             // h->launches is atomic: both threads count launches
+    } else {
+        copy_all();
+        if (copy_rc != VGP_OK) return fail2(copy_rc);
     }
-    cudaEventRecord(ev[1], cs);                     // the last byte has arrived (overlaps the factorisation)
     RowGate gate;
     gate.base = h->fac;
     gate.ld = h->n_pad;
@@ -865,12 +904,23 @@ int vgp_placement_host_ex(int device, const double *cov_host, int64_t n, int64_t
     gate.chunk_rows = CHUNK_ROWS;
     gate.events = chunk_ev.data();
     gate.nchunks = nchunks;
-    if (option(VGP_OPT_H2D_OVERLAP) == 0)                // measurement knob: finish the copy before factorising
+    if (pageable) {
+        gate.recorded = &recorded;
+        gate.failed = &copy_failed;
+    }
+    if (option(VGP_OPT_H2D_OVERLAP) == 0) {              // measurement knob: finish the copy before factorising
+        join_copier();
         gate.waited = nchunks, cudaStreamWaitEvent(s, chunk_ev[(size_t)nchunks - 1], 0);
+    }
     dense_set_gate(&gate);
     int info = 0;
     rc = lazy_factor_staged(h, &info, s);
     dense_set_gate(nullptr);
+    join_copier();
+    if (rc == VGP_OK && copy_rc != VGP_OK) {
+        if (pageable) set_error("the host-to-device copy of cov_vv failed (status %d)", copy_rc);
+        rc = copy_rc;
+    }
     if (rc != VGP_OK) return fail2(rc);
     cudaStreamWaitEvent(s, chunk_ev[(size_t)nchunks - 1], 0);     // (already implied; keeps `cov` ordered before the steps)
     cudaEventRecord(ev[2], s);
