@@ -401,12 +401,20 @@ def resident_run(args, n, rank, world, dev, dist, stream, kmax):
     step_ms = ctypes.c_double()
     call("vgp_greedy_profile_step_ms", shard.handle, ctypes.byref(step_ms))
     call("vgp_greedy_profile", shard.handle, 0)
+    per_rank = None
     if dist:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda:%d" % dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        # every rank's own kernel times (the step kernel's includes its wait for the slowest rank's record)
+        mine = torch.tensor([kms.value / max(kcount.value, 1), step_ms.value / max(kcount.value, 1)],
+                            dtype=torch.float64, device="cuda:%d" % dev)
+        allr = torch.empty(2 * world, dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_gather_into_tensor(allr, mine)
+        v = allr.cpu().tolist()
+        per_rank = {"downdate_ms_avg": [round(x, 5) for x in v[0::2]], "step_kernel_ms_avg": [round(x, 5) for x in v[1::2]]}
     sel, scores = shard.results()
-    return {"shard": shard, "xd": xd, "kernel": (amp, ls, nugget), "c0": c0, "c1": c1, "ms": ms, "kms": kms.value,
+    return {"per_rank": per_rank, "shard": shard, "xd": xd, "kernel": (amp, ls, nugget), "c0": c0, "c1": c1, "ms": ms, "kms": kms.value,
             "kcount": kcount.value, "step_kernel_ms": step_ms.value, "launches": launches, "clocks": clocks.summary(), "sel": sel, "scores": scores,
             "build_ms": build_ms, "factor_s": factor_s, "dist_stats": dist_stats}
 
@@ -427,7 +435,8 @@ def roofline_of(r, n, hbm_peak, peak_kind, steps):
             "kernel_launches_timed": r["kcount"],
             "kernel_share_of_step": r["kms"] / r["ms"] if r["ms"] > 0 else None,
             "peer_step_kernel_ms_avg": (r["step_kernel_ms"] / max(r["kcount"], 1)) if r.get("step_kernel_ms") else None,
-            "whole_step_frac": algo_bytes * steps / (r["ms"] * 1e-3) / 1e9 / hbm_peak if r["ms"] > 0 else None}
+            "whole_step_frac": algo_bytes * steps / (r["ms"] * 1e-3) / 1e9 / hbm_peak if r["ms"] > 0 else None,
+            "per_rank": r.get("per_rank")}
 
 
 def run_ours(args, rank, world, local_rank):

@@ -69,13 +69,6 @@ __device__ __forceinline__ bool tile_of_cta(const GemmArgs &p, int tiles_m, int 
     tn = sc * SUPER + (int)(rem % width);
     return true;
 }
-__device__ __forceinline__ void store_pair(const GemmArgs &p, double *dst, double2 o) {
-    if (p.dist_n > 0) {
-        for (int q = 0; q < p.dist_n; ++q) *(reinterpret_cast<double2 *>(dst) + (p.delta[q] >> 1)) = o;    // peers: NVLink
-    } else {
-        *reinterpret_cast<double2 *>(dst) = o;
-    }
-}
 __device__ __forceinline__ void store_one(const GemmArgs &p, double *dst, double o) {
     if (p.dist_n > 0) {
         for (int q = 0; q < p.dist_n; ++q) dst[p.delta[q]] = o;
@@ -275,30 +268,27 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
             for (int c = 0; c < 32; ++c) acc[c] = fma((double)v[c], scale, acc[c]);
         }
+        // Every MMA has completed (tfull), so the operand stages are free: each warp turns its 32 x 32 block (one ROW per
+        // thread out of tensor memory) through 8.4 KB of them and stores one row segment of 32 consecutive doubles per
+        // instruction -- 256 contiguous bytes instead of 32 scattered 16-byte pieces.  That is what the replicas on the
+        // other GPUs need: the scattered form turned every piece into its own NVLink packet, and the distributed
+        // factorisation took 19 s on 8 GPUs (1.0 s on 2) instead of well under a second.
         const int64_t i = m0 + row;
-        if (i < p.m) {
-            const int ea = p.ea[i];
-            double *crow = p.c + (int64_t)blockIdx.z * p.split_stride + i * p.ldc + n0 + half * 32;
+        const int ea = i < p.m_pad ? p.ea[i] : 0;
+        double *buf = reinterpret_cast<double *>(sm) + (warp - 2) * (32 * 33);
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-                const int64_t j = n0 + half * 32 + c;
-                if (p.lower && j / BM > i / BM) continue;           // keep to the 128 x 128 tiles on or below the diagonal
-                if (j + 1 < p.n) {
-                    double2 o;
-                    o.x = p.alpha * mul_pow2(acc[c], ea + eb_tile[half * 32 + c]);
-                    o.y = p.alpha * mul_pow2(acc[c + 1], ea + eb_tile[half * 32 + c + 1]);
-                    if (p.beta != 0.0) {
-                        const double2 old = *reinterpret_cast<const double2 *>(crow + c);
-                        o.x = fma(p.beta, old.x, o.x);
-                        o.y = fma(p.beta, old.y, o.y);
-                    }
-                    store_pair(p, crow + c, o);
-                } else if (j < p.n) {
-                    double o = p.alpha * mul_pow2(acc[c], ea + eb_tile[half * 32 + c]);
-                    if (p.beta != 0.0) o = fma(p.beta, crow[c], o);
-                    store_one(p, crow + c, o);
-                }
-            }
+        for (int c = 0; c < 32; ++c) buf[lane * 33 + c] = p.alpha * mul_pow2(acc[c], ea + eb_tile[half * 32 + c]);
+        __syncwarp();
+        const int64_t j = n0 + half * 32 + lane;                    // this lane's column
+        double *cbase = p.c + (int64_t)blockIdx.z * p.split_stride;
+        for (int r = 0; r < 32; ++r) {
+            const int64_t ir = m0 + q * 32 + r;
+            if (ir >= p.m) break;
+            if (j >= p.n || (p.lower && j / BM > ir / BM)) continue;    // keep to the 128 x 128 tiles on or below the diagonal
+            double o = buf[r * 33 + lane];
+            double *dst = cbase + ir * p.ldc + j;
+            if (p.beta != 0.0) o = fma(p.beta, *dst, o);
+            store_one(p, dst, o);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
