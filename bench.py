@@ -488,6 +488,10 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if float(t.item()) < 125e9:
             cfg5 = {"skipped": "%.0f GB free on the fullest GPU, 125 GB needed" % (float(t.item()) / 1e9)}
+        t = torch.tensor([float(res["factor_s"])], dtype=torch.float64, device="cuda:%d" % dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if cfg5 is None and float(t.item()) > 6.0:      # 8 x the work: keep the whole run within minutes
+            cfg5 = {"skipped": "the n = 50 000 inverse took %.1f s: the n = 100 000 one would take minutes" % float(t.item())}
     if world == 8 and not args.no_cfg5 and n != 100000 and cfg5 is None:
         try:
             r5 = resident_run(args, 100000, rank, world, dev, dist, stream, args.steps + args.warmup)

@@ -77,10 +77,13 @@ int current_device() {
 size_t cache_limit(int device) {
     const int64_t v = option(VGP_OPT_WORKSPACE_CACHE_BYTES);
     if (v >= 0) return (size_t)v;
-    size_t f = 0, t = 0;
-    if (cudaMemGetInfo(&f, &t) != cudaSuccess) return 0;
-    (void)device;
-    return t / 2;
+    static size_t half_of_device[MAX_DEV] = {};      // cudaMemGetInfo costs milliseconds with tens of GB mapped: once
+    if (half_of_device[device] == 0) {
+        size_t f = 0, t = 0;
+        if (cudaMemGetInfo(&f, &t) != cudaSuccess) return 0;
+        half_of_device[device] = t / 2;
+    }
+    return half_of_device[device];
 }
 size_t trim_locked(int device) {
     size_t freed = 0;
