@@ -49,6 +49,7 @@ struct GemmArgs {
     // distributed form (dist.cu): tiles dealt round-robin to the ranks (linear tile = rank + dist_n * blockIdx.x), every
     // finished tile stored into all dist_n replicas (delta[q] = replica q minus the local one, in doubles)
     int dist_n, rank, tiles_n;
+    int local_only;               // distributed form: store the tile into this rank's replica only (push_tiles follows)
     int64_t delta[DIST_MAX];
 };
 
@@ -57,6 +58,7 @@ struct GemmArgs {
 // (16 x ~9 tiles per wave: ~150 MB of digit planes per wave instead of one strip of A and ALL of B -- the row-major walk
 // read 34.9 GB from DRAM for 1.07 GB of planes at 8192^3, L2 hit rate 61 %: profiles/r02_ncu_emulated_gemm.txt).
 constexpr int SUPER = 16;
+constexpr int v2_BN = 64;                             // tile width of the GEMM kernel (v2::BN2, declared below)
 __device__ __forceinline__ bool tile_of_cta(const GemmArgs &p, int tiles_m, int &tm, int &tn) {
     const int64_t lin = p.dist_n > 0 ? (int64_t)p.rank + (int64_t)p.dist_n * blockIdx.x
                                      : (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
@@ -70,7 +72,7 @@ __device__ __forceinline__ bool tile_of_cta(const GemmArgs &p, int tiles_m, int 
     return true;
 }
 __device__ __forceinline__ void store_one(const GemmArgs &p, double *dst, double o) {
-    if (p.dist_n > 0) {
+    if (p.dist_n > 0 && !p.local_only) {
         for (int q = 0; q < p.dist_n; ++q) dst[p.delta[q]] = o;
     } else {
         *dst = o;
@@ -165,6 +167,7 @@ __device__ __forceinline__ void tmem_ld32(unsigned addr, int (&v)[32]) {   // th
 // All digit planes of a k block resident: 96 KB per stage feed 72 MMAs (42 bytes of shared-memory fill per MMA cycle).
 namespace v2 {
 constexpr int BN2 = 64, BKB2 = 64, STAGES2 = 2, S2_MAX = 8;
+static_assert(BN2 == v2_BN, "push_tiles_kernel walks the same tiles");
 constexpr int A2 = BM * BKB2, B2 = BN2 * BKB2;                    // one plane tile of A / B
 constexpr int STAGE2 = S2_MAX * (A2 + B2);
 constexpr int BAR2 = (2 * STAGES2 + 1) * 8 + 8;
@@ -300,6 +303,36 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
 }
 }  // namespace v2
+
+// Distributed form: the tiles this rank has just computed (same tile walk as the GEMM kernel), copied from its replica
+// into every other replica.  blockIdx.y = peer.  Done by a kernel of its own -- thousands of small CTAs keep NVLink busy
+// -- because the GEMM kernel runs one CTA per SM with a serial epilogue: storing every tile to seven peers from there
+// left the tensor pipe waiting on remote stores (distributed potrf + trtri + lauum at n = 50k on 8 GPUs: 3.8 s; with the
+// scattered 16-byte stores of the first epilogue: 19 s).
+__global__ void __launch_bounds__(256) push_tiles_kernel(GemmArgs p) {
+    int tm, tn;
+    if (!tile_of_cta(p, (int)(p.m_pad / BM), tm, tn)) return;
+    if (p.lower && tn * v2_BN > tm * BM + (BM - 1)) return;
+    int q = blockIdx.y;
+    if (q >= p.rank) ++q;                                           // skip this rank
+    const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * v2_BN;
+    // 128 rows x 64 doubles: a row is 32 double2, 8 rows per pass
+    const int cpair = threadIdx.x & 31, rsub = threadIdx.x >> 5;
+    const int64_t j = n0 + 2 * cpair;
+    for (int r = rsub; r < BM && j < p.n; r += 8) {
+        const int64_t i = m0 + r;
+        if (i >= p.m) break;
+        if (p.lower && j / BM > i / BM) continue;
+        const double *src = p.c + i * p.ldc + j;
+        double *dst = const_cast<double *>(src) + p.delta[q];
+        if (j + 1 < p.n)
+            *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(src);
+        else
+            *dst = *src;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+}
 
 // ------------------------------------------------------------------------------------------------ digit planes
 // Element (r, k) of the operand lives at x[r * rs + k * ks] (one of rs, ks is 1).
@@ -560,6 +593,7 @@ int emulated_gemm_splitk(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, 
     p.lower = lower;
     p.dist_n = 0;
     p.rank = 0;
+    p.local_only = 0;
     p.kb_split = (int)(K_CHUNK / v2::BKB2);
     p.split_stride = m * n;
     p.tiles_n = (int)(n_pad / v2::BN2);
@@ -610,6 +644,7 @@ int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t
         p.lower = lower;
         p.dist_n = 0;
         p.rank = 0;
+        p.local_only = 0;
         p.kb_split = 0;
         p.split_stride = 0;
         const int64_t tiles_n = n_pad / v2::BN2, tiles_m = m_pad / BM;
@@ -620,9 +655,15 @@ int emulated_gemm(EmuWorkspace &ws, int trans_a, int trans_b, int64_t m, int64_t
             p.rank = dc->rank;
             for (int q = 0; q < dc->nranks; ++q) p.delta[q] = dc->delta[q];
             grid = dim3((unsigned)((tiles_n * tiles_m + dc->nranks - 1) / dc->nranks), 1);
+            p.local_only = dc->nranks > 2 ? 1 : 0;       // two ranks: the epilogue's peer stores are cheap enough
         }
         v2::emu_gemm_resident_kernel<<<grid, THREADS, v2::SMEM2, st>>>(ma, mb, p);
         VGP_LAUNCH_CHECK();
+        const bool last_chunk = k0 + K_CHUNK >= k;
+        if (p.dist_n > 0 && p.local_only && last_chunk) {
+            push_tiles_kernel<<<dim3(grid.x, (unsigned)(dc->nranks - 1)), 256, 0, st>>>(p);
+            VGP_LAUNCH_CHECK();
+        }
         if (k == 0) break;
     }
     return VGP_OK;
