@@ -5,6 +5,13 @@ import sys
 import numpy as np
 import pytest
 
+# Some GPU tests run several ranks as THREADS on one device (kernels of different streams that wait on one another's
+# flags).  Streams share hardware work queues (8 by default): two ranks' streams on one queue put a spinning barrier
+# kernel in front of the kernel that would release it, and the test dies in bounded-spin time-outs depending on how many
+# streams earlier tests created.  One queue per stream (set before CUDA initialises) removes that artefact of the
+# single-device emulation; the product path (one process per GPU) is not affected.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

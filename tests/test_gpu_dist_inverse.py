@@ -96,13 +96,8 @@ def test_two_processes_ipc():
     assert "DIST_WORKER_OK" in res.stdout
 
 
-# Ranks as THREADS on one device only with the FP64 products here: with the int8 products (1 CTA per SM, all of tensor
-# memory) the [1000-2-12] case met barrier time-outs in this single-device emulation (two ranks' kernels that wait on
-# one another are not guaranteed to be co-scheduled on one GPU: B200_PROFILING.md) although the same sequence passes as
-# a script and as two processes on two GPUs -- the int8 products of the sharded path are covered by
-# test_two_processes_ipc (tests/dist_worker.py sets gemm_emulate_min = 512) and by test_ranks_as_threads_one_device.
 @pytest.mark.timeout(240)
-@pytest.mark.parametrize("emulate_min", [4096], ids=["fp64_products"])
+@pytest.mark.parametrize("emulate_min", [4096, 512], ids=["fp64_products", "int8_products"])
 @pytest.mark.parametrize("n,world,k", [(1000, 2, 12), (1664, 3, 20), (2050, 4, 9), (700, 2, 600)])
 def test_sharded_lazy_factor_greedy_threads(n, world, k, emulate_min, vgp_options):
     """The one-call path on G ranks: replicas factorised to L^-1 by the distributed potrf + trtri, the triangular
