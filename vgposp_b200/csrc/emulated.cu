@@ -528,6 +528,10 @@ int emulated_preload() {
         cudaFuncAttributes fa;
         VGP_CUDA(cudaFuncGetAttributes(&fa, row_exponent_kernel));
         VGP_CUDA(cudaFuncGetAttributes(&fa, digit_planes_kernel));
+        // every kernel a distributed product may launch is loaded NOW: a first launch loads its module lazily, which can
+        // wait for the device to drain -- not while another rank's barrier kernel is spinning on it
+        VGP_CUDA(cudaFuncGetAttributes(&fa, push_tiles_kernel));
+        VGP_CUDA(cudaFuncGetAttributes(&fa, constant_exponent_kernel));
         configured[device] = true;
     }
     return VGP_OK;

@@ -105,16 +105,32 @@ size_t cache_trim_current(size_t *cached_before) {
     return trim_locked(d);
 }
 
-static void forget_live(void *ptr) {      // an address cudaMalloc hands out is not (or no longer) a cache block
+// An address range cudaMalloc has just handed out must not overlap anything the cache believes it owns: that would mean
+// a cached block was released behind the cache's back (two owners of one range: silent corruption).  Fatal by design.
+static bool overlaps_cache_locked(int d, const void *ptr, size_t bytes) {
+    const char *a0 = (const char *)ptr, *a1 = a0 + bytes;
+    for (const Block &b : g_cache_free[d])
+        if (a0 < (const char *)b.ptr + b.bytes && (const char *)b.ptr < a1) return true;
+    for (const auto &kv : g_cache_live[d])
+        if (kv.first != ptr && a0 < (const char *)kv.first + kv.second && (const char *)kv.first < a1) return true;
+    return false;
+}
+
+static cudaError_t checked_new_range(void *ptr, size_t bytes) {
     const int d = current_device();
-    if (d < 0 || !ptr) return;
+    if (d < 0 || !ptr) return cudaSuccess;
     std::lock_guard<std::mutex> lock(g_cache_mu);
-    g_cache_live[d].erase(ptr);
+    g_cache_live[d].erase(ptr);           // an address cudaMalloc hands out is not (or no longer) a cache block
+    if (overlaps_cache_locked(d, ptr, bytes)) {
+        set_error("internal error: a new device allocation overlaps a block of the workspace cache");
+        return cudaErrorUnknown;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t device_malloc(void **ptr, size_t bytes) {
     cudaError_t e = cudaMalloc(ptr, bytes);
-    if (e == cudaSuccess) forget_live(*ptr);
+    if (e == cudaSuccess) return checked_new_range(*ptr, bytes);
     if (e != cudaErrorMemoryAllocation) return e;
     cudaGetLastError();
     const int d = current_device();
@@ -124,7 +140,7 @@ cudaError_t device_malloc(void **ptr, size_t bytes) {
         if (trim_locked(d) == 0) return e;
     }
     e = cudaMalloc(ptr, bytes);
-    if (e == cudaSuccess) forget_live(*ptr);
+    if (e == cudaSuccess) return checked_new_range(*ptr, bytes);
     return e;
 }
 
@@ -150,7 +166,14 @@ cudaError_t cache_alloc(void **ptr, size_t bytes) {
         cudaGetLastError();
         if (trim_locked(d) > 0) e = cudaMalloc(ptr, bytes);
     }
-    if (e == cudaSuccess) g_cache_live[d][*ptr] = bytes;
+    if (e == cudaSuccess) {
+        g_cache_live[d].erase(*ptr);
+        if (overlaps_cache_locked(d, *ptr, bytes)) {
+            set_error("internal error: a new device allocation overlaps a block of the workspace cache");
+            return cudaErrorUnknown;
+        }
+        g_cache_live[d][*ptr] = bytes;
+    }
     return e;
 }
 
