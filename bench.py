@@ -292,7 +292,7 @@ def ncu_traffic(n, nloc):
 
 def config_dict(args):
     _, amp, ls, nugget = workload(args.n)
-    return {"workload": "greedy_mi_placement_n%d_k%d_expquad_cloud" % (args.n, args.k), "n": args.n, "k": args.k,
+    cfg = {"workload": "greedy_mi_placement_n%d_k%d_expquad_cloud" % (args.n, args.k), "n": args.n, "k": args.k,
             "amplitude": amp, "length_scale": round(ls, 6), "nugget": nugget, "seed": SEED,
             "parallelism": "column-panel shards x%d" % args.gpus,
             "exchange": ("none" if args.gpus == 1 else
@@ -300,6 +300,9 @@ def config_dict(args):
                           else "2 NCCL all-gathers per selection")),
             "l2": "inputs larger than L2: every step streams the %.1f GB precision panel"
                   % (8.0 * args.n * args.n / args.gpus / 1e9)}
+    if getattr(args, "option", None):
+        cfg["library_options"] = list(args.option)           # non-default vgp_set_option values of this run
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -386,8 +389,10 @@ def resident_run(args, n, rank, world, dev, dist, stream, kmax):
     shard.restore_precision()
     call("vgp_greedy_profile", shard.handle, 1)
     launches0 = shard.launch_count()
-    barrier()
+    # the clock sampler (NVML init + a thread) starts BEFORE the barrier: anything between the barrier and the first
+    # launch is start skew between the ranks, which the earliest rank's event pair would count as step time
     with ClockSampler(dev) as clocks:
+        barrier()
         a = ev()
         run_steps(args.steps)
         b = ev()
@@ -446,6 +451,9 @@ def run_ours(args, rank, world, local_rank):
 
     dev = local_rank
     torch.cuda.set_device(dev)
+    for item in args.option:                                  # every rank sets the same table (checked at connect)
+        name, _, value = item.partition("=")
+        _ffi.set_option(name, int(value))
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -911,6 +919,8 @@ def main():
     ap.add_argument("--k", type=int, default=None, help="selections of the e2e call (default: --steps)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: per-selection exchange through peer-memory mailboxes (default) or two NCCL all-gathers")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=INT",
+                    help="library option for this run (vgp_set_option; e.g. gemm_emulate_slices=0), recorded in config")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-elbo", action="store_true")
