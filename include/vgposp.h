@@ -59,6 +59,10 @@ int vgp_device_info(int device, char *name, int len, int *sm_count, size_t *tota
  *   GEMM_TILE_CONFIG     [-1] measurement knob: force the DMMA tile configuration (0 base, 1 pair, 2 tma)
  *   GEMM_SMALL_BELOW     [74] products with fewer 128 x 64 tiles use the 64 x 64 tile shape
  *   DIST_MIN_TILES / DIST_MIN_K [96 / 256] smallest product the distributed factorisation shares out over the ranks
+ *   DIST_EMULATE_MIN     [-1] smallest DISTRIBUTED product on the int8 tensor cores.  Every rank cuts the digit planes
+ *                             of the whole operands but multiplies only its share of the tiles, so the break-even
+ *                             size grows with the rank count: -1 = max(GEMM_EMULATE_MIN, 512 x ranks) (n = 50 000,
+ *                             8 ranks: inverse 2.58 s with 1024, 1.99 s on the FP64 pipe alone; 2 ranks: 1.54 s vs 2.38 s)
  *   ELBO_OVERLAP         [3]  side streams of the ELBO step (0: single stream)
  *   WORKSPACE_CACHE_BYTES [-1] cap of the per-device workspace cache; -1 = half of the device memory, 0 = no caching */
 enum {
@@ -71,7 +75,8 @@ enum {
     VGP_OPT_DIST_MIN_K = 6,
     VGP_OPT_ELBO_OVERLAP = 7,
     VGP_OPT_WORKSPACE_CACHE_BYTES = 8,
-    VGP_OPT_COUNT = 9
+    VGP_OPT_DIST_EMULATE_MIN = 9,
+    VGP_OPT_COUNT = 10
 };
 int vgp_set_option(int option, int64_t value);
 int vgp_get_option(int option, int64_t *value);

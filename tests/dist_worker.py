@@ -19,6 +19,7 @@ def main():
     _ffi.set_option("dist_min_tiles", 2)
     _ffi.set_option("dist_min_k", 256)
     _ffi.set_option("gemm_emulate_min", 512)       # small n: still exercise the int8 products, distributed
+    _ffi.set_option("dist_emulate_min", 512)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))

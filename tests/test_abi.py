@@ -119,6 +119,9 @@ def test_options_table_roundtrip_and_validation():
     assert _ffi.get_option("gemm_emulate_slices") == 8
     assert _ffi.get_option("gemm_emulate_min") == 1024
     assert _ffi.get_option("dist_min_tiles") == 96 and _ffi.get_option("dist_min_k") == 256
+    assert _ffi.get_option("dist_emulate_min") == -1
+    with pytest.raises(_ffi.VgpError):
+        _ffi.set_option("dist_emulate_min", 64)
     old = _ffi.set_option("gemm_emulate_slices", 0)
     assert old == 8 and _ffi.get_option("gemm_emulate_slices") == 0
     _ffi.set_option("gemm_emulate_slices", old)

@@ -40,7 +40,7 @@ def single_inverse(a):
 @pytest.mark.parametrize("n,world", [(1000, 2), (1664, 3), (2050, 4)])
 def test_ranks_as_threads_one_device(n, world, emulate_min, vgp_options):
     """G ranks as threads of this process on one device (each with its own stream and replica)."""
-    vgp_options(dist_min_tiles=2, dist_min_k=256, gemm_emulate_min=emulate_min)
+    vgp_options(dist_min_tiles=2, dist_min_k=256, gemm_emulate_min=emulate_min, dist_emulate_min=emulate_min)
     a = spd(n, n)
     want = single_inverse(a)
     streams = []
@@ -105,7 +105,7 @@ def test_sharded_lazy_factor_greedy_threads(n, world, k, emulate_min, vgp_option
     must return the single-device lazy-factor result bit for bit, and the CPU oracle's selection."""
     from oracle import greedy_oracle as go
     from vgposp_b200 import greedy
-    vgp_options(dist_min_tiles=2, dist_min_k=256, gemm_emulate_min=emulate_min)
+    vgp_options(dist_min_tiles=2, dist_min_k=256, gemm_emulate_min=emulate_min, dist_emulate_min=emulate_min)
     a = spd(n, n + 1)
     want = greedy.place_single(a, k, D, want_step_scores=True, formulation="lazy_factor")
     streams = []

@@ -165,7 +165,8 @@ _NO_STATUS = {"vgp_abi_version", "vgp_last_error"}
 
 # vgp_set_option identifiers (include/vgposp.h)
 OPTIONS = {"gemm_emulate_slices": 0, "gemm_emulate_min": 1, "h2d_overlap": 2, "gemm_tile_config": 3,
-           "gemm_small_below": 4, "dist_min_tiles": 5, "dist_min_k": 6, "elbo_overlap": 7, "workspace_cache_bytes": 8}
+           "gemm_small_below": 4, "dist_min_tiles": 5, "dist_min_k": 6, "elbo_overlap": 7, "workspace_cache_bytes": 8,
+           "dist_emulate_min": 9}
 
 _lib = None
 LOADED = {"path": None, "stamp": None, "stamp_matches_sources": None}     # what load() bound; bench/tests print it

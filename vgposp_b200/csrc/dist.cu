@@ -33,7 +33,8 @@ unsigned long long options_fingerprint(int64_t n_pad, int64_t tail_rows) {
     unsigned long long h = 1469598103934665603ull;
     const int64_t words[] = {VGP_ABI_VERSION, n_pad, tail_rows, option(VGP_OPT_GEMM_EMULATE_SLICES),
                              option(VGP_OPT_GEMM_EMULATE_MIN), option(VGP_OPT_DIST_MIN_TILES), option(VGP_OPT_DIST_MIN_K),
-                             option(VGP_OPT_GEMM_TILE_CONFIG), option(VGP_OPT_GEMM_SMALL_BELOW)};
+                             option(VGP_OPT_GEMM_TILE_CONFIG), option(VGP_OPT_GEMM_SMALL_BELOW),
+                             option(VGP_OPT_DIST_EMULATE_MIN)};
     for (int64_t w : words) h = (h ^ (unsigned long long)w) * 1099511628211ull;
     return h | 1ull;
 }

@@ -54,6 +54,7 @@ static std::atomic<int64_t> g_options[VGP_OPT_COUNT] = {
     {256},     // VGP_OPT_DIST_MIN_K
     {3},       // VGP_OPT_ELBO_OVERLAP
     {-1},      // VGP_OPT_WORKSPACE_CACHE_BYTES (-1: half of the device's memory)
+    {-1},      // VGP_OPT_DIST_EMULATE_MIN (-1: max(GEMM_EMULATE_MIN, 512 x ranks))
 };
 int64_t option(int which) { return which >= 0 && which < VGP_OPT_COUNT ? g_options[which].load() : 0; }
 
@@ -271,6 +272,9 @@ int vgp_set_option(int option_id, int64_t value) {
             break;
         case VGP_OPT_GEMM_EMULATE_MIN:
             VGP_REQUIRE(value >= 128, "smallest emulated product must be >= 128");
+            break;
+        case VGP_OPT_DIST_EMULATE_MIN:
+            VGP_REQUIRE(value == -1 || value >= 128, "smallest distributed emulated product: -1 (auto) or >= 128");
             break;
         case VGP_OPT_GEMM_TILE_CONFIG:
             VGP_REQUIRE(value >= -1 && value <= 2, "tile configuration: -1 auto, 0 base, 1 pair, 2 tma");
