@@ -762,11 +762,14 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
             for (int q = 0; q < dc->nranks; ++q) p.delta[q] = dc->delta[q];
             ++dc->dist_gemms;
             VGP_TRY(dense_dist_barrier(*dc, s));                  // every rank is done with all earlier work
-            // every rank cuts the digit planes of the WHOLE operands and multiplies 1/nranks of the tiles: the int8
-            // path pays off from a size that grows with the rank count (VGP_OPT_DIST_EMULATE_MIN)
+            // every rank cuts the digit planes of the WHOLE operands and multiplies 1/nranks of the tiles, so the int8
+            // path loses its margin as the rank count grows: measured at n = 50 000 it wins with 2 ranks (inverse
+            // 1.54 s against 2.38 s) and never with 8 (profiles/r02_dist_inverse_bench_g8.jsonl: every threshold
+            // from 2048 up is slower than the FP64 pipe alone).  VGP_OPT_DIST_EMULATE_MIN = -1 follows that.
             int64_t dist_emu_min = option(VGP_OPT_DIST_EMULATE_MIN);
-            if (dist_emu_min < 0) dist_emu_min = emu_min > 512 * (int64_t)dc->nranks ? emu_min : 512 * (int64_t)dc->nranks;
-            if (emulate && m >= dist_emu_min && n >= dist_emu_min && 2 * k >= dist_emu_min) {
+            const bool dist_emulate = dist_emu_min < 0 ? dc->nranks <= 2
+                                                       : (m >= dist_emu_min && n >= dist_emu_min && 2 * k >= dist_emu_min);
+            if (emulate && dist_emulate) {
                 VGP_TRY(emulated_gemm(*g_emu_ws, trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc,
                                       emu_slices, tiles == GEMM_LOWER ? 1 : 0, s, dc));
                 return dense_dist_barrier(*dc, s);
