@@ -61,9 +61,10 @@ int vgp_device_info(int device, char *name, int len, int *sm_count, size_t *tota
  *   DIST_MIN_TILES / DIST_MIN_K [96 / 256] smallest product the distributed factorisation shares out over the ranks
  *   DIST_EMULATE_MIN     [-1] smallest DISTRIBUTED product on the int8 tensor cores.  Every rank cuts the digit planes
  *                             of the whole operands but multiplies only its share of the tiles, so the break-even
- *                             margin shrinks with the rank count.  -1 = GEMM_EMULATE_MIN with 2 ranks, FP64 pipe only
- *                             with more (n = 50 000 inverse: 2 ranks 1.54 s int8 vs 2.38 s; 8 ranks 1.24 s at 4096,
- *                             1.13 s at 8192, 1.07 s FP64 pipe alone -- profiles/r02_dist_inverse_bench_g8.jsonl)
+ *                             margin shrinks with the rank count.  -1 = GEMM_EMULATE_MIN with 2 ranks, 4096 with 3-4,
+ *                             FP64 pipe only with more (n = 50 000 inverse: 2 ranks 1.54 s int8 vs 2.38 s; 4 ranks
+ *                             1.28 s at 4096 vs 1.44 s FP64 pipe; 8 ranks 1.24 s at 4096, 1.13 s at 8192, 1.07 s FP64
+ *                             pipe alone -- profiles/r02_dist_inverse_bench_g4.jsonl, _g8.jsonl)
  *   ELBO_OVERLAP         [3]  side streams of the ELBO step (0: single stream)
  *   WORKSPACE_CACHE_BYTES [-1] cap of the per-device workspace cache; -1 = half of the device memory, 0 = no caching */
 enum {

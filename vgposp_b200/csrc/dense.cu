@@ -763,13 +763,13 @@ int dense_gemm(int trans_a, int trans_b, int64_t m, int64_t n, int64_t k, double
             ++dc->dist_gemms;
             VGP_TRY(dense_dist_barrier(*dc, s));                  // every rank is done with all earlier work
             // every rank cuts the digit planes of the WHOLE operands and multiplies 1/nranks of the tiles, so the int8
-            // path loses its margin as the rank count grows: measured at n = 50 000 it wins with 2 ranks (inverse
-            // 1.54 s against 2.38 s) and never with 8 (profiles/r02_dist_inverse_bench_g8.jsonl: every threshold
-            // from 2048 up is slower than the FP64 pipe alone).  VGP_OPT_DIST_EMULATE_MIN = -1 follows that.
+            // path loses its margin as the rank count grows.  Measured at n = 50 000 (profiles/r02_dist_inverse_bench_
+            // g4/g8.jsonl): 2 ranks, inverse 1.54 s against 2.38 s on the FP64 pipe; 4 ranks, 1.28 s with products from
+            // 4096 up against 1.41 s (from 1024) and 1.44 s (FP64 pipe); 8 ranks, every threshold loses to the FP64
+            // pipe alone (1.07 s).  VGP_OPT_DIST_EMULATE_MIN = -1 follows that table.
             int64_t dist_emu_min = option(VGP_OPT_DIST_EMULATE_MIN);
-            const bool dist_emulate = dist_emu_min < 0 ? dc->nranks <= 2
-                                                       : (m >= dist_emu_min && n >= dist_emu_min && 2 * k >= dist_emu_min);
-            if (emulate && dist_emulate) {
+            if (dist_emu_min < 0) dist_emu_min = dc->nranks <= 2 ? emu_min : dc->nranks <= 4 ? 4096 : INT64_MAX;
+            if (emulate && m >= dist_emu_min && n >= dist_emu_min && 2 * k >= dist_emu_min) {
                 VGP_TRY(emulated_gemm(*g_emu_ws, trans_a, trans_b, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc,
                                       emu_slices, tiles == GEMM_LOWER ? 1 : 0, s, dc));
                 return dense_dist_barrier(*dc, s);

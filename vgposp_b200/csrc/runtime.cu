@@ -54,7 +54,7 @@ static std::atomic<int64_t> g_options[VGP_OPT_COUNT] = {
     {256},     // VGP_OPT_DIST_MIN_K
     {3},       // VGP_OPT_ELBO_OVERLAP
     {-1},      // VGP_OPT_WORKSPACE_CACHE_BYTES (-1: half of the device's memory)
-    {-1},      // VGP_OPT_DIST_EMULATE_MIN (-1: GEMM_EMULATE_MIN with <= 2 ranks, FP64 pipe with more)
+    {-1},      // VGP_OPT_DIST_EMULATE_MIN (-1: by rank count, see dense_gemm)
 };
 int64_t option(int which) { return which >= 0 && which < VGP_OPT_COUNT ? g_options[which].load() : 0; }
 
