@@ -87,7 +87,11 @@ int vgp_dist_create(vgp_dist **handle, int device, int rank, int nranks, int64_t
     // everything that could allocate, free or load a module later happens now, before any rank can be spinning
     int rc0 = dense_preload();
     if (rc0 == VGP_OK) rc0 = h->ws.ensure(h->n_pad / TILE);
-    if (rc0 == VGP_OK && option(VGP_OPT_GEMM_EMULATE_SLICES) >= 2 && h->n_pad >= option(VGP_OPT_GEMM_EMULATE_MIN))
+    // digit-plane workspace of the int8 products -- not with more than 4 ranks on the default rule (dense_gemm keeps
+    // distributed products on the FP64 pipe there, and the local ones below the distribution thresholds are small)
+    const bool int8_never = option(VGP_OPT_DIST_EMULATE_MIN) < 0 && nranks > 4;
+    if (rc0 == VGP_OK && !int8_never && option(VGP_OPT_GEMM_EMULATE_SLICES) >= 2 &&
+        h->n_pad >= option(VGP_OPT_GEMM_EMULATE_MIN))
         rc0 = h->ws.emu.reserve(largest_half(h->n_pad), (int)option(VGP_OPT_GEMM_EMULATE_SLICES), nullptr);
     if (rc0 != VGP_OK) {
         vgp_dist_destroy(h);
