@@ -119,6 +119,10 @@ def test_sharded_lazy_factor_greedy_threads(n, world, k, emulate_min, vgp_option
         r.fill_padding()
         r.load_host(np.full((n, n), np.nan))        # poison: nothing may read the strict upper triangle
     lazies = [greedy.LazyGreedy.from_dist(r, k) for r in ranks]
+    for lz in lazies:
+        # allocates the per-step score buffer: here, not inside the rank threads -- a cudaMalloc (workspace-cache miss)
+        # may wait for the device, on which another rank's barrier kernel is spinning in this single-device emulation
+        lz.record_scores(True)
     bounds = [(n * g) // world for g in range(world + 1)]
     for r in ranks:     # each rank uploads the lower-triangle share of its row slab; the peer copies ride along
         r0, r1 = bounds[r.rank], bounds[r.rank + 1]
@@ -130,7 +134,6 @@ def test_sharded_lazy_factor_greedy_threads(n, world, k, emulate_min, vgp_option
             r, lz = ranks[i], lazies[i]
             r.barrier()
             lz.load_cov_device(r.ptr, r.ld)
-            lz.record_scores(True)
             r.factor_inverse()
             lz.adopt_factor()
             lz.run(k)
