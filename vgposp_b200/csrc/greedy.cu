@@ -635,12 +635,15 @@ int check_handle(vgp_greedy *h) {
 
 // The dominant kernel: one streaming read-modify-write pass over the local precision panel.
 static int launch_downdate(vgp_greedy *h, cudaStream_t s) {
-    constexpr int rows_per_block = 32, waves = 4, unroll = 4;     // tuned on B200 (profiles/r01_kernel_bench_n50000.json)
+    // One CTA per (8 rows x 512 columns), launched in address order, NO grid-stride loop: measured on the 20 GB panel
+    // (tools/downdate_sweep.cu, profiles/r02_downdate_sweep.log) 5.73 ms = 6.99 TB/s against 6.31 ms = 6.35 TB/s for
+    // 4 waves of CTAs striding over row blocks of 32 -- the block scheduler then walks the panel linearly and the
+    // write of a DRAM page follows its read closely; CTAs that loop drift apart and keep more pages open.
+    constexpr int rows_per_block = 8, unroll = 4;
     const unsigned gx = (unsigned)((h->ld + 511) / 512);
     const int64_t row_tiles = (h->n_pad + rows_per_block - 1) / rows_per_block;
-    int64_t gy = ((int64_t)h->sm_count * 8 * waves + gx - 1) / gx;
-    if (gy > row_tiles) gy = row_tiles;
-    if (gy > 65535) gy = 65535;
+    int64_t gy = row_tiles;
+    if (gy > 65535) gy = 65535;                                   // beyond that the kernel's row loop takes over
     if (gy < 1) gy = 1;
     dim3 grid(gx, (unsigned)gy);
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
@@ -1031,11 +1034,12 @@ int vgp_greedy_run_peer(vgp_greedy *h, int64_t k, void *stream) {
     int64_t step_blocks = (span + 255) / 256;
     if (step_blocks > h->sm_count) step_blocks = h->sm_count;       // every CTA waits on flags: all must be resident
     if (step_blocks > 256) step_blocks = 256;                       // size of the partials buffer beyond score_blocks
-    constexpr int rows_per_block = 32, waves = 4;
+    // one CTA per row block, no grid-stride loop (see launch_downdate: +7.5 % at 32 rows per block on the stand-alone
+    // kernel); 32 rows per CTA keep the per-CTA flag check and the staging of p_i small against 128 KB of traffic
+    constexpr int rows_per_block = 32;
     const unsigned gx = (unsigned)((h->ld + 511) / 512);
     const int64_t row_tiles = (h->n_pad + rows_per_block - 1) / rows_per_block;
-    int64_t gy = ((int64_t)h->sm_count * 8 * waves + gx - 1) / gx;
-    if (gy > row_tiles) gy = row_tiles;
+    int64_t gy = row_tiles;
     if (gy > 65535) gy = 65535;
     if (gy < 1) gy = 1;
     for (int64_t i = 0; i < k; ++i) {
